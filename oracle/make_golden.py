@@ -1,0 +1,182 @@
+"""Generate ``tests/golden/mcem_*.npz`` from the UNMODIFIED reference.  Oracle tooling: test infrastructure only.
+
+Run in the build container only (``/root/reference`` does not exist on the GPU box)::
+
+    python oracle/make_golden.py
+
+For each case it
+  1. builds the reference's own VAE container (``packages/models/models.py``) and loads seeded weights
+     produced by ``dvae_b200.synth.xavier_state_dict`` (which also pins the state_dict key layout),
+  2. runs the reference's ``MCEM_*`` class (``packages/models/mcem.py``) on a seeded synthetic spectrogram
+     while recording every ``torch.rand`` / ``torch.randn`` draw in consumption order,
+  3. replays the same draws into ``oracle.mcem_port.MCEMOracle`` and requires bit-identical outputs,
+  4. stores inputs, draws and the reference's outputs as a compressed ``.npz``.
+
+The fixtures are what pins the oracle (and, through it, the CUDA path) to the reference.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+from dvae_b200 import synth  # noqa: E402
+from oracle import mcem_port, stft_np  # noqa: E402
+
+CASES = [
+    # name, variant, x_dim(n_fft), N frames, K, L, h_dim, y_dim, niter, (nsE, bE, nsWF, bWF)
+    dict(name="tiny_M1", variant="M1", n_fft=64, T=64 * 5, K=3, L=4, h=[8, 8], y_dim=0, niter=3, sched=(2, 3, 3, 4)),
+    dict(name="tiny_M2", variant="M2", n_fft=64, T=64 * 5, K=3, L=4, h=[8, 8], y_dim=1, niter=3, sched=(2, 3, 3, 4)),
+    dict(name="tiny_M2v2", variant="M2v2", n_fft=64, T=64 * 5, K=3, L=4, h=[8, 6], y_dim=1, niter=3, sched=(2, 3, 3, 4)),
+    dict(name="tiny_M2v3", variant="M2v3", n_fft=64, T=64 * 5, K=3, L=4, h=[8, 6], y_dim=1, niter=3, sched=(2, 3, 3, 4)),
+    dict(name="full_M1", variant="M1", n_fft=1024, T=1024 + 256 * 23, K=10, L=16, h=[128, 128], y_dim=0, niter=2,
+         sched=(10, 6, 25, 8)),
+    dict(name="full_M2", variant="M2", n_fft=1024, T=1024 + 256 * 23, K=10, L=16, h=[128, 128], y_dim=1, niter=2,
+         sched=(4, 6, 5, 7)),
+    dict(name="full_M2v3", variant="M2v3", n_fft=1024, T=1024 + 256 * 23, K=10, L=16, h=[128, 128], y_dim=1, niter=2,
+         sched=(4, 6, 5, 7)),
+    dict(name="cfg1_M1", variant="M1", n_fft=1024, T=1024 + 256 * 15, K=10, L=32, h=[128], y_dim=0, niter=2,
+         sched=(10, 5, 25, 6)),
+]
+
+
+def synth_spectra(case, seed):
+    """Seeded noisy / clean STFTs (F, N) complex64 and labels for one case (any n_fft)."""
+    rng = np.random.default_rng(seed)
+    T, n_fft = case["T"], case["n_fft"]
+    t = np.arange(T) / 16000.0
+    s = np.sin(2 * np.pi * 180.0 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 5 * t)) ** 2 * 0.3
+    n = 0.05 * rng.standard_normal(T)
+    fs, wlen = 16000, n_fft / 16000.0
+    kw = dict(fs=fs, wlen_sec=wlen, win="hann", hop_percent=0.25, center=False, pad_at_end=True)
+    X = stft_np.stft(s + n, **kw)
+    S = stft_np.stft(s, **kw)
+    y = None
+    if case["y_dim"]:
+        y = (rng.uniform(size=(case["y_dim"], X.shape[1])) > 0.4).astype(np.float32)
+    return X, S, y
+
+
+def build_reference(case, sd):
+    sys.path.insert(0, REF)
+    from packages.models import mcem as ref_mcem          # noqa: E402  (reseeds numpy/torch to 0 on import)
+    from packages.models import models as ref_models      # noqa: E402
+    F = case["n_fft"] // 2 + 1
+    v = case["variant"]
+    if v == "M1":
+        model = ref_models.VariationalAutoencoder([F, case["L"], case["h"]])
+        algo_cls = ref_mcem.MCEM_M1
+    elif v == "M2":
+        model = ref_models.DeepGenerativeModel([F, case["y_dim"], case["L"], case["h"]], None)
+        algo_cls = ref_mcem.MCEM_M2
+    else:
+        model = ref_models.DeepGenerativeModel_v5([F, case["y_dim"], case["L"], case["h"]]).enc_dec_clf
+        algo_cls = ref_mcem.MCEM_M2v2 if v == "M2v2" else ref_mcem.MCEM_M2v3
+    missing, unexpected = model.load_state_dict({k: torch.tensor(a) for k, a in sd.items()}, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith("classifier.") for k in missing), missing
+    model.eval()
+    for p in model.parameters():
+        p.requires_grad = False
+    return model, algo_cls
+
+
+class Recorder:
+    """Patch torch.rand / torch.randn to log draws in consumption order."""
+
+    def __enter__(self):
+        self.log = []
+        self._rand, self._randn = torch.rand, torch.randn
+
+        def rand(*a, **k):
+            t = self._rand(*a, **k)
+            self.log.append(("rand", t.detach().clone().numpy()))
+            return t
+
+        def randn(*a, **k):
+            t = self._randn(*a, **k)
+            self.log.append(("randn", t.detach().clone().numpy()))
+            return t
+
+        torch.rand, torch.randn = rand, randn
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randn = self._rand, self._randn
+
+
+def run_case(case, seed=7):
+    F = case["n_fft"] // 2 + 1
+    X, S, y = synth_spectra(case, seed)
+    out_bias = float(np.log(np.mean(np.abs(X) ** 2)))
+    sd = synth.xavier_state_dict(case["variant"] if case["variant"] != "M2v2" else "M2v3", F, case["L"], case["h"],
+                                 case["y_dim"], seed=1234 + seed, out_bias=out_bias)
+    model, algo_cls = build_reference(case, sd)
+    # container forward (the reconstruct_* scripts' path): models.py:172-180 / 201-204 / 280-287
+    rows = torch.tensor(np.abs(S.T[:5]) ** 2)
+    yrows = None if y is None else torch.tensor(y.T[:5])
+    torch.manual_seed(55 + seed)
+    with Recorder() as frec:
+        out = model(rows) if case["variant"] == "M1" else model(rows, yrows)
+    fwd = dict(fwd_xmu=out[0].numpy(), fwd_mu=out[-2].numpy(), fwd_lv=out[-1].numpy(), fwd_eps=frec.log[0][1])
+    pv = "M2v3" if case["variant"] == "M2v2" else case["variant"]
+    px, _, pmu, plv = mcem_port.vae_forward(sd, pv, rows, yrows, mcem_port.ReplayDraws(frec.log))
+    assert np.array_equal(px.numpy(), fwd["fwd_xmu"]) and np.array_equal(pmu.numpy(), fwd["fwd_mu"])
+    assert np.array_equal(plv.numpy(), fwd["fwd_lv"])
+
+    nsE, bE, nsWF, bWF = case["sched"]
+    algo = algo_cls(niter=case["niter"], nsamples_E_step=nsE, burnin_E_step=bE, nsamples_WF=nsWF, burnin_WF=bWF,
+                    var_RW=0.01)
+    torch.manual_seed(100 + seed)
+    with Recorder() as rec:
+        if case["variant"] == "M1":
+            algo.init_parameters(X=X, S=S, vae=model, nmf_rank=case["K"], eps=1e-8, device="cpu")
+        else:
+            algo.init_parameters(X=X, S=S, y=torch.tensor(y), vae=model, nmf_rank=case["K"], eps=1e-8, device="cpu")
+        Z0 = algo.Z.clone().numpy()
+        cost = algo.run()
+    ref = dict(cost=cost, S_hat=algo.S_hat, N_hat=algo.N_hat, W=algo.W.numpy(), H=algo.H.numpy(), g=algo.g.numpy(),
+               Z=algo.Z.numpy(), Z0=Z0, Vs_shape=np.array(algo.Vs.shape), **fwd)
+
+    # the port must reproduce the reference bit-for-bit from the recorded draws
+    port = mcem_port.MCEMOracle(case["variant"], case["niter"], nsE, bE, nsWF, bWF, 0.01,
+                                draws=mcem_port.ReplayDraws(rec.log))
+    port.init_parameters(X, S, sd, case["K"], 1e-8, y=y)
+    pcost = port.run()
+    checks = dict(cost=pcost, S_hat=port.S_hat, N_hat=port.N_hat, W=port.W.numpy(), H=port.H.numpy(),
+                  g=port.g.numpy(), Z=port.Z.numpy())
+    for k, v in checks.items():
+        if not np.array_equal(np.asarray(v), np.asarray(ref[k])):
+            d = np.max(np.abs(np.asarray(v) - np.asarray(ref[k])))
+            raise SystemExit("port != reference for %s in %s (max abs diff %g)" % (k, case["name"], d))
+    assert port.draws.pos == len(rec.log)
+    assert tuple(ref["Vs_shape"]) == tuple(port.Vs.shape)
+
+    kinds = np.array([0 if k == "rand" else 1 for k, _ in rec.log], np.uint8)
+    sizes = np.array([v.size for _, v in rec.log], np.int64)
+    shapes = np.array([list(v.shape) + [0] * (2 - v.ndim) for _, v in rec.log], np.int32)
+    flat = np.concatenate([v.ravel() for _, v in rec.log]).astype(np.float32)
+    meta = dict(variant=case["variant"], n_fft=case["n_fft"], K=case["K"], L=case["L"], h=np.array(case["h"]),
+                y_dim=case["y_dim"], niter=case["niter"], sched=np.array(case["sched"]), weight_seed=1234 + seed,
+                out_bias=out_bias, eps=1e-8, var_RW=0.01)
+    path = os.path.join(ROOT, "tests", "golden", "mcem_%s.npz" % case["name"])
+    np.savez_compressed(path, X=X, S=S, y=(y if y is not None else np.zeros((0, X.shape[1]), np.float32)),
+                        draw_kinds=kinds, draw_sizes=sizes, draw_shapes=shapes, draw_flat=flat,
+                        **{"ref_" + k: v for k, v in ref.items()}, **{"meta_" + k: np.asarray(v) for k, v in meta.items()})
+    print("%-10s ok: %d draws (%.0f KB), bit-identical port, file %.0f KB" %
+          (case["name"], len(rec.log), flat.nbytes / 1024, os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    if not os.path.isdir(REF):
+        raise SystemExit("needs the reference at %s (build container only)" % REF)
+    torch.set_num_threads(1)
+    for c in CASES:
+        run_case(c)
