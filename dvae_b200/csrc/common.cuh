@@ -1,0 +1,112 @@
+// Shared device/host helpers for libdvae_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dvae_b200.h"
+
+namespace dvae {
+
+// ----------------------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+int  check_launch(const char* what);          // returns 0 or the cudaError_t of the launch
+
+#define DVAE_REQUIRE(cond, ...)                                  \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            dvae::set_error(__VA_ARGS__);                        \
+            return DVAE_ERR_ARG;                                 \
+        }                                                        \
+    } while (0)
+
+// ----------------------------------------------------------------------------- small device utilities
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum `v` over the whole block; result valid in every thread. `scratch` holds >= 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    float r = 0.f;
+    for (int i = 0; i < nw; ++i) r += scratch[i];   // fixed order: deterministic
+    return r;
+}
+
+// ----------------------------------------------------------------------------- Philox-4x32-10
+// Counter-based generator (Salmon et al., SC'11). One call yields four 32-bit words. Draws are addressed as
+//   key     = (seed_lo, seed_hi)
+//   counter = (utterance id, frame | chain << 20, global Metropolis-Hastings iteration, block)
+// so a draw does not depend on how utterances are sharded over GPUs or tiled over CTAs.
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                           uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// (0,1) uniform from 24 random bits: never 0, never 1.
+__device__ __forceinline__ float u01(uint32_t r) { return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+// Box-Muller on two words -> two standard normals. Uses the MUFU approximations on purpose: the FP32 and the
+// tensor-core Metropolis-Hastings kernels share this function, so both consume bit-identical draws.
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    const float u1 = u01(a), u2 = u01(b);
+    const float r = sqrtf(-2.0f * __logf(u1));
+    float s, c;
+    __sincosf(6.283185307179586f * u2 - 3.141592653589793f, &s, &c);   // argument in [-pi, pi): best MUFU accuracy
+    n0 = -r * c;                                                       // cos(t) = -cos(t - pi)
+    n1 = -r * s;
+}
+
+// Draws for one (frame, chain, iteration): L normals (L <= DVAE_MAX_L) and one uniform.
+// Block b of the counter yields normals 4b..4b+3; the uniform comes from block (L+3)/4, word 0.
+__device__ __forceinline__ void mh_draws(uint32_t seed_lo, uint32_t seed_hi, uint32_t utt, uint32_t frame_chain,
+                                         uint32_t iter, int L, float* eps, float& u) {
+    const int nb = (L + 3) >> 2;
+    for (int b = 0; b < nb; ++b) {
+        const Philox4 r = philox4x32_10(utt, frame_chain, iter, (uint32_t)b, seed_lo, seed_hi);
+        float n0, n1, n2, n3;
+        box_muller(r.x, r.y, n0, n1);
+        box_muller(r.z, r.w, n2, n3);
+        const int j = 4 * b;
+        if (j + 0 < L) eps[j + 0] = n0;
+        if (j + 1 < L) eps[j + 1] = n1;
+        if (j + 2 < L) eps[j + 2] = n2;
+        if (j + 3 < L) eps[j + 3] = n3;
+    }
+    const Philox4 r = philox4x32_10(utt, frame_chain, iter, (uint32_t)nb, seed_lo, seed_hi);
+    u = u01(r.x);
+}
+
+}  // namespace dvae

@@ -1,0 +1,377 @@
+// NMF noise model and Wiener filter (FP32): initialisation, Vb = WH, the multiplicative M-step, cost, Wiener masks.
+//
+// Replaces packages/models/mcem.py:36-58 (init), 76-83 (variance helpers), 91-153 (M_step), 69-71 (cost),
+// 310-329 + 176-177 (Wiener filter).
+//
+// All kernels here are HBM/L2-bound passes over the materialised speech variances Vs[NT][R][ld].  Per EM
+// iteration (after Vs was written by the decoder): the W pass reads Vs once; the H/g/cost kernel reads each
+// frame's R rows three times back to back from one CTA (first from HBM, then from L1/L2).
+//
+// The order of operations follows the reference exactly: the W update uses the Vb kept from the
+// previous iteration, Vb is refreshed after W and after H, W/H are renormalised WITHOUT refreshing Vb, g uses the
+// un-normalised product, the cost uses the new g.
+#include "common.cuh"
+
+namespace dvae {
+
+constexpr int KMAX = DVAE_MAX_K;
+
+// ----------------------------------------------------------------------------- init (mcem.py:42-44)
+__global__ void nmf_init_kernel(uint32_t seed_lo, uint32_t seed_hi, const int32_t* __restrict__ utt_ids,
+                                const int64_t* __restrict__ fr_off, int B, int64_t NT, int F, int K, int ld, float eps,
+                                float* __restrict__ W, float* __restrict__ H, float* __restrict__ g) {
+    const int64_t nW = (int64_t)B * K * ld, nH = NT * K;
+    const int64_t total = nW + nH + NT;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < nW) {
+            const int f = (int)(i % ld);
+            const int k = (int)((i / ld) % K);
+            const int u = (int)(i / ((int64_t)ld * K));
+            float v = 0.f;
+            if (f < F) {
+                const Philox4 r = philox4x32_10((uint32_t)utt_ids[u], (uint32_t)(f * KMAX + k), 0xFFFFFFF0u, 0u, seed_lo, seed_hi);
+                v = fmaxf(u01(r.x), eps);
+            }
+            W[i] = v;
+        } else if (i < nW + nH) {
+            const int64_t j = i - nW;
+            const int k = (int)(j % K);
+            const int64_t n = j / K;
+            int lo = 0, hi = B;
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (fr_off[mid] <= n) lo = mid; else hi = mid; }
+            const Philox4 r = philox4x32_10((uint32_t)utt_ids[lo], (uint32_t)((n - fr_off[lo]) * KMAX + k), 0xFFFFFFF1u, 0u,
+                                            seed_lo, seed_hi);
+            H[j] = fmaxf(u01(r.x), eps);
+        } else {
+            g[i - nW - nH] = 1.0f;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------- Vb = W H (mcem.py:82-83)
+__global__ void __launch_bounds__(128) nmf_vb_kernel(const float* __restrict__ W, const float* __restrict__ H,
+                                                     const int32_t* __restrict__ frame_utt, int64_t NT, int F, int K,
+                                                     int ld, float* __restrict__ Vb) {
+    const int64_t n = blockIdx.x;
+    if (n >= NT) return;
+    const float* Wu = W + (int64_t)frame_utt[n] * K * ld;
+    float h[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) v = fmaf(Wu[k * ld + f], h[k], v);
+        Vb[n * ld + f] = v;
+    }
+}
+
+// ----------------------------------------------------------------------------- W update (mcem.py:108-111)
+// grid (ceil(F/128), B); thread = bin f, loops over the utterance's frames and samples.
+__global__ void __launch_bounds__(128) nmf_w_kernel(const float* __restrict__ P, const float* __restrict__ Vs, int R,
+                                                    const float* __restrict__ W, const float* __restrict__ H,
+                                                    const float* __restrict__ g, const float* __restrict__ Vb,
+                                                    const int64_t* __restrict__ fr_off, int F, int K, int ld,
+                                                    float* __restrict__ Wtmp) {
+    const int u = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    float num[KMAX], den[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) num[k] = den[k] = 0.f;
+    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
+    for (int64_t n = n0; n < n1; ++n) {
+        const float gg = g[n], vb = Vb[n * ld + f];
+        const float* v = Vs + (n * R) * (int64_t)ld + f;
+        float a1 = 0.f, a2 = 0.f;
+        for (int r = 0; r < R; ++r) {
+            const float vx = __fadd_rn(__fmul_rn(gg, v[(int64_t)r * ld]), vb);
+            const float inv = __frcp_rn(vx);
+            a1 += inv;
+            a2 += __fmul_rn(inv, inv);
+        }
+        const float pa2 = P[n * ld + f] * a2;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) {
+                const float h = H[n * K + k];
+                num[k] = fmaf(pa2, h, num[k]);
+                den[k] = fmaf(a1, h, den[k]);
+            }
+    }
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k)
+        if (k < K) {
+            const int64_t i = ((int64_t)u * K + k) * ld + f;
+            Wtmp[i] = W[i] * sqrtf(num[k] / den[k]);
+        }
+}
+
+// column L1 norms of the updated W, normalised copy into W, cost accumulator reset (mcem.py:130-132)
+__global__ void __launch_bounds__(256) nmf_norm_kernel(const float* __restrict__ Wtmp, int F, int K, int ld,
+                                                       float* __restrict__ W, float* __restrict__ norm,
+                                                       double* __restrict__ cost) {
+    __shared__ float scratch[32];
+    const int u = blockIdx.x;
+    for (int k = 0; k < K; ++k) {
+        const float* src = Wtmp + ((int64_t)u * K + k) * ld;
+        float s = 0.f;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) s += fabsf(src[f]);
+        s = block_sum(s, scratch);
+        if (threadIdx.x == 0) norm[u * K + k] = s;
+        float* dst = W + ((int64_t)u * K + k) * ld;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) dst[f] = src[f] / s;
+    }
+    if (threadIdx.x == 0) cost[u] = 0.0;
+}
+
+// ----------------------------------------------------------------------------- H, g updates + cost (mcem.py:119-153, 69-71)
+// grid (ceil(max_frames/FPB), B); a CTA walks FPB consecutive frames of one utterance with W_new[u] in shared memory.
+constexpr int FPB = 4;
+
+__global__ void __launch_bounds__(256) nmf_hg_kernel(const float* __restrict__ P, const float* __restrict__ Vs, int R,
+                                                     const float* __restrict__ Wtmp, const float* __restrict__ norm,
+                                                     float* __restrict__ H, float* __restrict__ g, float* __restrict__ Vb,
+                                                     double* __restrict__ cost, const int64_t* __restrict__ fr_off,
+                                                     int F, int K, int ld) {
+    extern __shared__ float Ws[];                 // [K][ld]
+    __shared__ float red[2 * KMAX][8];
+    __shared__ float hnew[KMAX];
+    __shared__ float scratch[32];
+    const int u = blockIdx.y;
+    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
+    const int64_t nb = n0 + (int64_t)blockIdx.x * FPB;
+    if (nb >= n1) return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < K * ld; i += blockDim.x) Ws[i] = Wtmp[(int64_t)u * K * ld + i];
+    __syncthreads();
+    const double inv_count = 1.0 / ((double)R * (double)F * (double)(n1 - n0));
+    double cost_acc = 0.0;
+
+    for (int64_t n = nb; n < n1 && n < nb + FPB; ++n) {
+        const float gg = g[n];
+        const float* Vn = Vs + (n * R) * (int64_t)ld;
+        float h[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
+
+        // ---- H update: Vb1 = W_new H_old
+        float num[KMAX], den[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) num[k] = den[k] = 0.f;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            float vb = 0.f;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K) vb = fmaf(Ws[k * ld + f], h[k], vb);
+            float a1 = 0.f, a2 = 0.f;
+            for (int r = 0; r < R; ++r) {
+                const float vx = __fadd_rn(__fmul_rn(gg, Vn[(int64_t)r * ld + f]), vb);
+                const float inv = __frcp_rn(vx);
+                a1 += inv;
+                a2 += __fmul_rn(inv, inv);
+            }
+            const float pa2 = P[n * ld + f] * a2;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K) {
+                    const float w = Ws[k * ld + f];
+                    num[k] = fmaf(w, pa2, num[k]);
+                    den[k] = fmaf(w, a1, den[k]);
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k)
+            if (k < K) {
+                const float a = warp_sum(num[k]), b = warp_sum(den[k]);
+                if (lane == 0) { red[2 * k][wid] = a; red[2 * k + 1][wid] = b; }
+            }
+        __syncthreads();
+        if (threadIdx.x < K) {
+            float a = 0.f, b = 0.f;
+            for (int w = 0; w < 8; ++w) { a += red[2 * threadIdx.x][w]; b += red[2 * threadIdx.x + 1][w]; }
+            hnew[threadIdx.x] = H[n * K + threadIdx.x] * sqrtf(a / b);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) h[k] = (k < K) ? hnew[k] : 0.f;
+
+        // ---- g update with Vb2 = W_new H_new (kept as the model's Vb)
+        float ng = 0.f, dg = 0.f;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            float vb = 0.f;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k)
+                if (k < K) vb = fmaf(Ws[k * ld + f], h[k], vb);
+            Vb[n * ld + f] = vb;
+            float s2 = 0.f, s1 = 0.f;
+            for (int r = 0; r < R; ++r) {
+                const float v = Vn[(int64_t)r * ld + f];
+                const float vx = __fadd_rn(__fmul_rn(gg, v), vb);
+                const float inv = __frcp_rn(vx);
+                s1 = fmaf(v, inv, s1);
+                s2 = fmaf(v, __fmul_rn(inv, inv), s2);
+            }
+            ng = fmaf(P[n * ld + f], s2, ng);
+            dg += s1;
+        }
+        ng = block_sum(ng, scratch);
+        dg = block_sum(dg, scratch);
+        const float gnew = gg * sqrtf(ng / dg);
+
+        // ---- cost with the refreshed Vx = g_new Vs + Vb2
+        float c = 0.f;
+        for (int f = threadIdx.x; f < F; f += blockDim.x) {
+            const float vb = Vb[n * ld + f];          // written by this very thread above
+            const float p = P[n * ld + f];
+            for (int r = 0; r < R; ++r) {
+                const float vx = __fadd_rn(__fmul_rn(gnew, Vn[(int64_t)r * ld + f]), vb);
+                c += logf(vx) + __fdiv_rn(p, vx);
+            }
+        }
+        c = block_sum(c, scratch);
+        cost_acc += (double)c;
+
+        if (threadIdx.x < K) H[n * K + threadIdx.x] = hnew[threadIdx.x] * norm[u * K + threadIdx.x];
+        if (threadIdx.x == 0) g[n] = gnew;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(cost + u, cost_acc * inv_count);
+}
+
+// ----------------------------------------------------------------------------- Wiener masks (mcem.py:325-327)
+__global__ void wiener_accum_kernel(const float* __restrict__ Vs, int R, const float* __restrict__ Vb,
+                                    const float* __restrict__ g, int64_t NT, int F, int ld, float* __restrict__ WFs,
+                                    float* __restrict__ WFn, int first) {
+    const int64_t total = NT * ld;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / ld;
+        const int f = (int)(i - n * ld);
+        if (f >= F) continue;
+        const float gg = g[n], vb = Vb[i];
+        const float* v = Vs + (n * R) * (int64_t)ld + f;
+        float s = first ? 0.f : WFs[i], q = first ? 0.f : WFn[i];
+        for (int r = 0; r < R; ++r) {
+            const float vs = __fmul_rn(gg, v[(int64_t)r * ld]);
+            const float vx = __fadd_rn(vs, vb);
+            s += __fdiv_rn(vs, vx);
+            q += __fdiv_rn(vb, vx);
+        }
+        WFs[i] = s;
+        WFn[i] = q;
+    }
+}
+
+__global__ void wiener_apply_kernel(const float2* __restrict__ X, const float* __restrict__ WFs,
+                                    const float* __restrict__ WFn, float inv_R, int64_t NT, int F, int ld,
+                                    float2* __restrict__ S_hat, float2* __restrict__ N_hat) {
+    const int64_t total = NT * ld;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % ld);
+        float2 s = make_float2(0.f, 0.f), q = s;
+        if (f < F) {
+            const float2 x = X[i];
+            const float ws = WFs[i] * inv_R, wn = WFn[i] * inv_R;
+            s = make_float2(ws * x.x, ws * x.y);
+            q = make_float2(wn * x.x, wn * x.y);
+        }
+        S_hat[i] = s;
+        N_hat[i] = q;
+    }
+}
+
+static int grid_for(int64_t n, int block) {
+    const int64_t b = (n + block - 1) / block;
+    return (int)(b < 148 * 16 ? (b < 1 ? 1 : b) : 148 * 16);
+}
+
+}  // namespace dvae
+
+using namespace dvae;
+
+extern "C" int dvae_nmf_init(uint64_t seed, const int32_t* utt_ids, const int64_t* fr_off, int B, int64_t NT, int F,
+                             int K, int ld, float eps, float* W, float* H, float* g, void* stream) {
+    DVAE_REQUIRE(utt_ids && fr_off && W && H && g, "dvae_nmf_init: null pointer");
+    DVAE_REQUIRE(B >= 1 && NT >= 0 && F >= 1 && ld >= F && K >= 1 && K <= KMAX, "dvae_nmf_init: bad sizes (K<=%d)", KMAX);
+    const int64_t total = (int64_t)B * K * ld + NT * K + NT;
+    nmf_init_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32),
+                                                                          utt_ids, fr_off, B, NT, F, K, ld, eps, W, H, g);
+    return check_launch("nmf_init_kernel");
+}
+
+extern "C" int dvae_nmf_vb(const float* W, const float* H, const int32_t* frame_utt, int64_t NT, int F, int K, int ld,
+                           float* Vb, void* stream) {
+    DVAE_REQUIRE(W && H && frame_utt && Vb, "dvae_nmf_vb: null pointer");
+    DVAE_REQUIRE(NT >= 0 && F >= 1 && ld >= F && K >= 1 && K <= KMAX, "dvae_nmf_vb: bad sizes (K<=%d)", KMAX);
+    if (NT == 0) return 0;
+    nmf_vb_kernel<<<(unsigned)NT, 128, 0, (cudaStream_t)stream>>>(W, H, frame_utt, NT, F, K, ld, Vb);
+    return check_launch("nmf_vb_kernel");
+}
+
+extern "C" int64_t dvae_nmf_workspace_floats(int B, int K, int ld) {
+    if (B <= 0 || K <= 0 || ld <= 0) return 0;
+    return (int64_t)B * K * ld + (int64_t)B * K;       // un-normalised W_new + column norms
+}
+
+extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, float* H, float* g, float* Vb,
+                              double* cost, const int64_t* fr_off, const int32_t* frame_utt, int B, int64_t NT, int F,
+                              int K, int ld, int max_frames, float* ws, void* stream) {
+    (void)frame_utt;
+    DVAE_REQUIRE(P && Vs && W && H && g && Vb && cost && fr_off && ws, "dvae_nmf_mstep: null pointer");
+    DVAE_REQUIRE(B >= 1 && NT >= 0 && F >= 1 && ld >= F && R >= 1, "dvae_nmf_mstep: bad sizes");
+    DVAE_REQUIRE(K >= 1 && K <= KMAX, "dvae_nmf_mstep: K=%d out of range (<=%d)", K, KMAX);
+    DVAE_REQUIRE(max_frames >= 0, "dvae_nmf_mstep: max_frames < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* Wtmp = ws;
+    float* norm = ws + (int64_t)B * K * ld;
+    nmf_w_kernel<<<dim3((F + 127) / 128, B), 128, 0, st>>>(P, Vs, R, W, H, g, Vb, fr_off, F, K, ld, Wtmp);
+    int rc = check_launch("nmf_w_kernel");
+    if (rc) return rc;
+    nmf_norm_kernel<<<B, 256, 0, st>>>(Wtmp, F, K, ld, W, norm, cost);
+    rc = check_launch("nmf_norm_kernel");
+    if (rc) return rc;
+    if (max_frames == 0) return 0;
+    const size_t smem = sizeof(float) * (size_t)K * ld;
+    DVAE_REQUIRE(smem <= 200 * 1024, "dvae_nmf_mstep: K*ld too large for shared memory");
+    cudaFuncSetAttribute(nmf_hg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    nmf_hg_kernel<<<dim3((max_frames + FPB - 1) / FPB, B), 256, smem, st>>>(P, Vs, R, Wtmp, norm, H, g, Vb, cost, fr_off, F, K, ld);
+    return check_launch("nmf_hg_kernel");
+}
+
+extern "C" int dvae_wiener_accum(const float* Vs, int R, const float* Vb, const float* g, int64_t NT, int F, int ld,
+                                 float* WFs, float* WFn, int first, void* stream) {
+    DVAE_REQUIRE(Vs && Vb && g && WFs && WFn, "dvae_wiener_accum: null pointer");
+    DVAE_REQUIRE(R >= 1 && NT >= 0 && F >= 1 && ld >= F, "dvae_wiener_accum: bad sizes");
+    if (NT == 0) return 0;
+    wiener_accum_kernel<<<grid_for(NT * ld, 256), 256, 0, (cudaStream_t)stream>>>(Vs, R, Vb, g, NT, F, ld, WFs, WFn, first);
+    return check_launch("wiener_accum_kernel");
+}
+
+extern "C" int dvae_wiener_apply(const void* X, const float* WFs, const float* WFn, int R_total, int64_t NT, int F,
+                                 int ld, void* S_hat, void* N_hat, void* stream) {
+    DVAE_REQUIRE(X && WFs && WFn && S_hat && N_hat, "dvae_wiener_apply: null pointer");
+    DVAE_REQUIRE(R_total >= 1 && NT >= 0 && F >= 1 && ld >= F, "dvae_wiener_apply: bad sizes");
+    if (NT == 0) return 0;
+    wiener_apply_kernel<<<grid_for(NT * ld, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)X, WFs, WFn, 1.0f / (float)R_total,
+                                                                                NT, F, ld, (float2*)S_hat, (float2*)N_hat);
+    return check_launch("wiener_apply_kernel");
+}
+
+// P = |X|^2 (mcem.py:47: torch.tensor(np.abs(X)**2)) for spectra that did not come from dvae_stft_f32
+namespace dvae {
+__global__ void power_kernel(const float2* __restrict__ X, float* __restrict__ P, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 x = X[i];
+        const float a = hypotf(x.x, x.y);          // np.abs of complex64, then squared
+        P[i] = a * a;
+    }
+}
+}  // namespace dvae
+
+extern "C" int dvae_power(const void* X, float* P, int64_t n, void* stream) {
+    DVAE_REQUIRE(X && P && n >= 0, "dvae_power: bad arguments");
+    if (n == 0) return 0;
+    power_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)X, P, n);
+    return check_launch("power_kernel");
+}

@@ -1,0 +1,314 @@
+// STFT / ISTFT for the reference's only configuration: n_fft = 1024, periodic Hann, center=False.
+//
+// Replaces packages/processing/stft.py:13-60 / 63-99 (thin wrappers over librosa.core.stft / istft).
+//
+// One 1024-point real FFT is computed as a 512-point complex FFT of the even/odd-packed frame followed by the
+// standard split post-processing.  The 512-point FFT is three radix-8 passes (512 = 8*8*8) executed by 64 threads
+// that hold 8 points each in registers; the two digit exchanges go through shared memory (row stride 65 float2 so
+// the strided re-reads are conflict-free), twiddles come from a 1024-entry table built once per device in double.
+// A CTA of 256 threads works on four frames at a time.
+//
+// HBM traffic per utterance (T samples, N frames, F = 513): STFT reads 4T (frame overlap is served by L1/L2),
+// writes 8FN (+4FN for |X|^2); ISTFT reads 8FN, writes 4T.
+#include <float.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dvae {
+
+constexpr int kNfft = 1024;
+constexpr int kHalf = 512;
+constexpr int kRow = 65;                       // padded row stride (float2) of the 8 x 64 exchange buffer
+constexpr int kBuf = 8 * kRow;                 // float2 per frame group
+
+__device__ float2 g_tw[kNfft];                 // exp(-2*pi*i*k/1024)
+__device__ float g_win[kNfft];                 // periodic Hann
+__device__ double g_win2[kNfft];               // Hann^2 in double (librosa window_sumsquare accumulates these into f32)
+
+__global__ void init_tables_kernel() {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= kNfft) return;
+    double s, c;
+    sincospi(2.0 * (double)k / (double)kNfft, &s, &c);
+    g_tw[k] = make_float2((float)c, (float)(-s));
+    const double w = 0.5 - 0.5 * c;
+    g_win[k] = (float)w;
+    g_win2[k] = w * w;
+}
+
+static std::mutex g_init_mutex;
+static bool g_inited[64] = {false};
+
+int ensure_tables(cudaStream_t stream) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { set_error("cudaGetDevice: %s", cudaGetErrorString(e)); return (int)e; }
+    std::lock_guard<std::mutex> lock(g_init_mutex);
+    if (dev < 64 && g_inited[dev]) return 0;
+    init_tables_kernel<<<kNfft / 256, 256, 0, stream>>>();
+    int rc = check_launch("init_tables");
+    if (rc == 0 && dev < 64) g_inited[dev] = true;
+    return rc;
+}
+
+// ----------------------------------------------------------------------------- complex helpers
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }    // a * (-i)
+__device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }    // a * (+i)
+
+// 8-point forward DFT (e^{-2 pi i nk/8}), natural order in and out, in registers.
+__device__ __forceinline__ void fft8(float2* a) {
+    const float s = 0.70710678118654752440f;
+    const float2 b0 = cadd(a[0], a[4]), b1 = csub(a[0], a[4]);
+    const float2 b2 = cadd(a[2], a[6]), b3 = csub(a[2], a[6]);
+    const float2 b4 = cadd(a[1], a[5]), b5 = csub(a[1], a[5]);
+    const float2 b6 = cadd(a[3], a[7]), b7 = csub(a[3], a[7]);
+    const float2 e0 = cadd(b0, b2), e1 = cadd(b1, mul_mi(b3)), e2 = csub(b0, b2), e3 = cadd(b1, mul_pi(b3));
+    const float2 o0 = cadd(b4, b6), o1 = cadd(b5, mul_mi(b7)), o2 = csub(b4, b6), o3 = cadd(b5, mul_pi(b7));
+    const float2 t1 = make_float2(s * (o1.x + o1.y), s * (o1.y - o1.x));      // o1 * (1-i)/sqrt2
+    const float2 t2 = mul_mi(o2);                                             // o2 * (-i)
+    const float2 t3 = make_float2(s * (o3.y - o3.x), -s * (o3.x + o3.y));     // o3 * (-1-i)/sqrt2
+    a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
+    a[1] = cadd(e1, t1); a[5] = csub(e1, t1);
+    a[2] = cadd(e2, t2); a[6] = csub(e2, t2);
+    a[3] = cadd(e3, t3); a[7] = csub(e3, t3);
+}
+
+// 512-point forward complex FFT by the 64 threads of a frame group.
+// in : a[n1] = z[t + 64*n1]            (t = thread in group)
+// out: a[j2] = Z[t + 64*j2]
+// `buf` is the group's kBuf-float2 exchange buffer, `tw` the shared twiddle table.  Contains three CTA barriers:
+// every thread of the CTA must call it the same number of times.
+__device__ __forceinline__ void fft512(float2* a, float2* buf, const float2* tw, int t) {
+    fft8(a);
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) buf[k1 * kRow + t] = cmul(a[k1], tw[(2 * t * k1) & (kNfft - 1)]);
+    __syncthreads();
+    {
+        const int k1 = t >> 3, m2 = t & 7;
+#pragma unroll
+        for (int m1 = 0; m1 < 8; ++m1) a[m1] = buf[k1 * kRow + 8 * m1 + m2];
+        fft8(a);
+        // in place: this thread rewrites exactly the eight slots it has just read
+#pragma unroll
+        for (int j1 = 0; j1 < 8; ++j1) buf[k1 * kRow + 8 * j1 + m2] = cmul(a[j1], tw[(16 * m2 * j1) & (kNfft - 1)]);
+    }
+    __syncthreads();
+    {
+        const int k1 = t & 7, j1 = t >> 3;
+#pragma unroll
+        for (int m2 = 0; m2 < 8; ++m2) a[m2] = buf[k1 * kRow + 8 * j1 + m2];
+        fft8(a);                                   // a[j2] = Z[k1 + 8*j1 + 64*j2] = Z[t + 64*j2]
+    }
+    __syncthreads();                               // buf may be reused by the caller
+}
+
+__device__ __forceinline__ int find_utt(const int64_t* __restrict__ fr_off, int B, int64_t n) {
+    int lo = 0, hi = B;                            // largest u with fr_off[u] <= n
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (fr_off[mid] <= n) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ----------------------------------------------------------------------------- STFT
+__global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, const int64_t* __restrict__ x_off,
+                                                   const int32_t* __restrict__ x_len, int B, float2* __restrict__ X,
+                                                   float* __restrict__ P, const int64_t* __restrict__ fr_off,
+                                                   int64_t NT, int hop, int ld) {
+    __shared__ float2 tw[kNfft];
+    __shared__ float2 bufs[4][kBuf];
+    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) tw[i] = g_tw[i];
+    __syncthreads();
+
+    const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
+    float2* buf = bufs[grp];
+    const int64_t n_pass = (NT + 3) / 4;
+    for (int64_t pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+        const int64_t n = pass * 4 + grp;
+        const bool live = n < NT;
+        float2 a[8];
+        if (live) {
+            const int u = find_utt(fr_off, B, n);
+            const int64_t j = n - fr_off[u];
+            const float* xu = x + x_off[u];
+            const int64_t len = x_len[u];
+            const int64_t s0 = j * (int64_t)hop;
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) {
+                const int p = 2 * (t + 64 * n1);
+                const int64_t q = s0 + p;
+                const float v0 = (q < len) ? __ldg(xu + q) : 0.f;
+                const float v1 = (q + 1 < len) ? __ldg(xu + q + 1) : 0.f;
+                a[n1] = make_float2(v0 * (0.5f - 0.5f * tw[p].x), v1 * (0.5f - 0.5f * tw[p + 1].x));
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) a[n1] = make_float2(0.f, 0.f);
+        }
+        fft512(a, buf, tw, t);
+#pragma unroll
+        for (int j2 = 0; j2 < 8; ++j2) buf[j2 * kRow + t] = a[j2];          // natural order Z[k] at (k>>6, k&63)
+        __syncthreads();
+        if (live) {
+            float2* Xn = X + n * (int64_t)ld;
+            float* Pn = P ? P + n * (int64_t)ld : nullptr;
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                const int k = t + 64 * j;
+                if (k > kHalf) break;
+                const int km = (kHalf - k) & (kHalf - 1);
+                const float2 zk = buf[((k & (kHalf - 1)) >> 6) * kRow + (k & 63)];
+                float2 zm = buf[(km >> 6) * kRow + (km & 63)];
+                zm.y = -zm.y;                                               // conj(Z[512-k])
+                const float2 s = cadd(zk, zm), d = csub(zk, zm);
+                const float2 wd = cmul(tw[k], d);                           // W^k (Zk - conj Zm)
+                // X[k] = 0.5*s - 0.5*i*wd
+                const float2 r = make_float2(0.5f * (s.x + wd.y), 0.5f * (s.y - wd.x));
+                Xn[k] = r;
+                if (Pn) Pn[k] = r.x * r.x + r.y * r.y;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------- ISTFT
+constexpr int kSegFrames = 28;                   // frames touched per CTA (7 passes of 4)
+
+__global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ X, const int64_t* __restrict__ fr_off,
+                                                    float* __restrict__ y, const int64_t* __restrict__ y_off,
+                                                    const int32_t* __restrict__ y_len, int hop, int ld, int seg_hops) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tw = reinterpret_cast<float2*>(smem_raw);                         // 1024 float2
+    float2* bufs = tw + kNfft;                                                // 4 * kBuf float2
+    float* fbuf = reinterpret_cast<float*>(bufs + 4 * kBuf);                  // 4 * 1024 floats
+    float* acc = fbuf + 4 * kNfft;                                            // (kSegFrames-1)*hop + 1024 floats
+
+    const int u = blockIdx.y;
+    const int ov = kNfft / hop;                                               // frames overlapping one sample
+    const int64_t f0 = fr_off[u];
+    const int N = (int)(fr_off[u + 1] - f0);
+    const int len = y_len[u];
+    const int h0 = blockIdx.x * seg_hops;                                     // first output hop of this CTA
+    const int out_lo = h0 * hop, out_hi = min(len, (h0 + seg_hops) * hop);
+    if (out_lo >= len) return;
+    const int jstart = max(0, h0 - (ov - 1));
+    const int jend = min(N - 1, h0 + seg_hops - 1);                           // inclusive; may be < jstart
+    const int a0 = jstart * hop;                                              // sample index of acc[0]
+    const int span = (kSegFrames - 1) * hop + kNfft;
+
+    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) tw[i] = g_tw[i];
+    for (int i = threadIdx.x; i < span; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+
+    const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
+    float2* buf = bufs + grp * kBuf;
+    for (int jp = jstart; jp <= jend; jp += 4) {
+        const int j = jp + grp;
+        const bool live = j <= jend;
+        float2 a[8];
+        if (live) {
+            const float2* Xn = X + (f0 + j) * (int64_t)ld;
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) {
+                const int k = t + 64 * n1;
+                float2 xk = Xn[k], xm = Xn[kHalf - k];
+                if (k == 0) { xk.y = 0.f; xm.y = 0.f; }                       // irfft ignores Im of DC and Nyquist
+                xm.y = -xm.y;                                                 // conj(X[512-k])
+                const float2 s = cadd(xk, xm), d = csub(xk, xm);
+                float2 w = tw[k];
+                w.y = -w.y;                                                   // conj(W^k)
+                const float2 wd = cmul(w, d);
+                const float2 zb = make_float2(s.x - wd.y, s.y + wd.x);        // s + i*wd
+                a[n1] = make_float2(zb.x, -zb.y);                             // conj -> inverse via forward FFT
+            }
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 8; ++n1) a[n1] = make_float2(0.f, 0.f);
+        }
+        fft512(a, buf, tw, t);
+        if (live) {
+            float2* fb = reinterpret_cast<float2*>(fbuf + grp * kNfft);
+#pragma unroll
+            for (int j2 = 0; j2 < 8; ++j2) {
+                const int m = t + 64 * j2;
+                const float xe = a[j2].x * (1.0f / 1024.0f), xo = -a[j2].y * (1.0f / 1024.0f);
+                fb[m] = make_float2(xe * (0.5f - 0.5f * tw[2 * m].x), xo * (0.5f - 0.5f * tw[2 * m + 1].x));
+            }
+        }
+        __syncthreads();
+        // overlap-add the (up to) four frames of this pass in ascending frame order, like the reference's loop
+        const int base = (jp - jstart) * hop;
+        for (int i = threadIdx.x; i < 3 * hop + kNfft; i += blockDim.x) {
+            float v = acc[base + i];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int off = i - g * hop;
+                if (jp + g <= jend && off >= 0 && off < kNfft) v += fbuf[g * kNfft + off];
+            }
+            acc[base + i] = v;
+        }
+        __syncthreads();
+    }
+
+    float* yu = y + y_off[u];
+    const int sig_len = (N > 0) ? kNfft + hop * (N - 1) : 0;
+    for (int s = out_lo + threadIdx.x; s < out_hi; s += blockDim.x) {
+        float v = 0.f;
+        if (s < sig_len) {
+            v = acc[s - a0];
+            const int jlo = max(0, (s - kNfft + hop) / hop), jhi = min(N - 1, s / hop);
+            float wss = 0.f;
+            for (int j = jlo; j <= jhi; ++j) wss = (float)((double)wss + g_win2[s - j * hop]);
+            if (wss > FLT_MIN) v /= wss;
+        }
+        yu[s] = v;
+    }
+}
+
+}  // namespace dvae
+
+using namespace dvae;
+
+extern "C" int dvae_stft_f32(const float* x, const int64_t* x_off, const int32_t* x_len, int B, void* X, float* P,
+                             const int64_t* fr_off, int64_t NT, int n_fft, int hop, int ld, void* stream) {
+    DVAE_REQUIRE(n_fft == kNfft, "dvae_stft_f32: only n_fft=1024 is implemented (got %d)", n_fft);
+    DVAE_REQUIRE(hop >= 1 && hop <= kNfft, "dvae_stft_f32: bad hop %d", hop);
+    DVAE_REQUIRE(B >= 1 && NT >= 0 && ld >= kHalf + 1, "dvae_stft_f32: bad sizes B=%d NT=%lld ld=%d", B, (long long)NT, ld);
+    DVAE_REQUIRE(x && x_off && x_len && X && fr_off, "dvae_stft_f32: null pointer");
+    if (NT == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_tables(st);
+    if (rc) return rc;
+    const int64_t n_pass = (NT + 3) / 4;
+    const int grid = (int)(n_pass < 148 * 8 ? n_pass : 148 * 8);
+    stft_kernel<<<grid, 256, 0, st>>>(x, x_off, x_len, B, (float2*)X, P, fr_off, NT, hop, ld);
+    return check_launch("stft_kernel");
+}
+
+extern "C" int dvae_istft_f32(const void* X, const int64_t* fr_off, int B, float* y, const int64_t* y_off,
+                              const int32_t* y_len, int max_y_len, int n_fft, int hop, int ld, void* stream) {
+    DVAE_REQUIRE(n_fft == kNfft, "dvae_istft_f32: only n_fft=1024 is implemented (got %d)", n_fft);
+    DVAE_REQUIRE(hop == 256, "dvae_istft_f32: only hop=256 is implemented (got %d)", hop);
+    DVAE_REQUIRE(B >= 1 && max_y_len >= 0 && ld >= kHalf + 1, "dvae_istft_f32: bad sizes");
+    DVAE_REQUIRE(X && fr_off && y && y_off && y_len, "dvae_istft_f32: null pointer");
+    if (max_y_len == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_tables(st);
+    if (rc) return rc;
+    const int ov = kNfft / hop;
+    const int seg_hops = kSegFrames - (ov - 1);
+    const int n_seg = (max_y_len + seg_hops * hop - 1) / (seg_hops * hop);
+    const size_t smem = sizeof(float2) * (kNfft + 4 * kBuf) + sizeof(float) * (4 * kNfft + (kSegFrames - 1) * hop + kNfft);
+    cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    istft_kernel<<<dim3(n_seg, B), 256, smem, st>>>((const float2*)X, fr_off, y, y_off, y_len, hop, ld, seg_hops);
+    return check_launch("istft_kernel");
+}

@@ -1,0 +1,147 @@
+/*
+ * libdvae_b200 -- C ABI of the B200-native (sm_100a) MCEM VAE-NMF speech-enhancement hot path.
+ *
+ * The reference (sp-uhh/disentangled-vae) has no FFI layer: its "operator API" for this path is the Python call
+ * surface used by scripts/evaluate_ntcd_{M1,M2,M2_info_vad}.py and scripts/reconstruct_*.py.  This header is the
+ * boundary a maintainer binds instead (ctypes stub in INTEGRATION.md); every entry point names the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer on the current CUDA device unless marked [host];
+ *   - the caller owns every buffer; the library never allocates device memory (workspace sizes are queried);
+ *   - all work is enqueued on the passed stream (a cudaStream_t passed as void*); nothing synchronises;
+ *   - return 0 = OK, DVAE_ERR_ARG (<0) = argument error detected before any launch, >0 = cudaError_t;
+ *     dvae_last_error() returns a thread-local description of the last non-zero return;
+ *   - there is no CPU fallback: the library only contains sm_100a code.
+ *
+ * Batch layout ("frame-major, ragged")
+ *   A batch holds B utterances; utterance u owns frames [fr_off[u], fr_off[u+1]) of NT = fr_off[B] frames in total.
+ *   Per-frame spectra are rows of `ld` floats (ld >= F, ld % 4 == 0; the library's Python host uses ld = 520 for
+ *   F = 513): X[NT][ld] (float2), P[NT][ld], Vb[NT][ld], Vs[NT][R][ld].  Latents are Z[NT*C][L] (C chains per
+ *   frame), kept samples Zs[NT][C*R][L], labels y[NT][y_dim], activations H[NT][K], gains g[NT], and the
+ *   per-utterance dictionaries W[B][K][ld].  The reference's (F,N) / (K,N) / (L,N) matrices are the transposes of
+ *   one utterance's slice.
+ */
+#ifndef DVAE_B200_H
+#define DVAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVAE_ABI_VERSION 1
+#define DVAE_ERR_ARG (-1)
+#define DVAE_MAX_LAYERS 6
+#define DVAE_MAX_L 64          /* latent dimension limit of the Metropolis-Hastings kernels */
+#define DVAE_MAX_K 16          /* NMF rank limit */
+
+/* activation applied after the LAST layer of dvae_mlp_fwd (hidden layers are always tanh, models.py:102-104,119-121) */
+#define DVAE_ACT_NONE 0
+#define DVAE_ACT_TANH 1
+#define DVAE_ACT_EXP 2
+
+/* A tanh MLP (Encoder trunk + one head, or Decoder) with transposed weights:
+ * wt[i] is [dims[i]][dims[i+1]] row-major = nn.Linear(dims[i], dims[i+1]).weight.T, bias[i] is [dims[i+1]].
+ * Replaces packages/models/models.py:91-105 (Encoder), 108-122 (Decoder).  The struct lives in HOST memory. */
+typedef struct DvaeMlp {
+    int32_t n_layers;
+    int32_t dims[DVAE_MAX_LAYERS + 1];
+    const float* wt[DVAE_MAX_LAYERS];
+    const float* bias[DVAE_MAX_LAYERS];
+} DvaeMlp;
+
+/* Random draws of the Metropolis-Hastings sampler.  Either counter-based Philox-4x32-10 keyed by `seed`
+ * (eps == NULL) or injected draws (parity runs): eps[it][NT*C][L] standard normals and u[it][NT*C] uniforms,
+ * `it` counting the iterations of THIS call from 0.  Struct in HOST memory.  (mcem.py:243,256) */
+typedef struct DvaeRng {
+    uint64_t seed;
+    uint32_t iter0;            /* global iteration number of this call's first iteration (Philox counter word 2) */
+    uint32_t reserved;
+    const float* eps;          /* nullable */
+    const float* u;            /* nullable; required when eps is given */
+} DvaeRng;
+
+int dvae_version(void);
+const char* dvae_last_error(void);
+
+/* ---- STFT: packages/processing/stft.py:13-60 (librosa.core.stft, center=False, periodic Hann, n_fft=1024) ----
+ * x: concatenated float32 signals; utterance u = x[x_off[u] .. x_off[u]+x_len[u]).  Frame j covers samples
+ * [j*hop, j*hop+n_fft) with zeros past x_len[u] (this realises the end-padding rule of stft.py:45-50; the caller
+ * chooses the frame count).  Writes X[fr_off[u]+j][0..F) (complex64) and, if P != NULL, P = |X|^2 (mcem.py:47). */
+int dvae_stft_f32(const float* x, const int64_t* x_off, const int32_t* x_len, int B, void* X /* float2 */, float* P,
+                  const int64_t* fr_off, int64_t NT, int n_fft, int hop, int ld, void* stream);
+
+/* ---- ISTFT: packages/processing/stft.py:63-99 (librosa.core.istft, center=False, length=max_len) ----
+ * y[y_off[u] .. +y_len[u]) <- overlap-add of window * irfft(frame), divided by the float32 sum of squared windows
+ * where that sum exceeds FLT_MIN, zero beyond n_fft + hop*(N_u-1).  max_y_len = max_u y_len[u] (grid sizing). */
+int dvae_istft_f32(const void* X /* float2 */, const int64_t* fr_off, int B, float* y, const int64_t* y_off,
+                   const int32_t* y_len, int max_y_len, int n_fft, int hop, int ld, void* stream);
+
+/* ---- dense tanh MLP: models.py:102-105 (Encoder trunk + head) and 119-122 (Decoder) ----
+ * out[r][0..dims[n_layers]) = act_last(Linear_n(tanh(... tanh(Linear_1([x[r] ; x2[r / x2_row_div]])))))
+ * x: rows x k1 (row stride ldx); x2 (nullable): k2 extra input columns (labels y), row r uses x2 row r / x2_row_div.
+ * ws: workspace of dvae_mlp_workspace_floats(mlp, rows) floats. */
+int64_t dvae_mlp_workspace_floats(const DvaeMlp* mlp, int64_t rows);
+int dvae_mlp_fwd(const DvaeMlp* mlp, const float* x, int ldx, int k1, const float* x2, int ldx2, int k2, int x2_row_div,
+                 int64_t rows, int act_last, float* out, int ldo, float* ws, void* stream);
+
+/* z = mu + exp(0.5*log_var)*eps   (models.py:8-22) */
+int dvae_reparam(const float* mu, const float* log_var, const float* eps, float* z, int64_t n, void* stream);
+
+/* P[i] = |X[i]|^2 over n complex64 elements (mcem.py:47, for spectrograms handed in by the caller) */
+int dvae_power(const void* X /* float2 */, float* P, int64_t n, void* stream);
+
+/* ---- NMF noise model: mcem.py:36-58, 76-83, 91-153, 69-71 ---- */
+/* Vb[n][f] = sum_k W[utt(n)][k][f] * H[n][k]   (compute_Vb, mcem.py:82-83) */
+int dvae_nmf_vb(const float* W, const float* H, const int32_t* frame_utt, int64_t NT, int F, int K, int ld, float* Vb,
+                void* stream);
+
+/* One M-step (mcem.py:91-153) + cost (mcem.py:69-71) on materialised speech variances Vs[NT][R][ld]:
+ *   W <- W*sqrt(((P*sum_r Vx^-2) H^T)/((sum_r Vx^-1) H^T)), Vb,Vx refreshed;  H likewise with W^T;  Vb,Vx refreshed;
+ *   W <- W/||W||_1col, H <- H*||W||_1col (Vb NOT recomputed);  g <- g*sqrt(sum_f P sum_r Vs Vx^-2 / sum_f sum_r Vs Vx^-1);
+ *   cost[u] = mean_{r,f,n in u}(log Vx + P/Vx) with the new g.
+ * In/out: W[B][K][ld], H[NT][K], g[NT], Vb[NT][ld] (in: product used by the E-step; out: W_new H_new before
+ * normalisation, as the reference keeps it).  cost: [B] doubles, overwritten.
+ * ws: dvae_nmf_workspace_floats(B, K, ld) floats. */
+int64_t dvae_nmf_workspace_floats(int B, int K, int ld);
+int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, float* H, float* g, float* Vb, double* cost,
+                   const int64_t* fr_off, const int32_t* frame_utt, int B, int64_t NT, int F, int K, int ld,
+                   int max_frames /* max_u frames of one utterance, for grid sizing */, float* ws, void* stream);
+
+/* ---- Metropolis-Hastings E-step sampler: mcem.py:207-277 / 372-448 / 544-620 / 716-792 ----
+ * FP32 CUDA-core decoder ("exact" mode).  Runs n_burn + n_keep random-walk iterations on every (frame, chain):
+ *   z' = z + sqrt(var_rw)*eps;  a = sum_f[log Vx - log Vx' + (1/Vx - 1/Vx')P] + .5 sum_l(z^2 - z'^2),  Vx = g*D(z)+Vb;
+ *   accept iff log(u) < a.
+ * Z[NT*C][L] in: chain starts, out: last states.  Zs[NT][C*n_keep][L]: kept samples, chain c sample r at slot c*n_keep+r.
+ * frame_utt / frame_idx [NT]: Philox counter words (global utterance id, frame index inside the utterance).
+ * n_accept (nullable): [NT*C] accepted-proposal counters, incremented.  a_trace (nullable): [n_iter][NT*C] log ratios.
+ * ws: dvae_mh_workspace_floats(dec, NT*C) floats. */
+int64_t dvae_mh_workspace_floats(const DvaeMlp* dec, int64_t chains, int F);
+int dvae_mh_chain_f32(const DvaeMlp* dec, const float* P, const float* Vb, const float* g, const float* y, int y_dim,
+                      const int32_t* frame_utt, const int32_t* frame_idx, float* Z, float* Zs, int64_t NT, int F, int ld,
+                      int L, int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng, uint32_t* n_accept,
+                      float* a_trace, float* ws, void* stream);
+
+/* The draws the Philox mode of dvae_mh_chain_* consumes, dumped as eps[n_iter][NT*C][L], u[n_iter][NT*C]
+ * (so a parity test can inject the very same draws into the reference / oracle). */
+int dvae_rng_dump(const DvaeRng* rng, const int32_t* frame_utt, const int32_t* frame_idx, int64_t NT, int n_chains,
+                  int L, int n_iter, float* eps, float* u, void* stream);
+
+/* ---- Wiener filter: mcem.py:310-329 + 176-177 ----
+ * accumulate: WFs[n][f] += sum_r g*Vs/Vx, WFn[n][f] += sum_r Vb/Vx over the R samples present in Vs[NT][R][ld];
+ * apply: S_hat = X*WFs/R_total, N_hat = X*WFn/R_total (complex64). */
+int dvae_wiener_accum(const float* Vs, int R, const float* Vb, const float* g, int64_t NT, int F, int ld, float* WFs,
+                      float* WFn, int first /* 1: overwrite instead of add */, void* stream);
+int dvae_wiener_apply(const void* X, const float* WFs, const float* WFn, int R_total, int64_t NT, int F, int ld,
+                      void* S_hat, void* N_hat, void* stream);
+
+/* uniform [eps,1) initialisation of W, H and g = 1 from Philox (mcem.py:42-44: max(rand, eps)) */
+int dvae_nmf_init(uint64_t seed, const int32_t* utt_ids /*[B] global ids*/, const int64_t* fr_off, int B, int64_t NT, int F,
+                  int K, int ld, float eps, float* W, float* H, float* g, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVAE_B200_H */

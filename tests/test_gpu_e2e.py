@@ -1,0 +1,133 @@
+"""End-to-end parity: the CUDA path against the reference's golden outputs and against the oracle.
+
+Bit parity over a whole run is not attainable (a Metropolis-Hastings accept is a discontinuous function of an FP32
+sum; one flipped decision decorrelates that frame's chain), so whole runs are judged on what the
+north star names: enhanced-speech SI-SDR within 0.05 dB, plus the cost curve and the model parameters to a few percent.
+"""
+import numpy as np
+import pytest
+import torch
+
+from dvae_b200 import synth
+from oracle import mcem_port, stft_np
+from tests.golden_io import Golden
+from tests.gpu_util import DEV, engine_for, golden_draws, relerr, unfm
+
+pytestmark = pytest.mark.gpu
+KW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False, pad_at_end=True)
+IKW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False)
+
+
+@pytest.mark.parametrize("name", ["tiny_M1", "tiny_M2", "tiny_M2v2", "tiny_M2v3", "full_M1", "full_M2", "full_M2v3", "cfg1_M1"])
+def test_full_run_against_reference_golden(name):
+    g = Golden(name)
+    sched = mcem_port.MCEMOracle(g.variant, g.niter, *g.sched).schedule()
+    eng, X, P, y, batch = engine_for(g, sched)
+    draws = golden_draws(g, sched)
+    eng.init_parameters(X, P, batch, y, draws)
+    cost = eng.run(draws).cpu().numpy()[:, 0]
+    F = g.F
+    S_hat, N_hat = unfm(eng.S_hat, F), unfm(eng.N_hat, F)
+    assert tuple(g.ref["Vs_shape"]) == (eng.R_wf, F, g.X.shape[1])
+    np.testing.assert_allclose(cost, g.ref["cost"], rtol=2e-2)
+    # relative L2 error of the estimates; a handful of flipped accepts moves single frames only
+    def l2(a, b):
+        return np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert l2(S_hat, g.ref["S_hat"]) <= 5e-2
+    assert l2(N_hat, g.ref["N_hat"]) <= 5e-2
+    assert l2(eng.W[0, :, :F].t().cpu().numpy(), g.ref["W"]) <= 5e-2
+    assert l2(eng.H.t().cpu().numpy(), g.ref["H"]) <= 5e-2
+    assert l2(eng.g.cpu().numpy(), g.ref["g"]) <= 5e-2
+    # S_hat + N_hat = X * (mean Vs/Vx + mean Vb/Vx) = X exactly in real arithmetic
+    assert relerr(S_hat + N_hat, g.X) <= 1e-5
+
+
+def _si_sdr(est, ref):
+    return mcem_port.si_sdr(est[800:-800], ref[800:-800])
+
+
+@pytest.mark.parametrize("variant", ["M1", "M2", "M2v3"])
+def test_dropin_si_sdr_within_0p05_db_of_oracle(variant):
+    """The reference-signature classes with the reference's own draw order vs the oracle on a synthetic utterance."""
+    from dvae_b200.packages.models import mcem as shim_mcem
+    from dvae_b200.packages.models import models as shim_models
+    from dvae_b200.packages.processing.stft import istft, stft
+    x, s, _ = synth.synth_utterance(21, 1.0)
+    X_ref, S_ref = stft_np.stft(x, **KW), stft_np.stft(s, **KW)
+    X = stft(x, **KW)
+    S = stft(s, **KW)
+    F, N = X.shape
+    y = synth.energy_vad(s) if variant != "M1" else None
+    sd = synth.xavier_state_dict(variant, F, 16, [128, 128], 0 if variant == "M1" else 1, seed=3,
+                                 out_bias=float(np.log(np.mean(np.abs(X_ref) ** 2))))
+    niter = 12
+    # oracle
+    torch.manual_seed(77)
+    o = mcem_port.MCEMOracle(variant, niter, 10, 30, 25, 75, 0.01)
+    o.init_parameters(X_ref, S_ref, sd, 10, 1e-8, y=y)
+    cost_ref = o.run()
+    s_ref = stft_np.istft(o.S_hat, max_len=len(x), **IKW)
+    # drop-in
+    if variant == "M1":
+        model = shim_models.VariationalAutoencoder([F, 16, [128, 128]])
+        algo = shim_mcem.MCEM_M1(niter, 10, 30, 25, 75, 0.01, rng="torch")
+    elif variant == "M2":
+        model = shim_models.DeepGenerativeModel([F, 1, 16, [128, 128]], None)
+        algo = shim_mcem.MCEM_M2(niter, 10, 30, 25, 75, 0.01, rng="torch")
+    else:
+        model = shim_models.DeepGenerativeModel_v5([F, 1, 16, [128, 128]]).enc_dec_clf
+        algo = shim_mcem.MCEM_M2v3(niter, 10, 30, 25, 75, 0.01, rng="torch")
+    model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()}, strict=False)
+    model.to(DEV).eval()
+    torch.manual_seed(77)
+    if variant == "M1":
+        algo.init_parameters(X=X, S=S, vae=model, nmf_rank=10, eps=1e-8, device=0)
+    else:
+        algo.init_parameters(X=X, S=S, y=torch.tensor(y).to(DEV), vae=model, nmf_rank=10, eps=1e-8, device=0)
+    cost = algo.run()
+    assert cost.shape == (niter,) and cost.dtype == np.float64
+    assert algo.S_hat.shape == (F, N) and algo.S_hat.dtype == np.complex64
+    s_hat = istft(algo.S_hat, max_len=len(x), **IKW)
+    d = abs(_si_sdr(s_hat, s) - _si_sdr(s_ref, s))
+    assert d <= 0.05, "SI-SDR differs by %.3f dB" % d
+    np.testing.assert_allclose(cost, cost_ref, rtol=2e-2)
+    assert 0.02 < algo.acceptance_rate < 0.98
+    # a second utterance through the same object: init_parameters resets everything
+    if variant == "M1":
+        algo.init_parameters(X=X[:, :50], S=S[:, :50], vae=model, nmf_rank=10, eps=1e-8, device="cuda:0")
+        assert algo.run().shape == (niter,) and algo.S_hat.shape == (F, 50)
+
+
+def test_enhancer_batch_matches_single_and_is_deterministic():
+    """Philox draws are keyed by (utterance id, frame, iteration): batch composition must not change any result."""
+    from dvae_b200.engine import Enhancer, McemConfig
+    lens = [16000, 12000, 20000]
+    xs = [synth.synth_utterance(30 + i, l / 16000.0)[0] for i, l in enumerate(lens)]
+    P0 = np.abs(stft_np.stft(xs[0], **KW)) ** 2
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128], 0, seed=5, out_bias=float(np.log(P0.mean())))
+    cfg = McemConfig(niter=3, keep_E=4, burn_E=6, keep_WF=5, burn_WF=7, seed=11)
+    enh = Enhancer(sd, "M1", cfg, device=0)
+    s_all, n_all, c_all = enh.enhance(xs, utt_ids=[100, 101, 102])
+    s_again, _, c_again = enh.enhance(xs, utt_ids=[100, 101, 102])
+    for a, b in zip(s_all, s_again):
+        assert np.array_equal(a, b)
+    assert np.array_equal(c_all, c_again)
+    s_one, n_one, c_one = enh.enhance([xs[1]], utt_ids=[101])
+    assert np.array_equal(s_one[0], s_all[1]) and np.array_equal(n_one[0], n_all[1])
+    np.testing.assert_allclose(c_one[0], c_all[1], rtol=1e-12)
+    for x, s, n in zip(xs, s_all, n_all):
+        assert s.shape == x.shape and s.dtype == np.float32
+        assert np.max(np.abs((s + n)[800:-800] - x[800:-800])) <= 1e-4      # masks sum to one
+
+
+def test_multi_chain_pools_samples():
+    from dvae_b200.engine import Enhancer, McemConfig
+    x = synth.synth_utterance(40, 1.0)[0]
+    P0 = np.abs(stft_np.stft(x, **KW)) ** 2
+    sd = synth.xavier_state_dict("M2v3", 513, 16, [128, 128], 1, seed=6, out_bias=float(np.log(P0.mean())))
+    y = synth.energy_vad(synth.synth_utterance(40, 1.0)[1])
+    cfg = McemConfig(niter=2, keep_E=3, burn_E=4, keep_WF=4, burn_WF=5, seed=1, n_chains=4)
+    enh = Enhancer(sd, "M2v3", cfg, device=0)
+    s, n, c = enh.enhance([x], y_list=[y])
+    assert enh.engine.R == 12 and enh.engine.R_wf == 16
+    assert np.isfinite(s[0]).all() and np.isfinite(c).all()

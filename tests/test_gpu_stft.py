@@ -1,0 +1,102 @@
+"""CUDA STFT / ISTFT (through the C ABI and the reference-signature wrappers) against the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+
+from dvae_b200 import synth
+from oracle import stft_np
+from tests.gpu_util import DEV, relerr
+
+pytestmark = pytest.mark.gpu
+KW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False, pad_at_end=True)
+IKW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False)
+
+
+def test_stft_wrapper_matches_oracle():
+    from dvae_b200.packages.processing.stft import stft
+    for u, secs in ((0, 3.0), (1, 1.0), (2, 2.048), (3, 0.5)):
+        x, _, _ = synth.synth_utterance(u, secs)
+        ref = stft_np.stft(x, **KW)
+        got = stft(x, **KW)
+        assert got.dtype == np.complex64 and got.shape == ref.shape
+        assert relerr(got, ref) <= 1e-4          # north-star tolerance for STFT (FP32 FFT vs FP64 reference)
+        assert relerr(got, ref) <= 2e-6          # what an FP32 radix-8 FFT actually delivers
+
+
+def test_stft_batch_ragged_and_power():
+    from dvae_b200.engine import RaggedBatch, stft_batch
+    lens = [48000, 16000, 20000, 1024, 33333]
+    xs = [synth.synth_utterance(10 + i, l / 16000.0)[0][:l] for i, l in enumerate(lens)]
+    off = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    flat = torch.from_numpy(np.concatenate(xs)).to(DEV)
+    nfr = [synth.num_frames(l) for l in lens]
+    batch = RaggedBatch(nfr, DEV)
+    X, P = stft_batch(flat, torch.from_numpy(off[:-1].copy()).to(DEV), torch.tensor(lens, dtype=torch.int32, device=DEV), batch)
+    X, P = X.cpu().numpy(), P.cpu().numpy()
+    for u, x in enumerate(xs):
+        ref = stft_np.stft(x, **KW)
+        a, b = batch.fr_off_host[u], batch.fr_off_host[u + 1]
+        assert b - a == ref.shape[1]
+        assert relerr(X[a:b, :513].T, ref) <= 2e-6
+        assert relerr(P[a:b, :513].T, np.abs(ref) ** 2) <= 1e-5
+
+
+def test_istft_wrapper_matches_oracle():
+    from dvae_b200.packages.processing.stft import istft
+    rng = np.random.default_rng(0)
+    for u, secs in ((4, 3.0), (5, 1.0)):
+        x, _, _ = synth.synth_utterance(u, secs)
+        X = stft_np.stft(x, **KW)
+        X = (X * rng.uniform(0.0, 1.0, size=X.shape)).astype(np.complex64)      # a Wiener-like real mask
+        ref = stft_np.istft(X, max_len=len(x), **IKW)
+        got = istft(X, max_len=len(x), **IKW)
+        assert got.dtype == np.float32 and got.shape == ref.shape
+        # interior: the reference's own metric drops 50 ms at both ends (scripts/run_metrics.py:117-121)
+        assert relerr(got[800:-800], ref[800:-800]) <= 1e-4
+        assert relerr(got[800:-800], ref[800:-800]) <= 5e-6
+        # edges: sum of squared windows is tiny there, errors are amplified by up to 1/w^2 -> absolute bound
+        scale = np.max(np.abs(ref[800:-800]))
+        assert np.max(np.abs(got[:800] - ref[:800])) <= 2e-2 * scale
+        assert np.max(np.abs(got[2:800] - ref[2:800])) <= 1e-3 * scale
+        assert got[0] == 0.0
+
+
+def test_istft_truncated_frames_zero_pad():
+    from dvae_b200.packages.processing.stft import istft
+    x, _, _ = synth.synth_utterance(6)
+    X = stft_np.stft(x, **KW)[:, :100]
+    ref = stft_np.istft(X, max_len=len(x), **IKW)
+    got = istft(X, max_len=len(x), **IKW)
+    assert len(got) == len(x)
+    assert np.all(got[1024 + 256 * 99:] == 0)
+    assert relerr(got[800:20000], ref[800:20000]) <= 5e-6
+    got2 = istft(X, **IKW)                                  # max_len=None: natural length
+    assert len(got2) == 1024 + 256 * 99
+
+
+def test_round_trip_full_batch_property():
+    """Size-independent property at the benchmark's full batch: STFT -> ISTFT reproduces the interior of every utterance."""
+    from dvae_b200.engine import RaggedBatch, istft_batch, stft_batch
+    B, T = 512, 48000
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = (torch.rand((B, T), device=DEV, generator=g) - 0.5)
+    off = torch.arange(B, device=DEV, dtype=torch.int64) * T
+    lens = torch.full((B,), T, dtype=torch.int32, device=DEV)
+    batch = RaggedBatch([synth.num_frames(T)] * B, DEV)
+    X, _ = stft_batch(x.view(-1), off, lens, batch)
+    y = istft_batch(X, batch, off, lens, B * T, T).view(B, T)
+    err = (y[:, 800:-800] - x[:, 800:-800]).abs().max().item()
+    assert err <= 5e-6
+
+
+def test_errors():
+    from dvae_b200.packages.processing.stft import istft, stft
+    with pytest.raises(ValueError):
+        stft(np.zeros(4000, np.float32), fs=16000, wlen_sec=50.01e-3)
+    with pytest.raises(NotImplementedError):
+        stft(np.zeros(4000, np.float32), fs=16000, wlen_sec=50e-3, center=False)
+    with pytest.raises(NotImplementedError):
+        stft(np.zeros(4000, np.float32), fs=16000, wlen_sec=64e-3, center=True)
+    with pytest.raises(ValueError):
+        istft(np.zeros((513, 4), np.complex64), fs=16000, wlen_sec=50.01e-3)

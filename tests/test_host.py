@@ -1,0 +1,110 @@
+"""CPU-side checks: the C ABI library loads and exports what include/dvae_b200.h declares, host logic, sharding."""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from dvae_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "dvae_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dvae_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dvae_b200 import build
+    build.build()                                   # nvcc cross-compiles sm_100a without a GPU
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libdvae_b200.so does not export %s" % n
+    assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
+    assert _lib.load().dvae_version() == 1
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_path_fails_loudly_without_gpu():
+    from dvae_b200.engine import Enhancer, McemConfig
+    from dvae_b200.packages.processing.stft import stft
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128])
+    with pytest.raises(_lib.DvaeError):
+        Enhancer(sd, "M1", McemConfig(), device=0)
+    with pytest.raises(_lib.DvaeError):
+        stft(np.zeros(16000, np.float32), fs=16000, wlen_sec=64e-3, center=False)
+    from dvae_b200.packages.models.models import VariationalAutoencoder
+    with pytest.raises(_lib.DvaeError):
+        VariationalAutoencoder([513, 16, [128, 128]])(torch.zeros(2, 513))
+
+
+def test_shim_signatures_and_schedules():
+    from dvae_b200.packages.models import mcem
+    m1 = mcem.MCEM_M1(niter=100, nsamples_E_step=10, burnin_E_step=30, nsamples_WF=25, burnin_WF=75, var_RW=0.01)
+    assert m1.schedule() == ((30, 30), (75, 30))
+    for cls in (mcem.MCEM_M2, mcem.MCEM_M2v2, mcem.MCEM_M2v3):
+        assert cls(100, 10, 30, 25, 75, 0.01).schedule() == ((10, 30), (25, 75))
+    m2 = pickle.loads(pickle.dumps(m1))                    # spawn pools pickle the algorithm object
+    assert m2.schedule() == m1.schedule() and m2.niter == 100
+
+    class RVAE:                                             # mcem.py:196-197
+        pass
+    with pytest.raises(NameError):
+        m1.init_parameters(X=np.zeros((513, 4), np.complex64), S=np.zeros((513, 4), np.complex64), vae=RVAE(),
+                           nmf_rank=10, eps=1e-8, device="cpu")
+
+
+def test_state_dict_layout_matches_reference_keys():
+    from dvae_b200.packages.models import models
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128])
+    m = models.VariationalAutoencoder([513, 16, [128, 128]])
+    assert set(m.state_dict()) == set(sd)
+    m.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    sd2 = synth.xavier_state_dict("M2", 513, 16, [128, 128], 1)
+    m2 = models.DeepGenerativeModel([513, 1, 16, [128, 128]], None)
+    assert set(m2.state_dict()) == set(sd2)
+    assert m2.encoder.hidden[0].weight.shape == (128, 514) and m2.decoder.hidden[0].weight.shape == (128, 17)
+    v5 = models.DeepGenerativeModel_v5([513, 1, 16, [128, 128]])
+    keys = set(v5.state_dict())
+    assert {"enc_dec_clf.encoder.hidden.0.weight", "enc_dec_clf.decoder.reconstruction.bias",
+            "enc_dec_clf.classifier.output_layer.weight", "auxiliary.hidden.0.weight"} <= keys
+    # xavier-normal weights, zero biases (models.py:137-141)
+    assert float(m.decoder.reconstruction.bias.abs().max()) == 0.0
+    pickle.loads(pickle.dumps(m))
+
+
+def test_ragged_batch_bookkeeping():
+    from dvae_b200.engine import RaggedBatch
+    b = RaggedBatch([3, 0, 2], "cpu", utt_ids=[10, 11, 12])
+    assert b.NT == 5 and b.max_frames == 3
+    assert b.fr_off.tolist() == [0, 3, 3, 5]
+    assert b.frame_utt.tolist() == [0, 0, 0, 2, 2] and b.frame_gid.tolist() == [10, 10, 10, 12, 12]
+    assert b.frame_idx.tolist() == [0, 1, 2, 0, 1]
+    with pytest.raises(ValueError):
+        RaggedBatch([], "cpu")
+
+
+def test_synthetic_inputs_are_seeded_and_mixed_at_snr():
+    x, s, n = synth.synth_utterance(5)
+    x2, _, _ = synth.synth_utterance(5)
+    assert np.array_equal(x, x2) and x.dtype == np.float32 and len(x) == 48000
+    assert np.max(np.abs(x)) <= 1.0 + 1e-6
+    np.testing.assert_allclose(s + n, x, atol=1e-6)
+    snr = 10 * np.log10(np.sum(s.astype(np.float64) ** 2) / np.sum(n.astype(np.float64) ** 2))
+    assert abs(snr - 0.0) < 1e-3                            # u % 4 == 1 -> 0 dB
+    y = synth.energy_vad(s)
+    assert y.shape == (1, 185) and set(np.unique(y)) <= {0.0, 1.0}
