@@ -44,7 +44,7 @@ PROTOTYPES = {
     "dvae_reparam": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, c_ptr]),
     "dvae_power": (C.c_int, [c_ptr, c_ptr, C.c_int64, c_ptr]),
     "dvae_nmf_vb": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
-    "dvae_nmf_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "dvae_nmf_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dvae_nmf_mstep": (C.c_int, [c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64,
                                  C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_mh_workspace_floats": (C.c_int64, [C.POINTER(DvaeMlp), C.c_int64, C.c_int]),

@@ -110,8 +110,7 @@ __global__ void __launch_bounds__(128) nmf_w_kernel(const float* __restrict__ P,
 
 // column L1 norms of the updated W, normalised copy into W, cost accumulator reset (mcem.py:130-132)
 __global__ void __launch_bounds__(256) nmf_norm_kernel(const float* __restrict__ Wtmp, int F, int K, int ld,
-                                                       float* __restrict__ W, float* __restrict__ norm,
-                                                       double* __restrict__ cost) {
+                                                       float* __restrict__ W, float* __restrict__ norm) {
     __shared__ float scratch[32];
     const int u = blockIdx.x;
     for (int k = 0; k < K; ++k) {
@@ -123,7 +122,6 @@ __global__ void __launch_bounds__(256) nmf_norm_kernel(const float* __restrict__
         float* dst = W + ((int64_t)u * K + k) * ld;
         for (int f = threadIdx.x; f < F; f += blockDim.x) dst[f] = src[f] / s;
     }
-    if (threadIdx.x == 0) cost[u] = 0.0;
 }
 
 // ----------------------------------------------------------------------------- H, g updates + cost (mcem.py:119-153, 69-71)
@@ -133,7 +131,7 @@ constexpr int FPB = 4;
 __global__ void __launch_bounds__(256) nmf_hg_kernel(const float* __restrict__ P, const float* __restrict__ Vs, int R,
                                                      const float* __restrict__ Wtmp, const float* __restrict__ norm,
                                                      float* __restrict__ H, float* __restrict__ g, float* __restrict__ Vb,
-                                                     double* __restrict__ cost, const int64_t* __restrict__ fr_off,
+                                                     double* __restrict__ cost_part, const int64_t* __restrict__ fr_off,
                                                      int F, int K, int ld) {
     extern __shared__ float Ws[];                 // [K][ld]
     __shared__ float red[2 * KMAX][8];
@@ -142,7 +140,10 @@ __global__ void __launch_bounds__(256) nmf_hg_kernel(const float* __restrict__ P
     const int u = blockIdx.y;
     const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
     const int64_t nb = n0 + (int64_t)blockIdx.x * FPB;
-    if (nb >= n1) return;
+    if (nb >= n1) {
+        if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
+        return;
+    }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < K * ld; i += blockDim.x) Ws[i] = Wtmp[(int64_t)u * K * ld + i];
     __syncthreads();
@@ -237,7 +238,16 @@ __global__ void __launch_bounds__(256) nmf_hg_kernel(const float* __restrict__ P
         if (threadIdx.x == 0) g[n] = gnew;
         __syncthreads();
     }
-    if (threadIdx.x == 0) atomicAdd(cost + u, cost_acc * inv_count);
+    if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = cost_acc * inv_count;
+}
+
+// cost[u] = sum of the per-CTA partials in block order (deterministic, unlike an atomic accumulation)
+__global__ void cost_reduce_kernel(const double* __restrict__ cost_part, int nblk, double* __restrict__ cost) {
+    const int u = blockIdx.x;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nblk; i += 32) s += cost_part[(int64_t)u * nblk + i];
+    s = warp_sum_d(s);
+    if (threadIdx.x == 0) cost[u] = s;
 }
 
 // ----------------------------------------------------------------------------- Wiener masks (mcem.py:325-327)
@@ -309,9 +319,14 @@ extern "C" int dvae_nmf_vb(const float* W, const float* H, const int32_t* frame_
     return check_launch("nmf_vb_kernel");
 }
 
-extern "C" int64_t dvae_nmf_workspace_floats(int B, int K, int ld) {
-    if (B <= 0 || K <= 0 || ld <= 0) return 0;
-    return (int64_t)B * K * ld + (int64_t)B * K;       // un-normalised W_new + column norms
+static int64_t hg_blocks(int max_frames) { return max_frames > 0 ? (max_frames + FPB - 1) / FPB : 1; }
+
+extern "C" int64_t dvae_nmf_workspace_floats(int B, int K, int ld, int max_frames) {
+    if (B <= 0 || K <= 0 || ld <= 0 || max_frames < 0) return 0;
+    // un-normalised W_new + column norms (+1 pad to keep the doubles 8-byte aligned) + per-CTA cost partials (doubles)
+    int64_t n = (int64_t)B * K * ld + (int64_t)B * K;
+    n += n & 1;
+    return n + 2 * (int64_t)B * hg_blocks(max_frames);
 }
 
 extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, float* H, float* g, float* Vb,
@@ -325,18 +340,29 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
     cudaStream_t st = (cudaStream_t)stream;
     float* Wtmp = ws;
     float* norm = ws + (int64_t)B * K * ld;
+    int64_t off = (int64_t)B * K * ld + (int64_t)B * K;
+    off += off & 1;
+    double* cost_part = reinterpret_cast<double*>(ws + off);
+    DVAE_REQUIRE((reinterpret_cast<uintptr_t>(cost_part) & 7) == 0, "dvae_nmf_mstep: workspace must be 8-byte aligned");
+    const int nblk = (int)hg_blocks(max_frames);
     nmf_w_kernel<<<dim3((F + 127) / 128, B), 128, 0, st>>>(P, Vs, R, W, H, g, Vb, fr_off, F, K, ld, Wtmp);
     int rc = check_launch("nmf_w_kernel");
     if (rc) return rc;
-    nmf_norm_kernel<<<B, 256, 0, st>>>(Wtmp, F, K, ld, W, norm, cost);
+    nmf_norm_kernel<<<B, 256, 0, st>>>(Wtmp, F, K, ld, W, norm);
     rc = check_launch("nmf_norm_kernel");
     if (rc) return rc;
-    if (max_frames == 0) return 0;
+    if (max_frames == 0) {
+        cudaMemsetAsync(cost, 0, sizeof(double) * B, st);
+        return 0;
+    }
     const size_t smem = sizeof(float) * (size_t)K * ld;
     DVAE_REQUIRE(smem <= 200 * 1024, "dvae_nmf_mstep: K*ld too large for shared memory");
     cudaFuncSetAttribute(nmf_hg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nmf_hg_kernel<<<dim3((max_frames + FPB - 1) / FPB, B), 256, smem, st>>>(P, Vs, R, Wtmp, norm, H, g, Vb, cost, fr_off, F, K, ld);
-    return check_launch("nmf_hg_kernel");
+    nmf_hg_kernel<<<dim3(nblk, B), 256, smem, st>>>(P, Vs, R, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
+    rc = check_launch("nmf_hg_kernel");
+    if (rc) return rc;
+    cost_reduce_kernel<<<B, 32, 0, st>>>(cost_part, nblk, cost);
+    return check_launch("cost_reduce_kernel");
 }
 
 extern "C" int dvae_wiener_accum(const float* Vs, int R, const float* Vb, const float* g, int64_t NT, int F, int ld,

@@ -402,13 +402,13 @@ class McemEngine:
 
     def m_step(self, it: int):
         b, cfg = self.batch, self.cfg
-        need = _lib.load().dvae_nmf_workspace_floats(b.B, cfg.nmf_rank, self.ld)
+        need = _lib.load().dvae_nmf_workspace_floats(b.B, cfg.nmf_rank, self.ld, b.max_frames)
         ws = self._get("nmf_ws", (int(need),))
         with self.stage("mstep"):
             _lib.call("dvae_nmf_mstep", _p(self.P), _p(self.Vs), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
                       C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), _p(b.frame_utt), b.B, b.NT, self.F, cfg.nmf_rank,
                       self.ld, b.max_frames, _p(ws), _stream())
-        self.kernel_launches += 3
+        self.kernel_launches += 4
 
     def wiener(self, draws=None):
         """``compute_WF(sample=True)`` + the mask application of ``EM.run`` (mcem.py:310-329, 176-177)."""

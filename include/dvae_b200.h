@@ -104,8 +104,8 @@ int dvae_nmf_vb(const float* W, const float* H, const int32_t* frame_utt, int64_
  *   cost[u] = mean_{r,f,n in u}(log Vx + P/Vx) with the new g.
  * In/out: W[B][K][ld], H[NT][K], g[NT], Vb[NT][ld] (in: product used by the E-step; out: W_new H_new before
  * normalisation, as the reference keeps it).  cost: [B] doubles, overwritten.
- * ws: dvae_nmf_workspace_floats(B, K, ld) floats. */
-int64_t dvae_nmf_workspace_floats(int B, int K, int ld);
+ * ws: dvae_nmf_workspace_floats(B, K, ld, max_frames) floats, 8-byte aligned. */
+int64_t dvae_nmf_workspace_floats(int B, int K, int ld, int max_frames);
 int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, float* H, float* g, float* Vb, double* cost,
                    const int64_t* fr_off, const int32_t* frame_utt, int B, int64_t NT, int F, int K, int ld,
                    int max_frames /* max_u frames of one utterance, for grid sizing */, float* ws, void* stream);

@@ -27,7 +27,8 @@ def unfm(t, F):
 
 
 def relerr(a, b):
-    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a, b = np.asarray(a, dt), np.asarray(b, dt)
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
 
 

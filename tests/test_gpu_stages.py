@@ -99,7 +99,7 @@ def test_m_step_matches_oracle(F, N, K, R):
         if B > 1:
             continue   # a split batch updates each half's own W: only the Vb kernel is comparable
         cost = torch.zeros(B, dtype=torch.float64, device=DEV)
-        ws = torch.empty(int(_lib.load().dvae_nmf_workspace_floats(B, K, ld)), device=DEV)
+        ws = torch.empty(int(_lib.load().dvae_nmf_workspace_floats(B, K, ld, batch.max_frames)), device=DEV)
         _lib.call("dvae_nmf_mstep", _p(Pd), _p(Vsd), R, _p(Wd), _p(Hd), _p(gd), _p(Vbd), _p(cost), _p(batch.fr_off),
                   _p(batch.frame_utt), B, N, F, K, ld, batch.max_frames, _p(ws), _stream())
         assert relerr(Wd[0, :, :F].t().cpu().numpy(), ref["W"].numpy()) <= 1e-4
@@ -130,7 +130,7 @@ def test_m_step_batch_equals_single():
         Vbd = torch.zeros((N, ld), device=DEV)
         _lib.call("dvae_nmf_vb", _p(Wd), _p(Hd), _p(batch.frame_utt), N, F, K, ld, _p(Vbd), _stream())
         cost = torch.zeros(len(idx), dtype=torch.float64, device=DEV)
-        ws = torch.empty(int(_lib.load().dvae_nmf_workspace_floats(len(idx), K, ld)), device=DEV)
+        ws = torch.empty(int(_lib.load().dvae_nmf_workspace_floats(len(idx), K, ld, batch.max_frames)), device=DEV)
         _lib.call("dvae_nmf_mstep", _p(Pd), _p(Vsd), R, _p(Wd), _p(Hd), _p(gd), _p(Vbd), _p(cost), _p(batch.fr_off),
                   _p(batch.frame_utt), len(idx), N, F, K, ld, batch.max_frames, _p(ws), _stream())
         return Wd.cpu(), Hd.cpu(), gd.cpu(), cost.cpu(), batch
@@ -158,7 +158,8 @@ def test_wiener_matches_oracle():
     Vsd[:, :, :F] = torch.from_numpy(np.ascontiguousarray(Vs.transpose(2, 0, 1))).to(DEV)
     a = torch.empty((N, ld), device=DEV)
     b = torch.empty((N, ld), device=DEV)
-    _lib.call("dvae_wiener_accum", _p(Vsd), R, _p(fm(Vb)), _p(torch.from_numpy(g).to(DEV)), N, F, ld, _p(a), _p(b), 1, _stream())
+    Vbd, gd = fm(Vb), torch.from_numpy(g).to(DEV)          # keep the tensors alive while the kernel runs
+    _lib.call("dvae_wiener_accum", _p(Vsd), R, _p(Vbd), _p(gd), N, F, ld, _p(a), _p(b), 1, _stream())
     Xd = fm(X, dtype=torch.complex64)
     S = torch.empty_like(Xd)
     Nn = torch.empty_like(Xd)

@@ -56,9 +56,11 @@ def test_istft_wrapper_matches_oracle():
         assert relerr(got[800:-800], ref[800:-800]) <= 1e-4
         assert relerr(got[800:-800], ref[800:-800]) <= 5e-6
         # edges: sum of squared windows is tiny there, errors are amplified by up to 1/w^2 -> absolute bound
+        # (sample 1: w^2 = 9e-11, the FP32 irfft rounding is amplified ~1e5 times in BOTH implementations)
         scale = np.max(np.abs(ref[800:-800]))
-        assert np.max(np.abs(got[:800] - ref[:800])) <= 2e-2 * scale
-        assert np.max(np.abs(got[2:800] - ref[2:800])) <= 1e-3 * scale
+        tol = 2e-3 * np.abs(ref[:800]) + 1e-4 * scale
+        assert np.all(np.abs(got[:800] - ref[:800]) <= tol)
+        assert np.all(np.abs(got[-800:] - ref[-800:]) <= 2e-3 * np.abs(ref[-800:]) + 1e-4 * scale)
         assert got[0] == 0.0
 
 
