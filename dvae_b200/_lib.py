@@ -54,6 +54,15 @@ PROTOTYPES = {
     "dvae_rng_dump": (C.c_int, [C.POINTER(DvaeRng), c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
     "dvae_wiener_accum": (C.c_int, [c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr]),
     "dvae_wiener_apply": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "dvae_tc_image_bytes": (C.c_int64, [C.POINTER(DvaeMlp), C.c_int, C.c_int]),
+    "dvae_tc_pack_decoder": (C.c_int, [C.POINTER(DvaeMlp), C.c_int, C.c_int, c_ptr, c_ptr]),
+    "dvae_tc_packed_floats": (C.c_int64, [C.c_int64]),
+    "dvae_tc_pack_rows": (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "dvae_mh_chain_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                   C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(DvaeRng), c_ptr, c_ptr,
+                                   c_ptr, c_ptr]),
+    "dvae_decode_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int,
+                                 c_ptr, c_ptr]),
     "dvae_nmf_init": (C.c_int, [C.c_uint64, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float,
                                 c_ptr, c_ptr, c_ptr, c_ptr]),
 }

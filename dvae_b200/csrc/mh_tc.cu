@@ -1,0 +1,687 @@
+// tcgen05 (5th-gen tensor core) decoder kernels: the fused Metropolis-Hastings sampler and the kept-sample decode.
+//
+// Replaces packages/models/mcem.py:207-277 (sample_posterior; + the M2 copies) and 280-290 (compute_Vs) on top of
+// packages/models/models.py:119-122 (Decoder.forward), in BF16 x BF16 -> FP32 on the tensor cores.
+//
+// One CTA owns a tile of 128 rows (one row = one Markov chain, or one kept sample for the decode) and keeps it for
+// the whole call: all decoder weights sit in shared memory as UMMA operands (K-major, 128-byte swizzle), the
+// activations of the tile go registers -> shared memory (A operand) -> tcgen05.mma -> TMEM -> registers, and nothing
+// but the observation P, the noise variance Vb and the kept samples touches global memory inside the chain loop.
+//
+//   layer 1   [128 x K1] x [K1 x 128]   K1 = 64*nkb1: columns = [bf16 hi(z) | bf16 lo(z) | y hi,lo ... | 1 | 0..];
+//                                        the hi/lo split keeps the random-walk step (0.1 sigma) resolved, the
+//                                        constant-one column carries the bias.
+//   layer 2   [128 x 128] x [128 x 128] (absent for single-hidden-layer decoders)
+//   layer 3   [128 x 128] x [128 x 528] issued as 4 chunks of N=128 + one of N=16 (bin 512), double-buffered in
+//                                        TMEM so the epilogue of chunk j overlaps the MMA of chunk j+1.
+//   W3, b3 are pre-scaled by log2(e): Vs = 2^(acc + b3').
+//
+// Epilogue of layer 3, sampler: per row,  l(z') = sum_f [ln Vx' + P/Vx'],  Vx' = g*Vs' + Vb.  Two bins share one
+// reciprocal and one logarithm:  ln(v0 v1) and (p0 v1 + p1 v0)/(v0 v1)  -> 2 MUFU ops per bin instead of 3.
+// Epilogue of layer 3, decode: Vs rows are written to global memory in FP32.
+//
+// Threads: 8 epilogue warps (warp w reads TMEM lanes 32*(w%4).., columns half w/4) + 1 control warp whose lane 0
+// issues every tcgen05.mma and whose 32 lanes allocate / free the 512 TMEM columns.  Warps 0-3 also own the chain
+// state of row 32*w+lane (z, l(z), Philox counters).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace dvae {
+namespace tc {
+
+constexpr int TM = 128;             // rows per tile
+constexpr int HID = 128;            // hidden width (both hidden layers)
+constexpr int NPAD = 528;           // output bins padded: 4*128 + 16
+constexpr int NQ = NPAD / 4;        // bin quads in the packed P / Vb layout
+constexpr int NTHREADS = 288;
+constexpr int A_BYTES = 32768;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+enum { MODE_MH = 0, MODE_DECODE = 1 };
+
+struct Dims {
+    int L, y_dim, n_hidden, F, nkb1;
+    int off_w2, off_w3, off_bias, image_bytes;      // byte offsets inside the image
+};
+
+__host__ __device__ inline Dims make_dims(int L, int y_dim, int n_hidden, int F) {
+    Dims d;
+    d.L = L; d.y_dim = y_dim; d.n_hidden = n_hidden; d.F = F;
+    const int k1 = 2 * L + 2 * y_dim + 1;
+    d.nkb1 = (k1 + 63) / 64;
+    d.off_w2 = d.nkb1 * 16384;
+    d.off_w3 = d.off_w2 + (n_hidden == 2 ? 2 * HID * 128 : 0);
+    d.off_bias = d.off_w3 + 2 * NPAD * 128;
+    d.image_bytes = d.off_bias + 4 * ((n_hidden == 2 ? HID : 0) + NPAD);
+    return d;
+}
+
+// byte offset of element (row n, column k) of a K-major SWIZZLE_128B operand with `rows` rows
+__host__ __device__ inline int sw128_offset(int rows, int n, int k) {
+    const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
+    return kb * rows * 128 + n * 128 + ((c ^ (n & 7)) << 4) + e * 2;
+}
+
+// ----------------------------------------------------------------------------- packing kernels
+__global__ void pack_decoder_kernel(Dims d, const float* __restrict__ wt0, const float* __restrict__ b0,
+                                    const float* __restrict__ wt1, const float* __restrict__ b1,
+                                    const float* __restrict__ wt2, const float* __restrict__ b2,
+                                    unsigned char* __restrict__ image) {
+    // wt0: [L+y][128], wt1: [128][128] (two hidden layers only), wt2 = reconstruction: [128][F]
+    const int K1 = 64 * d.nkb1;
+    const int n1 = HID * K1, n2 = (d.n_hidden == 2) ? HID * HID : 0, n3 = NPAD * HID;
+    const int nb = (d.n_hidden == 2 ? HID : 0) + NPAD;
+    const int total = n1 + n2 + n3 + nb;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        if (i < n1) {
+            const int n = i / K1, k = i % K1;
+            float v = 0.f;
+            if (k < d.L) v = wt0[k * HID + n];
+            else if (k < 2 * d.L) v = wt0[(k - d.L) * HID + n];
+            else if (k < 2 * d.L + 2 * d.y_dim) v = wt0[(d.L + (k - 2 * d.L) / 2) * HID + n];
+            else if (k == 2 * d.L + 2 * d.y_dim) v = b0[n];
+            *reinterpret_cast<__nv_bfloat16*>(image + sw128_offset(HID, n, k)) = __float2bfloat16_rn(v);
+        } else if (i < n1 + n2) {
+            const int j = i - n1, n = j / HID, k = j % HID;
+            *reinterpret_cast<__nv_bfloat16*>(image + d.off_w2 + sw128_offset(HID, n, k)) = __float2bfloat16_rn(wt1[k * HID + n]);
+        } else if (i < n1 + n2 + n3) {
+            const int j = i - n1 - n2, n = j / HID, k = j % HID;
+            const float v = (n < d.F) ? wt2[k * d.F + n] * kLog2e : 0.f;
+            *reinterpret_cast<__nv_bfloat16*>(image + d.off_w3 + sw128_offset(NPAD, n, k)) = __float2bfloat16_rn(v);
+        } else {
+            const int j = i - n1 - n2 - n3;
+            float* bias = reinterpret_cast<float*>(image + d.off_bias);
+            if (d.n_hidden == 2 && j < HID) bias[j] = b1[j];
+            else {
+                const int n = j - (d.n_hidden == 2 ? HID : 0);
+                bias[j] = (n < d.F) ? b2[n] * kLog2e : 0.f;
+            }
+        }
+    }
+}
+
+// src [NT][ld] (frame-major) -> dst [tile][quad][128 rows][4 bins], row m of the chain grid reads frame m / C
+__global__ void pack_rows_kernel(const float* __restrict__ src, int64_t chains, int C, int F, int ld, float4* __restrict__ dst) {
+    const int64_t n_tiles = (chains + TM - 1) / TM;
+    const int64_t total = n_tiles * NQ * TM;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i % TM);
+        const int q = (int)((i / TM) % NQ);
+        const int64_t tile = i / ((int64_t)TM * NQ);
+        const int64_t m = tile * TM + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < chains) {
+            const float* s = src + (m / C) * ld;
+            const int f = 4 * q;
+            if (f + 3 < F) v = *reinterpret_cast<const float4*>(s + f);
+            else {
+                if (f < F) v.x = s[f];
+                if (f + 1 < F) v.y = s[f + 1];
+                if (f + 2 < F) v.z = s[f + 2];
+            }
+        }
+        dst[i] = v;
+    }
+}
+
+// ----------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_128B: start>>4 | LBO=1 (ignored) | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ uint32_t umma_idesc(int N) {
+    // kind::f16: D=F32 (bit 4), A=BF16 (bits 7-9 = 1), B=BF16 (bits 10-12 = 1), K-major A and B, N>>3 at 17, M>>4 at 24
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+
+// Bounded wait: a broken pipeline must never hang the GPU. On timeout the CTA-wide `dead` flag makes every later
+// wait fall through and the host sees status != 0.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* dead, int* status) {
+    if (*dead) return;
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    *dead = 1;
+    atomicExch(status, 1);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // first source -> upper half
+    return r;
+}
+
+// ----------------------------------------------------------------------------- kernel
+struct Params {
+    Dims d;
+    const unsigned char* image;
+    // chains / rows
+    int64_t rows;                 // MH: NT*C chains; DECODE: rows of Zs
+    int C;                        // chains per frame (MH); x2 row divisor (DECODE)
+    const float* y;               // [frames][y_dim] or null
+    // MH
+    const float4* Ppk;            // [tiles][NQ][128] quads
+    const float4* Vbpk;
+    const float* g;               // [frames]
+    float* Z;                     // [rows][L] in/out
+    float* Zs;                    // [rows*keep][L] out
+    const int32_t* frame_gid;
+    const int32_t* frame_idx;
+    const float* inj_eps;
+    const float* inj_u;
+    uint32_t* n_accept;
+    float* a_trace;
+    int n_burn, n_keep;
+    uint32_t seed_lo, seed_hi, iter0;
+    float sd;
+    // DECODE
+    const float* Zin;             // [rows][L]
+    float* Vs;                    // [rows][ld]
+    int ld;
+    int* status;
+};
+
+struct Ctx {
+    unsigned char* base;          // 1024-aligned smem base (image at offset 0)
+    unsigned char* A;             // activation operand buffer
+    float* red;                   // [128] cross-warp reduction scratch
+    uint32_t bar12, bar3[2];
+    uint32_t tmem;
+    volatile int* dead;
+    int* status;
+    uint32_t ph12, ph3[2];
+    int warp, lane, q, h, row;    // q: TMEM lane quadrant, h: column half, row: tile row of this thread
+};
+
+// issue D[tmem] (+)= A[128 x 64*nkb] * B[N x 64*nkb]^T as 4*nkb tcgen05.mma of K=16
+__device__ __forceinline__ void issue_gemm(uint32_t a_addr, uint32_t b_addr, int b_kb_stride, int nkb, uint32_t d_tmem, int N) {
+    const uint32_t idesc = umma_idesc(N);
+    uint32_t acc = 0;
+    for (int kb = 0; kb < nkb; ++kb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            umma(d_tmem, umma_desc(a_addr + kb * 16384 + 32 * k), umma_desc(b_addr + kb * b_kb_stride + 32 * k), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+// hidden-layer epilogue: D12[row][64h .. 64h+64) -> tanh(+bias) -> bf16 -> A operand K-block h
+__device__ __forceinline__ void hidden_epilogue(Ctx& c, const float* bias) {
+    float v[32];
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        const int col0 = 64 * c.h + 32 * part;
+        tmem_ld32(c.tmem + ((uint32_t)(32 * c.q) << 16) + col0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {          // 4 chunks of 8 columns
+            float t[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float x = v[8 * cc + e];
+                if (bias) x += bias[col0 + 8 * cc + e];
+                t[e] = tanh_approx(x);
+            }
+            const int chunk = 4 * part + cc;      // chunk inside the 64-column K block
+            uint4 pk = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+            *reinterpret_cast<uint4*>(c.A + c.h * 16384 + c.row * 128 + ((chunk ^ (c.row & 7)) << 4)) = pk;
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ float eval_tile(const Params& p, Ctx& c, int64_t tile, const float* zin /*owner rows: L values*/,
+                                           const float* yrow, bool valid, float g_row) {
+    const Dims& d = p.d;
+    const bool epi = c.warp < 8;
+    const bool owner = c.warp < 4;
+    const bool ctrl = (c.warp == 8 && c.lane == 0);
+    const uint32_t a_addr = smem_u32(c.A);
+    const uint32_t w1_addr = smem_u32(c.base), w2_addr = smem_u32(c.base + d.off_w2), w3_addr = smem_u32(c.base + d.off_w3);
+    const float* bias = reinterpret_cast<const float*>(c.base + d.off_bias);
+    const float* b2 = (d.n_hidden == 2) ? bias : nullptr;
+    const float* b3 = bias + (d.n_hidden == 2 ? HID : 0);
+
+    // ---- A1 operand: [hi(z) | lo(z) | y hi,lo | 1 | 0]
+    if (owner) {
+        const int K1 = 64 * d.nkb1;
+        for (int ch = 0; ch < K1 / 8; ++ch) {
+            float e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = 8 * ch + i;
+                float x = 0.f;
+                if (valid) {
+                    if (k < d.L) x = __bfloat162float(__float2bfloat16_rn(zin[k]));
+                    else if (k < 2 * d.L) { const float zz = zin[k - d.L]; x = zz - __bfloat162float(__float2bfloat16_rn(zz)); }
+                    else if (k < 2 * d.L + 2 * d.y_dim) {
+                        const float yy = yrow[(k - 2 * d.L) >> 1];
+                        const float hi = __bfloat162float(__float2bfloat16_rn(yy));
+                        x = ((k - 2 * d.L) & 1) ? (yy - hi) : hi;
+                    } else if (k == 2 * d.L + 2 * d.y_dim) x = 1.f;
+                }
+                e[i] = x;
+            }
+            const int kb = ch >> 3, cc = ch & 7;
+            uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+            *reinterpret_cast<uint4*>(c.A + kb * 16384 + c.row * 128 + ((cc ^ (c.row & 7)) << 4)) = pk;
+        }
+    }
+    fence_async_smem();
+    __syncthreads();                                                            // S1
+
+    // ---- layer 1
+    if (ctrl) {
+        tc_fence_after();
+        issue_gemm(a_addr, w1_addr, 16384, d.nkb1, c.tmem, HID);
+        umma_commit(c.bar12);
+    }
+    if (epi) {
+        mbar_wait(c.bar12, c.ph12, c.dead, c.status);
+        tc_fence_after();
+        hidden_epilogue(c, nullptr);                                            // bias rides on the constant-one column
+        fence_async_smem();
+        tc_fence_before();
+    }
+    c.ph12 ^= 1;
+    __syncthreads();                                                            // S2
+
+    // ---- layer 2
+    if (d.n_hidden == 2) {
+        if (ctrl) {
+            tc_fence_after();
+            issue_gemm(a_addr, w2_addr, 16384, 2, c.tmem, HID);
+            umma_commit(c.bar12);
+        }
+        if (epi) {
+            mbar_wait(c.bar12, c.ph12, c.dead, c.status);
+            tc_fence_after();
+            hidden_epilogue(c, b2);
+            fence_async_smem();
+            tc_fence_before();
+        }
+        c.ph12 ^= 1;
+        __syncthreads();                                                        // S3
+    }
+
+    // ---- layer 3 in 5 chunks, TMEM double buffer at columns 128 / 256
+    if (ctrl) {
+        tc_fence_after();
+        issue_gemm(a_addr, w3_addr, NPAD * 128, 2, c.tmem + 128, 128);
+        umma_commit(c.bar3[0]);
+        issue_gemm(a_addr, w3_addr + 16384, NPAD * 128, 2, c.tmem + 256, 128);
+        umma_commit(c.bar3[1]);
+    }
+    float acc = 0.f, accl = 0.f;
+    const int64_t row_g = tile * TM + c.row;
+    for (int j = 0; j < 5; ++j) {
+        const int b = j & 1;
+        if (epi) {
+            mbar_wait(c.bar3[b], c.ph3[b], c.dead, c.status);
+            tc_fence_after();
+            const uint32_t tbuf = c.tmem + 128 + 128 * b + ((uint32_t)(32 * c.q) << 16);
+            if (j < 4) {
+                float v[32];
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    const int col0 = 64 * c.h + 32 * part;              // column inside the chunk
+                    const int f0 = 128 * j + col0;                      // global bin
+                    tmem_ld32(tbuf + col0, v);
+                    tmem_wait_ld();
+                    if (MODE == MODE_MH) {
+                        const float4* Pq = p.Ppk + (tile * NQ + (f0 >> 2)) * TM + c.row;
+                        const float4* Vq = p.Vbpk + (tile * NQ + (f0 >> 2)) * TM + c.row;
+#pragma unroll
+                        for (int qd = 0; qd < 8; ++qd) {
+                            const float4 pp = __ldg(Pq + qd * TM);
+                            const float4 vb = __ldg(Vq + qd * TM);
+                            const float4 bb = *reinterpret_cast<const float4*>(b3 + f0 + 4 * qd);
+                            const float v0 = fmaf(g_row, ex2_approx(v[4 * qd + 0] + bb.x), vb.x);
+                            const float v1 = fmaf(g_row, ex2_approx(v[4 * qd + 1] + bb.y), vb.y);
+                            const float v2 = fmaf(g_row, ex2_approx(v[4 * qd + 2] + bb.z), vb.z);
+                            const float v3 = fmaf(g_row, ex2_approx(v[4 * qd + 3] + bb.w), vb.w);
+                            const float p01 = v0 * v1, p23 = v2 * v3;
+                            const float n01 = fmaf(pp.y, v0, pp.x * v1), n23 = fmaf(pp.w, v2, pp.z * v3);
+                            acc = fmaf(n01, rcp_approx(p01), acc);
+                            acc = fmaf(n23, rcp_approx(p23), acc);
+                            accl += lg2_approx(p01) + lg2_approx(p23);
+                        }
+                    } else {
+                        if (row_g < p.rows) {
+                            float* dst = p.Vs + row_g * p.ld + f0;
+#pragma unroll
+                            for (int qd = 0; qd < 8; ++qd) {
+                                const float4 bb = *reinterpret_cast<const float4*>(b3 + f0 + 4 * qd);
+                                float4 o;
+                                o.x = ex2_approx(v[4 * qd + 0] + bb.x);
+                                o.y = ex2_approx(v[4 * qd + 1] + bb.y);
+                                o.z = ex2_approx(v[4 * qd + 2] + bb.z);
+                                o.w = ex2_approx(v[4 * qd + 3] + bb.w);
+                                *reinterpret_cast<float4*>(dst + 4 * qd) = o;
+                            }
+                        }
+                    }
+                }
+            } else if (c.h == 0) {                                     // tail chunk: only bin 512 is real
+                float v[4];
+                tmem_ld4(tbuf, v);
+                tmem_wait_ld();
+                const float e = ex2_approx(v[0] + b3[512]);
+                if (MODE == MODE_MH) {
+                    const float4 pp = __ldg(p.Ppk + (tile * NQ + 128) * TM + c.row);
+                    const float4 vb = __ldg(p.Vbpk + (tile * NQ + 128) * TM + c.row);
+                    const float v0 = fmaf(g_row, e, vb.x);
+                    acc = fmaf(pp.x, rcp_approx(v0), acc);
+                    accl += lg2_approx(v0);
+                } else if (row_g < p.rows && p.d.F > 512) {
+                    p.Vs[row_g * p.ld + 512] = e;
+                }
+            }
+            tc_fence_before();
+        }
+        c.ph3[b] ^= 1;
+        __syncthreads();                                                        // S4..S8
+        if (ctrl && j + 2 < 5) {
+            tc_fence_after();
+            const int jn = j + 2;
+            issue_gemm(a_addr, w3_addr + jn * 16384, NPAD * 128, 2, c.tmem + 128 + 128 * b, jn < 4 ? 128 : 16);
+            umma_commit(c.bar3[b]);
+        }
+    }
+
+    float ll = 0.f;
+    if (MODE == MODE_MH) {
+        const float part = fmaf(kLn2, accl, acc);
+        if (epi && c.h == 1) c.red[c.row] = part;
+        __syncthreads();                                                        // S9
+        if (owner) ll = part + c.red[c.row];
+    }
+    return ll;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(Params p) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bars[3];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int dead_flag;
+
+    Ctx c;
+    c.base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int a_off = (p.d.image_bytes + 1023) & ~1023;
+    c.A = c.base + a_off;
+    c.red = reinterpret_cast<float*>(c.A + A_BYTES);
+    c.bar12 = smem_u32(&bars[0]);
+    c.bar3[0] = smem_u32(&bars[1]);
+    c.bar3[1] = smem_u32(&bars[2]);
+    c.dead = &dead_flag;
+    c.status = p.status;
+    c.ph12 = 0; c.ph3[0] = 0; c.ph3[1] = 0;
+    c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
+    c.q = c.warp & 3; c.h = (c.warp >> 2) & 1;
+    c.row = 32 * c.q + c.lane;
+
+    // weights -> shared memory (generic proxy writes, made visible to the tensor core by the fence in eval_tile)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.image);
+        uint4* dst = reinterpret_cast<uint4*>(c.base);
+        for (int i = threadIdx.x; i < p.d.image_bytes / 16; i += NTHREADS) dst[i] = __ldg(src + i);
+    }
+    if (threadIdx.x == 0) {
+        dead_flag = 0;
+        mbar_init(c.bar12, 1);
+        mbar_init(c.bar3[0], 1);
+        mbar_init(c.bar3[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (c.warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    c.tmem = tmem_slot;
+
+    const Dims& d = p.d;
+    const int L = d.L;
+    const int64_t n_tiles = (p.rows + TM - 1) / TM;
+    const bool owner = c.warp < 4;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row_g = tile * TM + c.row;
+        const bool valid = row_g < p.rows;
+        float z[DVAE_MAX_L], zp[DVAE_MAX_L], yrow[8];
+        float g_row = 1.f;
+        int64_t fr = 0;
+        if (valid) fr = row_g / p.C;
+        if (c.warp < 8 && valid && MODE == MODE_MH) g_row = p.g[fr];
+        if (owner && valid) {
+            const float* src = (MODE == MODE_MH ? p.Z : p.Zin) + row_g * L;
+            for (int l = 0; l < L; ++l) z[l] = src[l];
+            for (int i = 0; i < d.y_dim; ++i) yrow[i] = p.y[fr * d.y_dim + i];
+        } else {
+            for (int l = 0; l < L; ++l) z[l] = 0.f;
+        }
+
+        if (MODE == MODE_DECODE) {
+            eval_tile<MODE_DECODE>(p, c, tile, z, yrow, valid, 1.f);
+            continue;
+        }
+
+        float ll_cur = eval_tile<MODE_MH>(p, c, tile, z, yrow, valid, g_row);
+        const int n_iter = p.n_burn + p.n_keep;
+        uint32_t utt = 0, fc = 0;
+        if (owner && valid && !p.inj_eps) {
+            utt = (uint32_t)p.frame_gid[fr];
+            fc = (uint32_t)p.frame_idx[fr] | ((uint32_t)(row_g - fr * p.C) << 20);
+        }
+        uint32_t n_acc = 0;
+        for (int it = 0; it < n_iter; ++it) {
+            float u = 0.5f;
+            if (owner && valid) {
+                float eps[DVAE_MAX_L];
+                if (p.inj_eps) {
+                    const float* e = p.inj_eps + ((int64_t)it * p.rows + row_g) * L;
+                    for (int l = 0; l < L; ++l) eps[l] = e[l];
+                    u = p.inj_u[(int64_t)it * p.rows + row_g];
+                } else {
+                    mh_draws(p.seed_lo, p.seed_hi, utt, fc, p.iter0 + (uint32_t)it, L, eps, u);
+                }
+                for (int l = 0; l < L; ++l) zp[l] = __fadd_rn(z[l], __fmul_rn(p.sd, eps[l]));
+            }
+            const float ll_prop = eval_tile<MODE_MH>(p, c, tile, zp, yrow, valid, g_row);
+            if (owner && valid) {
+                float prior = 0.f;
+                for (int l = 0; l < L; ++l) prior += __fsub_rn(__fmul_rn(z[l], z[l]), __fmul_rn(zp[l], zp[l]));
+                const float a = (ll_cur - ll_prop) + 0.5f * prior;
+                if (p.a_trace) p.a_trace[(int64_t)it * p.rows + row_g] = a;
+                if (__logf(u) < a) {
+                    for (int l = 0; l < L; ++l) z[l] = zp[l];
+                    ll_cur = ll_prop;
+                    ++n_acc;
+                }
+                if (it >= p.n_burn) {
+                    float* dst = p.Zs + (row_g * p.n_keep + (it - p.n_burn)) * L;
+                    for (int l = 0; l < L; ++l) dst[l] = z[l];
+                }
+            }
+        }
+        if (owner && valid) {
+            for (int l = 0; l < L; ++l) p.Z[row_g * L + l] = z[l];
+            if (p.n_accept) p.n_accept[row_g] += n_acc;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (c.warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(c.tmem), "r"(512) : "memory");
+    }
+}
+
+static size_t smem_bytes(const Dims& d) { return (size_t)((d.image_bytes + 1023) & ~1023) + A_BYTES + 512 + 1024; }
+
+static int check_dims(const DvaeMlp* dec, int L, int y_dim, const char* who, Dims* out) {
+    DVAE_REQUIRE(dec != nullptr, "%s: null decoder", who);
+    DVAE_REQUIRE(dec->n_layers == 2 || dec->n_layers == 3, "%s: the tensor-core path supports 1 or 2 hidden layers", who);
+    for (int i = 1; i < dec->n_layers; ++i) DVAE_REQUIRE(dec->dims[i] == HID, "%s: hidden width must be %d", who, HID);
+    const int F = dec->dims[dec->n_layers];
+    DVAE_REQUIRE(F > 512 && F <= 513, "%s: the tensor-core path is specialised for F=513 bins (got %d)", who, F);
+    DVAE_REQUIRE(L >= 1 && L <= DVAE_MAX_L && y_dim >= 0 && y_dim <= 8, "%s: bad L / y_dim", who);
+    DVAE_REQUIRE(dec->dims[0] == L + y_dim, "%s: decoder takes %d inputs, L+y_dim=%d", who, dec->dims[0], L + y_dim);
+    *out = make_dims(L, y_dim, dec->n_layers - 1, F);
+    DVAE_REQUIRE(out->nkb1 <= 2, "%s: 2L+2y+1 must be <= 128", who);
+    DVAE_REQUIRE(smem_bytes(*out) <= 227 * 1024, "%s: weights do not fit in shared memory", who);
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace dvae
+
+using namespace dvae;
+using namespace dvae::tc;
+
+extern "C" int64_t dvae_tc_image_bytes(const DvaeMlp* dec, int L, int y_dim) {
+    Dims d;
+    if (check_dims(dec, L, y_dim, "dvae_tc_image_bytes", &d)) return -1;
+    return d.image_bytes;
+}
+
+extern "C" int dvae_tc_pack_decoder(const DvaeMlp* dec, int L, int y_dim, void* image, void* stream) {
+    Dims d;
+    int rc = check_dims(dec, L, y_dim, "dvae_tc_pack_decoder", &d);
+    if (rc) return rc;
+    DVAE_REQUIRE(image != nullptr && (reinterpret_cast<uintptr_t>(image) & 15) == 0, "dvae_tc_pack_decoder: image must be 16-byte aligned");
+    const bool two = d.n_hidden == 2;
+    pack_decoder_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(d, dec->wt[0], dec->bias[0], two ? dec->wt[1] : nullptr,
+                                                              two ? dec->bias[1] : nullptr, dec->wt[two ? 2 : 1],
+                                                              dec->bias[two ? 2 : 1], (unsigned char*)image);
+    return check_launch("pack_decoder_kernel");
+}
+
+extern "C" int64_t dvae_tc_packed_floats(int64_t chains) {
+    if (chains <= 0) return 0;
+    return ((chains + TM - 1) / TM) * (int64_t)NQ * TM * 4;
+}
+
+extern "C" int dvae_tc_pack_rows(const float* src, int64_t NT, int n_chains, int F, int ld, float* dst, void* stream) {
+    DVAE_REQUIRE(src && dst && NT >= 0 && n_chains >= 1 && F >= 1 && F <= NPAD && ld >= F && (ld & 3) == 0, "dvae_tc_pack_rows: bad arguments");
+    DVAE_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dvae_tc_pack_rows: 16-byte alignment required");
+    if (NT == 0) return 0;
+    pack_rows_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(src, NT * n_chains, n_chains, F, ld, (float4*)dst);
+    return check_launch("pack_rows_kernel");
+}
+
+static int launch_tc(int mode, const Params& p, cudaStream_t st) {
+    const size_t smem = smem_bytes(p.d);
+    const int64_t n_tiles = (p.rows + TM - 1) / TM;
+    const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
+    cudaError_t e;
+    if (mode == MODE_MH) {
+        e = cudaFuncSetAttribute(decoder_tc_kernel<MODE_MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        decoder_tc_kernel<MODE_MH><<<grid, NTHREADS, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(decoder_tc_kernel<MODE_DECODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        decoder_tc_kernel<MODE_DECODE><<<grid, NTHREADS, smem, st>>>(p);
+    }
+    return check_launch("decoder_tc_kernel");
+}
+
+extern "C" int dvae_mh_chain_tc(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
+                                const float* y, int y_dim, const int32_t* frame_utt, const int32_t* frame_idx, float* Z,
+                                float* Zs, int64_t NT, int L, int n_chains, int n_burn, int n_keep, float var_rw,
+                                const DvaeRng* rng, uint32_t* n_accept, float* a_trace, int* status, void* stream) {
+    Params p{};
+    int rc = check_dims(dec, L, y_dim, "dvae_mh_chain_tc", &p.d);
+    if (rc) return rc;
+    DVAE_REQUIRE(image && Ppk && Vbpk && g && Z && Zs && rng && status, "dvae_mh_chain_tc: null pointer");
+    DVAE_REQUIRE(y_dim == 0 || y, "dvae_mh_chain_tc: y_dim=%d but y is null", y_dim);
+    DVAE_REQUIRE(NT >= 0 && n_chains >= 1 && n_chains < 4096 && n_burn >= 0 && n_keep >= 1 && var_rw > 0.f, "dvae_mh_chain_tc: bad sizes");
+    DVAE_REQUIRE((rng->eps == nullptr) == (rng->u == nullptr), "dvae_mh_chain_tc: eps and u must be injected together");
+    DVAE_REQUIRE(rng->eps || (frame_utt && frame_idx), "dvae_mh_chain_tc: Philox mode needs frame_utt/frame_idx");
+    if (NT == 0) return 0;
+    p.image = (const unsigned char*)image;
+    p.rows = NT * n_chains; p.C = n_chains; p.y = y;
+    p.Ppk = (const float4*)Ppk; p.Vbpk = (const float4*)Vbpk; p.g = g; p.Z = Z; p.Zs = Zs;
+    p.frame_gid = frame_utt; p.frame_idx = frame_idx; p.inj_eps = rng->eps; p.inj_u = rng->u;
+    p.n_accept = n_accept; p.a_trace = a_trace; p.n_burn = n_burn; p.n_keep = n_keep;
+    p.seed_lo = (uint32_t)(rng->seed & 0xffffffffu); p.seed_hi = (uint32_t)(rng->seed >> 32); p.iter0 = rng->iter0;
+    p.sd = sqrtf(var_rw);
+    p.status = status;
+    return launch_tc(MODE_MH, p, (cudaStream_t)stream);
+}
+
+extern "C" int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64_t rows, int L, const float* y,
+                              int y_dim, int x2_row_div, float* Vs, int ld, int* status, void* stream) {
+    Params p{};
+    int rc = check_dims(dec, L, y_dim, "dvae_decode_tc", &p.d);
+    if (rc) return rc;
+    DVAE_REQUIRE(image && Zs && Vs && status, "dvae_decode_tc: null pointer");
+    DVAE_REQUIRE(y_dim == 0 || (y && x2_row_div >= 1), "dvae_decode_tc: bad label arguments");
+    DVAE_REQUIRE(rows >= 0 && ld >= p.d.F && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(Vs) & 15) == 0, "dvae_decode_tc: bad sizes / alignment");
+    if (rows == 0) return 0;
+    p.image = (const unsigned char*)image;
+    p.rows = rows; p.C = x2_row_div < 1 ? 1 : x2_row_div; p.y = y;
+    p.Zin = Zs; p.Vs = Vs; p.ld = ld; p.status = status;
+    return launch_tc(MODE_DECODE, p, (cudaStream_t)stream);
+}

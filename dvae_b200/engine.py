@@ -344,6 +344,7 @@ class McemEngine:
         self.n_accept.zero_()
         self.mh_calls = 0
         self.mh_iter0 = 0
+        self._Ppk_for = None
         # speech variances of the kept samples: NT * R_E rows, and at least one frame's worth of Wiener samples
         self.Vs_flat = self._get("Vs", (max(NT * C_ * cfg.keep_E, C_ * cfg.keep_WF), ld))
         self.cost = self._get("cost", (cfg.niter, B), torch.float64)
@@ -388,10 +389,15 @@ class McemEngine:
         rows = (n1 - n0) * R
         x = Zs[n0:n1].reshape(rows, L)
         x2 = None if self.y is None else self.y[n0:n1]
-        ws = self._get("mlp_ws", (max(int(_lib.load().dvae_mlp_workspace_floats(self.w.dec.ref, rows)), 1),))
+        out = Vs.view(-1, self.ld)[:rows]
         with self.stage("decode"):
-            mlp_forward(self.w.dec, x, _lib.ACT_EXP, x2=x2, x2_row_div=R, out=Vs.view(-1, self.ld)[:rows], ws=ws)
-        self.kernel_launches += len(self.w.dec.dims) - 1
+            if self.cfg.sampler == "tc":
+                from . import tc
+                tc.decode_tc(self, x, x2, R, out)
+            else:
+                ws = self._get("mlp_ws", (max(int(_lib.load().dvae_mlp_workspace_floats(self.w.dec.ref, rows)), 1),))
+                mlp_forward(self.w.dec, x, _lib.ACT_EXP, x2=x2, x2_row_div=R, out=out, ws=ws)
+                self.kernel_launches += len(self.w.dec.dims) - 1
 
     def e_step(self, draws=None):
         cfg = self.cfg
@@ -527,6 +533,9 @@ class Enhancer:
         hn.copy_(n_dev, non_blocking=True)
         cost_h = cost.t().contiguous().cpu()                   # synchronises the stream
         torch.cuda.current_stream().synchronize()
+        if self.cfg.sampler == "tc":
+            from . import tc
+            tc.check_status(eng)
         s_np, n_np = hs.numpy(), hn.numpy()
         s_list = [s_np[off[u]:off[u] + lens[u]].copy() for u in range(B)]
         n_list = [n_np[off[u]:off[u] + lens[u]].copy() for u in range(B)]

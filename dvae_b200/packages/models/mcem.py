@@ -112,6 +112,9 @@ class _MCEM:
         eng = self._engine
         cost = eng.run(self._draws)
         F = eng.F
+        if eng.cfg.sampler == "tc":
+            from ... import tc
+            tc.check_status(eng)
         self.S_hat = np.ascontiguousarray(eng.S_hat[:, :F].t().cpu().numpy())
         self.N_hat = np.ascontiguousarray(eng.N_hat[:, :F].t().cpu().numpy())
         return cost[:, 0].cpu().numpy().astype(np.float64)

@@ -1,0 +1,82 @@
+"""Host glue of the tcgen05 (BF16 tensor-core) sampler and decode: packed operands and the C ABI calls.
+
+``mh_chain_tc`` / ``decode_tc`` are what ``McemEngine`` runs when ``McemConfig.sampler == "tc"``.  Everything here is
+bookkeeping: building the decoder's shared-memory image once per model, re-tiling P once per batch and Vb once per
+``sample_posterior`` call, and checking the kernel's status word.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def decoder_image(weights):
+    """The UMMA-ready image of ``weights.dec`` (cached on the weights object)."""
+    img = getattr(weights, "_tc_image", None)
+    if img is None:
+        lib = _lib.load()
+        n = lib.dvae_tc_image_bytes(weights.dec.ref, weights.z_dim, weights.y_dim)
+        if n < 0:
+            _lib.check(-1, "dvae_tc_image_bytes")
+        img = torch.empty(int(n), dtype=torch.uint8, device=weights.device)
+        _lib.call("dvae_tc_pack_decoder", weights.dec.ref, weights.z_dim, weights.y_dim, _p(img), _stream())
+        weights._tc_image = img
+    return img
+
+
+def pack_rows(eng, name, src):
+    """Frame-major [NT][ld] -> [tile][quad][128 chains][4] (see dvae_tc_pack_rows)."""
+    b, C_ = eng.batch, eng.cfg.n_chains
+    n = int(_lib.load().dvae_tc_packed_floats(b.NT * C_))
+    dst = eng._get(name, (max(n, 4),))
+    _lib.call("dvae_tc_pack_rows", _p(src), b.NT, C_, eng.F, eng.ld, _p(dst), _stream())
+    eng.kernel_launches += 1
+    return dst
+
+
+def _status(eng):
+    st = eng._buf.get("tc_status")
+    if st is None:
+        st = torch.zeros(1, dtype=torch.int32, device=eng.dev)
+        eng._buf["tc_status"] = st
+    return st
+
+
+def check_status(eng):
+    """Raise if any tensor-core kernel of this engine reported a pipeline timeout (synchronises)."""
+    st = eng._buf.get("tc_status")
+    if st is not None and int(st.item()) != 0:
+        raise _lib.DvaeError("tcgen05 kernel reported a pipeline timeout (status %d): results are invalid" % int(st.item()))
+
+
+def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
+    w, b, cfg = eng.w, eng.batch, eng.cfg
+    img = decoder_image(w)
+    if getattr(eng, "_Ppk_for", None) is not eng.P:
+        eng._Ppk = pack_rows(eng, "Ppk", eng.P)
+        eng._Ppk_for = eng.P
+    Vbpk = pack_rows(eng, "Vbpk", eng.Vb)
+    _lib.call("dvae_mh_chain_tc", w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim,
+              _p(b.frame_gid), _p(b.frame_idx), _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep,
+              float(cfg.var_rw), C.byref(rng), _p(eng.n_accept), _p(a_trace), _p(_status(eng)), _stream())
+    eng.kernel_launches += 1
+
+
+def decode_tc(eng, x, x2, x2_row_div, out):
+    """Vs rows for the kept samples ``x [rows][L]`` (+ labels) through the tensor-core decoder."""
+    w = eng.w
+    img = decoder_image(w)
+    _lib.call("dvae_decode_tc", w.dec.ref, _p(img), _p(x), x.shape[0], w.z_dim, _p(x2), w.y_dim, max(1, x2_row_div), _p(out),
+              out.stride(0), _p(_status(eng)), _stream())
+    eng.kernel_launches += 1

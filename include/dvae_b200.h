@@ -137,6 +137,25 @@ int dvae_wiener_accum(const float* Vs, int R, const float* Vb, const float* g, i
 int dvae_wiener_apply(const void* X, const float* WFs, const float* WFn, int R_total, int64_t NT, int F, int ld,
                       void* S_hat, void* N_hat, void* stream);
 
+/* ---- tensor-core (tcgen05, BF16 x BF16 -> FP32) decoder path: mcem.py:207-277 + 280-290 over models.py:119-122 ----
+ * Specialised for F = 513 bins, hidden width 128, 1 or 2 hidden layers, 2L + 2*y_dim + 1 <= 128.
+ * dvae_tc_pack_decoder builds the shared-memory image of the decoder (UMMA K-major 128B-swizzled BF16 operands +
+ * FP32 biases; W3/b3 pre-scaled by log2 e) into `image` (dvae_tc_image_bytes bytes, 16-byte aligned).
+ * dvae_tc_pack_rows re-tiles a frame-major [NT][ld] array (P or Vb) to [tile][bin quad][128 chains][4] for the
+ * sampler's coalesced 16-byte loads (dvae_tc_packed_floats floats).
+ * dvae_mh_chain_tc: same contract as dvae_mh_chain_f32 with packed P / Vb; *status is set non-zero if the kernel's
+ * internal pipeline timed out (results invalid).  dvae_decode_tc: Vs[r][0..F) = decoder([Zs[r]; y[r / x2_row_div]]). */
+int64_t dvae_tc_image_bytes(const DvaeMlp* dec, int L, int y_dim);
+int dvae_tc_pack_decoder(const DvaeMlp* dec, int L, int y_dim, void* image, void* stream);
+int64_t dvae_tc_packed_floats(int64_t chains);
+int dvae_tc_pack_rows(const float* src, int64_t NT, int n_chains, int F, int ld, float* dst, void* stream);
+int dvae_mh_chain_tc(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
+                     const float* y, int y_dim, const int32_t* frame_utt, const int32_t* frame_idx, float* Z, float* Zs,
+                     int64_t NT, int L, int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng,
+                     uint32_t* n_accept, float* a_trace, int* status, void* stream);
+int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64_t rows, int L, const float* y, int y_dim,
+                   int x2_row_div, float* Vs, int ld, int* status, void* stream);
+
 /* uniform [eps,1) initialisation of W, H and g = 1 from Philox (mcem.py:42-44: max(rand, eps)) */
 int dvae_nmf_init(uint64_t seed, const int32_t* utt_ids /*[B] global ids*/, const int64_t* fr_off, int B, int64_t NT, int F,
                   int K, int ld, float eps, float* W, float* H, float* g, void* stream);
