@@ -241,6 +241,145 @@ __global__ void __launch_bounds__(256) nmf_hg_kernel(const float* __restrict__ P
     if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = cost_acc * inv_count;
 }
 
+// ----------------------------------------------------------------------------- H, g, cost: register-resident fast path
+// One thread per bin (544 threads >= F = 513), R samples of the current frame in registers: Vs is read from HBM
+// exactly once per EM iteration (coalesced 2 KB rows), the three dependent passes (H, g, cost) run out of registers,
+// and the next frame's rows are prefetched into a second register set while the current frame is reduced.
+// MUFU budget: one reciprocal per (sample, bin) in the H and g passes, one reciprocal + one log2 per PAIR in the cost.
+constexpr int HG2_THREADS = 544;
+constexpr int HG2_FPB = 8;
+constexpr int HG2_KT = 10;                    // NMF ranks up to 10 take the fast path
+
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// second half of a CTA-wide multi-value sum: red[v][t] holds thread t's term of value v; after the call tot[v] is the
+// total (valid for every thread).  Two barriers.
+__device__ __forceinline__ void block_reduce_tail(int nv, const float* red, float* tot) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    for (int v = wid; v < nv; v += HG2_THREADS / 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < HG2_THREADS / 32; ++i) s += red[v * HG2_THREADS + lane + 32 * i];
+        s = warp_sum(s);
+        if (lane == 0) tot[v] = s;
+    }
+    __syncthreads();
+}
+
+template <int R, int KT>
+__global__ void __launch_bounds__(HG2_THREADS, 1) nmf_hg2_kernel(const float* __restrict__ P, const float* __restrict__ Vs,
+                                                                 const float* __restrict__ Wtmp, const float* __restrict__ norm,
+                                                                 float* __restrict__ H, float* __restrict__ g,
+                                                                 float* __restrict__ Vb, double* __restrict__ cost_part,
+                                                                 const int64_t* __restrict__ fr_off, int F, int K, int ld) {
+    extern __shared__ float red[];                 // [2*KT][HG2_THREADS]
+    __shared__ float tot[2 * KT];
+    const int u = blockIdx.y;
+    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
+    const int64_t nb = n0 + (int64_t)blockIdx.x * HG2_FPB;
+    if (nb >= n1) {
+        if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
+        return;
+    }
+    const int64_t ne = (nb + HG2_FPB < n1) ? nb + HG2_FPB : n1;
+    const int t = threadIdx.x;
+    const bool live = t < F;
+    const int fc = live ? t : 0;                   // dead threads shadow bin 0 and contribute zeros
+    float w[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) w[k] = (k < K && live) ? Wtmp[((int64_t)u * K + k) * ld + fc] : 0.f;
+    const double inv_count = 1.0 / ((double)R * (double)F * (double)(n1 - n0));
+    double cost_acc = 0.0;
+
+    float va[R], vn[R];
+    {
+        const float* src = Vs + (nb * R) * (int64_t)ld + fc;
+#pragma unroll
+        for (int r = 0; r < R; ++r) va[r] = src[(int64_t)r * ld];
+    }
+    for (int64_t n = nb; n < ne; ++n) {
+        if (n + 1 < ne) {                          // prefetch the next frame's samples
+            const float* src = Vs + ((n + 1) * R) * (int64_t)ld + fc;
+#pragma unroll
+            for (int r = 0; r < R; ++r) vn[r] = src[(int64_t)r * ld];
+        }
+        const float gg = g[n];
+        const float p = live ? P[n * ld + fc] : 0.f;
+        float h[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
+
+        // ---- H update (Vb1 = W_new H_old)
+        float vb = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) vb = fmaf(w[k], h[k], vb);
+        float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float inv = rcp_fast(fmaf(gg, va[r], vb));
+            a1 += inv;
+            a2 = fmaf(inv, inv, a2);
+        }
+        const float pa2 = p * a2;                  // w == 0 for dead threads, so their terms vanish
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            red[(2 * k) * HG2_THREADS + t] = w[k] * pa2;
+            red[(2 * k + 1) * HG2_THREADS + t] = w[k] * a1;
+        }
+        block_reduce_tail(2 * K, red, tot);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? h[k] * sqrtf(tot[2 * k] / tot[2 * k + 1]) : 0.f;
+
+        // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
+        vb = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) vb = fmaf(w[k], h[k], vb);
+        if (live) Vb[n * ld + t] = vb;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float inv = rcp_fast(fmaf(gg, va[r], vb));
+            const float q = va[r] * inv;
+            s1 += q;
+            s2 = fmaf(q, inv, s2);
+        }
+        red[t] = live ? p * s2 : 0.f;
+        red[HG2_THREADS + t] = live ? s1 : 0.f;
+        block_reduce_tail(2, red, tot);
+        const float gnew = gg * sqrtf(tot[0] / tot[1]);
+
+        // ---- cost with Vx = g_new Vs + Vb2: pairs share one reciprocal and one log2
+        float cl = 0.f, cp = 0.f;
+#pragma unroll
+        for (int r = 0; r + 1 < R; r += 2) {
+            const float v0 = fmaf(gnew, va[r], vb), v1 = fmaf(gnew, va[r + 1], vb);
+            const float pr = v0 * v1;
+            cl += lg2_fast(pr);
+            cp = fmaf(v0 + v1, rcp_fast(pr), cp);
+        }
+        if (R & 1) {
+            const float v0 = fmaf(gnew, va[R - 1], vb);
+            cl += lg2_fast(v0);
+            cp += rcp_fast(v0);
+        }
+        red[t] = live ? fmaf(0.6931471805599453f, cl, p * cp) : 0.f;
+        block_reduce_tail(1, red, tot);
+        cost_acc += (double)tot[0];
+
+        if (t == 0) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k)
+                if (k < K) H[n * K + k] = h[k] * norm[u * K + k];
+            g[n] = gnew;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) va[r] = vn[r];
+    }
+    if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = cost_acc * inv_count;
+}
+
 // cost[u] = sum of the per-CTA partials in block order (deterministic, unlike an atomic accumulation)
 __global__ void cost_reduce_kernel(const double* __restrict__ cost_part, int nblk, double* __restrict__ cost) {
     const int u = blockIdx.x;
@@ -319,7 +458,7 @@ extern "C" int dvae_nmf_vb(const float* W, const float* H, const int32_t* frame_
     return check_launch("nmf_vb_kernel");
 }
 
-static int64_t hg_blocks(int max_frames) { return max_frames > 0 ? (max_frames + FPB - 1) / FPB : 1; }
+static int64_t hg_blocks(int max_frames) { return max_frames > 0 ? (max_frames + FPB - 1) / FPB : 1; }   // generic path: upper bound for both
 
 extern "C" int64_t dvae_nmf_workspace_floats(int B, int K, int ld, int max_frames) {
     if (B <= 0 || K <= 0 || ld <= 0 || max_frames < 0) return 0;
@@ -355,13 +494,25 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
         cudaMemsetAsync(cost, 0, sizeof(double) * B, st);
         return 0;
     }
-    const size_t smem = sizeof(float) * (size_t)K * ld;
-    DVAE_REQUIRE(smem <= 200 * 1024, "dvae_nmf_mstep: K*ld too large for shared memory");
-    cudaFuncSetAttribute(nmf_hg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    nmf_hg_kernel<<<dim3(nblk, B), 256, smem, st>>>(P, Vs, R, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
-    rc = check_launch("nmf_hg_kernel");
+    int nblk_used = nblk;
+    if (F <= HG2_THREADS && K <= HG2_KT && (R == 10 || R == 30)) {
+        nblk_used = (max_frames + HG2_FPB - 1) / HG2_FPB;
+        const size_t smem2 = sizeof(float) * (size_t)2 * HG2_KT * HG2_THREADS;
+        if (R == 10) {
+            nmf_hg2_kernel<10, HG2_KT><<<dim3(nblk_used, B), HG2_THREADS, smem2, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
+        } else {
+            nmf_hg2_kernel<30, HG2_KT><<<dim3(nblk_used, B), HG2_THREADS, smem2, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
+        }
+        rc = check_launch("nmf_hg2_kernel");
+    } else {
+        const size_t smem = sizeof(float) * (size_t)K * ld;
+        DVAE_REQUIRE(smem <= 200 * 1024, "dvae_nmf_mstep: K*ld too large for shared memory");
+        cudaFuncSetAttribute(nmf_hg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        nmf_hg_kernel<<<dim3(nblk, B), 256, smem, st>>>(P, Vs, R, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
+        rc = check_launch("nmf_hg_kernel");
+    }
     if (rc) return rc;
-    cost_reduce_kernel<<<B, 32, 0, st>>>(cost_part, nblk, cost);
+    cost_reduce_kernel<<<B, 32, 0, st>>>(cost_part, nblk_used, cost);
     return check_launch("cost_reduce_kernel");
 }
 

@@ -127,5 +127,22 @@ def xavier_state_dict(variant: str, x_dim: int, z_dim: int, h_dim, y_dim: int = 
         sd[f"decoder.hidden.{i}.weight"], sd[f"decoder.hidden.{i}.bias"] = lin(dims[i], dims[i + 1])
     w, b = lin(rh[-1], x_dim)
     sd["decoder.reconstruction.weight"] = w
-    sd["decoder.reconstruction.bias"] = b + np.float32(out_bias)
+    sd["decoder.reconstruction.bias"] = (b + np.asarray(out_bias, np.float32)).astype(np.float32)   # scalar or per-bin
     return sd
+
+
+def speech_prior_bias(s, n_fft: int = N_FFT, hop: int = HOP):
+    """Per-bin log of the mean clean-speech power spectrum of ``s`` (float64 numpy STFT, Hann, no centring).
+
+    Used as the decoder's output bias so that randomly initialised weights behave like a (crude) speech model:
+    the Wiener filter then separates speech from noise and SI-SDR comparisons are well conditioned.
+    """
+    s = np.asarray(s, np.float64)
+    Tp = padded_length(len(s), FS, n_fft / FS, hop / n_fft)
+    y = np.zeros(Tp)
+    y[: len(s)] = s
+    N = 1 + (Tp - n_fft) // hop
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(N)[:, None]
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / n_fft)
+    P = np.abs(np.fft.rfft(y[idx] * w, axis=1)) ** 2
+    return np.log(P.mean(axis=0) + 1e-10).astype(np.float32)

@@ -59,7 +59,7 @@ def test_dropin_si_sdr_within_0p05_db_of_oracle(variant):
     F, N = X.shape
     y = synth.energy_vad(s) if variant != "M1" else None
     sd = synth.xavier_state_dict(variant, F, 16, [128, 128], 0 if variant == "M1" else 1, seed=3,
-                                 out_bias=float(np.log(np.mean(np.abs(X_ref) ** 2))))
+                                 out_bias=synth.speech_prior_bias(s))
     niter = 12
     # oracle
     torch.manual_seed(77)

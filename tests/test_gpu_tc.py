@@ -1,0 +1,159 @@
+"""Tensor-core (tcgen05 BF16) decoder path against the FP32 CUDA path and the oracle.
+
+Stated tolerance of the BF16 path (weights and hidden activations rounded to BF16, FP32 accumulation, MUFU
+approximations for tanh / exp2 / log2 / reciprocal): decoder outputs within 1 % relative, log-acceptance values
+within 0.05 absolute of FP32, enhanced-speech SI-SDR within 0.05 dB (BASELINE.json north star).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from dvae_b200 import _lib, synth, tc
+from dvae_b200.engine import (Enhancer, InjectedDraws, McemConfig, McemEngine, RaggedBatch, VaeWeights, _p, _stream,
+                              mlp_forward)
+from oracle import mcem_port, stft_np
+from tests.golden_io import Golden
+from tests.gpu_util import DEV, engine_for, golden_draws, unfm
+
+pytestmark = pytest.mark.gpu
+KW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False, pad_at_end=True)
+IKW = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False)
+
+
+def test_decoder_image_layout():
+    """The packed image is the documented K-major 128B-swizzled BF16 layout (checked element by element)."""
+    g = Golden("full_M2")
+    w = VaeWeights(g.sd, "M2", torch.device(DEV))
+    img = tc.decoder_image(w).cpu().numpy()
+    L, y_dim, HID, NPAD = 16, 1, 128, 528
+
+    def elem(base, rows, n, k):
+        off = base + (k >> 6) * rows * 128 + n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4) + (k & 7) * 2
+        return torch.tensor(img[off:off + 2].copy()).view(torch.bfloat16).float().item()
+
+    def bf(x):
+        return torch.tensor(np.float32(x)).to(torch.bfloat16).float().item()
+
+    W1, b1 = g.sd["decoder.hidden.0.weight"], g.sd["decoder.hidden.0.bias"]
+    W2 = g.sd["decoder.hidden.1.weight"]
+    W3, b3 = g.sd["decoder.reconstruction.weight"], g.sd["decoder.reconstruction.bias"]
+    for n, k in ((0, 0), (5, 3), (127, 15)):
+        assert elem(0, HID, n, k) == bf(W1[n, k]) and elem(0, HID, n, k + L) == bf(W1[n, k])
+    assert elem(0, HID, 9, 2 * L) == bf(W1[9, L]) and elem(0, HID, 9, 2 * L + 1) == bf(W1[9, L])
+    assert elem(0, HID, 9, 2 * L + 2) == bf(b1[9]) and elem(0, HID, 9, 2 * L + 3) == 0.0
+    for n, k in ((0, 0), (77, 100), (127, 127)):
+        assert elem(16384, HID, n, k) == bf(W2[n, k])
+    log2e = np.float32(1.4426950408889634)
+    for n, k in ((0, 0), (300, 64), (512, 127)):
+        assert elem(16384 + 32768, NPAD, n, k) == bf(W3[n, k] * log2e)
+    assert elem(16384 + 32768, NPAD, 513, 7) == 0.0
+    bias = np.frombuffer(img[16384 + 32768 + 2 * NPAD * 128:].tobytes(), np.float32)
+    np.testing.assert_allclose(bias[:128], g.sd["decoder.hidden.1.bias"])
+    np.testing.assert_allclose(bias[128:128 + 513], b3 * log2e, rtol=1e-6)
+
+
+@pytest.mark.parametrize("variant,L,h", [("M1", 16, [128, 128]), ("M2", 16, [128, 128]), ("M1", 32, [128])])
+def test_decode_tc_within_one_percent_of_fp32(variant, L, h):
+    y_dim = 0 if variant == "M1" else 1
+    sd = synth.xavier_state_dict(variant, 513, L, h, y_dim, seed=7, out_bias=-3.0)
+    w = VaeWeights(sd, variant, torch.device(DEV))
+    rows, div = 2000, 25                                   # 15.6 tiles: exercises the partial last tile
+    x = torch.randn((rows, L), device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    y = (torch.rand((rows // div, 1), device=DEV) > 0.5).float() if y_dim else None
+    ref = mlp_forward(w.dec, x, _lib.ACT_EXP, x2=y, x2_row_div=div)
+    out = torch.full((rows + 3, 520), -1.0, device=DEV)
+    st = torch.zeros(1, dtype=torch.int32, device=DEV)
+    _lib.call("dvae_decode_tc", w.dec.ref, _p(tc.decoder_image(w)), _p(x), rows, L, _p(y), y_dim, div, _p(out), 520, _p(st), _stream())
+    assert int(st.item()) == 0
+    rel = ((out[:rows, :513] - ref) / ref).abs()
+    assert rel.max().item() <= 1e-2 and rel.mean().item() <= 2e-3
+    assert torch.all(out[rows:] == -1.0) and torch.all(out[:rows, 513:] == -1.0)      # nothing written out of bounds
+
+
+@pytest.mark.parametrize("name", ["full_M1", "full_M2", "full_M2v3", "cfg1_M1"])
+def test_sampler_tc_log_acceptance_vs_oracle(name):
+    g = Golden(name)
+    o = mcem_port.MCEMOracle(g.variant, g.niter, *g.sched, g.var_RW, draws=mcem_port.ReplayDraws(g.draws))
+    o.init_parameters(g.X, g.S, g.sd, g.K, g.eps, y=g.y)
+    (kE, bE), _ = o.schedule()
+    o.taps = []
+    o.sample_posterior(o.Z, kE, bE)
+    eng, X, P, y, batch = engine_for(g, o.schedule(), sampler="tc")
+    draws = golden_draws(g, o.schedule())
+    eng.init_parameters(X, P, batch, y, draws)
+    N = g.X.shape[1]
+    a = torch.zeros((kE + bE, N), device=DEV)
+    eng.sample_posterior(kE, bE, draws, a_trace=a)
+    a = a.cpu().numpy()
+    tc.check_status(eng)
+    same = np.ones(N, bool)
+    n_dec = n_flip = 0
+    Pt = torch.tensor(np.abs(g.X) ** 2)
+    for it, tap in enumerate(o.taps):
+        a_ref = tap["a"].numpy()
+        # a 1 % error of a decoder output moves its log-likelihood term by 1 % of (1 + P/Vx): scale the bound with it
+        Vx = o.g * o._decode_cols(tap["Z"]) + o.Vb
+        Vxp = o.g * o._decode_cols(tap["Zp"]) + o.Vb
+        scale = (2.0 + Pt / Vx + Pt / Vxp).sum(0).numpy()
+        assert np.all(np.abs(a[it] - a_ref)[same] <= 0.05 + 2e-3 * scale[same]), "iteration %d" % it
+        acc_gpu = np.log(tap["u"].numpy()) < a[it]
+        n_dec += int(same.sum())
+        n_flip += int((same & (acc_gpu != tap["acc"].numpy())).sum())
+        same &= acc_gpu == tap["acc"].numpy()
+    assert n_flip <= max(2, int(0.03 * n_dec)), "%d of %d decisions flipped" % (n_flip, n_dec)
+
+
+@pytest.mark.parametrize("name", ["full_M1", "full_M2", "cfg1_M1"])
+def test_full_run_tc_against_reference_golden(name):
+    g = Golden(name)
+    sched = mcem_port.MCEMOracle(g.variant, g.niter, *g.sched).schedule()
+    eng, X, P, y, batch = engine_for(g, sched, sampler="tc")
+    draws = golden_draws(g, sched)
+    eng.init_parameters(X, P, batch, y, draws)
+    cost = eng.run(draws).cpu().numpy()[:, 0]
+    tc.check_status(eng)
+    S_hat = unfm(eng.S_hat, g.F)
+    np.testing.assert_allclose(cost, g.ref["cost"], rtol=3e-2)
+    assert np.linalg.norm(S_hat - g.ref["S_hat"]) / np.linalg.norm(g.ref["S_hat"]) <= 8e-2
+
+
+def test_tc_si_sdr_within_0p05_db_of_oracle_and_fp32():
+    from dvae_b200.packages.models import mcem as shim_mcem
+    from dvae_b200.packages.models import models as shim_models
+    from dvae_b200.packages.processing.stft import istft
+    x, s, _ = synth.synth_utterance(21, 1.0)
+    X_ref, S_ref = stft_np.stft(x, **KW), stft_np.stft(s, **KW)
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128], 0, seed=3, out_bias=synth.speech_prior_bias(s))
+    niter = 12
+    torch.manual_seed(77)
+    o = mcem_port.MCEMOracle("M1", niter, 10, 30, 25, 75, 0.01)
+    o.init_parameters(X_ref, S_ref, sd, 10, 1e-8)
+    o.run()
+    s_ref = stft_np.istft(o.S_hat, max_len=len(x), **IKW)
+    ref = mcem_port.si_sdr(s_ref[800:-800], s[800:-800])
+    base = mcem_port.si_sdr(x[800:-800], s[800:-800])
+    assert ref > base + 1.0, "the synthetic speech prior should enhance (%.2f -> %.2f dB)" % (base, ref)
+    model = shim_models.VariationalAutoencoder([513, 16, [128, 128]])
+    model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()})
+    model.to(DEV).eval()
+    sdr = {}
+    for sampler in ("fp32", "tc"):
+        algo = shim_mcem.MCEM_M1(niter, 10, 30, 25, 75, 0.01, rng="torch", sampler=sampler)
+        torch.manual_seed(77)                                  # the reference's own draw order, same numbers
+        algo.init_parameters(X=X_ref, S=S_ref, vae=model, nmf_rank=10, eps=1e-8, device=0)
+        algo.run()
+        s_hat = istft(algo.S_hat, max_len=len(x), **IKW)
+        sdr[sampler] = mcem_port.si_sdr(s_hat[800:-800], s[800:-800])
+    assert abs(sdr["tc"] - ref) <= 0.05 and abs(sdr["fp32"] - ref) <= 0.05, (sdr, ref, base)
+
+
+def test_tc_rejects_unsupported_shapes():
+    sd = synth.xavier_state_dict("M1", 257, 16, [128, 128], 0)
+    w = VaeWeights(sd, "M1", torch.device(DEV))
+    with pytest.raises(ValueError):
+        tc.decoder_image(w)
+    sd = synth.xavier_state_dict("M1", 513, 16, [64, 64], 0)
+    with pytest.raises(ValueError):
+        tc.decoder_image(VaeWeights(sd, "M1", torch.device(DEV)))
