@@ -46,7 +46,11 @@ PROTOTYPES = {
     "dvae_nmf_vb": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_nmf_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dvae_nmf_mstep": (C.c_int, [c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64,
-                                 C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+                                 C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr]),
+    "dvae_decode_ws_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "dvae_decode_ws_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                    C.c_int, c_ptr, C.c_int, C.c_int64, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr]),
+    "dvae_nmf_w_from_stats": (C.c_int, [c_ptr, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_mh_workspace_floats": (C.c_int64, [C.POINTER(DvaeMlp), C.c_int64, C.c_int]),
     "dvae_mh_chain_f32": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                                     C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,

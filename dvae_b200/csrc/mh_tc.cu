@@ -23,46 +23,10 @@
 // Threads: 8 epilogue warps (warp w reads TMEM lanes 32*(w%4).., columns half w/4) + 1 control warp whose lane 0
 // issues every tcgen05.mma and whose 32 lanes allocate / free the 512 TMEM columns.  Warps 0-3 also own the chain
 // state of row 32*w+lane (z, l(z), Philox counters).
-#include <cuda_bf16.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dvae {
 namespace tc {
-
-constexpr int TM = 128;             // rows per tile
-constexpr int HID = 128;            // hidden width (both hidden layers)
-constexpr int NPAD = 528;           // output bins padded: 4*128 + 16
-constexpr int NQ = NPAD / 4;        // bin quads in the packed P / Vb layout
-constexpr int NTHREADS = 288;
-constexpr int A_BYTES = 32768;
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-
-enum { MODE_MH = 0, MODE_DECODE = 1 };
-
-struct Dims {
-    int L, y_dim, n_hidden, F, nkb1;
-    int off_w2, off_w3, off_bias, image_bytes;      // byte offsets inside the image
-};
-
-__host__ __device__ inline Dims make_dims(int L, int y_dim, int n_hidden, int F) {
-    Dims d;
-    d.L = L; d.y_dim = y_dim; d.n_hidden = n_hidden; d.F = F;
-    const int k1 = 2 * L + 2 * y_dim + 1;
-    d.nkb1 = (k1 + 63) / 64;
-    d.off_w2 = d.nkb1 * 16384;
-    d.off_w3 = d.off_w2 + (n_hidden == 2 ? 2 * HID * 128 : 0);
-    d.off_bias = d.off_w3 + 2 * NPAD * 128;
-    d.image_bytes = d.off_bias + 4 * ((n_hidden == 2 ? HID : 0) + NPAD);
-    return d;
-}
-
-// byte offset of element (row n, column k) of a K-major SWIZZLE_128B operand with `rows` rows
-__host__ __device__ inline int sw128_offset(int rows, int n, int k) {
-    const int kb = k >> 6, c = (k & 63) >> 3, e = k & 7;
-    return kb * rows * 128 + n * 128 + ((c ^ (n & 7)) << 4) + e * 2;
-}
 
 // ----------------------------------------------------------------------------- packing kernels
 __global__ void pack_decoder_kernel(Dims d, const float* __restrict__ wt0, const float* __restrict__ b0,
@@ -124,86 +88,6 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, int64_t chains, 
         }
         dst[i] = v;
     }
-}
-
-// ----------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    // K-major, SWIZZLE_128B: start>>4 | LBO=1 (ignored) | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-__device__ __forceinline__ uint32_t umma_idesc(int N) {
-    // kind::f16: D=F32 (bit 4), A=BF16 (bits 7-9 = 1), B=BF16 (bits 10-12 = 1), K-major A and B, N>>3 at 17, M>>4 at 24
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :: "r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-
-// Bounded wait: a broken pipeline must never hang the GPU. On timeout the CTA-wide `dead` flag makes every later
-// wait fall through and the host sees status != 0.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* dead, int* status) {
-    if (*dead) return;
-    for (int spin = 0; spin < (1 << 22); ++spin) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (done) return;
-    }
-    *dead = 1;
-    atomicExch(status, 1);
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
-}
-
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));      // first source -> upper half
-    return r;
 }
 
 // ----------------------------------------------------------------------------- kernel
@@ -577,9 +461,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(Params p) {
     }
 }
 
-static size_t smem_bytes(const Dims& d) { return (size_t)((d.image_bytes + 1023) & ~1023) + A_BYTES + 512 + 1024; }
+size_t smem_bytes(const Dims& d) { return (size_t)((d.image_bytes + 1023) & ~1023) + A_BYTES + 512 + 1024; }
 
-static int check_dims(const DvaeMlp* dec, int L, int y_dim, const char* who, Dims* out) {
+int check_dims(const DvaeMlp* dec, int L, int y_dim, const char* who, Dims* out) {
     DVAE_REQUIRE(dec != nullptr, "%s: null decoder", who);
     DVAE_REQUIRE(dec->n_layers == 2 || dec->n_layers == 3, "%s: the tensor-core path supports 1 or 2 hidden layers", who);
     for (int i = 1; i < dec->n_layers; ++i) DVAE_REQUIRE(dec->dims[i] == HID, "%s: hidden width must be %d", who, HID);

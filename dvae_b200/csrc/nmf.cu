@@ -470,7 +470,7 @@ extern "C" int64_t dvae_nmf_workspace_floats(int B, int K, int ld, int max_frame
 
 extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, float* H, float* g, float* Vb,
                               double* cost, const int64_t* fr_off, const int32_t* frame_utt, int B, int64_t NT, int F,
-                              int K, int ld, int max_frames, float* ws, void* stream) {
+                              int K, int ld, int max_frames, float* ws, const float* wstat, int n_parts, void* stream) {
     (void)frame_utt;
     DVAE_REQUIRE(P && Vs && W && H && g && Vb && cost && fr_off && ws, "dvae_nmf_mstep: null pointer");
     DVAE_REQUIRE(B >= 1 && NT >= 0 && F >= 1 && ld >= F && R >= 1, "dvae_nmf_mstep: bad sizes");
@@ -484,8 +484,13 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
     double* cost_part = reinterpret_cast<double*>(ws + off);
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(cost_part) & 7) == 0, "dvae_nmf_mstep: workspace must be 8-byte aligned");
     const int nblk = (int)hg_blocks(max_frames);
-    nmf_w_kernel<<<dim3((F + 127) / 128, B), 128, 0, st>>>(P, Vs, R, W, H, g, Vb, fr_off, F, K, ld, Wtmp);
-    int rc = check_launch("nmf_w_kernel");
+    int rc;
+    if (wstat) {                                   // numerator / denominator already reduced by dvae_decode_ws_tc
+        rc = dvae_nmf_w_from_stats(wstat, n_parts, W, B, F, K, ld, Wtmp, stream);
+    } else {
+        nmf_w_kernel<<<dim3((F + 127) / 128, B), 128, 0, st>>>(P, Vs, R, W, H, g, Vb, fr_off, F, K, ld, Wtmp);
+        rc = check_launch("nmf_w_kernel");
+    }
     if (rc) return rc;
     nmf_norm_kernel<<<B, 256, 0, st>>>(Wtmp, F, K, ld, W, norm);
     rc = check_launch("nmf_norm_kernel");

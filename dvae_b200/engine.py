@@ -25,6 +25,7 @@ from . import _lib
 from .synth import FS, HOP, N_FFT, num_frames
 
 LD_ALIGN = 8
+WS_PARTS = 2                     # work items per utterance of the fused decode + W-statistics kernel
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -211,6 +212,7 @@ class McemConfig:
     n_chains: int = 1
     seed: int = 0
     sampler: str = "fp32"        # "fp32": CUDA-core exact mode; "tc": tcgen05 BF16 sampler
+    fuse_wstat: bool = True      # tc only: fold the W-update reductions into the kept-sample decode
 
 
 class InjectedDraws:
@@ -404,7 +406,13 @@ class McemEngine:
         Zs = self.sample_posterior(cfg.keep_E, cfg.burn_E, draws)
         self.R = Zs.shape[1]
         self.Vs = self.Vs_flat[: self.batch.NT * self.R].view(self.batch.NT, self.R, self.ld)
-        self.decode_samples(Zs, 0, self.batch.NT, self.Vs)
+        self.wstat = None
+        if cfg.sampler == "tc" and self.R in (10, 30) and cfg.nmf_rank <= 10 and cfg.fuse_wstat:
+            from . import tc
+            with self.stage("decode"):
+                self.wstat = tc.decode_wstat_tc(self, Zs, self.Vs)
+        else:
+            self.decode_samples(Zs, 0, self.batch.NT, self.Vs)
 
     def m_step(self, it: int):
         b, cfg = self.batch, self.cfg
@@ -413,7 +421,7 @@ class McemEngine:
         with self.stage("mstep"):
             _lib.call("dvae_nmf_mstep", _p(self.P), _p(self.Vs), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
                       C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), _p(b.frame_utt), b.B, b.NT, self.F, cfg.nmf_rank,
-                      self.ld, b.max_frames, _p(ws), _stream())
+                      self.ld, b.max_frames, _p(ws), _p(getattr(self, "wstat", None)), WS_PARTS, _stream())
         self.kernel_launches += 4
 
     def wiener(self, draws=None):

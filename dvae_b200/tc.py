@@ -80,3 +80,17 @@ def decode_tc(eng, x, x2, x2_row_div, out):
     _lib.call("dvae_decode_tc", w.dec.ref, _p(img), _p(x), x.shape[0], w.z_dim, _p(x2), w.y_dim, max(1, x2_row_div), _p(out),
               out.stride(0), _p(_status(eng)), _stream())
     eng.kernel_launches += 1
+
+
+def decode_wstat_tc(eng, Zs, Vs):
+    """Kept-sample decode fused with the W-update statistics (dvae_decode_ws_tc); returns the statistics buffer."""
+    from .engine import WS_PARTS
+    w, b, cfg = eng.w, eng.batch, eng.cfg
+    img = decoder_image(w)
+    n = int(_lib.load().dvae_decode_ws_workspace_floats(b.B, WS_PARTS, eng.ld))
+    ws = eng._get("wstat", (n,))
+    _lib.call("dvae_decode_ws_tc", w.dec.ref, _p(img), _p(Zs), Zs.shape[1], w.z_dim, _p(eng.y), w.y_dim, _p(eng.P), _p(eng.Vb),
+              _p(eng.g), _p(eng.H), cfg.nmf_rank, _p(b.fr_off), b.B, b.NT, eng.ld, _p(Vs), _p(ws), WS_PARTS, _p(_status(eng)),
+              _stream())
+    eng.kernel_launches += 1
+    return ws

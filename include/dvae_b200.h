@@ -108,7 +108,8 @@ int dvae_nmf_vb(const float* W, const float* H, const int32_t* frame_utt, int64_
 int64_t dvae_nmf_workspace_floats(int B, int K, int ld, int max_frames);
 int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, float* H, float* g, float* Vb, double* cost,
                    const int64_t* fr_off, const int32_t* frame_utt, int B, int64_t NT, int F, int K, int ld,
-                   int max_frames /* max_u frames of one utterance, for grid sizing */, float* ws, void* stream);
+                   int max_frames /* max_u frames of one utterance, for grid sizing */, float* ws,
+                   const float* wstat /* nullable: W statistics from dvae_decode_ws_tc */, int n_parts, void* stream);
 
 /* ---- Metropolis-Hastings E-step sampler: mcem.py:207-277 / 372-448 / 544-620 / 716-792 ----
  * FP32 CUDA-core decoder ("exact" mode).  Runs n_burn + n_keep random-walk iterations on every (frame, chain):
@@ -155,6 +156,15 @@ int dvae_mh_chain_tc(const DvaeMlp* dec, const void* image, const float* Ppk, co
                      uint32_t* n_accept, float* a_trace, int* status, void* stream);
 int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64_t rows, int L, const float* y, int y_dim,
                    int x2_row_div, float* Vs, int ld, int* status, void* stream);
+
+/* Fused decode + W-update statistics (mcem.py:280-290 + the reductions of 108-110), R in {10, 30}, K <= 10:
+ * writes Vs[NT][R][ld] and, per (utterance, part), num/den partial sums into ws (dvae_decode_ws_workspace_floats
+ * floats); dvae_nmf_mstep consumes them through its wstat argument, dvae_nmf_w_from_stats is the reduction it runs. */
+int64_t dvae_decode_ws_workspace_floats(int B, int n_parts, int ld);
+int dvae_decode_ws_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y, int y_dim,
+                      const float* P, const float* Vb, const float* g, const float* H, int K, const int64_t* fr_off, int B,
+                      int64_t NT, int ld, float* Vs, float* ws, int n_parts, int* status, void* stream);
+int dvae_nmf_w_from_stats(const float* ws, int n_parts, const float* W, int B, int F, int K, int ld, float* Wtmp, void* stream);
 
 /* uniform [eps,1) initialisation of W, H and g = 1 from Philox (mcem.py:42-44: max(rand, eps)) */
 int dvae_nmf_init(uint64_t seed, const int32_t* utt_ids /*[B] global ids*/, const int64_t* fr_off, int B, int64_t NT, int F,

@@ -157,3 +157,36 @@ def test_tc_rejects_unsupported_shapes():
     sd = synth.xavier_state_dict("M1", 513, 16, [64, 64], 0)
     with pytest.raises(ValueError):
         tc.decoder_image(VaeWeights(sd, "M1", torch.device(DEV)))
+
+
+@pytest.mark.parametrize("variant,keep", [("M1", 30), ("M2", 10), ("M2v3", 10)])
+def test_fused_decode_wstat_matches_unfused(variant, keep):
+    """dvae_decode_ws_tc (decode + W statistics in one pass) against decode_tc followed by the separate W kernel."""
+    y_dim = 0 if variant == "M1" else 1
+    lens = [185, 37, 1, 64]                                     # ragged: partial tiles, one-frame utterance
+    NT = sum(lens)
+    rng = np.random.default_rng(11)
+    P = torch.tensor(rng.gamma(1.0, 0.05, size=(NT, 520)).astype(np.float32)).to(DEV)
+    X = torch.zeros((NT, 520), dtype=torch.complex64, device=DEV)
+    y = (torch.rand((NT, 1), device=DEV, generator=torch.Generator(device=DEV).manual_seed(4)) > 0.5).float() if y_dim else None
+    sd = synth.xavier_state_dict(variant, 513, 16, [128, 128], y_dim, seed=9, out_bias=float(np.log(0.05)))
+    w = VaeWeights(sd, variant, torch.device(DEV))
+    out = {}
+    for fuse in (False, True):
+        cfg = McemConfig(niter=2, keep_E=keep, burn_E=5, keep_WF=3, burn_WF=3, sampler="tc", seed=3, fuse_wstat=fuse)
+        eng = McemEngine(w, cfg, DEV)
+        eng.init_parameters(X, P, RaggedBatch(lens, DEV), y)
+        for it in range(2):
+            eng.e_step()
+            assert (eng.wstat is not None) == fuse
+            vs = eng.Vs.clone()
+            eng.m_step(it)
+        tc.check_status(eng)
+        out[fuse] = (vs.cpu(), eng.W.cpu().clone(), eng.H.cpu().clone(), eng.g.cpu().clone(), eng.cost.cpu().clone())
+    a, b = out[False], out[True]
+    assert ((a[0][:, :, :513] - b[0][:, :, :513]).abs() / a[0][:, :, :513]).max().item() <= 1e-5      # same Vs
+    for i, name in ((1, "W"), (2, "H"), (3, "g"), (4, "cost")):
+        ref = a[i][..., :513] if i == 1 else a[i]
+        got = b[i][..., :513] if i == 1 else b[i]
+        err = ((got - ref).abs().max() / ref.abs().max()).item()
+        assert err <= 1e-4, "%s differs by %g" % (name, err)
