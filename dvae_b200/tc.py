@@ -7,6 +7,7 @@ bookkeeping: building the decoder's shared-memory image once per model, re-tilin
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -67,7 +68,8 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
         eng._Ppk = pack_rows(eng, "Ppk", eng.P)
         eng._Ppk_for = eng.P
     Vbpk = pack_rows(eng, "Vbpk", eng.Vb)
-    _lib.call("dvae_mh_chain_tc", w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim,
+    v2 = w.z_dim in (16, 32) and w.y_dim <= 3 and os.environ.get("DVAE_TC_SAMPLER", "v2") != "v1"
+    _lib.call("dvae_mh_chain_tc2" if v2 else "dvae_mh_chain_tc", w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim,
               _p(b.frame_gid), _p(b.frame_idx), _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep,
               float(cfg.var_rw), C.byref(rng), _p(eng.n_accept), _p(a_trace), _p(_status(eng)), _stream())
     eng.kernel_launches += 1

@@ -156,6 +156,12 @@ int dvae_mh_chain_tc(const DvaeMlp* dec, const void* image, const float* Ppk, co
                      uint32_t* n_accept, float* a_trace, int* status, void* stream);
 int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64_t rows, int L, const float* y, int y_dim,
                    int x2_row_div, float* Vs, int ld, int* status, void* stream);
+/* second-generation schedule of the same sampler (16 epilogue warps, mbarrier chunk hand-over, register-resident
+ * chain state); L in {16, 32}, y_dim <= 3, Zs 16-byte aligned.  Same arguments and results as dvae_mh_chain_tc. */
+int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
+                      const float* y, int y_dim, const int32_t* frame_utt, const int32_t* frame_idx, float* Z, float* Zs,
+                      int64_t NT, int L, int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng,
+                      uint32_t* n_accept, float* a_trace, int* status, void* stream);
 
 /* Fused decode + W-update statistics (mcem.py:280-290 + the reductions of 108-110), R in {10, 30}, K <= 10:
  * writes Vs[NT][R][ld] and, per (utterance, part), num/den partial sums into ws (dvae_decode_ws_workspace_floats
