@@ -4,21 +4,24 @@
 // the CTA, driven by the first ncu capture (profiles/r01_tc_v1_*): v1 ran at 0.7 IPC per SM because every phase was
 // serialised behind CTA barriers with only two warps per scheduler and a long single-warp "owner" phase.
 //
-//   * 16 epilogue warps (4 per TMEM lane quadrant, each 32 columns of a chunk) + the control warp: 4 warps per
-//     scheduler hide the L2 latency of the P / Vb loads and keep the MUFU pipe fed;
-//   * the layer-3 chunks are handed over with mbarriers only (chunk ready: tcgen05.commit; buffer free: 512 thread
-//     arrivals), no CTA barrier inside the chunk loop, so warps drift and MMA / epilogue overlap;
-//   * the chain state (z, z', l) lives in registers (latent size is a template parameter) and the layer-1 operand
-//     row is written with a static layout;
-//   * the Philox draws of iteration it+1 are produced by ALL 16 warps (one 4-word block each) right after the last
-//     chunk of iteration it and parked in the idle half of the activation buffer.
+// A second capture (profiles/r01_tc_v2a_*) showed 38 % of all stalls on local-memory traffic: with 223 KB of shared
+// memory carved out the L1 is tiny, so every spilled register or dynamically indexed array costs an L2 round trip.
+// Hence, in this version:
+//   * 8 warps only (2 per scheduler -> up to 255 registers per thread): nothing spills, nothing is indexed
+//     dynamically (latent size is a template parameter, every loop over chunks is fully unrolled);
+//   * the L2 latency of the P / Vb stream is hidden in software: the quads of sub-chunk t+2 (16 bins) are requested
+//     while sub-chunk t is evaluated (three rotating register buffers);
+//   * the layer-3 chunks are handed over with mbarriers only (chunk ready: tcgen05.commit; buffer free: 256 thread
+//     arrivals), no CTA barrier inside the chunk loop;
+//   * the random draws are read from global memory (either injected by the caller or produced beforehand by the
+//     Philox dump kernel with the same counters as every other sampler), prefetched one iteration ahead;
+//   * warp 0 lane 0 issues every tcgen05.mma; warps 0-3 own the chain state of row 32*w + lane in registers.
 #include "tc_common.cuh"
 
 namespace dvae {
 namespace tc {
 
-constexpr int MH2_THREADS = 544;
-constexpr int MH2_EPI = 512;
+constexpr int MH2_THREADS = 256;             // 8 warps: warp w -> TMEM lane quadrant w&3, column half w>>2
 
 struct Mh2Params {
     Dims d;
@@ -31,20 +34,35 @@ struct Mh2Params {
     const float* g;
     float* Z;
     float* Zs;
-    const int32_t* frame_gid;
-    const int32_t* frame_idx;
-    const float* inj_eps;
-    const float* inj_u;
+    const float* eps;             // [n_iter][rows][L] standard normals
+    const float* u;               // [n_iter][rows] uniforms
     uint32_t* n_accept;
     float* a_trace;
     int n_burn, n_keep;
-    uint32_t seed_lo, seed_hi, iter0;
     float sd;
     int* status;
+    long long* dbg;               // optional [64] clock stamps of CTA 0 (see dvae_debug_set_clock_buffer)
 };
+
+static long long* g_dbg_clocks = nullptr;
+
+#define DBG_STAMP(slot, cond)                                                        \
+    do {                                                                             \
+        if (p.dbg && blockIdx.x == 0 && tile == 0 && it == 4 && (cond)) p.dbg[slot] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ void mbar_arrive2(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
 }
 
 // hidden-layer epilogue, 32 columns per thread: D12[row][32s .. 32s+32) -> tanh(+bias) -> bf16 -> A operand
@@ -72,7 +90,8 @@ __device__ __forceinline__ float bf16_hi(float x) { return __bfloat162float(__fl
 
 // layer-1 operand row with a static layout: [hi(z) (L) | lo(z) (L) | y hi,lo ... | 1 | 0 ...]
 template <int L>
-__device__ __forceinline__ void write_a1_static(const Dims& d, unsigned char* A, int row, const float* z, const float* yrow, bool valid) {
+__device__ __forceinline__ void write_a1_static(int y_dim, int nkb1, unsigned char* A, int row, const float (&z)[L], float y0, float y1,
+                                                float y2, bool valid) {
     constexpr int CH = L / 8;                  // chunks of hi (and of lo)
     const int sw = row & 7;
 #pragma unroll
@@ -89,26 +108,41 @@ __device__ __forceinline__ void write_a1_static(const Dims& d, unsigned char* A,
         *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((cc ^ sw) << 4)) = pk;
     }
     {   // chunk 2*CH: labels (hi, lo pairs, y_dim <= 3) and the constant one
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = 0.f;
+        const float h0 = bf16_hi(y0), h1 = bf16_hi(y1), h2 = bf16_hi(y2);
+        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, e4 = 0.f, e5 = 0.f, e6 = 0.f;
         if (valid) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-                if (i < d.y_dim) { const float hi = bf16_hi(yrow[i]); e[2 * i] = hi; e[2 * i + 1] = yrow[i] - hi; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (i == 2 * d.y_dim) e[i] = 1.f;
+            if (y_dim == 0) { e0 = 1.f; }
+            else if (y_dim == 1) { e0 = h0; e1 = y0 - h0; e2 = 1.f; }
+            else if (y_dim == 2) { e0 = h0; e1 = y0 - h0; e2 = h1; e3 = y1 - h1; e4 = 1.f; }
+            else { e0 = h0; e1 = y0 - h0; e2 = h1; e3 = y1 - h1; e4 = h2; e5 = y2 - h2; e6 = 1.f; }
         }
         constexpr int c = 2 * CH;
         const int kb = c >> 3, cc = c & 7;
-        uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+        uint4 pk = make_uint4(pack_bf16x2(e0, e1), pack_bf16x2(e2, e3), pack_bf16x2(e4, e5), pack_bf16x2(e6, 0.f));
         *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((cc ^ sw) << 4)) = pk;
     }
-    const int K1c = 8 * d.nkb1;                // remaining chunks of the K blocks in use are zero
+    const int K1c = 8 * nkb1;                  // remaining chunks of the K blocks in use are zero
     for (int c = 2 * CH + 1; c < K1c; ++c) {
         const int kb = c >> 3, cc = c & 7;
         *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((cc ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// 16 bins of the log-likelihood: v = TMEM accumulators, pp / vb = observation and noise variance quads
+__device__ __forceinline__ void loglik16(const float* v, const float4* pp, const float4* vb, const float* b3f, float g_row,
+                                         float& acc, float& accl) {
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        const float4 bb = *reinterpret_cast<const float4*>(b3f + 4 * qd);
+        const float v0 = fmaf(g_row, ex2_approx(v[4 * qd + 0] + bb.x), vb[qd].x);
+        const float v1 = fmaf(g_row, ex2_approx(v[4 * qd + 1] + bb.y), vb[qd].y);
+        const float v2 = fmaf(g_row, ex2_approx(v[4 * qd + 2] + bb.z), vb[qd].z);
+        const float v3 = fmaf(g_row, ex2_approx(v[4 * qd + 3] + bb.w), vb[qd].w);
+        const float p01 = v0 * v1, p23 = v2 * v3;
+        const float n01 = fmaf(pp[qd].y, v0, pp[qd].x * v1), n23 = fmaf(pp[qd].w, v2, pp[qd].z * v3);
+        acc = fmaf(n01, rcp_approx(p01), acc);
+        acc = fmaf(n23, rcp_approx(p23), acc);
+        accl += lg2_approx(p01) + lg2_approx(p23);
     }
 }
 
@@ -122,17 +156,16 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     const Dims& d = p.d;
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* A = base + ((d.image_bytes + 1023) & ~1023);
-    float* red = reinterpret_cast<float*>(A + A_BYTES);          // [3][128] partial l + [128] uniforms
-    float* uS = red + 3 * TM;
-    float* epsS = reinterpret_cast<float*>(A + 16384);          // [128][L] draws of the next iteration
+    float* red = reinterpret_cast<float*>(A + A_BYTES);          // [128] partial l(z') of the upper column half
     const uint32_t bar12 = smem_u32(&bars[0]);
-    const uint32_t bar3[2] = {smem_u32(&bars[1]), smem_u32(&bars[2])};
-    const uint32_t barf[2] = {smem_u32(&bars[3]), smem_u32(&bars[4])};
+    const uint32_t bar3_0 = smem_u32(&bars[1]), bar3_1 = smem_u32(&bars[2]);
+    const uint32_t barf_0 = smem_u32(&bars[3]), barf_1 = smem_u32(&bars[4]);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q = warp & 3, s = (warp >> 2) & 3;
+    const int q = warp & 3, h = warp >> 2;             // TMEM lane quadrant, column half
+    const bool owner = h == 0;                         // warps 0-3 carry the chain of row 32q + lane
+    const bool issuer = threadIdx.x == 0;              // lane 0 of warp 0 issues every tcgen05.mma
     const int row = 32 * q + lane;
-    const bool epi = warp < 16, owner = warp < 4, ctrl = (warp == 16 && lane == 0);
-    uint32_t ph12 = 0, ph3[2] = {0, 0}, phf[2] = {0, 0};
+    uint32_t ph12 = 0, ph3_0 = 0, ph3_1 = 0, phf_0 = 0, phf_1 = 0;
 
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.image);
@@ -142,13 +175,13 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     if (threadIdx.x == 0) {
         dead_flag = 0;
         mbar_init(bar12, 1);
-        mbar_init(bar3[0], 1);
-        mbar_init(bar3[1], 1);
-        mbar_init(barf[0], MH2_EPI);
-        mbar_init(barf[1], MH2_EPI);
+        mbar_init(bar3_0, 1);
+        mbar_init(bar3_1, 1);
+        mbar_init(barf_0, MH2_THREADS);
+        mbar_init(barf_1, MH2_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 16) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -165,168 +198,180 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     const float* b3 = biasp + (d.n_hidden == 2 ? HID : 0);
     const int n_iter = p.n_burn + p.n_keep;
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
+    const int y_dim = d.y_dim, nkb1 = d.nkb1;
+    const bool two_hidden = d.n_hidden == 2;
+    const uint32_t lane_off = (uint32_t)(32 * q) << 16;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row_g = tile * TM + row;
-        const bool valid = epi && row_g < p.rows;
+        const bool valid = row_g < p.rows;
         const int64_t fr = valid ? row_g / p.C : 0;
         const float g_row = valid ? p.g[fr] : 1.f;
-        uint32_t utt = 0, fc = 0;
-        if (valid && !p.inj_eps) {
-            utt = (uint32_t)p.frame_gid[fr];
-            fc = (uint32_t)p.frame_idx[fr] | ((uint32_t)(row_g - fr * p.C) << 20);
-        }
-        float z[L], zp[L], yrow[3] = {0.f, 0.f, 0.f};
-        float ll_cur = 0.f, u_cur = 0.5f;
+        const float4* Pt = p.Ppk + (tile * NQ) * TM + row;
+        const float4* Vt = p.Vbpk + (tile * NQ) * TM + row;
+
+        // chain state (owner threads only; dead code in the other warps)
+        float z[L], zp[L], en[L];
+        float y0 = 0.f, y1 = 0.f, y2 = 0.f, ll_cur = 0.f, u_cur = 0.5f, u_nxt = 0.5f;
         uint32_t n_acc = 0;
         if (owner) {
 #pragma unroll
-            for (int l = 0; l < L; ++l) z[l] = valid ? p.Z[row_g * L + l] : 0.f;
-            if (valid)
-                for (int i = 0; i < d.y_dim; ++i) yrow[i] = p.y[fr * d.y_dim + i];
+            for (int l = 0; l < L; ++l) { z[l] = valid ? p.Z[row_g * L + l] : 0.f; zp[l] = 0.f; en[l] = 0.f; }
+            if (valid) {
+                if (y_dim > 0) y0 = p.y[fr * y_dim];
+                if (y_dim > 1) y1 = p.y[fr * y_dim + 1];
+                if (y_dim > 2) y2 = p.y[fr * y_dim + 2];
+            }
         }
 
-        // eval -1 scores the start state; eval it >= 0 scores proposal `it`
+        // eval -1 scores the start state, eval it >= 0 scores proposal `it`
         for (int it = -1; it < n_iter; ++it) {
+            DBG_STAMP(0, threadIdx.x == 0);
             if (owner) {
                 if (it >= 0) {
-                    u_cur = uS[row];
+                    u_cur = u_nxt;
 #pragma unroll
-                    for (int l = 0; l < L; ++l) zp[l] = __fadd_rn(z[l], __fmul_rn(p.sd, epsS[row * L + l]));
-                    write_a1_static<L>(d, A, row, zp, yrow, valid);
+                    for (int l = 0; l < L; ++l) zp[l] = __fadd_rn(z[l], __fmul_rn(p.sd, en[l]));
+                    write_a1_static<L>(y_dim, nkb1, A, row, zp, y0, y1, y2, valid);
                 } else {
-                    write_a1_static<L>(d, A, row, z, yrow, valid);
+                    write_a1_static<L>(y_dim, nkb1, A, row, z, y0, y1, y2, valid);
+                }
+                // draws of the next proposal: requested now, consumed after this evaluation
+                const int nxt = it + 1;
+                if (nxt < n_iter && valid) {
+                    const float4* e = reinterpret_cast<const float4*>(p.eps + ((int64_t)nxt * p.rows + row_g) * L);
+#pragma unroll
+                    for (int l = 0; l < L / 4; ++l) {
+                        const float4 t4 = __ldg(e + l);
+                        en[4 * l] = t4.x; en[4 * l + 1] = t4.y; en[4 * l + 2] = t4.z; en[4 * l + 3] = t4.w;
+                    }
+                    u_nxt = __ldg(p.u + (int64_t)nxt * p.rows + row_g);
                 }
             }
             fence_async_smem();
             __syncthreads();                                                    // S1: layer-1 operand ready
+            DBG_STAMP(1, threadIdx.x == 0);
 
-            if (ctrl) {
+            if (issuer) {
                 tc_fence_after();
-                issue_gemm2(a_addr, 16384, w1_addr, 16384, d.nkb1, tmem, HID);
+                issue_gemm2(a_addr, 16384, w1_addr, 16384, nkb1, tmem, HID);
                 umma_commit(bar12);
             }
-            if (epi) {
-                mbar_wait(bar12, ph12, dead, p.status);
-                tc_fence_after();
-                hidden_epilogue32(tmem, A, q, s, row, nullptr);
-                fence_async_smem();
-                tc_fence_before();
-            }
+            mbar_wait(bar12, ph12, dead, p.status);
             ph12 ^= 1;
+            tc_fence_after();
+            hidden_epilogue_rows(tmem, A, q, h, row, nullptr);              // bias rides on the constant-one column
+            fence_async_smem();
+            tc_fence_before();
+            DBG_STAMP(20, threadIdx.x == 0);
             __syncthreads();                                                    // S2
-            if (d.n_hidden == 2) {
-                if (ctrl) {
+            DBG_STAMP(2, threadIdx.x == 0);
+            if (two_hidden) {
+                if (issuer) {
                     tc_fence_after();
                     issue_gemm2(a_addr, 16384, w2_addr, 16384, 2, tmem, HID);
                     umma_commit(bar12);
                 }
-                if (epi) {
-                    mbar_wait(bar12, ph12, dead, p.status);
-                    tc_fence_after();
-                    hidden_epilogue32(tmem, A, q, s, row, b2);
-                    fence_async_smem();
-                    tc_fence_before();
-                }
+                mbar_wait(bar12, ph12, dead, p.status);
                 ph12 ^= 1;
+                tc_fence_after();
+                hidden_epilogue_rows(tmem, A, q, h, row, b2);
+                fence_async_smem();
+                tc_fence_before();
+                DBG_STAMP(21, threadIdx.x == 0);
                 __syncthreads();                                                // S3
+                DBG_STAMP(3, threadIdx.x == 0);
             }
-
-            // ---- layer 3: 4 chunks of 128 bins + bin 512, TMEM double buffer, mbarrier hand-over
-            float part = 0.f;
-            if (ctrl) {
+            if (issuer) {
                 tc_fence_after();
                 issue_gemm2(a_addr, 16384, w3_addr, NPAD * 128, 2, tmem + 128, 128);
-                umma_commit(bar3[0]);
+                umma_commit(bar3_0);
                 issue_gemm2(a_addr, 16384, w3_addr + 16384, NPAD * 128, 2, tmem + 256, 128);
-                umma_commit(bar3[1]);
-                for (int j = 2; j < 5; ++j) {
-                    const int b = j & 1;
-                    mbar_wait(barf[b], phf[b], dead, p.status);
-                    phf[b] ^= 1;
-                    tc_fence_after();
-                    issue_gemm2(a_addr, 16384, w3_addr + j * 16384, NPAD * 128, 2, tmem + 128 + 128 * b, j < 4 ? 128 : 16);
-                    umma_commit(bar3[b]);
-                }
-                mbar_wait(barf[1], phf[1], dead, p.status); phf[1] ^= 1;       // chunk 3 drained
-                mbar_wait(barf[0], phf[0], dead, p.status); phf[0] ^= 1;       // chunk 4 drained
+                umma_commit(bar3_1);
             }
-            if (epi) {
-                float acc = 0.f, accl = 0.f;
-#pragma unroll 1
-                for (int j = 0; j < 5; ++j) {
-                    const int b = j & 1;
-                    mbar_wait(bar3[b], ph3[b], dead, p.status);
-                    ph3[b] ^= 1;
-                    tc_fence_after();
-                    const uint32_t tbuf = tmem + 128 + 128 * b + ((uint32_t)(32 * q) << 16);
-                    if (j < 4) {
-                        float v[32];
-                        const int f0 = 128 * j + 32 * s;
-                        const float4* Pq = p.Ppk + (tile * NQ + (f0 >> 2)) * TM + row;
-                        const float4* Vq = p.Vbpk + (tile * NQ + (f0 >> 2)) * TM + row;
-                        float4 pp[8], vb[8];
-#pragma unroll
-                        for (int qd = 0; qd < 8; ++qd) { pp[qd] = __ldg(Pq + qd * TM); vb[qd] = __ldg(Vq + qd * TM); }
-                        tmem_ld32(tbuf + 32 * s, v);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int qd = 0; qd < 8; ++qd) {
-                            const float4 bb = *reinterpret_cast<const float4*>(b3 + f0 + 4 * qd);
-                            const float v0 = fmaf(g_row, ex2_approx(v[4 * qd + 0] + bb.x), vb[qd].x);
-                            const float v1 = fmaf(g_row, ex2_approx(v[4 * qd + 1] + bb.y), vb[qd].y);
-                            const float v2 = fmaf(g_row, ex2_approx(v[4 * qd + 2] + bb.z), vb[qd].z);
-                            const float v3 = fmaf(g_row, ex2_approx(v[4 * qd + 3] + bb.w), vb[qd].w);
-                            const float p01 = v0 * v1, p23 = v2 * v3;
-                            const float n01 = fmaf(pp[qd].y, v0, pp[qd].x * v1), n23 = fmaf(pp[qd].w, v2, pp[qd].z * v3);
-                            acc = fmaf(n01, rcp_approx(p01), acc);
-                            acc = fmaf(n23, rcp_approx(p23), acc);
-                            accl += lg2_approx(p01) + lg2_approx(p23);
-                        }
-                    } else if (s == 0) {                                   // bin 512
-                        float v[4];
-                        tmem_ld4(tbuf, v);
-                        tmem_wait_ld();
-                        const float4 pp = __ldg(p.Ppk + (tile * NQ + 128) * TM + row);
-                        const float4 vb = __ldg(p.Vbpk + (tile * NQ + 128) * TM + row);
-                        const float v0 = fmaf(g_row, ex2_approx(v[0] + b3[512]), vb.x);
-                        acc = fmaf(pp.x, rcp_approx(v0), acc);
-                        accl += lg2_approx(v0);
-                    }
-                    tc_fence_before();
-                    mbar_arrive2(barf[b]);
-                }
-                part = fmaf(kLn2, accl, acc);
-                if (s > 0) red[(s - 1) * TM + row] = part;
 
-                // ---- draws of the next iteration (A is idle: every layer-3 MMA of this eval has completed)
-                const int nxt = it + 1;
-                if (nxt < n_iter) {
-                    if (p.inj_eps) {
-                        if (valid) {
-                            const float* e = p.inj_eps + ((int64_t)nxt * p.rows + row_g) * L;
-                            for (int l = s; l < L; l += 4) epsS[row * L + l] = e[l];
-                            if (s == 0) uS[row] = p.inj_u[(int64_t)nxt * p.rows + row_g];
+            // ---- layer 3: 16 sub-chunks of 16 bins per thread; the P / Vb quads of sub-chunk t+2 are requested
+            // while sub-chunk t is evaluated (three rotating register buffers, everything statically indexed)
+            float acc = 0.f, accl = 0.f;
+            float4 pp0[4], vb0[4], pp1[4], vb1[4], pp2[4], vb2[4];
+            // sub-chunk t covers bins 128*(t>>2) + 64*h + 16*(t&3): first quad index below
+#define MH2_QUAD(t) (32 * ((t) >> 2) + 16 * h + 4 * ((t) & 3))
+#define MH2_LOAD(t, PP, VB)                                                                          \
+    do {                                                                                             \
+        _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) {                                           \
+            PP[qd] = __ldg(Pt + (MH2_QUAD(t) + qd) * TM);                                            \
+            VB[qd] = __ldg(Vt + (MH2_QUAD(t) + qd) * TM);                                            \
+        }                                                                                            \
+    } while (0)
+            MH2_LOAD(0, pp0, vb0);
+            MH2_LOAD(1, pp1, vb1);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int j = t >> 2, sub = t & 3;
+                if (t + 2 < 16) {
+                    if ((t + 2) % 3 == 0) MH2_LOAD(t + 2, pp0, vb0);
+                    else if ((t + 2) % 3 == 1) MH2_LOAD(t + 2, pp1, vb1);
+                    else MH2_LOAD(t + 2, pp2, vb2);
+                }
+                if (sub == 0) {
+                    if ((j & 1) == 0) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; }
+                    else { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; }
+                    tc_fence_after();
+                    DBG_STAMP(15 + j, threadIdx.x == 0);
+                }
+                float v[16];
+                tmem_ld16(tmem + 128 + 128 * (j & 1) + lane_off + 64 * h + 16 * sub, v);
+                tmem_wait_ld();
+                const float* b3f = b3 + 128 * j + 64 * h + 16 * sub;
+                if (t % 3 == 0) loglik16(v, pp0, vb0, b3f, g_row, acc, accl);
+                else if (t % 3 == 1) loglik16(v, pp1, vb1, b3f, g_row, acc, accl);
+                else loglik16(v, pp2, vb2, b3f, g_row, acc, accl);
+                if (sub == 3) {
+                    DBG_STAMP(4 + j, threadIdx.x == 0);
+                    DBG_STAMP(10 + j, threadIdx.x == 224);
+                    if (j < 3) {                                                // chunks 0..2: hand the TMEM buffer back
+                        tc_fence_before();
+                        mbar_arrive2((j & 1) ? barf_1 : barf_0);
+                        if (warp == 0) {
+                            if (lane == 0) {
+                                if ((j & 1) == 0) { mbar_wait(barf_0, phf_0, dead, p.status); }
+                                else { mbar_wait(barf_1, phf_1, dead, p.status); }
+                                tc_fence_after();
+                                issue_gemm2(a_addr, 16384, w3_addr + (j + 2) * 16384, NPAD * 128, 2, tmem + 128 + 128 * (j & 1),
+                                            (j + 2) < 4 ? 128 : 16);
+                                umma_commit((j & 1) ? bar3_1 : bar3_0);
+                            }
+                            __syncwarp();
                         }
-                    } else {
-                        for (int blk = s; blk < L / 4; blk += 4) {
-                            const Philox4 r = philox4x32_10(utt, fc, p.iter0 + (uint32_t)nxt, (uint32_t)blk, p.seed_lo, p.seed_hi);
-                            float n0, n1, n2, n3;
-                            box_muller(r.x, r.y, n0, n1);
-                            box_muller(r.z, r.w, n2, n3);
-                            *reinterpret_cast<float4*>(epsS + row * L + 4 * blk) = make_float4(n0, n1, n2, n3);
-                        }
-                        if (s == 3) {
-                            const Philox4 r = philox4x32_10(utt, fc, p.iter0 + (uint32_t)nxt, (uint32_t)(L / 4), p.seed_lo, p.seed_hi);
-                            uS[row] = u01(r.x);
-                        }
+                        if ((j & 1) == 0) phf_0 ^= 1; else phf_1 ^= 1;
                     }
                 }
             }
-            __syncthreads();                                                    // S4: partials and draws visible
+#undef MH2_LOAD
+#undef MH2_QUAD
+            // bin 512 (chunk 4, TMEM buffer 0)
+            mbar_wait(bar3_0, ph3_0, dead, p.status);
+            ph3_0 ^= 1;
+            tc_fence_after();
+            if (h == 0) {
+                float v[4];
+                tmem_ld4(tmem + 128 + lane_off, v);
+                tmem_wait_ld();
+                const float4 pp = __ldg(Pt + 128 * TM);
+                const float4 vb = __ldg(Vt + 128 * TM);
+                const float v0 = fmaf(g_row, ex2_approx(v[0] + b3[512]), vb.x);
+                acc = fmaf(pp.x, rcp_approx(v0), acc);
+                accl += lg2_approx(v0);
+            }
+            tc_fence_before();
+            const float part = fmaf(kLn2, accl, acc);
+            if (h == 1) red[row] = part;
+            DBG_STAMP(8, threadIdx.x == 0);
+            __syncthreads();                                                    // S4: both halves of l(z') available
+            DBG_STAMP(9, threadIdx.x == 0);
 
             if (owner) {
-                const float ll_prop = part + red[row] + red[TM + row] + red[2 * TM + row];
+                const float ll_prop = part + red[row];
                 if (it < 0) {
                     ll_cur = ll_prop;
                 } else if (valid) {
@@ -348,6 +393,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                     }
                 }
             }
+            DBG_STAMP(23, threadIdx.x == 0);
         }
         if (owner && valid) {
 #pragma unroll
@@ -358,7 +404,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) {
+    if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
     }
@@ -371,31 +417,29 @@ using namespace dvae;
 using namespace dvae::tc;
 
 extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
-                                 const float* y, int y_dim, const int32_t* frame_utt, const int32_t* frame_idx, float* Z,
-                                 float* Zs, int64_t NT, int L, int n_chains, int n_burn, int n_keep, float var_rw,
-                                 const DvaeRng* rng, uint32_t* n_accept, float* a_trace, int* status, void* stream) {
+                                 const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
+                                 int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept,
+                                 float* a_trace, int* status, void* stream) {
     Mh2Params p{};
     int rc = check_dims(dec, L, y_dim, "dvae_mh_chain_tc2", &p.d);
     if (rc) return rc;
     DVAE_REQUIRE(L == 16 || L == 32, "dvae_mh_chain_tc2: latent size must be 16 or 32 (got %d)", L);
     DVAE_REQUIRE(y_dim <= 3, "dvae_mh_chain_tc2: at most 3 label inputs");
-    DVAE_REQUIRE(image && Ppk && Vbpk && g && Z && Zs && rng && status, "dvae_mh_chain_tc2: null pointer");
+    DVAE_REQUIRE(image && Ppk && Vbpk && g && Z && Zs && eps && u && status, "dvae_mh_chain_tc2: null pointer");
     DVAE_REQUIRE(y_dim == 0 || y, "dvae_mh_chain_tc2: y_dim=%d but y is null", y_dim);
     DVAE_REQUIRE(NT >= 0 && n_chains >= 1 && n_chains < 4096 && n_burn >= 0 && n_keep >= 1 && var_rw > 0.f, "dvae_mh_chain_tc2: bad sizes");
-    DVAE_REQUIRE((rng->eps == nullptr) == (rng->u == nullptr), "dvae_mh_chain_tc2: eps and u must be injected together");
-    DVAE_REQUIRE(rng->eps || (frame_utt && frame_idx), "dvae_mh_chain_tc2: Philox mode needs frame_utt/frame_idx");
-    DVAE_REQUIRE((reinterpret_cast<uintptr_t>(Zs) & 15) == 0, "dvae_mh_chain_tc2: Zs must be 16-byte aligned");
+    DVAE_REQUIRE((reinterpret_cast<uintptr_t>(Zs) & 15) == 0 && (reinterpret_cast<uintptr_t>(eps) & 15) == 0,
+                 "dvae_mh_chain_tc2: Zs and eps must be 16-byte aligned");
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
     p.rows = NT * n_chains; p.C = n_chains; p.y = y;
     p.Ppk = (const float4*)Ppk; p.Vbpk = (const float4*)Vbpk; p.g = g; p.Z = Z; p.Zs = Zs;
-    p.frame_gid = frame_utt; p.frame_idx = frame_idx; p.inj_eps = rng->eps; p.inj_u = rng->u;
+    p.eps = eps; p.u = u;
     p.n_accept = n_accept; p.a_trace = a_trace; p.n_burn = n_burn; p.n_keep = n_keep;
-    p.seed_lo = (uint32_t)(rng->seed & 0xffffffffu); p.seed_hi = (uint32_t)(rng->seed >> 32); p.iter0 = rng->iter0;
     p.sd = sqrtf(var_rw);
     p.status = status;
-    const size_t smem = smem_bytes(p.d) + 2048;
-    DVAE_REQUIRE(smem <= 227 * 1024, "dvae_mh_chain_tc2: shared memory budget exceeded");
+    p.dbg = g_dbg_clocks;
+    const size_t smem = smem_bytes(p.d);
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
     const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
     cudaStream_t st = (cudaStream_t)stream;
@@ -407,4 +451,11 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const fl
         mh2_kernel<32><<<grid, MH2_THREADS, smem, st>>>(p);
     }
     return check_launch("mh2_kernel");
+}
+
+// Debug aid: when a device buffer of 64 int64 is registered, CTA 0 of the sampler stamps clock64() at its phase
+// boundaries during iteration 4 of its first tile (slot map in tools/tc_phase_clocks.py).  Pass NULL to disable.
+extern "C" int dvae_debug_set_clock_buffer(void* dev_buffer) {
+    g_dbg_clocks = reinterpret_cast<long long*>(dev_buffer);
+    return 0;
 }

@@ -69,9 +69,26 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
         eng._Ppk_for = eng.P
     Vbpk = pack_rows(eng, "Vbpk", eng.Vb)
     v2 = w.z_dim in (16, 32) and w.y_dim <= 3 and os.environ.get("DVAE_TC_SAMPLER", "v2") != "v1"
-    _lib.call("dvae_mh_chain_tc2" if v2 else "dvae_mh_chain_tc", w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim,
-              _p(b.frame_gid), _p(b.frame_idx), _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep,
-              float(cfg.var_rw), C.byref(rng), _p(eng.n_accept), _p(a_trace), _p(_status(eng)), _stream())
+    if not v2:
+        _lib.call("dvae_mh_chain_tc", w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim,
+                  _p(b.frame_gid), _p(b.frame_idx), _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep,
+                  float(cfg.var_rw), C.byref(rng), _p(eng.n_accept), _p(a_trace), _p(_status(eng)), _stream())
+        eng.kernel_launches += 1
+        return
+    # v2 reads its draws from global memory: injected ones as they are, Philox ones dumped by the generator kernel
+    n_iter, chains = keep + burn, b.NT * cfg.n_chains
+    if rng.eps:
+        eps_ptr, u_ptr = C.c_void_p(rng.eps), C.c_void_p(rng.u)
+    else:
+        eps = eng._get("tc_eps", (n_iter * chains * w.z_dim,))
+        u = eng._get("tc_u", (n_iter * chains,))
+        _lib.call("dvae_rng_dump", C.byref(rng), _p(b.frame_gid), _p(b.frame_idx), b.NT, cfg.n_chains, w.z_dim, n_iter,
+                  _p(eps), _p(u), _stream())
+        eng.kernel_launches += 1
+        eps_ptr, u_ptr = _p(eps), _p(u)
+    _lib.call("dvae_mh_chain_tc2", w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim, _p(eng.Z),
+              _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep, float(cfg.var_rw), eps_ptr, u_ptr, _p(eng.n_accept),
+              _p(a_trace), _p(_status(eng)), _stream())
     eng.kernel_launches += 1
 
 

@@ -156,12 +156,17 @@ int dvae_mh_chain_tc(const DvaeMlp* dec, const void* image, const float* Ppk, co
                      uint32_t* n_accept, float* a_trace, int* status, void* stream);
 int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64_t rows, int L, const float* y, int y_dim,
                    int x2_row_div, float* Vs, int ld, int* status, void* stream);
-/* second-generation schedule of the same sampler (16 epilogue warps, mbarrier chunk hand-over, register-resident
- * chain state); L in {16, 32}, y_dim <= 3, Zs 16-byte aligned.  Same arguments and results as dvae_mh_chain_tc. */
+/* second-generation schedule of the same sampler (software-pipelined P / Vb stream, mbarrier chunk hand-over,
+ * register-resident chain state); L in {16, 32}, y_dim <= 3.  The draws always come from global memory:
+ * eps[n_iter][NT*C][L], u[n_iter][NT*C] (16-byte aligned), either injected by the caller or produced by
+ * dvae_rng_dump with the Philox counters every sampler of this library uses.  Same results as dvae_mh_chain_tc. */
 int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
-                      const float* y, int y_dim, const int32_t* frame_utt, const int32_t* frame_idx, float* Z, float* Zs,
-                      int64_t NT, int L, int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng,
-                      uint32_t* n_accept, float* a_trace, int* status, void* stream);
+                      const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
+                      int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
+                      int* status, void* stream);
+
+/* debug aid: register a device buffer of 64 int64; the tc2 sampler's CTA 0 stamps clock64() at its phase boundaries */
+int dvae_debug_set_clock_buffer(void* dev_buffer);
 
 /* Fused decode + W-update statistics (mcem.py:280-290 + the reductions of 108-110), R in {10, 30}, K <= 10:
  * writes Vs[NT][R][ld] and, per (utterance, part), num/den partial sums into ws (dvae_decode_ws_workspace_floats
