@@ -149,7 +149,7 @@ __device__ __forceinline__ void loglik16(const float* v, const float4* pp, const
 template <int L>
 __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     extern __shared__ unsigned char smem_raw[];
-    __shared__ uint64_t bars[5];                       // layer 1/2 ready, chunk ready x2, buffer free x2
+    __shared__ uint64_t bars[6];                       // layer 1/2 ready, chunk ready x3, buffer free x2
     __shared__ uint32_t tmem_slot;
     __shared__ int dead_flag;
 
@@ -157,15 +157,16 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* A = base + ((d.image_bytes + 1023) & ~1023);
     float* red = reinterpret_cast<float*>(A + A_BYTES);          // [128] partial l(z') of the upper column half
+    float* zpS = red + TM;                                       // [128][L] proposals (written and read by the row's owner)
     const uint32_t bar12 = smem_u32(&bars[0]);
-    const uint32_t bar3_0 = smem_u32(&bars[1]), bar3_1 = smem_u32(&bars[2]);
-    const uint32_t barf_0 = smem_u32(&bars[3]), barf_1 = smem_u32(&bars[4]);
+    const uint32_t bar3_0 = smem_u32(&bars[1]), bar3_1 = smem_u32(&bars[2]), bar3_2 = smem_u32(&bars[3]);
+    const uint32_t barf_0 = smem_u32(&bars[4]), barf_1 = smem_u32(&bars[5]);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, h = warp >> 2;             // TMEM lane quadrant, column half
     const bool owner = h == 0;                         // warps 0-3 carry the chain of row 32q + lane
     const bool issuer = threadIdx.x == 0;              // lane 0 of warp 0 issues every tcgen05.mma
     const int row = 32 * q + lane;
-    uint32_t ph12 = 0, ph3_0 = 0, ph3_1 = 0, phf_0 = 0, phf_1 = 0;
+    uint32_t ph12 = 0, ph3_0 = 0, ph3_1 = 0, ph3_2 = 0, phf_0 = 0, phf_1 = 0;
 
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.image);
@@ -177,6 +178,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         mbar_init(bar12, 1);
         mbar_init(bar3_0, 1);
         mbar_init(bar3_1, 1);
+        mbar_init(bar3_2, 1);
         mbar_init(barf_0, MH2_THREADS);
         mbar_init(barf_1, MH2_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -211,12 +213,15 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         const float4* Vt = p.Vbpk + (tile * NQ) * TM + row;
 
         // chain state (owner threads only; dead code in the other warps)
-        float z[L], zp[L], en[L];
-        float y0 = 0.f, y1 = 0.f, y2 = 0.f, ll_cur = 0.f, u_cur = 0.5f, u_nxt = 0.5f;
+        float z[L];
+        float4 en[L / 4];                                  // draws of the next proposal (live only around the accept step)
+        float y0 = 0.f, y1 = 0.f, y2 = 0.f, ll_cur = 0.f, u_cur = 0.5f, u_nxt = 0.5f, prior = 0.f;
         uint32_t n_acc = 0;
         if (owner) {
 #pragma unroll
-            for (int l = 0; l < L; ++l) { z[l] = valid ? p.Z[row_g * L + l] : 0.f; zp[l] = 0.f; en[l] = 0.f; }
+            for (int l = 0; l < L; ++l) z[l] = valid ? p.Z[row_g * L + l] : 0.f;
+#pragma unroll
+            for (int l = 0; l < L / 4; ++l) en[l] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
                 if (y_dim > 0) y0 = p.y[fr * y_dim];
                 if (y_dim > 1) y1 = p.y[fr * y_dim + 1];
@@ -230,22 +235,23 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             if (owner) {
                 if (it >= 0) {
                     u_cur = u_nxt;
+                    float zp[L];
+                    prior = 0.f;
 #pragma unroll
-                    for (int l = 0; l < L; ++l) zp[l] = __fadd_rn(z[l], __fmul_rn(p.sd, en[l]));
+                    for (int l = 0; l < L / 4; ++l) {
+                        zp[4 * l + 0] = __fadd_rn(z[4 * l + 0], __fmul_rn(p.sd, en[l].x));
+                        zp[4 * l + 1] = __fadd_rn(z[4 * l + 1], __fmul_rn(p.sd, en[l].y));
+                        zp[4 * l + 2] = __fadd_rn(z[4 * l + 2], __fmul_rn(p.sd, en[l].z));
+                        zp[4 * l + 3] = __fadd_rn(z[4 * l + 3], __fmul_rn(p.sd, en[l].w));
+                    }
+#pragma unroll
+                    for (int l = 0; l < L; ++l) prior += __fsub_rn(__fmul_rn(z[l], z[l]), __fmul_rn(zp[l], zp[l]));
+#pragma unroll
+                    for (int l = 0; l < L / 4; ++l)
+                        *reinterpret_cast<float4*>(zpS + row * L + 4 * l) = make_float4(zp[4 * l], zp[4 * l + 1], zp[4 * l + 2], zp[4 * l + 3]);
                     write_a1_static<L>(y_dim, nkb1, A, row, zp, y0, y1, y2, valid);
                 } else {
                     write_a1_static<L>(y_dim, nkb1, A, row, z, y0, y1, y2, valid);
-                }
-                // draws of the next proposal: requested now, consumed after this evaluation
-                const int nxt = it + 1;
-                if (nxt < n_iter && valid) {
-                    const float4* e = reinterpret_cast<const float4*>(p.eps + ((int64_t)nxt * p.rows + row_g) * L);
-#pragma unroll
-                    for (int l = 0; l < L / 4; ++l) {
-                        const float4 t4 = __ldg(e + l);
-                        en[4 * l] = t4.x; en[4 * l + 1] = t4.y; en[4 * l + 2] = t4.z; en[4 * l + 3] = t4.w;
-                    }
-                    u_nxt = __ldg(p.u + (int64_t)nxt * p.rows + row_g);
                 }
             }
             fence_async_smem();
@@ -288,6 +294,8 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 umma_commit(bar3_0);
                 issue_gemm2(a_addr, 16384, w3_addr + 16384, NPAD * 128, 2, tmem + 256, 128);
                 umma_commit(bar3_1);
+                issue_gemm2(a_addr, 16384, w3_addr + 2 * 16384, NPAD * 128, 2, tmem + 384, 128);
+                umma_commit(bar3_2);
             }
 
             // ---- layer 3: 16 sub-chunks of 16 bins per thread; the P / Vb quads of sub-chunk t+2 are requested
@@ -313,14 +321,15 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                     else if ((t + 2) % 3 == 1) MH2_LOAD(t + 2, pp1, vb1);
                     else MH2_LOAD(t + 2, pp2, vb2);
                 }
-                if (sub == 0) {
-                    if ((j & 1) == 0) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; }
-                    else { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; }
+                if (sub == 0) {                                                 // chunk j lives in TMEM buffer j % 3
+                    if (j % 3 == 0) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; }
+                    else if (j % 3 == 1) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; }
+                    else { mbar_wait(bar3_2, ph3_2, dead, p.status); ph3_2 ^= 1; }
                     tc_fence_after();
                     DBG_STAMP(15 + j, threadIdx.x == 0);
                 }
                 float v[16];
-                tmem_ld16(tmem + 128 + 128 * (j & 1) + lane_off + 64 * h + 16 * sub, v);
+                tmem_ld16(tmem + 128 + 128 * (j % 3) + lane_off + 64 * h + 16 * sub, v);
                 tmem_wait_ld();
                 const float* b3f = b3 + 128 * j + 64 * h + 16 * sub;
                 if (t % 3 == 0) loglik16(v, pp0, vb0, b3f, g_row, acc, accl);
@@ -329,33 +338,47 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 if (sub == 3) {
                     DBG_STAMP(4 + j, threadIdx.x == 0);
                     DBG_STAMP(10 + j, threadIdx.x == 224);
-                    if (j < 3) {                                                // chunks 0..2: hand the TMEM buffer back
+                    if (j < 2) {                                                // buffers 0 and 1 are reused by chunks 3 and 4
                         tc_fence_before();
-                        mbar_arrive2((j & 1) ? barf_1 : barf_0);
+                        mbar_arrive2(j == 0 ? barf_0 : barf_1);
+                    }
+                    if (j == 1 || j == 2) {
+                        // lagged hand-over: chunk j+2 goes into the buffer drained one chunk ago, so the wait below
+                        // never stalls and the MMA has a whole chunk epilogue to complete
                         if (warp == 0) {
                             if (lane == 0) {
-                                if ((j & 1) == 0) { mbar_wait(barf_0, phf_0, dead, p.status); }
+                                if (j == 1) { mbar_wait(barf_0, phf_0, dead, p.status); }
                                 else { mbar_wait(barf_1, phf_1, dead, p.status); }
                                 tc_fence_after();
-                                issue_gemm2(a_addr, 16384, w3_addr + (j + 2) * 16384, NPAD * 128, 2, tmem + 128 + 128 * (j & 1),
-                                            (j + 2) < 4 ? 128 : 16);
-                                umma_commit((j & 1) ? bar3_1 : bar3_0);
+                                issue_gemm2(a_addr, 16384, w3_addr + (j + 2) * 16384, NPAD * 128, 2, tmem + 128 + 128 * (j - 1),
+                                            j == 1 ? 128 : 16);
+                                umma_commit(j == 1 ? bar3_0 : bar3_1);
                             }
                             __syncwarp();
                         }
-                        if ((j & 1) == 0) phf_0 ^= 1; else phf_1 ^= 1;
+                        if (j == 1) phf_0 ^= 1; else phf_1 ^= 1;
+                    }
+                    if (j == 3 && owner) {
+                        // draws of the next proposal: requested here, consumed right after the accept step
+                        const int nxt = it + 1;
+                        if (nxt < n_iter && valid) {
+                            const float4* e = reinterpret_cast<const float4*>(p.eps + ((int64_t)nxt * p.rows + row_g) * L);
+#pragma unroll
+                            for (int l = 0; l < L / 4; ++l) en[l] = __ldg(e + l);
+                            u_nxt = __ldg(p.u + (int64_t)nxt * p.rows + row_g);
+                        }
                     }
                 }
             }
 #undef MH2_LOAD
 #undef MH2_QUAD
-            // bin 512 (chunk 4, TMEM buffer 0)
-            mbar_wait(bar3_0, ph3_0, dead, p.status);
-            ph3_0 ^= 1;
+            // bin 512 (chunk 4, TMEM buffer 1)
+            mbar_wait(bar3_1, ph3_1, dead, p.status);
+            ph3_1 ^= 1;
             tc_fence_after();
             if (h == 0) {
                 float v[4];
-                tmem_ld4(tmem + 128 + lane_off, v);
+                tmem_ld4(tmem + 256 + lane_off, v);
                 tmem_wait_ld();
                 const float4 pp = __ldg(Pt + 128 * TM);
                 const float4 vb = __ldg(Vt + 128 * TM);
@@ -375,14 +398,14 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 if (it < 0) {
                     ll_cur = ll_prop;
                 } else if (valid) {
-                    float prior = 0.f;
-#pragma unroll
-                    for (int l = 0; l < L; ++l) prior += __fsub_rn(__fmul_rn(z[l], z[l]), __fmul_rn(zp[l], zp[l]));
                     const float a = (ll_cur - ll_prop) + 0.5f * prior;
                     if (p.a_trace) p.a_trace[(int64_t)it * p.rows + row_g] = a;
                     if (__logf(u_cur) < a) {
 #pragma unroll
-                        for (int l = 0; l < L; ++l) z[l] = zp[l];
+                        for (int l = 0; l < L / 4; ++l) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(zpS + row * L + 4 * l);
+                            z[4 * l] = t4.x; z[4 * l + 1] = t4.y; z[4 * l + 2] = t4.z; z[4 * l + 3] = t4.w;
+                        }
                         ll_cur = ll_prop;
                         ++n_acc;
                     }
@@ -439,7 +462,8 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const fl
     p.sd = sqrtf(var_rw);
     p.status = status;
     p.dbg = g_dbg_clocks;
-    const size_t smem = smem_bytes(p.d);
+    const size_t smem = smem_bytes(p.d) + (size_t)TM * L * 4;
+    DVAE_REQUIRE(smem <= 227 * 1024, "dvae_mh_chain_tc2: shared memory budget exceeded");
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
     const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
     cudaStream_t st = (cudaStream_t)stream;
