@@ -380,6 +380,178 @@ __global__ void __launch_bounds__(HG2_THREADS, 1) nmf_hg2_kernel(const float* __
     if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = cost_acc * inv_count;
 }
 
+// ----------------------------------------------------------------------------- H, g, cost: shared-memory frame tile
+// Third version (the one dispatched for F <= 513 + slack, K <= 10): a CTA of 256 threads stages one frame's R x F
+// speech variances in shared memory with cp.async (no registers tied up, coalesced 16-byte chunks) and runs the three
+// dependent passes out of shared memory; three CTAs fit per SM (R = 30: 3 x 62 KB), so one CTA's staging overlaps the
+// others' arithmetic.  Each thread owns bins t and t + 256; the R samples of the odd last bin (512) are spread over
+// threads 0..R-1.  H and g passes spend one reciprocal per PAIR of samples, the cost pass one reciprocal + one log2.
+constexpr int HG3_THREADS = 256;
+constexpr int HG3_FPB = 8;
+constexpr int HG3_NV = 2 * HG2_KT;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// reduce red[v][0..256) -> tot[v] for v < nv (8 warps); two barriers
+__device__ __forceinline__ void hg3_reduce(int nv, const float* red, float* tot) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    for (int v = wid; v < nv; v += HG3_THREADS / 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < HG3_THREADS / 32; ++i) s += red[v * HG3_THREADS + lane + 32 * i];
+        s = warp_sum(s);
+        if (lane == 0) tot[v] = s;
+    }
+    __syncthreads();
+}
+
+template <int R>
+__global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __restrict__ P, const float* __restrict__ Vs,
+                                                                 const float* __restrict__ Wtmp, const float* __restrict__ norm,
+                                                                 float* __restrict__ H, float* __restrict__ g,
+                                                                 float* __restrict__ Vb, double* __restrict__ cost_part,
+                                                                 const int64_t* __restrict__ fr_off, int F, int K, int ld) {
+    constexpr int KT = HG2_KT;
+    extern __shared__ __align__(16) float sm[];
+    float* S = sm;                                  // [R][ld] samples of the current frame
+    float* red = S + R * ld;                        // [HG3_NV][256]
+    __shared__ float tot[HG3_NV];
+    __shared__ float hs[KT];
+    const int u = blockIdx.y;
+    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
+    const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
+    if (nb >= n1) {
+        if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
+        return;
+    }
+    const int64_t ne = (nb + HG3_FPB < n1) ? nb + HG3_FPB : n1;
+    const int t = threadIdx.x;
+    const int fA = t, fB = t + 256;                 // the two bins of this thread (F >= 512 is checked by the host)
+    const bool xl = (t < R) && (F > 512);           // this thread also holds sample t of bin 512
+    float wA[KT], wB[KT], wX[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const float* wk = Wtmp + ((int64_t)u * K + k) * ld;
+        wA[k] = (k < K) ? wk[fA] : 0.f;
+        wB[k] = (k < K) ? wk[fB] : 0.f;
+        wX[k] = (k < K && F > 512) ? wk[512] : 0.f;
+    }
+    const double inv_count = 1.0 / ((double)R * (double)F * (double)(n1 - n0));
+    double cost_acc = 0.0;
+    const int chunks_per_row = ld / 4;
+
+    for (int64_t n = nb; n < ne; ++n) {
+        // ---- stage the frame: R rows of ld floats, 16-byte cp.async chunks
+        __syncthreads();                            // previous frame fully consumed
+        {
+            const float* src = Vs + (n * R) * (int64_t)ld;
+            for (int i = t; i < R * chunks_per_row; i += HG3_THREADS) cp_async16(S + 4 * i, src + 4 * i);
+        }
+        const float gg = g[n];
+        const float pA = P[n * ld + fA], pB = P[n * ld + fB];
+        const float pX = (F > 512) ? P[n * ld + 512] : 0.f;
+        float h[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
+        cp_async_wait_all();
+        __syncthreads();
+
+        // ---- H update (Vb1 = W_new H_old)
+        float vbA = 0.f, vbB = 0.f, vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vbA = fmaf(wA[k], h[k], vbA); vbB = fmaf(wB[k], h[k], vbB); vbX = fmaf(wX[k], h[k], vbX); }
+        float a1A = 0.f, a2A = 0.f, a1B = 0.f, a2B = 0.f;
+#pragma unroll 5
+        for (int r = 0; r + 1 < R; r += 2) {
+            const float x0 = fmaf(gg, S[r * ld + fA], vbA), x1 = fmaf(gg, S[(r + 1) * ld + fA], vbA);
+            const float y0 = fmaf(gg, S[r * ld + fB], vbB), y1 = fmaf(gg, S[(r + 1) * ld + fB], vbB);
+            const float rx = rcp_fast(x0 * x1), ry = rcp_fast(y0 * y1);
+            const float ix0 = x1 * rx, ix1 = x0 * rx, iy0 = y1 * ry, iy1 = y0 * ry;
+            a1A += ix0 + ix1; a2A = fmaf(ix0, ix0, fmaf(ix1, ix1, a2A));
+            a1B += iy0 + iy1; a2B = fmaf(iy0, iy0, fmaf(iy1, iy1, a2B));
+        }
+        if (R & 1) {
+            const float ix = rcp_fast(fmaf(gg, S[(R - 1) * ld + fA], vbA)), iy = rcp_fast(fmaf(gg, S[(R - 1) * ld + fB], vbB));
+            a1A += ix; a2A = fmaf(ix, ix, a2A);
+            a1B += iy; a2B = fmaf(iy, iy, a2B);
+        }
+        float a1X = 0.f, a2X = 0.f;                 // bin 512: this thread's single sample
+        if (xl) { const float ix = rcp_fast(fmaf(gg, S[t * ld + 512], vbX)); a1X = ix; a2X = ix * ix; }
+        const float qA = pA * a2A, qB = pB * a2B, qX = pX * a2X;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            red[(2 * k) * HG3_THREADS + t] = fmaf(wA[k], qA, fmaf(wB[k], qB, wX[k] * qX));
+            red[(2 * k + 1) * HG3_THREADS + t] = fmaf(wA[k], a1A, fmaf(wB[k], a1B, wX[k] * a1X));
+        }
+        hg3_reduce(2 * K, red, tot);
+        if (t < K) hs[t] = H[n * K + t] * sqrtf(tot[2 * t] / tot[2 * t + 1]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? hs[k] : 0.f;
+
+        // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
+        vbA = 0.f; vbB = 0.f; vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vbA = fmaf(wA[k], h[k], vbA); vbB = fmaf(wB[k], h[k], vbB); vbX = fmaf(wX[k], h[k], vbX); }
+        Vb[n * ld + fA] = vbA;
+        Vb[n * ld + fB] = vbB;
+        if (t == 0 && F > 512) Vb[n * ld + 512] = vbX;
+        float s1A = 0.f, s2A = 0.f, s1B = 0.f, s2B = 0.f;
+#pragma unroll 5
+        for (int r = 0; r + 1 < R; r += 2) {
+            const float sa0 = S[r * ld + fA], sa1 = S[(r + 1) * ld + fA], sb0 = S[r * ld + fB], sb1 = S[(r + 1) * ld + fB];
+            const float x0 = fmaf(gg, sa0, vbA), x1 = fmaf(gg, sa1, vbA), y0 = fmaf(gg, sb0, vbB), y1 = fmaf(gg, sb1, vbB);
+            const float rx = rcp_fast(x0 * x1), ry = rcp_fast(y0 * y1);
+            const float ix0 = x1 * rx, ix1 = x0 * rx, iy0 = y1 * ry, iy1 = y0 * ry;
+            const float ta0 = sa0 * ix0, ta1 = sa1 * ix1, tb0 = sb0 * iy0, tb1 = sb1 * iy1;
+            s1A += ta0 + ta1; s2A = fmaf(ta0, ix0, fmaf(ta1, ix1, s2A));
+            s1B += tb0 + tb1; s2B = fmaf(tb0, iy0, fmaf(tb1, iy1, s2B));
+        }
+        if (R & 1) {
+            const float sa = S[(R - 1) * ld + fA], sb = S[(R - 1) * ld + fB];
+            const float ix = rcp_fast(fmaf(gg, sa, vbA)), iy = rcp_fast(fmaf(gg, sb, vbB));
+            s1A += sa * ix; s2A = fmaf(sa * ix, ix, s2A);
+            s1B += sb * iy; s2B = fmaf(sb * iy, iy, s2B);
+        }
+        float s1X = 0.f, s2X = 0.f;
+        if (xl) { const float sx = S[t * ld + 512]; const float ix = rcp_fast(fmaf(gg, sx, vbX)); s1X = sx * ix; s2X = s1X * ix; }
+        red[t] = fmaf(pA, s2A, fmaf(pB, s2B, pX * s2X));
+        red[HG3_THREADS + t] = s1A + s1B + s1X;
+        hg3_reduce(2, red, tot);
+        const float gnew = gg * sqrtf(tot[0] / tot[1]);
+
+        // ---- cost with Vx = g_new Vs + Vb2: a pair of samples shares one reciprocal and one log2
+        float clA = 0.f, cpA = 0.f, clB = 0.f, cpB = 0.f;
+#pragma unroll 5
+        for (int r = 0; r + 1 < R; r += 2) {
+            const float x0 = fmaf(gnew, S[r * ld + fA], vbA), x1 = fmaf(gnew, S[(r + 1) * ld + fA], vbA);
+            const float y0 = fmaf(gnew, S[r * ld + fB], vbB), y1 = fmaf(gnew, S[(r + 1) * ld + fB], vbB);
+            const float px = x0 * x1, py = y0 * y1;
+            clA += lg2_fast(px); cpA = fmaf(x0 + x1, rcp_fast(px), cpA);
+            clB += lg2_fast(py); cpB = fmaf(y0 + y1, rcp_fast(py), cpB);
+        }
+        if (R & 1) {
+            const float x0 = fmaf(gnew, S[(R - 1) * ld + fA], vbA), y0 = fmaf(gnew, S[(R - 1) * ld + fB], vbB);
+            clA += lg2_fast(x0); cpA += rcp_fast(x0);
+            clB += lg2_fast(y0); cpB += rcp_fast(y0);
+        }
+        float cX = 0.f;
+        if (xl) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
+        red[t] = fmaf(0.6931471805599453f, clA + clB, fmaf(pA, cpA, pB * cpB)) + cX;
+        hg3_reduce(1, red, tot);
+        cost_acc += (double)tot[0];
+
+        if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
+        if (t == 0) g[n] = gnew;
+    }
+    if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = cost_acc * inv_count;
+}
+
 // cost[u] = sum of the per-CTA partials in block order (deterministic, unlike an atomic accumulation)
 __global__ void cost_reduce_kernel(const double* __restrict__ cost_part, int nblk, double* __restrict__ cost) {
     const int u = blockIdx.x;
@@ -500,7 +672,18 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
         return 0;
     }
     int nblk_used = nblk;
-    if (F <= HG2_THREADS && K <= HG2_KT && (R == 10 || R == 30)) {
+    if (F >= 512 && F <= 513 && (ld & 3) == 0 && K <= HG2_KT && (R == 10 || R == 30)) {
+        nblk_used = (max_frames + HG3_FPB - 1) / HG3_FPB;
+        const size_t smem3 = sizeof(float) * ((size_t)R * ld + (size_t)HG3_NV * HG3_THREADS);
+        if (R == 10) {
+            cudaFuncSetAttribute(nmf_hg3_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+            nmf_hg3_kernel<10><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
+        } else {
+            cudaFuncSetAttribute(nmf_hg3_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+            nmf_hg3_kernel<30><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
+        }
+        rc = check_launch("nmf_hg3_kernel");
+    } else if (F <= HG2_THREADS && K <= HG2_KT && (R == 10 || R == 30)) {
         nblk_used = (max_frames + HG2_FPB - 1) / HG2_FPB;
         const size_t smem2 = sizeof(float) * (size_t)2 * HG2_KT * HG2_THREADS;
         if (R == 10) {
