@@ -58,41 +58,53 @@ template <> __device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, float*
         : "r"(taddr) : "memory");
 }
 
-// epilogue of one transposed chunk for the thread that owns bin f: all frames of the tile
-template <int R, int RL>
+// epilogue of one transposed chunk for the thread that owns bin f: all frames of the tile.
+// vb / pw: the frame's noise variance and observation at bin f, loaded by the caller BEFORE it waited for the chunk.
+template <int R, int RL, int FT>
 __device__ __forceinline__ void chunk_epilogue(const WsParams& p, uint32_t tbuf, int f, bool fvalid, float bias, int64_t t0,
-                                               int n_fr, const float* gS, const float* HS, float* num, float* den) {
-    for (int fi = 0; fi < n_fr; ++fi) {
-        float v[RL];
-        tmem_ld_n<RL>(tbuf + fi * R, v);
-        tmem_wait_ld();
-        const int64_t n = t0 + fi;
-        if (fvalid) {
-            const float gg = gS[fi];
-            const float vb = __ldg(p.Vb + n * p.ld + f);
-            const float pw = __ldg(p.P + n * p.ld + f);
-            float* dst = p.Vs + (n * R) * (int64_t)p.ld + f;
-            float a1 = 0.f, a2 = 0.f;
+                                               int n_fr, const float* gS, const float* HS, const float (&vb)[FT],
+                                               const float (&pw)[FT], float* num, float* den) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float vs = ex2_approx(v[r] + bias);
-                dst[(int64_t)r * p.ld] = vs;
-                const float inv = rcp_approx(fmaf(gg, vs, vb));
-                a1 += inv;
-                a2 = fmaf(inv, inv, a2);
-            }
-            const float pa2 = pw * a2;
+    for (int fi = 0; fi < FT; ++fi) {
+        if (fi < n_fr) {
+            float v[RL];
+            tmem_ld_n<RL>(tbuf + fi * R, v);
+            tmem_wait_ld();
+            if (fvalid) {
+                const float gg = gS[fi];
+                float* dst = p.Vs + ((t0 + fi) * R) * (int64_t)p.ld + f;
+                float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-            for (int k = 0; k < WS_KT; ++k) {
-                const float hk = HS[fi * WS_KT + k];
-                num[k] = fmaf(pa2, hk, num[k]);
-                den[k] = fmaf(a1, hk, den[k]);
+                for (int r = 0; r + 1 < R; r += 2) {                 // two samples share one reciprocal
+                    const float s0 = ex2_approx(v[r] + bias), s1 = ex2_approx(v[r + 1] + bias);
+                    dst[(int64_t)r * p.ld] = s0;
+                    dst[(int64_t)(r + 1) * p.ld] = s1;
+                    const float x0 = fmaf(gg, s0, vb[fi]), x1 = fmaf(gg, s1, vb[fi]);
+                    const float rr = rcp_approx(x0 * x1);
+                    const float i0 = x1 * rr, i1 = x0 * rr;
+                    a1 += i0 + i1;
+                    a2 = fmaf(i0, i0, fmaf(i1, i1, a2));
+                }
+                if (R & 1) {
+                    const float s0 = ex2_approx(v[R - 1] + bias);
+                    dst[(int64_t)(R - 1) * p.ld] = s0;
+                    const float i0 = rcp_approx(fmaf(gg, s0, vb[fi]));
+                    a1 += i0;
+                    a2 = fmaf(i0, i0, a2);
+                }
+                const float pa2 = pw[fi] * a2;
+#pragma unroll
+                for (int k = 0; k < WS_KT; ++k) {
+                    const float hk = HS[fi * WS_KT + k];
+                    num[k] = fmaf(pa2, hk, num[k]);
+                    den[k] = fmaf(a1, hk, den[k]);
+                }
             }
         }
     }
 }
 
-template <int R>
+template <int R, int L>
 __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
     constexpr int RL = (R <= 16) ? 16 : 32;               // TMEM load width covering one frame's samples
     constexpr int FT = 128 / R;                           // frames per tile
@@ -107,13 +119,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
     const Dims& d = p.d;
     unsigned char* A = base + ((d.image_bytes + 1023) & ~1023);
     const uint32_t bar12 = smem_u32(&bars[0]);
-    const uint32_t bar3[2] = {smem_u32(&bars[1]), smem_u32(&bars[2])};
-    const uint32_t barf[2] = {smem_u32(&bars[3]), smem_u32(&bars[4])};
+    const uint32_t bar3_0 = smem_u32(&bars[1]), bar3_1 = smem_u32(&bars[2]);
+    const uint32_t barf_0 = smem_u32(&bars[3]), barf_1 = smem_u32(&bars[4]);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, h = (warp >> 2) & 1;
     const int row = 32 * q + lane;
     const bool epi = warp < 8, owner = warp < 4, ctrl = (warp == 8 && lane == 0);
-    uint32_t ph12 = 0, ph3 = 0, phf[2] = {0, 0};          // ph3: parity of THIS group's chunk-ready barrier
+    uint32_t ph12 = 0, ph3 = 0, phf_0 = 0, phf_1 = 0;     // ph3: parity of THIS group's chunk-ready barrier
+    const uint32_t my_bar3 = h ? bar3_1 : bar3_0, my_barf = h ? barf_1 : barf_0;
 
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.image);
@@ -123,10 +136,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
     if (threadIdx.x == 0) {
         dead_flag = 0;
         mbar_init(bar12, 1);
-        mbar_init(bar3[0], 1);
-        mbar_init(bar3[1], 1);
-        mbar_init(barf[0], 128);
-        mbar_init(barf[1], 128);
+        mbar_init(bar3_0, 1);
+        mbar_init(bar3_1, 1);
+        mbar_init(barf_0, 128);
+        mbar_init(barf_1, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
@@ -144,8 +157,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
     const float* biasp = reinterpret_cast<const float*>(base + d.off_bias);
     const float* b2 = (d.n_hidden == 2) ? biasp : nullptr;
     const float* b3 = biasp + (d.n_hidden == 2 ? HID : 0);
-    const int L = d.L;
     const int n_items = p.B * p.n_parts;
+    const int y_dim = d.y_dim, nkb1 = d.nkb1;
 
     for (;;) {
         if (threadIdx.x == 0) item_slot = atomicAdd(p.work_counter, 1);
@@ -179,13 +192,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
             if (owner) {
                 const int fi = row / R, r = row - fi * R;
                 const bool valid = fi < n_fr;
-                float z[DVAE_MAX_L], yrow[8];
+                float z[L];
+                float y0 = 0.f, y1 = 0.f, y2 = 0.f;
                 if (valid) {
-                    const float* src = p.Zs + ((t0 + fi) * R + r) * (int64_t)L;
-                    for (int l = 0; l < L; ++l) z[l] = src[l];
-                    for (int i = 0; i < d.y_dim; ++i) yrow[i] = p.y[(t0 + fi) * d.y_dim + i];
+                    const float4* src = reinterpret_cast<const float4*>(p.Zs + ((t0 + fi) * R + r) * (int64_t)L);
+#pragma unroll
+                    for (int l = 0; l < L / 4; ++l) {
+                        const float4 t4 = __ldg(src + l);
+                        z[4 * l] = t4.x; z[4 * l + 1] = t4.y; z[4 * l + 2] = t4.z; z[4 * l + 3] = t4.w;
+                    }
+                    if (y_dim > 0) y0 = p.y[(t0 + fi) * y_dim];
+                    if (y_dim > 1) y1 = p.y[(t0 + fi) * y_dim + 1];
+                    if (y_dim > 2) y2 = p.y[(t0 + fi) * y_dim + 2];
+                } else {
+#pragma unroll
+                    for (int l = 0; l < L; ++l) z[l] = 0.f;
                 }
-                write_a1_row(d, A, row, z, yrow, valid);
+                write_a1_static<L>(y_dim, nkb1, A, row, z, y0, y1, y2, valid);
             }
             fence_async_smem();
             __syncthreads();                                                    // S1
@@ -224,20 +247,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
             if (ctrl) {
                 tc_fence_after();
                 issue_gemm2(w3_addr, NPAD * 128, a_addr, 16384, 2, tmem + 128, 128);
-                umma_commit(bar3[0]);
+                umma_commit(bar3_0);
                 issue_gemm2(w3_addr + 16384, NPAD * 128, a_addr, 16384, 2, tmem + 256, 128);
-                umma_commit(bar3[1]);
-                for (int j = 2; j < 5; ++j) {
-                    const int b = j & 1;
-                    mbar_wait(barf[b], phf[b], dead, p.status);             // group b has drained its buffer
-                    phf[b] ^= 1;
-                    tc_fence_after();
-                    issue_gemm2(w3_addr + j * 16384, NPAD * 128, a_addr, 16384, 2, tmem + 128 + 128 * b, 128);
-                    umma_commit(bar3[b]);
-                }
+                umma_commit(bar3_1);
+                mbar_wait(barf_0, phf_0, dead, p.status); phf_0 ^= 1;       // group 0 drained chunk 0
+                tc_fence_after();
+                issue_gemm2(w3_addr + 2 * 16384, NPAD * 128, a_addr, 16384, 2, tmem + 128, 128);
+                umma_commit(bar3_0);
+                mbar_wait(barf_1, phf_1, dead, p.status); phf_1 ^= 1;       // group 1 drained chunk 1
+                tc_fence_after();
+                issue_gemm2(w3_addr + 3 * 16384, NPAD * 128, a_addr, 16384, 2, tmem + 256, 128);
+                umma_commit(bar3_1);
+                mbar_wait(barf_0, phf_0, dead, p.status); phf_0 ^= 1;       // group 0 drained chunk 2
+                tc_fence_after();
+                issue_gemm2(w3_addr + 4 * 16384, NPAD * 128, a_addr, 16384, 2, tmem + 128, 128);
+                umma_commit(bar3_0);
                 // consume the last "free" of each group so the parities line up for the next tile
-                mbar_wait(barf[1], phf[1], dead, p.status); phf[1] ^= 1;    // after chunk 3
-                mbar_wait(barf[0], phf[0], dead, p.status); phf[0] ^= 1;    // after chunk 4
+                mbar_wait(barf_1, phf_1, dead, p.status); phf_1 ^= 1;       // after chunk 3
+                mbar_wait(barf_0, phf_0, dead, p.status); phf_0 ^= 1;       // after chunk 4
             }
             if (epi) {
                 const uint32_t tbuf = tmem + 128 + 128 * h + ((uint32_t)(32 * q) << 16);
@@ -245,15 +272,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
                 for (int c = 0; c < 3; ++c) {
                     const int j = h + 2 * c;
                     if (j < 5) {
-                        mbar_wait(bar3[h], ph3, dead, p.status);
-                        ph3 ^= 1;
-                        tc_fence_after();
                         const int f = 128 * j + row;
                         const bool fvalid = f < d.F;
                         const float bias = (f < NPAD) ? b3[f] : 0.f;
-                        chunk_epilogue<R, RL>(p, tbuf, f, fvalid, bias, t0, n_fr, gS, HS, num[c], den[c]);
+                        float vbr[FT], pwr[FT];                              // requested before the chunk is waited for
+#pragma unroll
+                        for (int fi = 0; fi < FT; ++fi) {
+                            const bool ok = fvalid && fi < n_fr;
+                            vbr[fi] = ok ? __ldg(p.Vb + (t0 + fi) * p.ld + f) : 1.f;
+                            pwr[fi] = ok ? __ldg(p.P + (t0 + fi) * p.ld + f) : 0.f;
+                        }
+                        mbar_wait(my_bar3, ph3, dead, p.status);
+                        ph3 ^= 1;
+                        tc_fence_after();
+                        chunk_epilogue<R, RL, FT>(p, tbuf, f, fvalid, bias, t0, n_fr, gS, HS, vbr, pwr, num[c], den[c]);
                         tc_fence_before();
-                        mbar_arrive(barf[h]);
+                        mbar_arrive(my_barf);
                     }
                 }
             }
@@ -323,6 +357,8 @@ extern "C" int dvae_decode_ws_tc(const DvaeMlp* dec, const void* image, const fl
     if (rc) return rc;
     DVAE_REQUIRE(image && Zs && P && Vb && g && H && fr_off && Vs && ws && status, "dvae_decode_ws_tc: null pointer");
     DVAE_REQUIRE(R == 10 || R == 30, "dvae_decode_ws_tc: R must be 10 or 30 (got %d)", R);
+    DVAE_REQUIRE(L == 16 || L == 32, "dvae_decode_ws_tc: latent size must be 16 or 32 (got %d)", L);
+    DVAE_REQUIRE(y_dim <= 3 && (reinterpret_cast<uintptr_t>(Zs) & 15) == 0, "dvae_decode_ws_tc: y_dim <= 3 and 16-byte aligned Zs required");
     DVAE_REQUIRE(K >= 1 && K <= WS_KT, "dvae_decode_ws_tc: K must be <= %d", WS_KT);
     DVAE_REQUIRE(y_dim == 0 || y, "dvae_decode_ws_tc: labels missing");
     DVAE_REQUIRE(B >= 1 && NT >= 0 && n_parts >= 1 && n_parts <= 16 && ld >= p.d.F, "dvae_decode_ws_tc: bad sizes");
@@ -338,11 +374,13 @@ extern "C" int dvae_decode_ws_tc(const DvaeMlp* dec, const void* image, const fl
     const int n_items = B * n_parts;
     const int grid = n_items < 148 ? n_items : 148;
     if (R == 10) {
-        cudaFuncSetAttribute(decode_ws_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        decode_ws_kernel<10><<<grid, NTHREADS, smem, st>>>(p);
+        cudaFuncSetAttribute(decode_ws_kernel<10, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(decode_ws_kernel<10, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (L == 16) decode_ws_kernel<10, 16><<<grid, NTHREADS, smem, st>>>(p); else decode_ws_kernel<10, 32><<<grid, NTHREADS, smem, st>>>(p);
     } else {
-        cudaFuncSetAttribute(decode_ws_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        decode_ws_kernel<30><<<grid, NTHREADS, smem, st>>>(p);
+        cudaFuncSetAttribute(decode_ws_kernel<30, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(decode_ws_kernel<30, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (L == 16) decode_ws_kernel<30, 16><<<grid, NTHREADS, smem, st>>>(p); else decode_ws_kernel<30, 32><<<grid, NTHREADS, smem, st>>>(p);
     }
     return check_launch("decode_ws_kernel");
 }

@@ -86,48 +86,6 @@ __device__ __forceinline__ void hidden_epilogue32(uint32_t tmem, unsigned char* 
     }
 }
 
-__device__ __forceinline__ float bf16_hi(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
-// layer-1 operand row with a static layout: [hi(z) (L) | lo(z) (L) | y hi,lo ... | 1 | 0 ...]
-template <int L>
-__device__ __forceinline__ void write_a1_static(int y_dim, int nkb1, unsigned char* A, int row, const float (&z)[L], float y0, float y1,
-                                                float y2, bool valid) {
-    constexpr int CH = L / 8;                  // chunks of hi (and of lo)
-    const int sw = row & 7;
-#pragma unroll
-    for (int c = 0; c < 2 * CH; ++c) {
-        float e[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float zz = valid ? z[(c % CH) * 8 + i] : 0.f;
-            const float hi = bf16_hi(zz);
-            e[i] = (c < CH) ? hi : (zz - hi);
-        }
-        const int kb = c >> 3, cc = c & 7;
-        uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
-        *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((cc ^ sw) << 4)) = pk;
-    }
-    {   // chunk 2*CH: labels (hi, lo pairs, y_dim <= 3) and the constant one
-        const float h0 = bf16_hi(y0), h1 = bf16_hi(y1), h2 = bf16_hi(y2);
-        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, e4 = 0.f, e5 = 0.f, e6 = 0.f;
-        if (valid) {
-            if (y_dim == 0) { e0 = 1.f; }
-            else if (y_dim == 1) { e0 = h0; e1 = y0 - h0; e2 = 1.f; }
-            else if (y_dim == 2) { e0 = h0; e1 = y0 - h0; e2 = h1; e3 = y1 - h1; e4 = 1.f; }
-            else { e0 = h0; e1 = y0 - h0; e2 = h1; e3 = y1 - h1; e4 = h2; e5 = y2 - h2; e6 = 1.f; }
-        }
-        constexpr int c = 2 * CH;
-        const int kb = c >> 3, cc = c & 7;
-        uint4 pk = make_uint4(pack_bf16x2(e0, e1), pack_bf16x2(e2, e3), pack_bf16x2(e4, e5), pack_bf16x2(e6, 0.f));
-        *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((cc ^ sw) << 4)) = pk;
-    }
-    const int K1c = 8 * nkb1;                  // remaining chunks of the K blocks in use are zero
-    for (int c = 2 * CH + 1; c < K1c; ++c) {
-        const int kb = c >> 3, cc = c & 7;
-        *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((cc ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-    }
-}
-
 // 16 bins of the log-likelihood: v = TMEM accumulators, pp / vb = observation and noise variance quads
 __device__ __forceinline__ void loglik16(const float* v, const float4* pp, const float4* vb, const float* b3f, float g_row,
                                          float& acc, float& accl) {
