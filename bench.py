@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=512, help="utterances per GPU")
     ap.add_argument("--niter", type=int, default=100)
     ap.add_argument("--variant", default="M1", choices=["M1", "M2", "M2v3"])
-    ap.add_argument("--sampler", default=os.environ.get("DVAE_SAMPLER", "fp32"), choices=["fp32", "tc"])
+    ap.add_argument("--sampler", default=os.environ.get("DVAE_SAMPLER", "tc"), choices=["fp32", "tc"])
     ap.add_argument("--chains", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

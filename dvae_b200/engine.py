@@ -211,7 +211,7 @@ class McemConfig:
     eps: float = 1e-8
     n_chains: int = 1
     seed: int = 0
-    sampler: str = "fp32"        # "fp32": CUDA-core exact mode; "tc": tcgen05 BF16 sampler
+    sampler: str = "fp32"        # "fp32": CUDA-core exact mode; "tc": tcgen05 BF16 kernels; "auto": tc when supported
     fuse_wstat: bool = True      # tc only: fold the W-update reductions into the kept-sample decode
 
 
@@ -251,6 +251,13 @@ class TorchCpuDraws(InjectedDraws):
         return eps, u
 
 
+def tc_supported(w: "VaeWeights") -> bool:
+    """True when the decoder fits the tcgen05 kernels: 513 bins, 1-2 hidden layers of 128 units, L in {16, 32}, <= 3 labels."""
+    dims = w.dec.dims
+    return (dims[-1] == 513 and len(dims) in (3, 4) and all(d == 128 for d in dims[1:-1]) and w.z_dim in (16, 32)
+            and w.y_dim <= 3)
+
+
 class McemEngine:
     """EM driver for one ragged batch (replaces ``EM.run`` + ``MCEM_*`` of packages/models/mcem.py)."""
 
@@ -258,8 +265,11 @@ class McemEngine:
         self.dev = _require_cuda(device)
         self.w = weights
         self.cfg = cfg
-        if cfg.sampler not in ("fp32", "tc"):
-            raise ValueError("sampler must be 'fp32' or 'tc'")
+        if cfg.sampler not in ("fp32", "tc", "auto"):
+            raise ValueError("sampler must be 'fp32', 'tc' or 'auto'")
+        if cfg.sampler == "auto":            # tensor cores whenever the decoder has the shape the tcgen05 kernels serve
+            cfg = dataclasses.replace(cfg, sampler="tc" if tc_supported(weights) else "fp32")
+            self.cfg = cfg
         if not 1 <= cfg.nmf_rank <= _lib.MAX_K:
             raise ValueError("nmf_rank must be in 1..%d" % _lib.MAX_K)
         if weights.z_dim > _lib.MAX_L:

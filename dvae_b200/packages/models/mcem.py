@@ -17,7 +17,8 @@ Behaviour carried over on purpose:
   Q3  ``S`` is required but only consumes a random draw.
   Q5  ``device`` may be an int, a str or a ``torch.device``.
 
-Extra keyword-only knobs (not in the reference): ``sampler`` ("fp32" exact CUDA-core decoder | "tc" tcgen05 BF16),
+Extra keyword-only knobs (not in the reference): ``sampler`` ("auto": tcgen05 BF16 kernels when the decoder has the
+shipped shape, else "fp32"; "fp32": exact CUDA-core decoder; "tc": force the tensor-core kernels),
 ``n_chains``, ``seed`` and ``rng`` ("philox": counter-based draws on the device; "torch": the reference's own draw
 order taken from torch's CPU generator, for like-for-like comparisons).
 """
@@ -41,7 +42,7 @@ class _MCEM:
     _variant = None
 
     def __init__(self, niter, nsamples_E_step=10, burnin_E_step=30, nsamples_WF=25, burnin_WF=75, var_RW=0.01, *,
-                 sampler="fp32", n_chains=1, seed=0, rng="philox"):
+                 sampler="auto", n_chains=1, seed=0, rng="philox"):
         self.niter = niter
         self.nsamples_E_step, self.burnin_E_step = nsamples_E_step, burnin_E_step
         self.nsamples_WF, self.burnin_WF = nsamples_WF, burnin_WF

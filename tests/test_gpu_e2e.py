@@ -70,13 +70,13 @@ def test_dropin_si_sdr_within_0p05_db_of_oracle(variant):
     # drop-in
     if variant == "M1":
         model = shim_models.VariationalAutoencoder([F, 16, [128, 128]])
-        algo = shim_mcem.MCEM_M1(niter, 10, 30, 25, 75, 0.01, rng="torch")
+        algo = shim_mcem.MCEM_M1(niter, 10, 30, 25, 75, 0.01, rng="torch", sampler="fp32")
     elif variant == "M2":
         model = shim_models.DeepGenerativeModel([F, 1, 16, [128, 128]], None)
-        algo = shim_mcem.MCEM_M2(niter, 10, 30, 25, 75, 0.01, rng="torch")
+        algo = shim_mcem.MCEM_M2(niter, 10, 30, 25, 75, 0.01, rng="torch", sampler="fp32")
     else:
         model = shim_models.DeepGenerativeModel_v5([F, 1, 16, [128, 128]]).enc_dec_clf
-        algo = shim_mcem.MCEM_M2v3(niter, 10, 30, 25, 75, 0.01, rng="torch")
+        algo = shim_mcem.MCEM_M2v3(niter, 10, 30, 25, 75, 0.01, rng="torch", sampler="fp32")
     model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()}, strict=False)
     model.to(DEV).eval()
     torch.manual_seed(77)
