@@ -117,14 +117,16 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     float* red = reinterpret_cast<float*>(A + A_BYTES);          // [128] partial l(z') of the upper column half
     float* zpS = red + TM;                                       // [128][L] proposals (written and read by the row's owner)
     const uint32_t bar12 = smem_u32(&bars[0]);
-    const uint32_t bar3_0 = smem_u32(&bars[1]), bar3_1 = smem_u32(&bars[2]), bar3_2 = smem_u32(&bars[3]);
-    const uint32_t barf_0 = smem_u32(&bars[4]), barf_1 = smem_u32(&bars[5]);
+    const uint32_t bar3_0 = smem_u32(&bars[1]), bar3_1 = smem_u32(&bars[2]);
+    const uint32_t barf_0 = smem_u32(&bars[3]);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, h = warp >> 2;             // TMEM lane quadrant, column half
     const bool owner = h == 0;                         // warps 0-3 carry the chain of row 32q + lane
-    const bool issuer = threadIdx.x == 0;              // lane 0 of warp 0 issues every tcgen05.mma
+    // tcgen05.mma issue is spread over lane 0 of different warps so that no single warp pays for all of it:
+    // layer 1: warp 1, layer 2: warp 2, layer-3 chunks 0 / 1 / 2: warps 3 / 4 / 5
+    const bool lead = lane == 0;
     const int row = 32 * q + lane;
-    uint32_t ph12 = 0, ph3_0 = 0, ph3_1 = 0, ph3_2 = 0, phf_0 = 0, phf_1 = 0;
+    uint32_t ph12 = 0, ph3_0 = 0, ph3_1 = 0, phf_0 = 0;
 
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.image);
@@ -136,9 +138,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         mbar_init(bar12, 1);
         mbar_init(bar3_0, 1);
         mbar_init(bar3_1, 1);
-        mbar_init(bar3_2, 1);
         mbar_init(barf_0, MH2_THREADS);
-        mbar_init(barf_1, MH2_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -216,107 +216,104 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             __syncthreads();                                                    // S1: layer-1 operand ready
             DBG_STAMP(1, threadIdx.x == 0);
 
-            if (issuer) {
+            if (warp == 1 && lead) {
                 tc_fence_after();
-                issue_gemm2(a_addr, 16384, w1_addr, 16384, nkb1, tmem, HID);
+                issue_gemm2(a_addr, 16384, w1_addr, 16384, nkb1, tmem + 384, HID);
                 umma_commit(bar12);
             }
             mbar_wait(bar12, ph12, dead, p.status);
             ph12 ^= 1;
             tc_fence_after();
-            hidden_epilogue_rows(tmem, A, q, h, row, nullptr);              // bias rides on the constant-one column
+            hidden_epilogue_rows(tmem + 384, A, q, h, row, nullptr);              // bias rides on the constant-one column
             fence_async_smem();
             tc_fence_before();
             DBG_STAMP(20, threadIdx.x == 0);
             __syncthreads();                                                    // S2
             DBG_STAMP(2, threadIdx.x == 0);
             if (two_hidden) {
-                if (issuer) {
+                if (warp == 2 && lead) {
                     tc_fence_after();
-                    issue_gemm2(a_addr, 16384, w2_addr, 16384, 2, tmem, HID);
+                    issue_gemm2(a_addr, 16384, w2_addr, 16384, 2, tmem + 384, HID);
                     umma_commit(bar12);
                 }
                 mbar_wait(bar12, ph12, dead, p.status);
                 ph12 ^= 1;
                 tc_fence_after();
-                hidden_epilogue_rows(tmem, A, q, h, row, b2);
+                hidden_epilogue_rows(tmem + 384, A, q, h, row, b2);
                 fence_async_smem();
                 tc_fence_before();
                 DBG_STAMP(21, threadIdx.x == 0);
                 __syncthreads();                                                // S3
                 DBG_STAMP(3, threadIdx.x == 0);
             }
-            if (issuer) {
+            // ---- layer 3 as three chunks of 192 / 192 / 160 bins (the last one over-reads 16 rows of padding):
+            // chunk 0 -> TMEM columns [0,192), chunk 1 -> [192,384), chunk 2 -> [0,160) once chunk 0 is drained
+            if (warp == 3 && lead) {
                 tc_fence_after();
-                issue_gemm2(a_addr, 16384, w3_addr, NPAD * 128, 2, tmem + 128, 128);
+                issue_gemm2(a_addr, 16384, w3_addr, NPAD * 128, 2, tmem, 192);
                 umma_commit(bar3_0);
-                issue_gemm2(a_addr, 16384, w3_addr + 16384, NPAD * 128, 2, tmem + 256, 128);
+            }
+            if (warp == 4 && lead) {
+                tc_fence_after();
+                issue_gemm2(a_addr, 16384, w3_addr + 192 * 128, NPAD * 128, 2, tmem + 192, 192);
                 umma_commit(bar3_1);
-                issue_gemm2(a_addr, 16384, w3_addr + 2 * 16384, NPAD * 128, 2, tmem + 384, 128);
-                umma_commit(bar3_2);
             }
 
-            // ---- layer 3: 16 sub-chunks of 16 bins per thread; the P / Vb quads of sub-chunk t+2 are requested
+            // per thread 17 (h = 0) or 16 (h = 1) sub-chunks of 16 bins; the P / Vb quads of sub-chunk t+2 are requested
             // while sub-chunk t is evaluated (three rotating register buffers, everything statically indexed)
             float acc = 0.f, accl = 0.f;
             float4 pp0[4], vb0[4], pp1[4], vb1[4], pp2[4], vb2[4];
-            // sub-chunk t covers bins 128*(t>>2) + 64*h + 16*(t&3): first quad index below
-#define MH2_QUAD(t) (32 * ((t) >> 2) + 16 * h + 4 * ((t) & 3))
+            // sub-chunk t: chunk c = t/6 (capped at 2), column inside the chunk = h*W_c + 16*(t - 6c), W = 96, 96, 80
+#define MH2_CH(t) ((t) < 6 ? 0 : ((t) < 12 ? 1 : 2))
+#define MH2_COL(t) (h * (MH2_CH(t) == 2 ? 80 : 96) + 16 * ((t) - 6 * MH2_CH(t)))
+#define MH2_BIN(t) (192 * MH2_CH(t) + MH2_COL(t))
 #define MH2_LOAD(t, PP, VB)                                                                          \
     do {                                                                                             \
         _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) {                                           \
-            PP[qd] = __ldg(Pt + (MH2_QUAD(t) + qd) * TM);                                            \
-            VB[qd] = __ldg(Vt + (MH2_QUAD(t) + qd) * TM);                                            \
+            PP[qd] = __ldg(Pt + ((MH2_BIN(t) >> 2) + qd) * TM);                                      \
+            VB[qd] = __ldg(Vt + ((MH2_BIN(t) >> 2) + qd) * TM);                                      \
         }                                                                                            \
     } while (0)
             MH2_LOAD(0, pp0, vb0);
             MH2_LOAD(1, pp1, vb1);
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const int j = t >> 2, sub = t & 3;
-                if (t + 2 < 16) {
+            for (int t = 0; t < 17; ++t) {
+                const int c = MH2_CH(t);
+                const bool live = (t < 16) || (h == 0);                         // bins 528..543 do not exist
+                if (t + 2 < 17 && ((t + 2 < 16) || (h == 0))) {
                     if ((t + 2) % 3 == 0) MH2_LOAD(t + 2, pp0, vb0);
                     else if ((t + 2) % 3 == 1) MH2_LOAD(t + 2, pp1, vb1);
                     else MH2_LOAD(t + 2, pp2, vb2);
                 }
-                if (sub == 0) {                                                 // chunk j lives in TMEM buffer j % 3
-                    if (j % 3 == 0) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; }
-                    else if (j % 3 == 1) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; }
-                    else { mbar_wait(bar3_2, ph3_2, dead, p.status); ph3_2 ^= 1; }
-                    tc_fence_after();
-                    DBG_STAMP(15 + j, threadIdx.x == 0);
+                if (t == 0 || t == 12) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); DBG_STAMP(15 + c, threadIdx.x == 0); }
+                if (t == 6) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; tc_fence_after(); DBG_STAMP(15 + c, threadIdx.x == 0); }
+                if (live) {
+                    float v[16];
+                    tmem_ld16(tmem + 192 * (c & 1) + lane_off + MH2_COL(t), v);
+                    tmem_wait_ld();
+                    const float* b3f = b3 + MH2_BIN(t);
+                    if (t % 3 == 0) loglik16(v, pp0, vb0, b3f, g_row, acc, accl);
+                    else if (t % 3 == 1) loglik16(v, pp1, vb1, b3f, g_row, acc, accl);
+                    else loglik16(v, pp2, vb2, b3f, g_row, acc, accl);
                 }
-                float v[16];
-                tmem_ld16(tmem + 128 + 128 * (j % 3) + lane_off + 64 * h + 16 * sub, v);
-                tmem_wait_ld();
-                const float* b3f = b3 + 128 * j + 64 * h + 16 * sub;
-                if (t % 3 == 0) loglik16(v, pp0, vb0, b3f, g_row, acc, accl);
-                else if (t % 3 == 1) loglik16(v, pp1, vb1, b3f, g_row, acc, accl);
-                else loglik16(v, pp2, vb2, b3f, g_row, acc, accl);
-                if (sub == 3) {
-                    DBG_STAMP(4 + j, threadIdx.x == 0);
-                    DBG_STAMP(10 + j, threadIdx.x == 224);
-                    if (j < 2) {                                                // buffers 0 and 1 are reused by chunks 3 and 4
-                        tc_fence_before();
-                        mbar_arrive2(j == 0 ? barf_0 : barf_1);
-                    }
-                    if (j == 1 || j == 2) {
-                        // lagged hand-over: chunk j+2 goes into the buffer drained one chunk ago, so the wait below
-                        // never stalls and the MMA has a whole chunk epilogue to complete
-                        if (warp == 0) {
-                            if (lane == 0) {
-                                if (j == 1) { mbar_wait(barf_0, phf_0, dead, p.status); }
-                                else { mbar_wait(barf_1, phf_1, dead, p.status); }
-                                tc_fence_after();
-                                issue_gemm2(a_addr, 16384, w3_addr + (j + 2) * 16384, NPAD * 128, 2, tmem + 128 + 128 * (j - 1),
-                                            j == 1 ? 128 : 16);
-                                umma_commit(j == 1 ? bar3_0 : bar3_1);
-                            }
-                            __syncwarp();
+                if (t == 5) {                                                   // chunk 0 drained by this thread
+                    DBG_STAMP(4, threadIdx.x == 0);
+                    tc_fence_before();
+                    mbar_arrive2(barf_0);
+                    if (warp == 5) {
+                        if (lead) {
+                            mbar_wait(barf_0, phf_0, dead, p.status);
+                            tc_fence_after();
+                            issue_gemm2(a_addr, 16384, w3_addr + 384 * 128, NPAD * 128, 2, tmem, 160);
+                            umma_commit(bar3_0);
                         }
-                        if (j == 1) phf_0 ^= 1; else phf_1 ^= 1;
+                        __syncwarp();
                     }
-                    if (j == 3 && owner) {
+                    phf_0 ^= 1;
+                }
+                if (t == 11) {
+                    DBG_STAMP(5, threadIdx.x == 0);
+                    if (owner) {
                         // draws of the next proposal: requested here, consumed right after the accept step
                         const int nxt = it + 1;
                         if (nxt < n_iter && valid) {
@@ -329,21 +326,9 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 }
             }
 #undef MH2_LOAD
-#undef MH2_QUAD
-            // bin 512 (chunk 4, TMEM buffer 1)
-            mbar_wait(bar3_1, ph3_1, dead, p.status);
-            ph3_1 ^= 1;
-            tc_fence_after();
-            if (h == 0) {
-                float v[4];
-                tmem_ld4(tmem + 256 + lane_off, v);
-                tmem_wait_ld();
-                const float4 pp = __ldg(Pt + 128 * TM);
-                const float4 vb = __ldg(Vt + 128 * TM);
-                const float v0 = fmaf(g_row, ex2_approx(v[0] + b3[512]), vb.x);
-                acc = fmaf(pp.x, rcp_approx(v0), acc);
-                accl += lg2_approx(v0);
-            }
+#undef MH2_BIN
+#undef MH2_COL
+#undef MH2_CH
             tc_fence_before();
             const float part = fmaf(kLn2, accl, acc);
             if (h == 1) red[row] = part;

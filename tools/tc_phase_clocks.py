@@ -32,9 +32,8 @@ print("sample_posterior(60 iters, %d chains): %.2f ms -> %.0f clk per tile-eval 
 c = buf.cpu().numpy()
 _lib.call("dvae_debug_set_clock_buffer", None)
 names = {0: "iter start", 1: "after S1 (A1 written)", 20: "warp0 done hidden-1", 2: "after S2", 21: "warp0 done hidden-2", 3: "after S3",
-         15: "chunk0 ready", 4: "warp0 done chunk0", 10: "warp15 done chunk0", 16: "chunk1 ready", 5: "warp0 done chunk1", 11: "warp15 done chunk1",
-         17: "chunk2 ready", 6: "warp0 done chunk2", 12: "warp15 done chunk2", 18: "chunk3 ready", 7: "warp0 done chunk3", 13: "warp15 done chunk3",
-         19: "chunk4 ready", 8: "warp0 done chunk4", 14: "warp15 done chunk4", 22: "warp0 done rng", 9: "after S4", 23: "accept done (end of iteration)"}
+         15: "chunk0 ready", 4: "warp0 done chunk0", 16: "chunk1 ready", 5: "warp0 done chunk1", 17: "chunk2 ready",
+         8: "warp0 done chunk2", 9: "after S4", 23: "accept done (end of iteration)"}
 base = c[0]
 for k, v in sorted(((k, c[k] - base) for k in names if c[k]), key=lambda kv: kv[1]):
     print("%8d  %s" % (v, names[k]))
