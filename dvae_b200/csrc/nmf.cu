@@ -396,16 +396,22 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// reduce red[v][0..256) -> tot[v] for v < nv (8 warps); two barriers
-__device__ __forceinline__ void hg3_reduce(int nv, const float* red, float* tot) {
+// CTA-wide sums of NV per-thread values: warp shuffles first, then 8 per-warp partials through shared memory
+// (red: [NV][8] floats).  After the call tot[v] holds the total for every thread.  Two barriers.
+template <int NV>
+__device__ __forceinline__ void hg3_reduce(float (&vals)[NV], float* red, float* tot) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        const float s = warp_sum(vals[v]);
+        if (lane == 0) red[v * 8 + wid] = s;
+    }
     __syncthreads();
-    for (int v = wid; v < nv; v += HG3_THREADS / 32) {
+    if (threadIdx.x < NV) {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < HG3_THREADS / 32; ++i) s += red[v * HG3_THREADS + lane + 32 * i];
-        s = warp_sum(s);
-        if (lane == 0) tot[v] = s;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x * 8 + w];
+        tot[threadIdx.x] = s;
     }
     __syncthreads();
 }
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
     constexpr int KT = HG2_KT;
     extern __shared__ __align__(16) float sm[];
     float* S = sm;                                  // [R][ld] samples of the current frame
-    float* red = S + R * ld;                        // [HG3_NV][256]
+    float* red = S + R * ld;                        // [HG3_NV][8] per-warp partials
     __shared__ float tot[HG3_NV];
     __shared__ float hs[KT];
     const int u = blockIdx.y;
@@ -483,12 +489,13 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
         float a1X = 0.f, a2X = 0.f;                 // bin 512: this thread's single sample
         if (xl) { const float ix = rcp_fast(fmaf(gg, S[t * ld + 512], vbX)); a1X = ix; a2X = ix * ix; }
         const float qA = pA * a2A, qB = pB * a2B, qX = pX * a2X;
+        float vals[HG3_NV];
 #pragma unroll
         for (int k = 0; k < KT; ++k) {
-            red[(2 * k) * HG3_THREADS + t] = fmaf(wA[k], qA, fmaf(wB[k], qB, wX[k] * qX));
-            red[(2 * k + 1) * HG3_THREADS + t] = fmaf(wA[k], a1A, fmaf(wB[k], a1B, wX[k] * a1X));
+            vals[2 * k] = fmaf(wA[k], qA, fmaf(wB[k], qB, wX[k] * qX));
+            vals[2 * k + 1] = fmaf(wA[k], a1A, fmaf(wB[k], a1B, wX[k] * a1X));
         }
-        hg3_reduce(2 * K, red, tot);
+        hg3_reduce<HG3_NV>(vals, red, tot);
         if (t < K) hs[t] = H[n * K + t] * sqrtf(tot[2 * t] / tot[2 * t + 1]);
         __syncthreads();
 #pragma unroll
@@ -520,9 +527,8 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
         }
         float s1X = 0.f, s2X = 0.f;
         if (xl) { const float sx = S[t * ld + 512]; const float ix = rcp_fast(fmaf(gg, sx, vbX)); s1X = sx * ix; s2X = s1X * ix; }
-        red[t] = fmaf(pA, s2A, fmaf(pB, s2B, pX * s2X));
-        red[HG3_THREADS + t] = s1A + s1B + s1X;
-        hg3_reduce(2, red, tot);
+        float v2[2] = {fmaf(pA, s2A, fmaf(pB, s2B, pX * s2X)), s1A + s1B + s1X};
+        hg3_reduce<2>(v2, red, tot);
         const float gnew = gg * sqrtf(tot[0] / tot[1]);
 
         // ---- cost with Vx = g_new Vs + Vb2: a pair of samples shares one reciprocal and one log2
@@ -542,8 +548,8 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
         }
         float cX = 0.f;
         if (xl) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
-        red[t] = fmaf(0.6931471805599453f, clA + clB, fmaf(pA, cpA, pB * cpB)) + cX;
-        hg3_reduce(1, red, tot);
+        float v1[1] = {fmaf(0.6931471805599453f, clA + clB, fmaf(pA, cpA, pB * cpB)) + cX};
+        hg3_reduce<1>(v1, red, tot);
         cost_acc += (double)tot[0];
 
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
@@ -674,7 +680,7 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
     int nblk_used = nblk;
     if (F >= 512 && F <= 513 && (ld & 3) == 0 && K <= HG2_KT && (R == 10 || R == 30)) {
         nblk_used = (max_frames + HG3_FPB - 1) / HG3_FPB;
-        const size_t smem3 = sizeof(float) * ((size_t)R * ld + (size_t)HG3_NV * HG3_THREADS);
+        const size_t smem3 = sizeof(float) * ((size_t)R * ld + (size_t)HG3_NV * 8);
         if (R == 10) {
             cudaFuncSetAttribute(nmf_hg3_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
             nmf_hg3_kernel<10><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
