@@ -67,6 +67,9 @@ PROTOTYPES = {
                                    c_ptr, c_ptr]),
     "dvae_mh_chain_tc2": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "dvae_mh_chain_tc3": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "dvae_debug_set_clock_buffer3": (C.c_int, [c_ptr]),
     "dvae_debug_set_clock_buffer": (C.c_int, [c_ptr]),
     "dvae_decode_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int,
                                  c_ptr, c_ptr]),

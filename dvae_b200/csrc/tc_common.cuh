@@ -231,6 +231,59 @@ __device__ __forceinline__ void write_a1_static(int y_dim, int nkb1, unsigned ch
     }
 }
 
+__device__ __forceinline__ void mbar_arrive2(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+
+// hidden-layer epilogue, 32 columns per thread: D12[row][32s .. 32s+32) -> tanh(+bias) -> bf16 -> A operand
+__device__ __forceinline__ void hidden_epilogue32(uint32_t tmem, unsigned char* A, int q, int s, int row, const float* bias) {
+    float v[32];
+    const int col0 = 32 * s;
+    tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + col0, v);
+    tmem_wait_ld();
+    const int kb = s >> 1, cbase = 4 * (s & 1);
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        float t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = v[8 * cc + e];
+            if (bias) x += bias[col0 + 8 * cc + e];
+            t[e] = tanh_approx(x);
+        }
+        uint4 pk = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+        *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + (((cbase + cc) ^ (row & 7)) << 4)) = pk;
+    }
+}
+
+// 16 bins of the log-likelihood: v = TMEM accumulators, pp / vb = observation and noise variance quads
+__device__ __forceinline__ void loglik16(const float* v, const float4* pp, const float4* vb, const float* b3f, float g_row,
+                                         float& acc, float& accl) {
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        const float4 bb = *reinterpret_cast<const float4*>(b3f + 4 * qd);
+        const float v0 = fmaf(g_row, ex2_approx(v[4 * qd + 0] + bb.x), vb[qd].x);
+        const float v1 = fmaf(g_row, ex2_approx(v[4 * qd + 1] + bb.y), vb[qd].y);
+        const float v2 = fmaf(g_row, ex2_approx(v[4 * qd + 2] + bb.z), vb[qd].z);
+        const float v3 = fmaf(g_row, ex2_approx(v[4 * qd + 3] + bb.w), vb[qd].w);
+        const float p01 = v0 * v1, p23 = v2 * v3;
+        const float n01 = fmaf(pp[qd].y, v0, pp[qd].x * v1), n23 = fmaf(pp[qd].w, v2, pp[qd].z * v3);
+        acc = fmaf(n01, rcp_approx(p01), acc);
+        acc = fmaf(n23, rcp_approx(p23), acc);
+        accl += lg2_approx(p01) + lg2_approx(p23);
+    }
+}
+
 size_t smem_bytes(const Dims& d);
 int check_dims(const DvaeMlp* dec, int L, int y_dim, const char* who, Dims* out);
 

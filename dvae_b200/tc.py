@@ -86,8 +86,10 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
                   _p(eps), _p(u), _stream())
         eng.kernel_launches += 1
         eps_ptr, u_ptr = _p(eps), _p(u)
+    gen = os.environ.get("DVAE_TC_SAMPLER", "v2")
+    fn = "dvae_mh_chain_tc3" if (gen == "v3" and w.z_dim == 16) else "dvae_mh_chain_tc2"
     with eng.stage("mh_kernel"):
-        _lib.call("dvae_mh_chain_tc2", w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim, _p(eng.Z),
+        _lib.call(fn, w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim, _p(eng.Z),
                   _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep, float(cfg.var_rw), eps_ptr, u_ptr, _p(eng.n_accept),
                   _p(a_trace), _p(_status(eng)), _stream())
     eng.kernel_launches += 1

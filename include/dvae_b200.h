@@ -165,6 +165,14 @@ int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const float* Ppk, c
                       int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
                       int* status, void* stream);
 
+/* third-generation schedule: two tile contexts per CTA, W3 streamed chunk-wise with cp.async.bulk (L = 16 only).
+ * Same arguments and results as dvae_mh_chain_tc2. */
+int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
+                      const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
+                      int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
+                      int* status, void* stream);
+int dvae_debug_set_clock_buffer3(void* dev_buffer);
+
 /* debug aid: register a device buffer of 64 int64; the tc2 sampler's CTA 0 stamps clock64() at its phase boundaries */
 int dvae_debug_set_clock_buffer(void* dev_buffer);
 

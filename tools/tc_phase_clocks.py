@@ -21,7 +21,7 @@ w = VaeWeights(sd, "M1", DEV)
 eng = McemEngine(w, McemConfig(niter=1, keep_E=30, burn_E=30, sampler="tc"), DEV)
 eng.init_parameters(X, P, RaggedBatch([N] * B, DEV))
 buf = torch.zeros(64, dtype=torch.int64, device=DEV)
-_lib.call("dvae_debug_set_clock_buffer", _p(buf))
+_lib.call("dvae_debug_set_clock_buffer", _p(buf)); _lib.call("dvae_debug_set_clock_buffer3", _p(buf))
 eng.timing = True
 for _ in range(2):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
@@ -30,10 +30,11 @@ print("stage events:", eng.stage_times_ms())
 print("sample_posterior(60 iters, %d chains): %.2f ms -> %.0f clk per tile-eval at 1.965 GHz" %
       (B * N, t0.elapsed_time(t1), t0.elapsed_time(t1) * 1e-3 * 1.965e9 / 61 / max(1, (B * N / 128) / 148)))
 c = buf.cpu().numpy()
-_lib.call("dvae_debug_set_clock_buffer", None)
+_lib.call("dvae_debug_set_clock_buffer", None); _lib.call("dvae_debug_set_clock_buffer3", None)
 names = {0: "iter start", 1: "after S1 (A1 written)", 20: "warp0 done hidden-1", 2: "after S2", 21: "warp0 done hidden-2", 3: "after S3",
          15: "chunk0 ready", 4: "warp0 done chunk0", 16: "chunk1 ready", 5: "warp0 done chunk1", 17: "chunk2 ready",
-         8: "warp0 done chunk2", 9: "after S4", 23: "accept done (end of iteration)"}
+         6: "warp0 done chunk2 (v3)", 18: "chunk3 ready (v3)", 7: "warp0 done chunk3 (v3)", 19: "chunk4 ready (v3)",
+         8: "warp0 done last chunk", 9: "after S4", 23: "accept done (end of iteration)"}
 base = c[0]
 for k, v in sorted(((k, c[k] - base) for k in names if c[k]), key=lambda kv: kv[1]):
     print("%8d  %s" % (v, names[k]))
