@@ -90,6 +90,28 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, int64_t chains, 
     }
 }
 
+// P, Vb [NT][ld] (frame-major FP32) -> dst [tile][quad][128 rows] of uint4 {P0P1, P2P3, V0V1, V2V3} in BF16 (round to nearest)
+__global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restrict__ Vb, int64_t chains, int C, int F, int ld,
+                               uint4* __restrict__ dst) {
+    const int64_t n_tiles = (chains + TM - 1) / TM;
+    const int64_t total = n_tiles * NQ * TM;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i % TM);
+        const int q = (int)((i / TM) % NQ);
+        const int64_t tile = i / ((int64_t)TM * NQ);
+        const int64_t m = tile * TM + r;
+        float pv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (m < chains) {
+            const int64_t fr = m / C;
+            const int f = 4 * q;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (f + j < F) { pv[j] = P[fr * ld + f + j]; pv[4 + j] = Vb[fr * ld + f + j]; }
+        }
+        dst[i] = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+    }
+}
+
 // ----------------------------------------------------------------------------- kernel
 struct Params {
     Dims d;
@@ -504,6 +526,19 @@ extern "C" int dvae_tc_pack_decoder(const DvaeMlp* dec, int L, int y_dim, void* 
 extern "C" int64_t dvae_tc_packed_floats(int64_t chains) {
     if (chains <= 0) return 0;
     return ((chains + TM - 1) / TM) * (int64_t)NQ * TM * 4;
+}
+
+extern "C" int64_t dvae_tc_packed_pv_bytes(int64_t chains) {
+    if (chains <= 0) return 0;
+    return ((chains + TM - 1) / TM) * (int64_t)NQ * TM * 16;
+}
+
+extern "C" int dvae_tc_pack_pv(const float* P, const float* Vb, int64_t NT, int n_chains, int F, int ld, void* dst, void* stream) {
+    DVAE_REQUIRE(P && Vb && dst && NT >= 0 && n_chains >= 1 && F >= 1 && F <= NPAD && ld >= F, "dvae_tc_pack_pv: bad arguments");
+    DVAE_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dvae_tc_pack_pv: 16-byte alignment required");
+    if (NT == 0) return 0;
+    pack_pv_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(P, Vb, NT * n_chains, n_chains, F, ld, (uint4*)dst);
+    return check_launch("pack_pv_kernel");
 }
 
 extern "C" int dvae_tc_pack_rows(const float* src, int64_t NT, int n_chains, int F, int ld, float* dst, void* stream) {

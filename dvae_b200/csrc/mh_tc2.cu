@@ -29,8 +29,7 @@ struct Mh2Params {
     int64_t rows;                 // NT*C chains
     int C;
     const float* y;
-    const float4* Ppk;
-    const float4* Vbpk;
+    const uint4* PVpk;            // [tile][quad][128] {P0P1, P2P3, V0V1, V2V3} in BF16
     const float* g;
     float* Z;
     float* Zs;
@@ -115,8 +114,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         const bool valid = row_g < p.rows;
         const int64_t fr = valid ? row_g / p.C : 0;
         const float g_row = valid ? p.g[fr] : 1.f;
-        const float4* Pt = p.Ppk + (tile * NQ) * TM + row;
-        const float4* Vt = p.Vbpk + (tile * NQ) * TM + row;
+        const uint4* PVt = p.PVpk + (tile * NQ) * TM + row;
 
         // chain state (owner threads only; dead code in the other warps)
         float z[L];
@@ -210,28 +208,25 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             // per thread 17 (h = 0) or 16 (h = 1) sub-chunks of 16 bins; the P / Vb quads of sub-chunk t+2 are requested
             // while sub-chunk t is evaluated (three rotating register buffers, everything statically indexed)
             float acc = 0.f, accl = 0.f;
-            float4 pp0[4], vb0[4], pp1[4], vb1[4], pp2[4], vb2[4];
+            uint4 pv0[4], pv1[4], pv2[4];
             // sub-chunk t: chunk c = t/6 (capped at 2), column inside the chunk = h*W_c + 16*(t - 6c), W = 96, 96, 80
 #define MH2_CH(t) ((t) < 6 ? 0 : ((t) < 12 ? 1 : 2))
 #define MH2_COL(t) (h * (MH2_CH(t) == 2 ? 80 : 96) + 16 * ((t) - 6 * MH2_CH(t)))
 #define MH2_BIN(t) (192 * MH2_CH(t) + MH2_COL(t))
-#define MH2_LOAD(t, PP, VB)                                                                          \
+#define MH2_LOAD(t, PV)                                                                              \
     do {                                                                                             \
-        _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) {                                           \
-            PP[qd] = __ldg(Pt + ((MH2_BIN(t) >> 2) + qd) * TM);                                      \
-            VB[qd] = __ldg(Vt + ((MH2_BIN(t) >> 2) + qd) * TM);                                      \
-        }                                                                                            \
+        _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) PV[qd] = __ldg(PVt + ((MH2_BIN(t) >> 2) + qd) * TM); \
     } while (0)
-            MH2_LOAD(0, pp0, vb0);
-            MH2_LOAD(1, pp1, vb1);
+            MH2_LOAD(0, pv0);
+            MH2_LOAD(1, pv1);
 #pragma unroll
             for (int t = 0; t < 17; ++t) {
                 const int c = MH2_CH(t);
                 const bool live = (t < 16) || (h == 0);                         // bins 528..543 do not exist
                 if (t + 2 < 17 && ((t + 2 < 16) || (h == 0))) {
-                    if ((t + 2) % 3 == 0) MH2_LOAD(t + 2, pp0, vb0);
-                    else if ((t + 2) % 3 == 1) MH2_LOAD(t + 2, pp1, vb1);
-                    else MH2_LOAD(t + 2, pp2, vb2);
+                    if ((t + 2) % 3 == 0) MH2_LOAD(t + 2, pv0);
+                    else if ((t + 2) % 3 == 1) MH2_LOAD(t + 2, pv1);
+                    else MH2_LOAD(t + 2, pv2);
                 }
                 if (t == 0 || t == 12) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); DBG_STAMP(15 + c, threadIdx.x == 0); }
                 if (t == 6) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; tc_fence_after(); DBG_STAMP(15 + c, threadIdx.x == 0); }
@@ -240,9 +235,9 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                     tmem_ld16(tmem + 192 * (c & 1) + lane_off + MH2_COL(t), v);
                     tmem_wait_ld();
                     const float* b3f = b3 + MH2_BIN(t);
-                    if (t % 3 == 0) loglik16(v, pp0, vb0, b3f, g_row, acc, accl);
-                    else if (t % 3 == 1) loglik16(v, pp1, vb1, b3f, g_row, acc, accl);
-                    else loglik16(v, pp2, vb2, b3f, g_row, acc, accl);
+                    if (t % 3 == 0) loglik16_pv(v, pv0, b3f, g_row, acc, accl);
+                    else if (t % 3 == 1) loglik16_pv(v, pv1, b3f, g_row, acc, accl);
+                    else loglik16_pv(v, pv2, b3f, g_row, acc, accl);
                 }
                 if (t == 5) {                                                   // chunk 0 drained by this thread
                     DBG_STAMP(4, threadIdx.x == 0);
@@ -330,7 +325,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
 using namespace dvae;
 using namespace dvae::tc;
 
-extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
+extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
                                  const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
                                  int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept,
                                  float* a_trace, int* status, void* stream) {
@@ -339,7 +334,7 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const fl
     if (rc) return rc;
     DVAE_REQUIRE(L == 16 || L == 32, "dvae_mh_chain_tc2: latent size must be 16 or 32 (got %d)", L);
     DVAE_REQUIRE(y_dim <= 3, "dvae_mh_chain_tc2: at most 3 label inputs");
-    DVAE_REQUIRE(image && Ppk && Vbpk && g && Z && Zs && eps && u && status, "dvae_mh_chain_tc2: null pointer");
+    DVAE_REQUIRE(image && PVpk && g && Z && Zs && eps && u && status, "dvae_mh_chain_tc2: null pointer");
     DVAE_REQUIRE(y_dim == 0 || y, "dvae_mh_chain_tc2: y_dim=%d but y is null", y_dim);
     DVAE_REQUIRE(NT >= 0 && n_chains >= 1 && n_chains < 4096 && n_burn >= 0 && n_keep >= 1 && var_rw > 0.f, "dvae_mh_chain_tc2: bad sizes");
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(Zs) & 15) == 0 && (reinterpret_cast<uintptr_t>(eps) & 15) == 0,
@@ -347,7 +342,7 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const fl
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
     p.rows = NT * n_chains; p.C = n_chains; p.y = y;
-    p.Ppk = (const float4*)Ppk; p.Vbpk = (const float4*)Vbpk; p.g = g; p.Z = Z; p.Zs = Zs;
+    p.PVpk = (const uint4*)PVpk; p.g = g; p.Z = Z; p.Zs = Zs;
     p.eps = eps; p.u = u;
     p.n_accept = n_accept; p.a_trace = a_trace; p.n_burn = n_burn; p.n_keep = n_keep;
     p.sd = sqrtf(var_rw);

@@ -28,8 +28,7 @@ struct Mh3Params {
     int64_t rows;
     int C;
     const float* y;
-    const float4* Ppk;
-    const float4* Vbpk;
+    const uint4* PVpk;            // [tile][quad][128] {P0P1, P2P3, V0V1, V2V3} in BF16
     const float* g;
     float* Z;
     float* Zs;
@@ -126,8 +125,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
         const bool valid = row_g < p.rows;
         const int64_t fr = valid ? row_g / p.C : 0;
         const float g_row = valid ? p.g[fr] : 1.f;
-        const float4* Pt = p.Ppk + (tile * NQ) * TM + row;
-        const float4* Vt = p.Vbpk + (tile * NQ) * TM + row;
+        const uint4* PVt = p.PVpk + (tile * NQ) * TM + row;
 
         float y0 = 0.f, y1 = 0.f, y2 = 0.f, ll_cur = 0.f, u_cur = 0.5f, prior = 0.f;
         uint32_t n_acc = 0;
@@ -222,15 +220,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
 
             // ---- layer 3: chunks of 128 bins (+ bin 512), W3 streamed chunk by chunk through the context's slot
             float acc = 0.f, accl = 0.f;
-            float4 ppA[4], vbA[4];
+            uint4 pvA[4], pvB[4];
 #define MH3_QUAD(t) (32 * ((t) >> 2) + 16 * h + 4 * ((t) & 3))
-#define MH3_LOAD(t, PP, VB)                                                                          \
+#define MH3_LOAD(t, PV)                                                                              \
     do {                                                                                             \
-        _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) {                                           \
-            PP[qd] = __ldg(Pt + (MH3_QUAD(t) + qd) * TM);                                            \
-            VB[qd] = __ldg(Vt + (MH3_QUAD(t) + qd) * TM);                                            \
-        }                                                                                            \
+        _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) PV[qd] = __ldg(PVt + (MH3_QUAD(t) + qd) * TM); \
     } while (0)
+            MH3_LOAD(0, pvA);
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
                 if (w == 3 && lead) {                                           // chunk j: weights landed -> MMA
@@ -254,22 +250,23 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
 #pragma unroll
                     for (int sub = 0; sub < 4; ++sub) {
                         const int t = 4 * j + sub;
-                        // the other context's work covers the L2 latency of these loads: no register double buffer
-                        MH3_LOAD(t, ppA, vbA);
+                        if (t + 1 < 16) {                                       // quads of the next sub-chunk
+                            if (t & 1) MH3_LOAD(t + 1, pvA); else MH3_LOAD(t + 1, pvB);
+                        }
                         float v[16];
                         tmem_ld16(tmem + 128 + lane_off + 64 * h + 16 * sub, v);
                         tmem_wait_ld();
                         const float* b3f = b3 + 128 * j + 64 * h + 16 * sub;
-                        loglik16(v, ppA, vbA, b3f, g_row, acc, accl);
+                        if (t & 1) loglik16_pv(v, pvB, b3f, g_row, acc, accl);
+                        else loglik16_pv(v, pvA, b3f, g_row, acc, accl);
                     }
                 } else if (h == 0) {                                            // bin 512
                     float v[4];
                     tmem_ld4(tmem + 128 + lane_off, v);
                     tmem_wait_ld();
-                    const float4 pp = __ldg(Pt + 128 * TM);
-                    const float4 vb = __ldg(Vt + 128 * TM);
-                    const float v0 = fmaf(g_row, ex2_approx(v[0] + b3[512]), vb.x);
-                    acc = fmaf(pp.x, rcp_approx(v0), acc);
+                    const uint4 pv = __ldg(PVt + 128 * TM);
+                    const float v0 = fmaf(g_row, ex2_approx(v[0] + b3[512]), bf_lo(pv.z));
+                    acc = fmaf(bf_lo(pv.x), rcp_approx(v0), acc);
                     accl += lg2_approx(v0);
                 }
                 tc_fence_before();
@@ -327,7 +324,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
 using namespace dvae;
 using namespace dvae::tc;
 
-extern "C" int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
+extern "C" int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
                                  const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
                                  int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept,
                                  float* a_trace, int* status, void* stream) {
@@ -336,7 +333,7 @@ extern "C" int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const fl
     if (rc) return rc;
     DVAE_REQUIRE(L == 16, "dvae_mh_chain_tc3: latent size must be 16 (got %d)", L);
     DVAE_REQUIRE(y_dim <= 3, "dvae_mh_chain_tc3: at most 3 label inputs");
-    DVAE_REQUIRE(image && Ppk && Vbpk && g && Z && Zs && eps && u && status, "dvae_mh_chain_tc3: null pointer");
+    DVAE_REQUIRE(image && PVpk && g && Z && Zs && eps && u && status, "dvae_mh_chain_tc3: null pointer");
     DVAE_REQUIRE(y_dim == 0 || y, "dvae_mh_chain_tc3: y_dim=%d but y is null", y_dim);
     DVAE_REQUIRE(NT >= 0 && n_chains >= 1 && n_chains < 4096 && n_burn >= 0 && n_keep >= 1 && var_rw > 0.f, "dvae_mh_chain_tc3: bad sizes");
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(Zs) & 15) == 0 && (reinterpret_cast<uintptr_t>(eps) & 15) == 0 &&
@@ -345,7 +342,7 @@ extern "C" int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const fl
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
     p.rows = NT * n_chains; p.C = n_chains; p.y = y;
-    p.Ppk = (const float4*)Ppk; p.Vbpk = (const float4*)Vbpk; p.g = g; p.Z = Z; p.Zs = Zs;
+    p.PVpk = (const uint4*)PVpk; p.g = g; p.Z = Z; p.Zs = Zs;
     p.eps = eps; p.u = u;
     p.n_accept = n_accept; p.a_trace = a_trace; p.n_burn = n_burn; p.n_keep = n_keep;
     p.sd = sqrtf(var_rw);

@@ -284,6 +284,28 @@ __device__ __forceinline__ void loglik16(const float* v, const float4* pp, const
     }
 }
 
+
+// Same with the observation / noise variance streamed as BF16: pv[qd] = {P0P1, P2P3, V0V1, V2V3} (bf16x2 words) of
+// four consecutive bins.  Half the L2 traffic and half the L2 working set of the FP32 stream; the rounding (2^-9
+// relative, identical for l(z) and l(z')) perturbs the log ratio far less than the BF16 decoder weights do.
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ void loglik16_pv(const float* v, const uint4* pv, const float* b3f, float g_row, float& acc, float& accl) {
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        const float4 bb = *reinterpret_cast<const float4*>(b3f + 4 * qd);
+        const float v0 = fmaf(g_row, ex2_approx(v[4 * qd + 0] + bb.x), bf_lo(pv[qd].z));
+        const float v1 = fmaf(g_row, ex2_approx(v[4 * qd + 1] + bb.y), bf_hi(pv[qd].z));
+        const float v2 = fmaf(g_row, ex2_approx(v[4 * qd + 2] + bb.z), bf_lo(pv[qd].w));
+        const float v3 = fmaf(g_row, ex2_approx(v[4 * qd + 3] + bb.w), bf_hi(pv[qd].w));
+        const float p01 = v0 * v1, p23 = v2 * v3;
+        const float n01 = fmaf(bf_hi(pv[qd].x), v0, bf_lo(pv[qd].x) * v1), n23 = fmaf(bf_hi(pv[qd].y), v2, bf_lo(pv[qd].y) * v3);
+        acc = fmaf(n01, rcp_approx(p01), acc);
+        acc = fmaf(n23, rcp_approx(p23), acc);
+        accl += lg2_approx(p01) + lg2_approx(p23);
+    }
+}
+
 size_t smem_bytes(const Dims& d);
 int check_dims(const DvaeMlp* dec, int L, int y_dim, const char* who, Dims* out);
 

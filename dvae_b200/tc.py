@@ -64,12 +64,12 @@ def check_status(eng):
 def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
     w, b, cfg = eng.w, eng.batch, eng.cfg
     img = decoder_image(w)
-    if getattr(eng, "_Ppk_for", None) is not eng.P:
-        eng._Ppk = pack_rows(eng, "Ppk", eng.P)
-        eng._Ppk_for = eng.P
-    Vbpk = pack_rows(eng, "Vbpk", eng.Vb)
     v2 = w.z_dim in (16, 32) and w.y_dim <= 3 and os.environ.get("DVAE_TC_SAMPLER", "v2") != "v1"
     if not v2:
+        if getattr(eng, "_Ppk_for", None) is not eng.P:
+            eng._Ppk = pack_rows(eng, "Ppk", eng.P)
+            eng._Ppk_for = eng.P
+        Vbpk = pack_rows(eng, "Vbpk", eng.Vb)
         _lib.call("dvae_mh_chain_tc", w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim,
                   _p(b.frame_gid), _p(b.frame_idx), _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep,
                   float(cfg.var_rw), C.byref(rng), _p(eng.n_accept), _p(a_trace), _p(_status(eng)), _stream())
@@ -88,8 +88,12 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
         eps_ptr, u_ptr = _p(eps), _p(u)
     gen = os.environ.get("DVAE_TC_SAMPLER", "v2")
     fn = "dvae_mh_chain_tc3" if (gen == "v3" and w.z_dim == 16) else "dvae_mh_chain_tc2"
+    nb = int(_lib.load().dvae_tc_packed_pv_bytes(chains))
+    pv = eng._get("PVpk", (max(nb, 16),), torch.uint8)
+    _lib.call("dvae_tc_pack_pv", _p(eng.P), _p(eng.Vb), b.NT, cfg.n_chains, eng.F, eng.ld, _p(pv), _stream())
+    eng.kernel_launches += 1
     with eng.stage("mh_kernel"):
-        _lib.call(fn, w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim, _p(eng.Z),
+        _lib.call(fn, w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, _p(eng.Z),
                   _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep, float(cfg.var_rw), eps_ptr, u_ptr, _p(eng.n_accept),
                   _p(a_trace), _p(_status(eng)), _stream())
     eng.kernel_launches += 1

@@ -159,15 +159,18 @@ int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64
 /* second-generation schedule of the same sampler (software-pipelined P / Vb stream, mbarrier chunk hand-over,
  * register-resident chain state); L in {16, 32}, y_dim <= 3.  The draws always come from global memory:
  * eps[n_iter][NT*C][L], u[n_iter][NT*C] (16-byte aligned), either injected by the caller or produced by
- * dvae_rng_dump with the Philox counters every sampler of this library uses.  Same results as dvae_mh_chain_tc. */
-int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
+ * dvae_rng_dump with the Philox counters every sampler of this library uses.  P and Vb are streamed as BF16
+ * (dvae_tc_pack_pv: [tile][bin quad][128 chains] x {P0P1, P2P3, V0V1, V2V3}, dvae_tc_packed_pv_bytes bytes). */
+int64_t dvae_tc_packed_pv_bytes(int64_t chains);
+int dvae_tc_pack_pv(const float* P, const float* Vb, int64_t NT, int n_chains, int F, int ld, void* dst, void* stream);
+int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
                       const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
                       int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
                       int* status, void* stream);
 
 /* third-generation schedule: two tile contexts per CTA, W3 streamed chunk-wise with cp.async.bulk (L = 16 only).
  * Same arguments and results as dvae_mh_chain_tc2. */
-int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
+int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
                       const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
                       int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
                       int* status, void* stream);
