@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             mbar_wait(bar12, ph12, dead, p.status);
             ph12 ^= 1;
             tc_fence_after();
-            hidden_epilogue_rows(tmem + 384, A, q, h, row, nullptr);              // bias rides on the constant-one column
+            hidden_epilogue_rows_bf(tmem + 384, A, q, h, row, nullptr);              // bias rides on the constant-one column
             fence_async_smem();
             tc_fence_before();
             DBG_STAMP(20, threadIdx.x == 0);
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 mbar_wait(bar12, ph12, dead, p.status);
                 ph12 ^= 1;
                 tc_fence_after();
-                hidden_epilogue_rows(tmem + 384, A, q, h, row, b2);
+                hidden_epilogue_rows_bf(tmem + 384, A, q, h, row, b2);
                 fence_async_smem();
                 tc_fence_before();
                 DBG_STAMP(21, threadIdx.x == 0);
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
 #undef MH2_COL
 #undef MH2_CH
             tc_fence_before();
-            const float part = fmaf(kLn2, accl, acc);
+            const float part = fmaf(kLn2, accl, acc * kQuadScale);
             if (h == 1) red[row] = part;
             DBG_STAMP(8, threadIdx.x == 0);
             __syncthreads();                                                    // S4: both halves of l(z') available

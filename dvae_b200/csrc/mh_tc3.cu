@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
             mbar_wait(bar12, ph12, dead, p.status);
             ph12 ^= 1;
             tc_fence_after();
-            hidden_epilogue_rows(tmem, A, q, h, row, nullptr);
+            hidden_epilogue_rows_bf(tmem, A, q, h, row, nullptr);
             fence_async_smem();
             tc_fence_before();
             ctx_bar(ctx);                                                       // S2
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
                 mbar_wait(bar12, ph12, dead, p.status);
                 ph12 ^= 1;
                 tc_fence_after();
-                hidden_epilogue_rows(tmem, A, q, h, row, b2);
+                hidden_epilogue_rows_bf(tmem, A, q, h, row, b2);
                 fence_async_smem();
                 tc_fence_before();
                 ctx_bar(ctx);                                                   // S3
@@ -266,11 +266,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
                     tmem_wait_ld();
                     const uint4 pv = __ldg(PVt + 128 * TM);
                     const float v0 = fmaf(g_row, ex2_approx(v[0] + b3[512]), bf_lo(pv.z));
-                    acc = fmaf(bf_lo(pv.x), rcp_approx(v0), acc);
+                    acc = fmaf(bf_lo(pv.x) * (1.0f / kQuadScale), rcp_approx(v0), acc);
                     accl += lg2_approx(v0);
                 }
                 tc_fence_before();
-                if (j == 4 && h == 1) red[row] = fmaf(kLn2, accl, acc);
+                if (j == 4 && h == 1) red[row] = fmaf(kLn2, accl, acc * kQuadScale);
                 DBG3(4 + j, threadIdx.x == 0);
                 ctx_bar(ctx);                                                   // chunk buffer drained (j = 4: S4)
             }
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
             DBG3(9, threadIdx.x == 0);
 
             if (owner) {
-                const float ll_prop = fmaf(kLn2, accl, acc) + red[row];
+                const float ll_prop = fmaf(kLn2, accl, acc * kQuadScale) + red[row];
                 if (it < 0) {
                     ll_cur = ll_prop;
                 } else if (valid) {
