@@ -50,6 +50,9 @@ PROTOTYPES = {
     "dvae_decode_ws_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "dvae_decode_ws_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                                     C.c_int, c_ptr, C.c_int, C.c_int64, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr]),
+    "dvae_decode_stats_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
+                                       C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "dvae_nmf_w_from_frame_stats": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_nmf_w_from_stats": (C.c_int, [c_ptr, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_mh_workspace_floats": (C.c_int64, [C.POINTER(DvaeMlp), C.c_int64, C.c_int]),
     "dvae_mh_chain_f32": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
@@ -72,6 +75,7 @@ PROTOTYPES = {
     "dvae_mh_chain_tc3": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "dvae_debug_set_clock_buffer3": (C.c_int, [c_ptr]),
+    "dvae_debug_set_clock_buffer_ws": (C.c_int, [c_ptr]),
     "dvae_debug_set_clock_buffer": (C.c_int, [c_ptr]),
     "dvae_decode_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int,
                                  c_ptr, c_ptr]),

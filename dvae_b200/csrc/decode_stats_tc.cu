@@ -1,0 +1,429 @@
+// Warp-specialised tcgen05 decode of the kept samples with per-frame reciprocal statistics (third decode kernel).
+//
+// Replaces packages/models/mcem.py:280-290 (compute_Vs) and the inner sums of mcem.py:108-110:
+//
+//   Vs[n][r][f] = D([Z_r(n); y(n)])[f]                         (FP32, written once, 128-byte coalesced warp stores)
+//   A1[n][f]    = sum_r 1 / Vx,   A2[n][f] = sum_r 1 / Vx^2,   Vx = g[n] Vs[n][r][f] + Vb[n][f]
+//
+// The W update then only needs  num[f,k] = sum_n P A2 H,  den[f,k] = sum_n A1 H  (w_from_frame_stats_kernel): no per-bin
+// accumulators have to live in registers across tiles, which is what allows the schedule below.
+//
+// Phase timing of the previous kernel (decode_ws_tc.cu, tools/ws_phase_clocks.py): 26 k cycles per 120-row tile, of
+// which the serial front (operand write, layers 1-2) took 10 k and each layer-3 chunk epilogue 5 k with two warps per
+// scheduler.  Here the CTA is a two-stage pipeline over tiles:
+//
+//   front  (warps 0-3,  thread = row)      z -> layer-1 operand -> MMA -> tanh -> MMA -> tanh -> h2 in A[tile & 1]
+//   back   (warps 4-19, thread = bin,      layer 3 TRANSPOSED (A = 128 bins of W3, B = h2): TMEM lanes are bins, a warp
+//           warp = lane quadrant x frame)   stores 128 contiguous bytes of Vs; two chunk buffers in TMEM; W3 is streamed
+//                                           from L2 chunk by chunk (cp.async.bulk) into two 32 KB slots
+//
+// so layers 1-2 of tile i+1 overlap layer 3 of tile i, and 4 back warps per scheduler keep MUFU / LSU busy.
+// Shared memory: W1 | W2 | biases resident (51 KB) + 2 activation buffers (64 KB) + 2 W3 slots (64 KB).
+// TMEM: [0,128) layers 1-2, [128,256) / [256,384) layer-3 chunks.
+#include "tc_common.cuh"
+
+namespace dvae {
+namespace tc {
+
+constexpr int DS_THREADS = 640;
+constexpr int DS_BACK = 512;
+
+struct DsParams {
+    Dims d;
+    const unsigned char* image;
+    const float* Zs;        // [NT][R][L]
+    const float* y;         // [NT][y_dim] or null
+    const float* Vb;        // [NT][ld]
+    const float* g;         // [NT]
+    float* Vs;              // [NT][R][ld]
+    float* A1;              // [NT][ld]
+    float* A2;              // [NT][ld]
+    int64_t NT;
+    int ld;
+    int* status;
+};
+
+__device__ __forceinline__ void ds_bar_front() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void ds_bar_tail() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void ds_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void ds_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
+template <int RL> __device__ __forceinline__ void ds_tmem_ld(uint32_t taddr, float* v);
+template <> __device__ __forceinline__ void ds_tmem_ld<32>(uint32_t taddr, float* v) { tmem_ld32(taddr, v); }
+template <> __device__ __forceinline__ void ds_tmem_ld<16>(uint32_t taddr, float* v) { tmem_ld16(taddr, v); }
+
+// front epilogue: the thread's row, all 128 hidden units: D12[row][0..128) -> tanh(+bias) -> bf16 -> activation operand
+__device__ __forceinline__ void ds_hidden_row(uint32_t tmem, unsigned char* A, int q, int row, const float* bias) {
+#pragma unroll 1
+    for (int part = 0; part < 4; ++part) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + 32 * part, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            float t[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float x = v[8 * cc + e];
+                if (bias) x += bias[32 * part + 8 * cc + e];
+                t[e] = tanh_approx(x);
+            }
+            const int kb = part >> 1, chunk = 4 * (part & 1) + cc;
+            uint4 pk = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+            *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4)) = pk;
+        }
+    }
+}
+
+template <int R, int L>
+__global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p) {
+    constexpr int RL = (R <= 16) ? 16 : 32;
+    constexpr int FT = 128 / R;                        // frames per tile
+    constexpr int FS = FT / 4;                         // frames per back warp
+    static_assert(FT % 4 == 0 && (FT - 1) * R + RL <= 128, "tile geometry");
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint64_t bars[11];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int dead_flag;
+    __shared__ float tailS[256];
+
+    const Dims& d = p.d;
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool front = warp < 4;
+    const int shared_bytes = (d.off_w3 + 4 * ((d.n_hidden == 2 ? HID : 0) + NPAD) + 1023) & ~1023;
+    float* biasp = reinterpret_cast<float*>(base + d.off_w3);
+    unsigned char* Abuf = base + shared_bytes;                       // 2 x 32 KB
+    unsigned char* Wslot = Abuf + 65536;                             // 2 x 32 KB
+    const uint32_t bar12 = smem_u32(&bars[0]);
+    const uint32_t a_full0 = smem_u32(&bars[1]), a_full1 = smem_u32(&bars[2]);
+    const uint32_t a_free0 = smem_u32(&bars[3]), a_free1 = smem_u32(&bars[4]);
+    const uint32_t w_full0 = smem_u32(&bars[5]), w_full1 = smem_u32(&bars[6]);
+    const uint32_t bar3_0 = smem_u32(&bars[7]), bar3_1 = smem_u32(&bars[8]);
+    const uint32_t barf_0 = smem_u32(&bars[9]), barf_1 = smem_u32(&bars[10]);
+
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(p.image);
+        uint4* dst = reinterpret_cast<uint4*>(base);
+        for (int i = threadIdx.x; i < d.off_w3 / 16; i += DS_THREADS) dst[i] = __ldg(src + i);
+        const uint4* bsrc = reinterpret_cast<const uint4*>(p.image + d.off_bias);
+        uint4* bdst = reinterpret_cast<uint4*>(biasp);
+        for (int i = threadIdx.x; i < (d.image_bytes - d.off_bias) / 16; i += DS_THREADS) bdst[i] = __ldg(bsrc + i);
+    }
+    if (threadIdx.x == 0) {
+        dead_flag = 0;
+        mbar_init(bar12, 1);
+        mbar_init(a_full0, 128); mbar_init(a_full1, 128);
+        mbar_init(a_free0, 1); mbar_init(a_free1, 1);
+        mbar_init(w_full0, 1); mbar_init(w_full1, 1);
+        mbar_init(bar3_0, 1); mbar_init(bar3_1, 1);
+        mbar_init(barf_0, DS_BACK); mbar_init(barf_1, DS_BACK);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    volatile int* dead = &dead_flag;
+
+    const uint32_t w1_addr = smem_u32(base), w2_addr = smem_u32(base + d.off_w2);
+    const float* b2 = (d.n_hidden == 2) ? biasp : nullptr;
+    const float* b3 = biasp + (d.n_hidden == 2 ? HID : 0);
+    const unsigned char* w3g = p.image + d.off_w3;
+    const int y_dim = d.y_dim, nkb1 = d.nkb1;
+    const bool two_hidden = d.n_hidden == 2;
+    const int64_t n_tiles = (p.NT + FT - 1) / FT;
+
+    if (front) {
+        // =========================================== front: layers 1-2 ===========================================
+        const int q = warp, row = 32 * warp + lane;
+        const int fi = row / R, r = row - fi * R;
+        uint32_t ph12 = 0, phfree0 = 0, phfree1 = 0;
+        int k = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            const int buf = k & 1;
+            unsigned char* A = Abuf + buf * 32768;
+            const uint32_t a_addr = smem_u32(A);
+            const int64_t n = tile * FT + fi;
+            const bool valid = (fi < FT) && (n < p.NT);
+            float z[L];
+            float y0 = 0.f, y1 = 0.f, y2 = 0.f;
+            if (valid) {
+                const float4* src = reinterpret_cast<const float4*>(p.Zs + (n * R + r) * (int64_t)L);
+#pragma unroll
+                for (int l = 0; l < L / 4; ++l) {
+                    const float4 t4 = __ldg(src + l);
+                    z[4 * l] = t4.x; z[4 * l + 1] = t4.y; z[4 * l + 2] = t4.z; z[4 * l + 3] = t4.w;
+                }
+                if (y_dim > 0) y0 = p.y[n * y_dim];
+                if (y_dim > 1) y1 = p.y[n * y_dim + 1];
+                if (y_dim > 2) y2 = p.y[n * y_dim + 2];
+            } else {
+#pragma unroll
+                for (int l = 0; l < L; ++l) z[l] = 0.f;
+            }
+            if (k >= 2) {                              // the layer-3 MMAs of tile k-2 have finished reading this buffer
+                if (buf == 0) { mbar_wait(a_free0, phfree0, dead, p.status); phfree0 ^= 1; }
+                else { mbar_wait(a_free1, phfree1, dead, p.status); phfree1 ^= 1; }
+            }
+            write_a1_static<L>(y_dim, nkb1, A, row, z, y0, y1, y2, valid);
+            fence_async_smem();
+            ds_bar_front();
+            if (threadIdx.x == 0) {
+                tc_fence_after();
+                issue_gemm2(a_addr, 16384, w1_addr, 16384, nkb1, tmem, HID);
+                umma_commit(bar12);
+            }
+            mbar_wait(bar12, ph12, dead, p.status);
+            ph12 ^= 1;
+            tc_fence_after();
+            ds_hidden_row(tmem, A, q, row, nullptr);
+            fence_async_smem();
+            tc_fence_before();
+            ds_bar_front();
+            if (two_hidden) {
+                if (threadIdx.x == 0) {
+                    tc_fence_after();
+                    issue_gemm2(a_addr, 16384, w2_addr, 16384, 2, tmem, HID);
+                    umma_commit(bar12);
+                }
+                mbar_wait(bar12, ph12, dead, p.status);
+                ph12 ^= 1;
+                tc_fence_after();
+                ds_hidden_row(tmem, A, q, row, b2);
+                fence_async_smem();
+                tc_fence_before();
+            }
+            mbar_arrive2(buf ? a_full1 : a_full0);      // h2 of this tile is in A[buf]
+        }
+    } else {
+        // =========================================== back: layer 3, Vs, statistics ===========================================
+        const int bw = warp - 4;
+        const int q = bw & 3, s = bw >> 2;              // TMEM lane quadrant (bins 32q..), frame slot
+        const bool issuer = (bw == 0) && (lane == 0);
+        const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+        uint32_t ph3_0 = 0, ph3_1 = 0, phf_0 = 0, phf_1 = 0, phw_0 = 0, phw_1 = 0, phfull0 = 0, phfull1 = 0;
+        const uint32_t slot_addr = smem_u32(Wslot);
+
+        // chunk c of the CTA's stream: tile k = c / 5, j = c % 5; W3 slot and TMEM buffer = c & 1
+        auto load_chunk = [&](int j, int sl) {          // issuer only
+            const uint32_t bytes = (j < 4) ? 16384u : 2048u;
+            const uint32_t bar = sl ? w_full1 : w_full0;
+            ds_expect_tx(bar, 2 * bytes);
+            ds_bulk_g2s(slot_addr + sl * 32768, w3g + (size_t)j * 128 * 128, bytes, bar);
+            ds_bulk_g2s(slot_addr + sl * 32768 + 16384, w3g + NPAD * 128 + (size_t)j * 128 * 128, bytes, bar);
+        };
+        auto issue_chunk = [&](int kk, int j, int sl, bool first_use) {   // issuer only
+            const int buf = kk & 1;
+            const uint32_t a_addr = smem_u32(Abuf + buf * 32768);
+            if (sl == 0) { mbar_wait(w_full0, phw_0, dead, p.status); phw_0 ^= 1; }
+            else { mbar_wait(w_full1, phw_1, dead, p.status); phw_1 ^= 1; }
+            if (j == 0) {
+                if (buf == 0) { mbar_wait(a_full0, phfull0, dead, p.status); phfull0 ^= 1; }
+                else { mbar_wait(a_full1, phfull1, dead, p.status); phfull1 ^= 1; }
+            }
+            if (!first_use) {                           // the TMEM buffer was drained by the chunk two steps earlier
+                if (sl == 0) { mbar_wait(barf_0, phf_0, dead, p.status); phf_0 ^= 1; }
+                else { mbar_wait(barf_1, phf_1, dead, p.status); phf_1 ^= 1; }
+            }
+            tc_fence_after();
+            const uint32_t tb = tmem + 128 + 128 * sl;
+            if (j < 4) issue_gemm2(slot_addr + sl * 32768, 16384, a_addr, 16384, 2, tb, 128);      // D^T = W3 chunk x h2^T
+            else issue_gemm2(a_addr, 16384, slot_addr + sl * 32768, 16384, 2, tb, 16);             // bin 512: D = h2 x w^T
+            umma_commit(sl ? bar3_1 : bar3_0);
+            if (j == 4) umma_commit(buf ? a_free1 : a_free0);                                       // A[buf] may be rewritten
+        };
+
+        const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t n_chunks = my_tiles * 5;
+        if (issuer && n_chunks > 0) {
+            load_chunk(0, 0);
+            load_chunk(1, 1);
+            issue_chunk(0, 0, 0, true);
+            issue_chunk(0, 1, 1, true);
+        }
+        int64_t c = 0;
+        int k = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            const int64_t t0 = tile * FT;
+#pragma unroll 1
+            for (int j = 0; j < 5; ++j, ++c) {
+                const int sl = (int)(c & 1);
+                if (sl == 0) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; }
+                else { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; }
+                tc_fence_after();
+                if (issuer && c + 2 < n_chunks) load_chunk((int)((c + 2) % 5), sl);   // the slot has been consumed
+                const uint32_t tb = tmem + 128 + 128 * sl;
+                if (j < 4) {
+                    const int f = 128 * j + 32 * q + lane;
+                    const float bias = b3[f];
+#pragma unroll
+                    for (int ff = 0; ff < FS; ++ff) {
+                        const int fi = s * FS + ff;
+                        const int64_t n = t0 + fi;
+                        if (n < p.NT) {
+                            float v[RL];
+                            ds_tmem_ld<RL>(tb + lane_off + fi * R, v);
+                            const float gg = __ldg(p.g + n);
+                            const float vb = __ldg(p.Vb + n * p.ld + f);
+                            tmem_wait_ld();
+                            float* dst = p.Vs + (n * R) * (int64_t)p.ld + f;
+                            float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                            for (int r = 0; r + 1 < R; r += 2) {
+                                const float s0 = ex2_approx(v[r] + bias), s1 = ex2_approx(v[r + 1] + bias);
+                                dst[(int64_t)r * p.ld] = s0;
+                                dst[(int64_t)(r + 1) * p.ld] = s1;
+                                const float x0 = fmaf(gg, s0, vb), x1 = fmaf(gg, s1, vb);
+                                const float rr = rcp_approx(x0 * x1);
+                                const float i0 = x1 * rr, i1 = x0 * rr;
+                                a1 += i0 + i1;
+                                a2 = fmaf(i0, i0, fmaf(i1, i1, a2));
+                            }
+                            if (R & 1) {
+                                const float s0 = ex2_approx(v[R - 1] + bias);
+                                dst[(int64_t)(R - 1) * p.ld] = s0;
+                                const float i0 = rcp_approx(fmaf(gg, s0, vb));
+                                a1 += i0;
+                                a2 = fmaf(i0, i0, a2);
+                            }
+                            p.A1[n * p.ld + f] = a1;
+                            p.A2[n * p.ld + f] = a2;
+                        }
+                    }
+                } else if (s == 0) {
+                    // bin 512: the MMA ran untransposed, TMEM lane = row of the tile, column 0 = bin 512
+                    const int row = 32 * q + lane;
+                    const int fi = row / R, r = row - fi * R;
+                    const int64_t n = t0 + fi;
+                    float v[4];
+                    tmem_ld4(tb + lane_off, v);
+                    tmem_wait_ld();
+                    float inv = 0.f;
+                    if (fi < FT && n < p.NT && d.F > 512) {
+                        const float vs = ex2_approx(v[0] + b3[512]);
+                        p.Vs[(n * R + r) * (int64_t)p.ld + 512] = vs;
+                        inv = rcp_approx(fmaf(__ldg(p.g + n), vs, __ldg(p.Vb + n * p.ld + 512)));
+                    }
+                    tailS[row] = inv;
+                    tailS[128 + row] = inv * inv;
+                    ds_bar_tail();
+                    if (row < 2 * FT) {
+                        const int fj = row >> 1, which = row & 1;
+                        const int64_t nn = t0 + fj;
+                        if (nn < p.NT && d.F > 512) {
+                            float sum = 0.f;
+                            for (int rr = 0; rr < R; ++rr) sum += tailS[which * 128 + fj * R + rr];
+                            (which ? p.A2 : p.A1)[nn * p.ld + 512] = sum;
+                        }
+                    }
+                    ds_bar_tail();
+                }
+                tc_fence_before();
+                mbar_arrive2(sl ? barf_1 : barf_0);
+                if (issuer && c + 2 < n_chunks) {
+                    const int64_t c2 = c + 2;
+                    issue_chunk(k + (int)((j + 2) / 5), (int)(c2 % 5), sl, false);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512) : "memory");
+    }
+}
+
+// W <- W * sqrt(num / den), num[f,k] = sum_n P A2 H, den[f,k] = sum_n A1 H   (mcem.py:108-111)
+__global__ void __launch_bounds__(128) w_from_frame_stats_kernel(const float* __restrict__ A1, const float* __restrict__ A2,
+                                                                 const float* __restrict__ P, const float* __restrict__ H,
+                                                                 const float* __restrict__ W, const int64_t* __restrict__ fr_off,
+                                                                 int F, int K, int ld, float* __restrict__ Wtmp) {
+    constexpr int KT = 10;
+    const int u = blockIdx.y;
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    float num[KT], den[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) num[k] = den[k] = 0.f;
+    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
+    for (int64_t n = n0; n < n1; ++n) {
+        const float a1 = A1[n * ld + f];
+        const float pa2 = P[n * ld + f] * A2[n * ld + f];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            const float h = (k < K) ? __ldg(H + n * K + k) : 0.f;
+            num[k] = fmaf(pa2, h, num[k]);
+            den[k] = fmaf(a1, h, den[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+        if (k < K) {
+            const int64_t i = ((int64_t)u * K + k) * ld + f;
+            Wtmp[i] = W[i] * sqrtf(num[k] / den[k]);
+        }
+}
+
+}  // namespace tc
+}  // namespace dvae
+
+using namespace dvae;
+using namespace dvae::tc;
+
+extern "C" int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y,
+                                    int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1,
+                                    float* A2, int* status, void* stream) {
+    DsParams p{};
+    int rc = check_dims(dec, L, y_dim, "dvae_decode_stats_tc", &p.d);
+    if (rc) return rc;
+    DVAE_REQUIRE(image && Zs && Vb && g && Vs && A1 && A2 && status, "dvae_decode_stats_tc: null pointer");
+    DVAE_REQUIRE(R == 10 || R == 30, "dvae_decode_stats_tc: R must be 10 or 30 (got %d)", R);
+    DVAE_REQUIRE(L == 16 || L == 32, "dvae_decode_stats_tc: latent size must be 16 or 32 (got %d)", L);
+    DVAE_REQUIRE(y_dim <= 3 && (y_dim == 0 || y), "dvae_decode_stats_tc: bad label arguments");
+    DVAE_REQUIRE(NT >= 0 && ld >= p.d.F, "dvae_decode_stats_tc: bad sizes");
+    DVAE_REQUIRE((reinterpret_cast<uintptr_t>(Zs) & 15) == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0,
+                 "dvae_decode_stats_tc: Zs and image must be 16-byte aligned");
+    if (NT == 0) return 0;
+    p.image = (const unsigned char*)image;
+    p.Zs = Zs; p.y = y; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status;
+    const int shared_bytes = (p.d.off_w3 + 4 * ((p.d.n_hidden == 2 ? HID : 0) + NPAD) + 1023) & ~1023;
+    const size_t smem = (size_t)shared_bytes + 65536 + 65536 + 1024;
+    DVAE_REQUIRE(smem <= 227 * 1024, "dvae_decode_stats_tc: shared memory budget exceeded");
+    const int FT = 128 / R;
+    const int64_t n_tiles = (NT + FT - 1) / FT;
+    const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
+    cudaStream_t st = (cudaStream_t)stream;
+#define DS_LAUNCH(RR, LL)                                                                                         \
+    do {                                                                                                          \
+        cudaFuncSetAttribute(decode_stats_kernel<RR, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        decode_stats_kernel<RR, LL><<<grid, DS_THREADS, smem, st>>>(p);                                           \
+    } while (0)
+    if (R == 10 && L == 16) DS_LAUNCH(10, 16);
+    else if (R == 10) DS_LAUNCH(10, 32);
+    else if (L == 16) DS_LAUNCH(30, 16);
+    else DS_LAUNCH(30, 32);
+#undef DS_LAUNCH
+    return check_launch("decode_stats_kernel");
+}
+
+extern "C" int dvae_nmf_w_from_frame_stats(const float* A1, const float* A2, const float* P, const float* H, const float* W,
+                                           const int64_t* fr_off, int B, int F, int K, int ld, float* Wtmp, void* stream) {
+    DVAE_REQUIRE(A1 && A2 && P && H && W && fr_off && Wtmp && B >= 1 && K >= 1 && K <= 10 && ld >= F,
+                 "dvae_nmf_w_from_frame_stats: bad arguments");
+    w_from_frame_stats_kernel<<<dim3((F + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(A1, A2, P, H, W, fr_off, F, K, ld, Wtmp);
+    return check_launch("w_from_frame_stats_kernel");
+}

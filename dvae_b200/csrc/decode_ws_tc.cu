@@ -37,7 +37,11 @@ struct WsParams {
     int* work_counter;
     int* status;
     int B, n_parts, K, ld;
+    long long* dbg;         // optional clock stamps of CTA 0 (third tile of its first item)
 };
+
+static long long* g_dbg_clocks_ws = nullptr;
+#define DBGW(slot, cond) do { if (p.dbg && blockIdx.x == 0 && tile_no == 2 && (cond)) p.dbg[slot] = clock64(); } while (0)
 
 template <int R, int NCH>
 struct Acc { float num[NCH][WS_KT], den[NCH][WS_KT]; };
@@ -181,7 +185,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
 #pragma unroll
             for (int k = 0; k < WS_KT; ++k) { num[c][k] = 0.f; den[c][k] = 0.f; }
 
-        for (int64_t t0 = n_lo; t0 < n_hi; t0 += FT) {
+        int tile_no = 0;
+        for (int64_t t0 = n_lo; t0 < n_hi; t0 += FT, ++tile_no) {
+            DBGW(0, threadIdx.x == 0);
             const int n_fr = (int)((n_hi - t0 < FT) ? (n_hi - t0) : FT);
             // ---- stage g, H of the tile's frames; layer-1 operand rows
             if (threadIdx.x < FT * (WS_KT + 1)) {
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
             }
             fence_async_smem();
             __syncthreads();                                                    // S1
+            DBGW(1, threadIdx.x == 0);
             if (ctrl) {
                 tc_fence_after();
                 issue_gemm2(a_addr, 16384, w1_addr, 16384, d.nkb1, tmem, HID);
@@ -226,6 +233,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
             }
             ph12 ^= 1;
             __syncthreads();                                                    // S2
+            DBGW(2, threadIdx.x == 0);
             if (d.n_hidden == 2) {
                 if (ctrl) {
                     tc_fence_after();
@@ -241,6 +249,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
                 }
                 ph12 ^= 1;
                 __syncthreads();                                                // S3
+                DBGW(3, threadIdx.x == 0);
             }
 
             // ---- layer 3, transposed: D^T[bins][rows] = W3[128 bins x 128] * h2[128 rows x 128]^T
@@ -285,13 +294,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) decode_ws_kernel(WsParams p) {
                         mbar_wait(my_bar3, ph3, dead, p.status);
                         ph3 ^= 1;
                         tc_fence_after();
+                        DBGW(10 + j, lane == 0 && q == 0);
                         chunk_epilogue<R, RL, FT>(p, tbuf, f, fvalid, bias, t0, n_fr, gS, HS, vbr, pwr, num[c], den[c]);
                         tc_fence_before();
                         mbar_arrive(my_barf);
+                        DBGW(20 + j, lane == 0 && q == 0);
                     }
                 }
             }
             __syncthreads();                                                    // tile done: A, gS, HS reusable
+            DBGW(4, threadIdx.x == 0);
         }
 
         // ---- partial sums of this item: wstat[item][0|1][k][f]
@@ -368,6 +380,7 @@ extern "C" int dvae_decode_ws_tc(const DvaeMlp* dec, const void* image, const fl
     p.Zs = Zs; p.y = y; p.P = P; p.Vb = Vb; p.g = g; p.H = H; p.fr_off = fr_off; p.Vs = Vs; p.wstat = ws;
     p.work_counter = reinterpret_cast<int*>(ws + (int64_t)B * n_parts * 2 * WS_KT * ld);
     p.status = status; p.B = B; p.n_parts = n_parts; p.K = K; p.ld = ld;
+    p.dbg = g_dbg_clocks_ws;
     cudaError_t e = cudaMemsetAsync(p.work_counter, 0, sizeof(int), st);
     if (e != cudaSuccess) { set_error("cudaMemsetAsync: %s", cudaGetErrorString(e)); return (int)e; }
     const size_t smem = smem_bytes(p.d);
@@ -390,4 +403,9 @@ extern "C" int dvae_nmf_w_from_stats(const float* ws, int n_parts, const float* 
     DVAE_REQUIRE(ws && W && Wtmp && B >= 1 && n_parts >= 1 && K >= 1 && K <= WS_KT && ld >= F, "dvae_nmf_w_from_stats: bad arguments");
     w_from_stats_kernel<<<dim3((F + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(ws, n_parts, W, F, K, ld, Wtmp);
     return check_launch("w_from_stats_kernel");
+}
+
+extern "C" int dvae_debug_set_clock_buffer_ws(void* dev_buffer) {
+    g_dbg_clocks_ws = reinterpret_cast<long long*>(dev_buffer);
+    return 0;
 }

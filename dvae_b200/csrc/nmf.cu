@@ -663,7 +663,9 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(cost_part) & 7) == 0, "dvae_nmf_mstep: workspace must be 8-byte aligned");
     const int nblk = (int)hg_blocks(max_frames);
     int rc;
-    if (wstat) {                                   // numerator / denominator already reduced by dvae_decode_ws_tc
+    if (wstat && n_parts == 0) {                   // per-frame reciprocal sums A1 | A2 from dvae_decode_stats_tc
+        rc = dvae_nmf_w_from_frame_stats(wstat, wstat + NT * (int64_t)ld, P, H, W, fr_off, B, F, K, ld, Wtmp, stream);
+    } else if (wstat) {                            // numerator / denominator already reduced by dvae_decode_ws_tc
         rc = dvae_nmf_w_from_stats(wstat, n_parts, W, B, F, K, ld, Wtmp, stream);
     } else {
         nmf_w_kernel<<<dim3((F + 127) / 128, B), 128, 0, st>>>(P, Vs, R, W, H, g, Vb, fr_off, F, K, ld, Wtmp);

@@ -16,6 +16,7 @@ from __future__ import annotations
 import ctypes as C
 import dataclasses
 import math
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -416,11 +417,14 @@ class McemEngine:
         Zs = self.sample_posterior(cfg.keep_E, cfg.burn_E, draws)
         self.R = Zs.shape[1]
         self.Vs = self.Vs_flat[: self.batch.NT * self.R].view(self.batch.NT, self.R, self.ld)
-        self.wstat = None
+        self.wstat, self.wstat_parts = None, 0
         if cfg.sampler == "tc" and self.R in (10, 30) and cfg.nmf_rank <= 10 and cfg.fuse_wstat:
             from . import tc
             with self.stage("decode"):
-                self.wstat = tc.decode_wstat_tc(self, Zs, self.Vs)
+                if os.environ.get("DVAE_TC_DECODE", "v3") == "v2":
+                    self.wstat, self.wstat_parts = tc.decode_wstat_tc(self, Zs, self.Vs), WS_PARTS
+                else:
+                    self.wstat = tc.decode_stats_tc(self, Zs, self.Vs)
         else:
             self.decode_samples(Zs, 0, self.batch.NT, self.Vs)
 
@@ -431,7 +435,7 @@ class McemEngine:
         with self.stage("mstep"):
             _lib.call("dvae_nmf_mstep", _p(self.P), _p(self.Vs), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
                       C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), _p(b.frame_utt), b.B, b.NT, self.F, cfg.nmf_rank,
-                      self.ld, b.max_frames, _p(ws), _p(getattr(self, "wstat", None)), WS_PARTS, _stream())
+                      self.ld, b.max_frames, _p(ws), _p(getattr(self, "wstat", None)), getattr(self, "wstat_parts", 0), _stream())
         self.kernel_launches += 4
 
     def wiener(self, draws=None):

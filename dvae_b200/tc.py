@@ -120,3 +120,15 @@ def decode_wstat_tc(eng, Zs, Vs):
               _stream())
     eng.kernel_launches += 1
     return ws
+
+
+def decode_stats_tc(eng, Zs, Vs):
+    """Warp-specialised decode + per-frame reciprocal sums (dvae_decode_stats_tc); returns the [2][NT][ld] statistics."""
+    w, b = eng.w, eng.batch
+    img = decoder_image(w)
+    st = eng._get("fstat", (2 * b.NT * eng.ld,))
+    A1, A2 = st[: b.NT * eng.ld], st[b.NT * eng.ld:]
+    _lib.call("dvae_decode_stats_tc", w.dec.ref, _p(img), _p(Zs), Zs.shape[1], w.z_dim, _p(eng.y), w.y_dim, _p(eng.Vb),
+              _p(eng.g), b.NT, eng.ld, _p(Vs), _p(A1), _p(A2), _p(_status(eng)), _stream())
+    eng.kernel_launches += 1
+    return st

@@ -168,6 +168,14 @@ int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, c
                       int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
                       int* status, void* stream);
 
+/* Warp-specialised decode with per-frame statistics (R in {10,30}): writes Vs[NT][R][ld], A1[n][f] = sum_r 1/Vx and
+ * A2[n][f] = sum_r 1/Vx^2; dvae_nmf_mstep takes them as wstat = A1 (A2 = A1 + NT*ld) with n_parts = 0. */
+int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y, int y_dim,
+                         const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1, float* A2, int* status,
+                         void* stream);
+int dvae_nmf_w_from_frame_stats(const float* A1, const float* A2, const float* P, const float* H, const float* W,
+                                const int64_t* fr_off, int B, int F, int K, int ld, float* Wtmp, void* stream);
+
 /* third-generation schedule: two tile contexts per CTA, W3 streamed chunk-wise with cp.async.bulk (L = 16 only).
  * Same arguments and results as dvae_mh_chain_tc2. */
 int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
@@ -175,6 +183,7 @@ int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const void* PVpk, c
                       int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
                       int* status, void* stream);
 int dvae_debug_set_clock_buffer3(void* dev_buffer);
+int dvae_debug_set_clock_buffer_ws(void* dev_buffer);
 
 /* debug aid: register a device buffer of 64 int64; the tc2 sampler's CTA 0 stamps clock64() at its phase boundaries */
 int dvae_debug_set_clock_buffer(void* dev_buffer);
