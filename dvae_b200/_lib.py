@@ -76,6 +76,7 @@ PROTOTYPES = {
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "dvae_debug_set_clock_buffer3": (C.c_int, [c_ptr]),
     "dvae_debug_set_clock_buffer_ws": (C.c_int, [c_ptr]),
+    "dvae_debug_set_clock_buffer_ds": (C.c_int, [c_ptr]),
     "dvae_debug_set_clock_buffer": (C.c_int, [c_ptr]),
     "dvae_decode_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int,
                                  c_ptr, c_ptr]),

@@ -25,7 +25,7 @@
 namespace dvae {
 namespace tc {
 
-constexpr int DS_THREADS = 640;
+constexpr int DS_THREADS = 672;                       // 4 front warps + 16 back warps + 1 issue warp
 constexpr int DS_BACK = 512;
 
 struct DsParams {
@@ -41,7 +41,11 @@ struct DsParams {
     int64_t NT;
     int ld;
     int* status;
+    long long* dbg;
 };
+
+static long long* g_dbg_clocks_ds = nullptr;
+#define DBGD(slot, cond) do { if (p.dbg && blockIdx.x == 0 && k == 3 && (cond)) p.dbg[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ void ds_bar_front() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void ds_bar_tail() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
@@ -151,6 +155,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
         uint32_t ph12 = 0, phfree0 = 0, phfree1 = 0;
         int k = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+            DBGD(0, threadIdx.x == 0);
             const int buf = k & 1;
             unsigned char* A = Abuf + buf * 32768;
             const uint32_t a_addr = smem_u32(A);
@@ -176,9 +181,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                 if (buf == 0) { mbar_wait(a_free0, phfree0, dead, p.status); phfree0 ^= 1; }
                 else { mbar_wait(a_free1, phfree1, dead, p.status); phfree1 ^= 1; }
             }
+            DBGD(1, threadIdx.x == 0);
             write_a1_static<L>(y_dim, nkb1, A, row, z, y0, y1, y2, valid);
             fence_async_smem();
             ds_bar_front();
+            DBGD(2, threadIdx.x == 0);
             if (threadIdx.x == 0) {
                 tc_fence_after();
                 issue_gemm2(a_addr, 16384, w1_addr, 16384, nkb1, tmem, HID);
@@ -191,6 +198,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
             fence_async_smem();
             tc_fence_before();
             ds_bar_front();
+            DBGD(3, threadIdx.x == 0);
             if (two_hidden) {
                 if (threadIdx.x == 0) {
                     tc_fence_after();
@@ -204,56 +212,31 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                 fence_async_smem();
                 tc_fence_before();
             }
+            DBGD(4, threadIdx.x == 0);
             mbar_arrive2(buf ? a_full1 : a_full0);      // h2 of this tile is in A[buf]
         }
-    } else {
+    } else if (warp < 20) {
         // =========================================== back: layer 3, Vs, statistics ===========================================
         const int bw = warp - 4;
         const int q = bw & 3, s = bw >> 2;              // TMEM lane quadrant (bins 32q..), frame slot
-        const bool issuer = (bw == 0) && (lane == 0);
         const uint32_t lane_off = (uint32_t)(32 * q) << 16;
-        uint32_t ph3_0 = 0, ph3_1 = 0, phf_0 = 0, phf_1 = 0, phw_0 = 0, phw_1 = 0, phfull0 = 0, phfull1 = 0;
-        const uint32_t slot_addr = smem_u32(Wslot);
+        uint32_t ph3_0 = 0, ph3_1 = 0;
 
-        // chunk c of the CTA's stream: tile k = c / 5, j = c % 5; W3 slot and TMEM buffer = c & 1
-        auto load_chunk = [&](int j, int sl) {          // issuer only
-            const uint32_t bytes = (j < 4) ? 16384u : 2048u;
-            const uint32_t bar = sl ? w_full1 : w_full0;
-            ds_expect_tx(bar, 2 * bytes);
-            ds_bulk_g2s(slot_addr + sl * 32768, w3g + (size_t)j * 128 * 128, bytes, bar);
-            ds_bulk_g2s(slot_addr + sl * 32768 + 16384, w3g + NPAD * 128 + (size_t)j * 128 * 128, bytes, bar);
-        };
-        auto issue_chunk = [&](int kk, int j, int sl, bool first_use) {   // issuer only
-            const int buf = kk & 1;
-            const uint32_t a_addr = smem_u32(Abuf + buf * 32768);
-            if (sl == 0) { mbar_wait(w_full0, phw_0, dead, p.status); phw_0 ^= 1; }
-            else { mbar_wait(w_full1, phw_1, dead, p.status); phw_1 ^= 1; }
-            if (j == 0) {
-                if (buf == 0) { mbar_wait(a_full0, phfull0, dead, p.status); phfull0 ^= 1; }
-                else { mbar_wait(a_full1, phfull1, dead, p.status); phfull1 ^= 1; }
-            }
-            if (!first_use) {                           // the TMEM buffer was drained by the chunk two steps earlier
-                if (sl == 0) { mbar_wait(barf_0, phf_0, dead, p.status); phf_0 ^= 1; }
-                else { mbar_wait(barf_1, phf_1, dead, p.status); phf_1 ^= 1; }
-            }
-            tc_fence_after();
-            const uint32_t tb = tmem + 128 + 128 * sl;
-            if (j < 4) issue_gemm2(slot_addr + sl * 32768, 16384, a_addr, 16384, 2, tb, 128);      // D^T = W3 chunk x h2^T
-            else issue_gemm2(a_addr, 16384, slot_addr + sl * 32768, 16384, 2, tb, 16);             // bin 512: D = h2 x w^T
-            umma_commit(sl ? bar3_1 : bar3_0);
-            if (j == 4) umma_commit(buf ? a_free1 : a_free0);                                       // A[buf] may be rewritten
-        };
-
-        const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const int64_t n_chunks = my_tiles * 5;
-        if (issuer && n_chunks > 0) {
-            load_chunk(0, 0);
-            load_chunk(1, 1);
-            issue_chunk(0, 0, 0, true);
-            issue_chunk(0, 1, 1, true);
-        }
         int64_t c = 0;
         int k = 0;
+        // Vb and g of the NEXT chunk are fetched while the current one is processed (their DRAM latency otherwise sits in
+        // front of every chunk: 18 % of the stall samples in profiles/r01_tc_ncu_decode_stats.txt)
+        float vbn[FS], ggn[FS];
+        auto prefetch = [&](int64_t tl, int j) {
+#pragma unroll
+            for (int ff = 0; ff < FS; ++ff) {
+                const int64_t n = tl * FT + s * FS + ff;
+                const bool ok = (tl < n_tiles) && (n < p.NT);
+                vbn[ff] = ok ? __ldg(p.Vb + n * p.ld + 128 * j + 32 * q + lane) : 0.f;
+                ggn[ff] = ok ? __ldg(p.g + n) : 0.f;
+            }
+        };
+        prefetch(blockIdx.x, 0);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
             const int64_t t0 = tile * FT;
 #pragma unroll 1
@@ -262,11 +245,17 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                 if (sl == 0) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; }
                 else { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; }
                 tc_fence_after();
-                if (issuer && c + 2 < n_chunks) load_chunk((int)((c + 2) % 5), sl);   // the slot has been consumed
+                DBGD(10 + j, threadIdx.x == 128);
+                DBGD(30 + j, threadIdx.x == 608);
                 const uint32_t tb = tmem + 128 + 128 * sl;
                 if (j < 4) {
                     const int f = 128 * j + 32 * q + lane;
                     const float bias = b3[f];
+                    float vbc[FS], ggc[FS];
+#pragma unroll
+                    for (int ff = 0; ff < FS; ++ff) { vbc[ff] = vbn[ff]; ggc[ff] = ggn[ff]; }
+                    if (j < 3) prefetch(tile, j + 1);
+                    else prefetch(tile + gridDim.x, 0);
 #pragma unroll
                     for (int ff = 0; ff < FS; ++ff) {
                         const int fi = s * FS + ff;
@@ -274,8 +263,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                         if (n < p.NT) {
                             float v[RL];
                             ds_tmem_ld<RL>(tb + lane_off + fi * R, v);
-                            const float gg = __ldg(p.g + n);
-                            const float vb = __ldg(p.Vb + n * p.ld + f);
+                            const float gg = ggc[ff];
+                            const float vb = vbc[ff];
                             tmem_wait_ld();
                             float* dst = p.Vs + (n * R) * (int64_t)p.ld + f;
                             float a1 = 0.f, a2 = 0.f;
@@ -331,11 +320,58 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                 }
                 tc_fence_before();
                 mbar_arrive2(sl ? barf_1 : barf_0);
-                if (issuer && c + 2 < n_chunks) {
-                    const int64_t c2 = c + 2;
-                    issue_chunk(k + (int)((j + 2) / 5), (int)(c2 % 5), sl, false);
-                }
+                DBGD(20 + j, threadIdx.x == 128);
+                DBGD(40 + j, threadIdx.x == 608);
             }
+        }
+    } else if (lane == 0) {
+        // =========================================== issue warp: W3 stream + layer-3 MMAs ===========================================
+        uint32_t ph3_0 = 0, ph3_1 = 0, phf_0 = 0, phf_1 = 0, phw_0 = 0, phw_1 = 0, phfull0 = 0, phfull1 = 0;
+        const uint32_t slot_addr = smem_u32(Wslot);
+        // chunk c of the CTA's stream: tile k = c / 5, j = c % 5; W3 slot and TMEM buffer = c & 1
+        auto load_chunk = [&](int j, int sl) {          // issuer only
+            const uint32_t bytes = (j < 4) ? 16384u : 2048u;
+            const uint32_t bar = sl ? w_full1 : w_full0;
+            ds_expect_tx(bar, 2 * bytes);
+            ds_bulk_g2s(slot_addr + sl * 32768, w3g + (size_t)j * 128 * 128, bytes, bar);
+            ds_bulk_g2s(slot_addr + sl * 32768 + 16384, w3g + NPAD * 128 + (size_t)j * 128 * 128, bytes, bar);
+        };
+        auto issue_chunk = [&](int kk, int j, int sl, bool first_use) {   // issuer only
+            const int buf = kk & 1;
+            const uint32_t a_addr = smem_u32(Abuf + buf * 32768);
+            if (sl == 0) { mbar_wait(w_full0, phw_0, dead, p.status); phw_0 ^= 1; }
+            else { mbar_wait(w_full1, phw_1, dead, p.status); phw_1 ^= 1; }
+            if (j == 0) {
+                if (buf == 0) { mbar_wait(a_full0, phfull0, dead, p.status); phfull0 ^= 1; }
+                else { mbar_wait(a_full1, phfull1, dead, p.status); phfull1 ^= 1; }
+            }
+            if (!first_use) {                           // the TMEM buffer was drained by the chunk two steps earlier
+                if (sl == 0) { mbar_wait(barf_0, phf_0, dead, p.status); phf_0 ^= 1; }
+                else { mbar_wait(barf_1, phf_1, dead, p.status); phf_1 ^= 1; }
+            }
+            tc_fence_after();
+            const uint32_t tb = tmem + 128 + 128 * sl;
+            if (j < 4) issue_gemm2(slot_addr + sl * 32768, 16384, a_addr, 16384, 2, tb, 128);      // D^T = W3 chunk x h2^T
+            else issue_gemm2(a_addr, 16384, slot_addr + sl * 32768, 16384, 2, tb, 16);             // bin 512: D = h2 x w^T
+            umma_commit(sl ? bar3_1 : bar3_0);
+            if (j == 4) umma_commit(buf ? a_free1 : a_free0);                                       // A[buf] may be rewritten
+        };
+
+        const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t n_chunks = my_tiles * 5;
+        if (n_chunks > 0) {
+            load_chunk(0, 0);
+            load_chunk(1, 1);
+            issue_chunk(0, 0, 0, true);
+            issue_chunk(0, 1, 1, true);
+        }
+        for (int64_t c = 0; c + 2 < n_chunks; ++c) {
+            const int sl = (int)(c & 1);
+            if (sl == 0) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; }      // MMAs of chunk c done: W slot free
+            else { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; }
+            const int64_t c2 = c + 2;
+            load_chunk((int)(c2 % 5), sl);
+            issue_chunk((int)(c2 / 5), (int)(c2 % 5), sl, false);
         }
     }
 
@@ -399,7 +435,7 @@ extern "C" int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const
                  "dvae_decode_stats_tc: Zs and image must be 16-byte aligned");
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
-    p.Zs = Zs; p.y = y; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status;
+    p.Zs = Zs; p.y = y; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status; p.dbg = g_dbg_clocks_ds;
     const int shared_bytes = (p.d.off_w3 + 4 * ((p.d.n_hidden == 2 ? HID : 0) + NPAD) + 1023) & ~1023;
     const size_t smem = (size_t)shared_bytes + 65536 + 65536 + 1024;
     DVAE_REQUIRE(smem <= 227 * 1024, "dvae_decode_stats_tc: shared memory budget exceeded");
@@ -426,4 +462,9 @@ extern "C" int dvae_nmf_w_from_frame_stats(const float* A1, const float* A2, con
                  "dvae_nmf_w_from_frame_stats: bad arguments");
     w_from_frame_stats_kernel<<<dim3((F + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(A1, A2, P, H, W, fr_off, F, K, ld, Wtmp);
     return check_launch("w_from_frame_stats_kernel");
+}
+
+extern "C" int dvae_debug_set_clock_buffer_ds(void* dev_buffer) {
+    g_dbg_clocks_ds = reinterpret_cast<long long*>(dev_buffer);
+    return 0;
 }

@@ -184,6 +184,7 @@ int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const void* PVpk, c
                       int* status, void* stream);
 int dvae_debug_set_clock_buffer3(void* dev_buffer);
 int dvae_debug_set_clock_buffer_ws(void* dev_buffer);
+int dvae_debug_set_clock_buffer_ds(void* dev_buffer);
 
 /* debug aid: register a device buffer of 64 int64; the tc2 sampler's CTA 0 stamps clock64() at its phase boundaries */
 int dvae_debug_set_clock_buffer(void* dev_buffer);
