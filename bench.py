@@ -244,7 +244,8 @@ def run_b200(args):
     # end-to-end through the public host API: pinned host buffers in, host arrays out, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        enh.enhance(x_host, y_host, utt_ids=utt_ids)                # warm the pinned staging buffers
+        for _ in range(2):                                           # warm the pinned staging / result buffers (two result sets alternate)
+            s_list, n_list, cost_h = enh.enhance(x_host, y_host, utt_ids=utt_ids)
         barrier()
         t0 = time.perf_counter()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

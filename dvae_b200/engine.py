@@ -484,6 +484,9 @@ class Enhancer:
         self.engine = McemEngine(self.weights, cfg, self.dev)
         self.fs, self.n_fft, self.hop = fs, n_fft, hop
         self._pinned = {}
+        self._out_pool = []
+        self._pool = None
+        self._stage_threads = max(1, min(8, (os.cpu_count() or 1) // 2))
 
     def _pin(self, name, n, dtype):
         t = self._pinned.get(name)
@@ -491,6 +494,44 @@ class Enhancer:
             t = torch.empty(n, dtype=dtype).pin_memory()
             self._pinned[name] = t
         return t[:n]
+
+    def _pin_out(self, n):
+        """A pinned float32 result buffer ``(tensor, ndarray)`` that no earlier result still views.
+
+        Results are returned as views of pinned memory (no host copy).  A buffer is recycled only when every array
+        handed out from it has been dropped (the ndarray's reference count is back to the pool's own), otherwise a
+        new one is pinned, so results never change under the caller.
+        """
+        import sys
+        for t, a in self._out_pool:
+            if t.numel() >= n and sys.getrefcount(a) <= 3:         # tuple + loop variable + getrefcount argument
+                return t, a
+        t = torch.empty(n, dtype=torch.float32).pin_memory()
+        a = t.numpy()
+        self._out_pool.append((t, a))
+        if len(self._out_pool) > 8:                                # drop the oldest unreferenced buffers
+            self._out_pool = [(tt, aa) for tt, aa in self._out_pool if sys.getrefcount(aa) > 3 or tt is t][-8:]
+        return t, a
+
+    def _stage(self, host_np, x_list, off, lens):
+        """Copy the utterances into the pinned staging buffer (a few threads: numpy releases the GIL while copying)."""
+        B = len(x_list)
+
+        def work(lo, hi):
+            for u in range(lo, hi):
+                host_np[off[u]:off[u] + lens[u]] = x_list[u]
+
+        nthr = min(self._stage_threads, max(1, B // 16))
+        if nthr <= 1:
+            work(0, B)
+            return
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(self._stage_threads)
+        step = (B + nthr - 1) // nthr
+        futs = [self._pool.submit(work, lo, min(lo + step, B)) for lo in range(0, B, step)]
+        for f in futs:
+            f.result()
 
     def run_device(self, x_dev, x_off, x_len, batch, y, total, max_len, draws=None):
         """The whole path on device-resident inputs: STFT -> MCEM -> Wiener -> ISTFT.  Nothing touches the host.
@@ -529,9 +570,7 @@ class Enhancer:
         np.cumsum((lens + 1) // 2 * 2, out=off[1:])            # even offsets
         total = int(off[-1])
         host = self._pin("x", total, torch.float32)
-        hx = host.numpy()
-        for u, x in enumerate(x_list):
-            hx[off[u]:off[u] + lens[u]] = x
+        self._stage(host.numpy(), x_list, off, lens)
         x_dev = host.to(dev, non_blocking=True)
         x_off = torch.from_numpy(off[:-1].copy()).to(dev)
         x_len = torch.from_numpy(lens).to(dev)
@@ -549,16 +588,17 @@ class Enhancer:
         self.d2h_bytes = 2 * total * 4 + cost.numel() * 8
         if return_device:
             return s_dev, n_dev, cost
-        hs = self._pin("s", total, torch.float32)
-        hn = self._pin("n", total, torch.float32)
-        hs.copy_(s_dev, non_blocking=True)
-        hn.copy_(n_dev, non_blocking=True)
+        hs, s_np = self._pin_out(total)
+        s_hold = s_np[:0]                                      # marks the buffer as taken while the second one is chosen
+        hn, n_np = self._pin_out(total)
+        del s_hold
+        hs[:total].copy_(s_dev, non_blocking=True)
+        hn[:total].copy_(n_dev, non_blocking=True)
         cost_h = cost.t().contiguous().cpu()                   # synchronises the stream
         torch.cuda.current_stream().synchronize()
         if self.cfg.sampler == "tc":
             from . import tc
             tc.check_status(eng)
-        s_np, n_np = hs.numpy(), hn.numpy()
-        s_list = [s_np[off[u]:off[u] + lens[u]].copy() for u in range(B)]
-        n_list = [n_np[off[u]:off[u] + lens[u]].copy() for u in range(B)]
+        s_list = [s_np[off[u]:off[u] + lens[u]] for u in range(B)]      # views of pinned memory, see _pin_out
+        n_list = [n_np[off[u]:off[u] + lens[u]] for u in range(B)]
         return s_list, n_list, cost_h.numpy()
