@@ -396,26 +396,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// CTA-wide sums of NV per-thread values: warp shuffles first, then 8 per-warp partials through shared memory
-// (red: [NV][8] floats).  After the call tot[v] holds the total for every thread.  Two barriers.
-template <int NV>
-__device__ __forceinline__ void hg3_reduce(float (&vals)[NV], float* red, float* tot) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        const float s = warp_sum(vals[v]);
-        if (lane == 0) red[v * 8 + wid] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < NV) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[threadIdx.x * 8 + w];
-        tot[threadIdx.x] = s;
-    }
-    __syncthreads();
-}
-
 template <int R>
 __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __restrict__ P, const float* __restrict__ Vs,
                                                                  const float* __restrict__ Wtmp, const float* __restrict__ norm,
@@ -425,8 +405,9 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
     constexpr int KT = HG2_KT;
     extern __shared__ __align__(16) float sm[];
     float* S = sm;                                  // [R][ld] samples of the current frame
-    float* red = S + R * ld;                        // [HG3_NV][8] per-warp partials
-    __shared__ float tot[HG3_NV];
+    float* red = S + R * ld;                        // [8][HG3_NV] per-warp partials of the H sums
+    __shared__ float2 red2[8];
+    __shared__ double redd[8];
     __shared__ float hs[KT];
     const int u = blockIdx.y;
     const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
@@ -436,7 +417,7 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
         return;
     }
     const int64_t ne = (nb + HG3_FPB < n1) ? nb + HG3_FPB : n1;
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int fA = t, fB = t + 256;                 // the two bins of this thread (F >= 512 is checked by the host)
     const bool xl = (t < R) && (F > 512);           // this thread also holds sample t of bin 512
     float wA[KT], wB[KT], wX[KT];
@@ -447,8 +428,7 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
         wB[k] = (k < K) ? wk[fB] : 0.f;
         wX[k] = (k < K && F > 512) ? wk[512] : 0.f;
     }
-    const double inv_count = 1.0 / ((double)R * (double)F * (double)(n1 - n0));
-    double cost_acc = 0.0;
+    double cost_d = 0.0;                            // per-thread partial, reduced once per CTA
     const int chunks_per_row = ld / 4;
 
     for (int64_t n = nb; n < ne; ++n) {
@@ -489,14 +469,49 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
         float a1X = 0.f, a2X = 0.f;                 // bin 512: this thread's single sample
         if (xl) { const float ix = rcp_fast(fmaf(gg, S[t * ld + 512], vbX)); a1X = ix; a2X = ix * ix; }
         const float qA = pA * a2A, qB = pB * a2B, qX = pX * a2X;
-        float vals[HG3_NV];
+        {
+            // 20 warp sums with 30 shuffles: fold over lane bit 4 (each lane keeps half of the values), then bit 3, then a
+            // butterfly over the remaining 8 lanes; lanes 0, 8, 16, 24 end up with five totals each
+            const bool b4 = lane & 16, b3 = lane & 8;
+            float a[10];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) {
-            vals[2 * k] = fmaf(wA[k], qA, fmaf(wB[k], qB, wX[k] * qX));
-            vals[2 * k + 1] = fmaf(wA[k], a1A, fmaf(wB[k], a1B, wX[k] * a1X));
+            for (int hf = 0; hf < 2; ++hf) {
+                float v[10];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int k = 5 * hf + j;
+                    v[2 * j] = fmaf(wA[k], qA, fmaf(wB[k], qB, wX[k] * qX));
+                    v[2 * j + 1] = fmaf(wA[k], a1A, fmaf(wB[k], a1B, wX[k] * a1X));
+                }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float send = b4 ? v[j] : v[5 + j], keep = b4 ? v[5 + j] : v[j];
+                    a[5 * hf + j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            }
+            float o5[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float send = b3 ? a[j] : a[5 + j], keep = b3 ? a[5 + j] : a[j];
+                o5[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) o5[j] += __shfl_xor_sync(0xffffffffu, o5[j], o);
+            if ((lane & 7) == 0) {                  // value index = 10 * bit3 + 5 * bit4 + j
+                float* dst = red + wid * HG3_NV + 10 * ((lane >> 3) & 1) + 5 * (lane >> 4);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) dst[j] = o5[j];
+            }
         }
-        hg3_reduce<HG3_NV>(vals, red, tot);
-        if (t < K) hs[t] = H[n * K + t] * sqrtf(tot[2 * t] / tot[2 * t + 1]);
+        __syncthreads();
+        if (t < K) {
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { num += red[w * HG3_NV + 2 * t]; den += red[w * HG3_NV + 2 * t + 1]; }
+            hs[t] = H[n * K + t] * sqrtf(num / den);
+        }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < KT; ++k) h[k] = (k < K) ? hs[k] : 0.f;
@@ -527,9 +542,15 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
         }
         float s1X = 0.f, s2X = 0.f;
         if (xl) { const float sx = S[t * ld + 512]; const float ix = rcp_fast(fmaf(gg, sx, vbX)); s1X = sx * ix; s2X = s1X * ix; }
-        float v2[2] = {fmaf(pA, s2A, fmaf(pB, s2B, pX * s2X)), s1A + s1B + s1X};
-        hg3_reduce<2>(v2, red, tot);
-        const float gnew = gg * sqrtf(tot[0] / tot[1]);
+        {
+            const float v2 = warp_sum(fmaf(pA, s2A, fmaf(pB, s2B, pX * s2X))), v1 = warp_sum(s1A + s1B + s1X);
+            if (lane == 0) red2[wid] = make_float2(v2, v1);
+        }
+        __syncthreads();
+        float t2 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const float2 rr = red2[w]; t2 += rr.x; t1 += rr.y; }
+        const float gnew = gg * sqrtf(t2 / t1);
 
         // ---- cost with Vx = g_new Vs + Vb2: a pair of samples shares one reciprocal and one log2
         float clA = 0.f, cpA = 0.f, clB = 0.f, cpB = 0.f;
@@ -548,14 +569,246 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
         }
         float cX = 0.f;
         if (xl) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
-        float v1[1] = {fmaf(0.6931471805599453f, clA + clB, fmaf(pA, cpA, pB * cpB)) + cX};
-        hg3_reduce<1>(v1, red, tot);
-        cost_acc += (double)tot[0];
+        cost_d += (double)(fmaf(0.6931471805599453f, clA + clB, fmaf(pA, cpA, pB * cpB)) + cX);
 
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
         if (t == 0) g[n] = gnew;
     }
-    if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = cost_acc * inv_count;
+    cost_d = warp_sum_d(cost_d);
+    if (lane == 0) redd[wid] = cost_d;
+    __syncthreads();
+    if (t == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += redd[w];
+        cost_part[(int64_t)u * gridDim.x + blockIdx.x] = sum / ((double)R * (double)F * (double)(n1 - n0));
+    }
+}
+
+// ----------------------------------------------------------------------------- H, g, cost: packed-math frame tile
+// Fifth version (dispatched for F = 513).  ncu on hg3 (profiles/r01_tc_ncu_hg3.txt) showed the kernel issue-bound: 68 % of
+// the issue slots busy, 16 k warp instructions per frame of which 9 % staged the frame and 45 % were scalar FP32 / LDS
+// of the three passes.  Same schedule as hg3 (one frame in shared memory, three CTAs per SM), three changes:
+//   * a thread owns the ADJACENT bins 2t, 2t+1: one 8-byte shared load fetches both, and the pair is processed with the
+//     sm_100 packed instructions fma/mul/add.f32x2 (two FP32 lanes per issue slot);
+//   * the frame is staged by the bulk-copy engine: lanes 0..R-1 of warp 0 each issue one cp.async.bulk row copy that
+//     completes on an mbarrier, instead of sixteen 16-byte cp.async per thread;
+//   * five barriers per frame instead of nine, 30 shuffles instead of 100 for the 20 H sums, cost reduced once per CTA.
+constexpr int HG5_LD = 520;                     // row pitch the engine uses for F = 513 (compile-time: shared addresses become immediates)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 rcp2(f32x2 a) { float lo, hi; upk2(a, lo, hi); return pk2(rcp_fast(lo), rcp_fast(hi)); }
+__device__ __forceinline__ f32x2 lg22(f32x2 a) { float lo, hi; upk2(a, lo, hi); return pk2(lg2_fast(lo), lg2_fast(hi)); }
+__device__ __forceinline__ f32x2 lds2(const float* p) { return *reinterpret_cast<const f32x2*>(p); }
+
+template <int R, int ld>
+__global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __restrict__ P, const float* __restrict__ Vs,
+                                                                 const float* __restrict__ Wtmp, const float* __restrict__ norm,
+                                                                 float* __restrict__ H, float* __restrict__ g,
+                                                                 float* __restrict__ Vb, double* __restrict__ cost_part,
+                                                                 const int64_t* __restrict__ fr_off, int K) {
+    constexpr int KT = HG2_KT;
+    static_assert(R % 2 == 0 && R <= 32 && ld % 4 == 0 && ld >= 513, "hg5: even R up to 32, row pitch a multiple of 16 bytes");
+    extern __shared__ __align__(128) float sm[];
+    float* S = sm;                                  // [R][ld] samples of the current frame
+    float* red = S + R * ld;                        // [8][HG3_NV] per-warp partials of the H sums
+    __shared__ float2 red2[8];
+    __shared__ double redd[8];
+    __shared__ float hs[KT];
+    __shared__ __align__(8) unsigned long long bar;
+    const int u = blockIdx.y;
+    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
+    const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
+    if (nb >= n1) {
+        if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
+        return;
+    }
+    const int64_t ne = (nb + HG3_FPB < n1) ? nb + HG3_FPB : n1;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int f2 = 2 * t;                           // bins 2t, 2t+1; sample t of bin 512 lives on threads t < R
+    const bool xl = t < R;
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_a), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    f32x2 w2[KT];
+    float wX[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const float* wk = Wtmp + ((int64_t)u * K + k) * ld;
+        w2[k] = (k < K) ? *reinterpret_cast<const f32x2*>(wk + f2) : 0ull;
+        wX[k] = (k < K) ? wk[512] : 0.f;
+    }
+    double cost_d = 0.0;                            // per-thread partial, reduced once per CTA
+    unsigned phase = 0;
+    constexpr unsigned row_bytes = (unsigned)ld * 4u;
+
+    for (int64_t n = nb; n < ne; ++n) {
+        // ---- stage the frame: R bulk row copies completing on the mbarrier
+        __syncthreads();                            // previous frame fully consumed (and the mbarrier initialised)
+        if (wid == 0) {
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(row_bytes * R) : "memory");
+            __syncwarp();
+            if (lane < R) {
+                const float* src = Vs + (n * R + lane) * (int64_t)ld;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(S + lane * ld);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(dst), "l"(src), "r"(row_bytes), "r"(bar_a) : "memory");
+            }
+        }
+        const float gg = g[n];
+        const f32x2 gg2 = pk2(gg, gg);
+        const f32x2 p2 = *reinterpret_cast<const f32x2*>(P + n * ld + f2);
+        const float pX = P[n * ld + 512];
+        float h[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
+        {
+            unsigned done = 0, spins = 0;
+            while (!done) {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+                if (!done && ++spins > (1u << 22)) __trap();        // a lost copy must not hang the device
+            }
+            phase ^= 1;
+        }
+
+        // ---- H update (Vb1 = W_new H_old)
+        f32x2 vb2 = 0ull;
+        float vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        f32x2 a1 = 0ull, a2 = 0ull;
+#pragma unroll 5
+        for (int r = 0; r < R; r += 2) {
+            const f32x2 x0 = fma2(gg2, lds2(S + r * ld + f2), vb2), x1 = fma2(gg2, lds2(S + (r + 1) * ld + f2), vb2);
+            const f32x2 rr = rcp2(mul2(x0, x1));
+            const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+            a1 = add2(a1, add2(i0, i1));
+            a2 = fma2(i0, i0, fma2(i1, i1, a2));
+        }
+        float a1X = 0.f, a2X = 0.f;                 // bin 512: this thread's single sample
+        if (xl) { const float ix = rcp_fast(fmaf(gg, S[t * ld + 512], vbX)); a1X = ix; a2X = ix * ix; }
+        {
+            const f32x2 q2 = mul2(p2, a2);
+            const float qX = pX * a2X;
+            // 20 warp sums with 30 shuffles: fold over lane bit 4 (each lane keeps half of the values), then bit 3, then a
+            // butterfly over the remaining 8 lanes; lanes 0, 8, 16, 24 end up with five totals each
+            const bool b4 = lane & 16, b3 = lane & 8;
+            float a[10];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float v[10];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int k = 5 * hf + j;
+                    float nlo, nhi, dlo, dhi;
+                    upk2(mul2(w2[k], q2), nlo, nhi);
+                    upk2(mul2(w2[k], a1), dlo, dhi);
+                    v[2 * j] = fmaf(wX[k], qX, nlo + nhi);
+                    v[2 * j + 1] = fmaf(wX[k], a1X, dlo + dhi);
+                }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float send = b4 ? v[j] : v[5 + j], keep = b4 ? v[5 + j] : v[j];
+                    a[5 * hf + j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            }
+            float o5[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float send = b3 ? a[j] : a[5 + j], keep = b3 ? a[5 + j] : a[j];
+                o5[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) o5[j] += __shfl_xor_sync(0xffffffffu, o5[j], o);
+            if ((lane & 7) == 0) {                  // value index = 10 * bit3 + 5 * bit4 + j
+                float* dst = red + wid * HG3_NV + 10 * ((lane >> 3) & 1) + 5 * (lane >> 4);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) dst[j] = o5[j];
+            }
+        }
+        __syncthreads();
+        if (t < K) {
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { num += red[w * HG3_NV + 2 * t]; den += red[w * HG3_NV + 2 * t + 1]; }
+            hs[t] = H[n * K + t] * sqrtf(num / den);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? hs[k] : 0.f;
+
+        // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
+        vb2 = 0ull; vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        *reinterpret_cast<f32x2*>(Vb + n * ld + f2) = vb2;
+        if (t == 0) Vb[n * ld + 512] = vbX;
+        f32x2 s1 = 0ull, s2 = 0ull;
+#pragma unroll 5
+        for (int r = 0; r < R; r += 2) {
+            const f32x2 v0 = lds2(S + r * ld + f2), v1 = lds2(S + (r + 1) * ld + f2);
+            const f32x2 x0 = fma2(gg2, v0, vb2), x1 = fma2(gg2, v1, vb2);
+            const f32x2 rr = rcp2(mul2(x0, x1));
+            const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+            const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
+            s1 = add2(s1, add2(t0, t1));
+            s2 = fma2(t0, i0, fma2(t1, i1, s2));
+        }
+        float s1X = 0.f, s2X = 0.f;
+        if (xl) { const float sx = S[t * ld + 512]; const float ix = rcp_fast(fmaf(gg, sx, vbX)); s1X = sx * ix; s2X = s1X * ix; }
+        {
+            float ps_lo, ps_hi, s1lo, s1hi;
+            upk2(mul2(p2, s2), ps_lo, ps_hi);
+            upk2(s1, s1lo, s1hi);
+            const float v2 = warp_sum(fmaf(pX, s2X, ps_lo + ps_hi)), v1 = warp_sum(s1lo + s1hi + s1X);
+            if (lane == 0) red2[wid] = make_float2(v2, v1);
+        }
+        __syncthreads();
+        float t2 = 0.f, t1s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const float2 rr = red2[w]; t2 += rr.x; t1s += rr.y; }
+        const float gnew = gg * sqrtf(t2 / t1s);
+        const f32x2 gn2 = pk2(gnew, gnew);
+
+        // ---- cost with Vx = g_new Vs + Vb2: a pair of samples shares one reciprocal and one log2
+        f32x2 cl = 0ull, cp = 0ull;
+#pragma unroll 5
+        for (int r = 0; r < R; r += 2) {
+            const f32x2 x0 = fma2(gn2, lds2(S + r * ld + f2), vb2), x1 = fma2(gn2, lds2(S + (r + 1) * ld + f2), vb2);
+            const f32x2 pr = mul2(x0, x1);
+            cl = add2(cl, lg22(pr));
+            cp = fma2(add2(x0, x1), rcp2(pr), cp);
+        }
+        float cX = 0.f;
+        if (xl) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
+        {
+            float cl_lo, cl_hi, pc_lo, pc_hi;
+            upk2(cl, cl_lo, cl_hi);
+            upk2(mul2(p2, cp), pc_lo, pc_hi);
+            cost_d += (double)(fmaf(0.6931471805599453f, cl_lo + cl_hi, pc_lo + pc_hi) + cX);
+        }
+
+        if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
+        if (t == 0) g[n] = gnew;
+    }
+    cost_d = warp_sum_d(cost_d);
+    if (lane == 0) redd[wid] = cost_d;
+    __syncthreads();
+    if (t == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += redd[w];
+        cost_part[(int64_t)u * gridDim.x + blockIdx.x] = sum / ((double)R * 513.0 * (double)(n1 - n0));
+    }
 }
 
 // cost[u] = sum of the per-CTA partials in block order (deterministic, unlike an atomic accumulation)
@@ -683,14 +936,23 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
     if (F >= 512 && F <= 513 && (ld & 3) == 0 && K <= HG2_KT && (R == 10 || R == 30)) {
         nblk_used = (max_frames + HG3_FPB - 1) / HG3_FPB;
         const size_t smem3 = sizeof(float) * ((size_t)R * ld + (size_t)HG3_NV * 8);
-        if (R == 10) {
+        if (F == 513 && ld == HG5_LD && (reinterpret_cast<uintptr_t>(Vs) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wtmp) & 7) == 0 &&
+            (reinterpret_cast<uintptr_t>(P) & 7) == 0 && (reinterpret_cast<uintptr_t>(Vb) & 7) == 0) {
+            if (R == 10) {
+                cudaFuncSetAttribute(nmf_hg5_kernel<10, HG5_LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+                nmf_hg5_kernel<10, HG5_LD><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, K);
+            } else {
+                cudaFuncSetAttribute(nmf_hg5_kernel<30, HG5_LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+                nmf_hg5_kernel<30, HG5_LD><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, K);
+            }
+        } else if (R == 10) {
             cudaFuncSetAttribute(nmf_hg3_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
             nmf_hg3_kernel<10><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
         } else {
             cudaFuncSetAttribute(nmf_hg3_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
             nmf_hg3_kernel<30><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
         }
-        rc = check_launch("nmf_hg3_kernel");
+        rc = check_launch("nmf_hg3/hg5_kernel");
     } else if (F <= HG2_THREADS && K <= HG2_KT && (R == 10 || R == 30)) {
         nblk_used = (max_frames + HG2_FPB - 1) / HG2_FPB;
         const size_t smem2 = sizeof(float) * (size_t)2 * HG2_KT * HG2_THREADS;
