@@ -9,6 +9,17 @@
 
 namespace dvae {
 
+// ----------------------------------------------------------------------------- packed FP32 pairs (sm_100: FFMA2 / FMUL2 / FADD2)
+// Two FP32 lanes per issue slot; a pair lives in an aligned 64-bit register pair, so packing adjacent registers is free.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t x) { return pk2(__uint_as_float(x << 16), __uint_as_float(x & 0xffff0000u)); }
+
+
 // ----------------------------------------------------------------------------- error plumbing
 void set_error(const char* fmt, ...);
 int  check_launch(const char* what);          // returns 0 or the cudaError_t of the launch

@@ -85,7 +85,8 @@ __device__ __forceinline__ void ds_hidden_row(uint32_t tmem, unsigned char* A, i
     }
 }
 
-template <int R, int L>
+// LDC: compile-time row pitch of Vs / Vb / A1 / A2 (520 for F = 513: store offsets become immediates), 0 = take p.ld
+template <int R, int L, int LDC>
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p) {
     constexpr int RL = (R <= 16) ? 16 : 32;
     constexpr int FT = 128 / R;                        // frames per tile
@@ -98,6 +99,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
     __shared__ float tailS[256];
 
     const Dims& d = p.d;
+    const int ldv = (LDC > 0) ? LDC : p.ld;
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool front = warp < 4;
@@ -232,7 +234,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
             for (int ff = 0; ff < FS; ++ff) {
                 const int64_t n = tl * FT + s * FS + ff;
                 const bool ok = (tl < n_tiles) && (n < p.NT);
-                vbn[ff] = ok ? __ldg(p.Vb + n * p.ld + 128 * j + 32 * q + lane) : 0.f;
+                vbn[ff] = ok ? __ldg(p.Vb + n * ldv + 128 * j + 32 * q + lane) : 0.f;
                 ggn[ff] = ok ? __ldg(p.g + n) : 0.f;
             }
         };
@@ -266,13 +268,40 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                             const float gg = ggc[ff];
                             const float vb = vbc[ff];
                             tmem_wait_ld();
-                            float* dst = p.Vs + (n * R) * (int64_t)p.ld + f;
-                            float a1 = 0.f, a2 = 0.f;
+                            float* dst = p.Vs + (n * R) * (int64_t)ldv + f;
+                            // packed FP32 pairs; four samples share two reciprocals: X = (Vx_r, Vx_r+1), Y = (Vx_r+2, Vx_r+3),
+                            // 1 / (X Y) gives 1 / X = Y / (X Y) and 1 / Y = X / (X Y) lane by lane
+                            const f32x2 g2 = pk2(gg, gg), vb2 = pk2(vb, vb), bias2 = pk2(bias, bias);
+                            f32x2 a1p = 0ull, a2p = 0ull;
+                            constexpr int R4 = R & ~3;
 #pragma unroll
-                            for (int r = 0; r + 1 < R; r += 2) {
+                            for (int r = 0; r < R4; r += 4) {
+                                float e0, e1, e2, e3;
+                                upk2(add2(pk2(v[r], v[r + 1]), bias2), e0, e1);
+                                upk2(add2(pk2(v[r + 2], v[r + 3]), bias2), e2, e3);
+                                const float s0 = ex2_approx(e0), s1 = ex2_approx(e1), s2 = ex2_approx(e2), s3 = ex2_approx(e3);
+                                dst[(int64_t)r * ldv] = s0;
+                                dst[(int64_t)(r + 1) * ldv] = s1;
+                                dst[(int64_t)(r + 2) * ldv] = s2;
+                                dst[(int64_t)(r + 3) * ldv] = s3;
+                                const f32x2 X = fma2(g2, pk2(s0, s1), vb2), Y = fma2(g2, pk2(s2, s3), vb2);
+                                float m0, m1;
+                                upk2(mul2(X, Y), m0, m1);
+                                const f32x2 rr = pk2(rcp_approx(m0), rcp_approx(m1));
+                                const f32x2 i0 = mul2(Y, rr), i1 = mul2(X, rr);
+                                a1p = add2(a1p, add2(i0, i1));
+                                a2p = fma2(i0, i0, fma2(i1, i1, a2p));
+                            }
+                            float a1, a2, a1h, a2h;
+                            upk2(a1p, a1, a1h);
+                            upk2(a2p, a2, a2h);
+                            a1 += a1h;
+                            a2 += a2h;
+#pragma unroll
+                            for (int r = R4; r + 1 < R; r += 2) {
                                 const float s0 = ex2_approx(v[r] + bias), s1 = ex2_approx(v[r + 1] + bias);
-                                dst[(int64_t)r * p.ld] = s0;
-                                dst[(int64_t)(r + 1) * p.ld] = s1;
+                                dst[(int64_t)r * ldv] = s0;
+                                dst[(int64_t)(r + 1) * ldv] = s1;
                                 const float x0 = fmaf(gg, s0, vb), x1 = fmaf(gg, s1, vb);
                                 const float rr = rcp_approx(x0 * x1);
                                 const float i0 = x1 * rr, i1 = x0 * rr;
@@ -281,13 +310,13 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                             }
                             if (R & 1) {
                                 const float s0 = ex2_approx(v[R - 1] + bias);
-                                dst[(int64_t)(R - 1) * p.ld] = s0;
+                                dst[(int64_t)(R - 1) * ldv] = s0;
                                 const float i0 = rcp_approx(fmaf(gg, s0, vb));
                                 a1 += i0;
                                 a2 = fmaf(i0, i0, a2);
                             }
-                            p.A1[n * p.ld + f] = a1;
-                            p.A2[n * p.ld + f] = a2;
+                            p.A1[n * ldv + f] = a1;
+                            p.A2[n * ldv + f] = a2;
                         }
                     }
                 } else if (s == 0) {
@@ -301,8 +330,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                     float inv = 0.f;
                     if (fi < FT && n < p.NT && d.F > 512) {
                         const float vs = ex2_approx(v[0] + b3[512]);
-                        p.Vs[(n * R + r) * (int64_t)p.ld + 512] = vs;
-                        inv = rcp_approx(fmaf(__ldg(p.g + n), vs, __ldg(p.Vb + n * p.ld + 512)));
+                        p.Vs[(n * R + r) * (int64_t)ldv + 512] = vs;
+                        inv = rcp_approx(fmaf(__ldg(p.g + n), vs, __ldg(p.Vb + n * ldv + 512)));
                     }
                     tailS[row] = inv;
                     tailS[128 + row] = inv * inv;
@@ -313,7 +342,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                         if (nn < p.NT && d.F > 512) {
                             float sum = 0.f;
                             for (int rr = 0; rr < R; ++rr) sum += tailS[which * 128 + fj * R + rr];
-                            (which ? p.A2 : p.A1)[nn * p.ld + 512] = sum;
+                            (which ? p.A2 : p.A1)[nn * ldv + 512] = sum;
                         }
                     }
                     ds_bar_tail();
@@ -384,33 +413,58 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
 }
 
 // W <- W * sqrt(num / den), num[f,k] = sum_n P A2 H, den[f,k] = sum_n A1 H   (mcem.py:108-111)
-__global__ void __launch_bounds__(128) w_from_frame_stats_kernel(const float* __restrict__ A1, const float* __restrict__ A2,
+// One thread per bin; the utterance's H rows are staged in shared memory (12 floats per frame, read back as three
+// 16-byte broadcasts) and (num_k, den_k) is one packed FP32 pair updated by a single FFMA2 per rank.
+constexpr int WFS_MAXFR = 256;                     // frames staged per pass (12 KB)
+__global__ void __launch_bounds__(128, 8) w_from_frame_stats_kernel(const float* __restrict__ A1, const float* __restrict__ A2,
                                                                  const float* __restrict__ P, const float* __restrict__ H,
                                                                  const float* __restrict__ W, const int64_t* __restrict__ fr_off,
                                                                  int F, int K, int ld, float* __restrict__ Wtmp) {
     constexpr int KT = 10;
+    __shared__ __align__(16) float Hs[WFS_MAXFR * 12];
     const int u = blockIdx.y;
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    float num[KT], den[KT];
+    const bool live = f < F;
+    f32x2 nd[KT];
 #pragma unroll
-    for (int k = 0; k < KT; ++k) num[k] = den[k] = 0.f;
+    for (int k = 0; k < KT; ++k) nd[k] = 0ull;
     const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
-    for (int64_t n = n0; n < n1; ++n) {
-        const float a1 = A1[n * ld + f];
-        const float pa2 = P[n * ld + f] * A2[n * ld + f];
-#pragma unroll
-        for (int k = 0; k < KT; ++k) {
-            const float h = (k < K) ? __ldg(H + n * K + k) : 0.f;
-            num[k] = fmaf(pa2, h, num[k]);
-            den[k] = fmaf(a1, h, den[k]);
+    for (int64_t base = n0; base < n1; base += WFS_MAXFR) {
+        const int cnt = (int)((n1 - base < WFS_MAXFR) ? n1 - base : WFS_MAXFR);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt * 12; i += blockDim.x) {
+            const int fr = i / 12, k = i - fr * 12;
+            Hs[i] = (k < K) ? __ldg(H + (base + fr) * K + k) : 0.f;
+        }
+        __syncthreads();
+        if (live) {
+            const float* a1p = A1 + base * ld + f;
+            const float* a2p = A2 + base * ld + f;
+            const float* pp = P + base * ld + f;
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const float a1 = __ldg(a1p + (int64_t)i * ld);
+                const float pa2 = __ldg(pp + (int64_t)i * ld) * __ldg(a2p + (int64_t)i * ld);
+                const f32x2 x = pk2(pa2, a1);
+                const float4 h0 = *reinterpret_cast<const float4*>(Hs + 12 * i);
+                const float4 h1 = *reinterpret_cast<const float4*>(Hs + 12 * i + 4);
+                const float4 h2 = *reinterpret_cast<const float4*>(Hs + 12 * i + 8);
+                nd[0] = fma2(x, pk2(h0.x, h0.x), nd[0]); nd[1] = fma2(x, pk2(h0.y, h0.y), nd[1]);
+                nd[2] = fma2(x, pk2(h0.z, h0.z), nd[2]); nd[3] = fma2(x, pk2(h0.w, h0.w), nd[3]);
+                nd[4] = fma2(x, pk2(h1.x, h1.x), nd[4]); nd[5] = fma2(x, pk2(h1.y, h1.y), nd[5]);
+                nd[6] = fma2(x, pk2(h1.z, h1.z), nd[6]); nd[7] = fma2(x, pk2(h1.w, h1.w), nd[7]);
+                nd[8] = fma2(x, pk2(h2.x, h2.x), nd[8]); nd[9] = fma2(x, pk2(h2.y, h2.y), nd[9]);
+            }
         }
     }
+    if (!live) return;
 #pragma unroll
     for (int k = 0; k < KT; ++k)
         if (k < K) {
+            float num, den;
+            upk2(nd[k], num, den);
             const int64_t i = ((int64_t)u * K + k) * ld + f;
-            Wtmp[i] = W[i] * sqrtf(num[k] / den[k]);
+            Wtmp[i] = W[i] * sqrtf(num / den);
         }
 }
 
@@ -445,8 +499,13 @@ extern "C" int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const
     cudaStream_t st = (cudaStream_t)stream;
 #define DS_LAUNCH(RR, LL)                                                                                         \
     do {                                                                                                          \
-        cudaFuncSetAttribute(decode_stats_kernel<RR, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        decode_stats_kernel<RR, LL><<<grid, DS_THREADS, smem, st>>>(p);                                           \
+        if (ld == 520) {                                                                                          \
+            cudaFuncSetAttribute(decode_stats_kernel<RR, LL, 520>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            decode_stats_kernel<RR, LL, 520><<<grid, DS_THREADS, smem, st>>>(p);                                  \
+        } else {                                                                                                  \
+            cudaFuncSetAttribute(decode_stats_kernel<RR, LL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            decode_stats_kernel<RR, LL, 0><<<grid, DS_THREADS, smem, st>>>(p);                                    \
+        }                                                                                                         \
     } while (0)
     if (R == 10 && L == 16) DS_LAUNCH(10, 16);
     else if (R == 10) DS_LAUNCH(10, 32);

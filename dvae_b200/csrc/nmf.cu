@@ -595,12 +595,6 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __
 //     completes on an mbarrier, instead of sixteen 16-byte cp.async per thread;
 //   * five barriers per frame instead of nine, 30 shuffles instead of 100 for the 20 H sums, cost reduced once per CTA.
 constexpr int HG5_LD = 520;                     // row pitch the engine uses for F = 513 (compile-time: shared addresses become immediates)
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 rcp2(f32x2 a) { float lo, hi; upk2(a, lo, hi); return pk2(rcp_fast(lo), rcp_fast(hi)); }
 __device__ __forceinline__ f32x2 lg22(f32x2 a) { float lo, hi; upk2(a, lo, hi); return pk2(lg2_fast(lo), lg2_fast(hi)); }
 __device__ __forceinline__ f32x2 lds2(const float* p) { return *reinterpret_cast<const f32x2*>(p); }

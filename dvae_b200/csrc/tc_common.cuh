@@ -299,17 +299,25 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 constexpr float kPairScale = 32768.0f;
 constexpr float kQuadScale = 32768.0f;
 __device__ __forceinline__ void loglik16_pv(const float* v, const uint4* pv, const float* b3f, float g_row, float& acc, float& accl) {
+    // Packed FP32 pairs: A = (Vx0, Vx1), B = (Vx2, Vx3).  M = k A * B = (k Vx0 Vx2, k Vx1 Vx3),
+    // N = P_A * B + P_B * A = (P0 Vx2 + P2 Vx0, P1 Vx3 + P3 Vx1), so that
+    // sum_i P_i / Vx_i = (N.lo M.hi + N.hi M.lo) / (M.lo M.hi) / k  and  sum_i log2 Vx_i = log2(M.lo M.hi) - 30.
+    const f32x2 g2 = pk2(g_row, g_row), k2 = pk2(kPairScale, kPairScale);
 #pragma unroll
     for (int qd = 0; qd < 4; ++qd) {
         const float4 bb = *reinterpret_cast<const float4*>(b3f + 4 * qd);
-        const float v0 = fmaf(g_row, ex2_approx(v[4 * qd + 0] + bb.x), bf_lo(pv[qd].z));
-        const float v1 = fmaf(g_row, ex2_approx(v[4 * qd + 1] + bb.y), bf_hi(pv[qd].z));
-        const float v2 = fmaf(g_row, ex2_approx(v[4 * qd + 2] + bb.z), bf_lo(pv[qd].w));
-        const float v3 = fmaf(g_row, ex2_approx(v[4 * qd + 3] + bb.w), bf_hi(pv[qd].w));
-        const float p01 = (v0 * kPairScale) * v1, p23 = (v2 * kPairScale) * v3;
-        const float n01 = fmaf(bf_hi(pv[qd].x), v0, bf_lo(pv[qd].x) * v1), n23 = fmaf(bf_hi(pv[qd].y), v2, bf_lo(pv[qd].y) * v3);
-        const float pq = p01 * p23;
-        acc = fmaf(fmaf(n01, p23, n23 * p01), rcp_approx(pq), acc);
+        float e0, e1, e2, e3;
+        upk2(add2(pk2(v[4 * qd + 0], v[4 * qd + 1]), pk2(bb.x, bb.y)), e0, e1);
+        upk2(add2(pk2(v[4 * qd + 2], v[4 * qd + 3]), pk2(bb.z, bb.w)), e2, e3);
+        const f32x2 A = fma2(g2, pk2(ex2_approx(e0), ex2_approx(e1)), bf16x2_to_f32x2(pv[qd].z));
+        const f32x2 B = fma2(g2, pk2(ex2_approx(e2), ex2_approx(e3)), bf16x2_to_f32x2(pv[qd].w));
+        const f32x2 M = mul2(mul2(A, k2), B);
+        const f32x2 N = fma2(bf16x2_to_f32x2(pv[qd].x), B, mul2(bf16x2_to_f32x2(pv[qd].y), A));
+        float mlo, mhi, nlo, nhi;
+        upk2(M, mlo, mhi);
+        upk2(N, nlo, nhi);
+        const float pq = mlo * mhi;
+        acc = fmaf(fmaf(nlo, mhi, nhi * mlo), rcp_approx(pq), acc);
         accl += lg2_approx(pq);
     }
 }
