@@ -90,9 +90,29 @@ __global__ void pack_rows_kernel(const float* __restrict__ src, int64_t chains, 
     }
 }
 
-// P, Vb [NT][ld] (frame-major FP32) -> dst [tile][quad][128 rows] of uint4 {P0P1, P2P3, V0V1, V2V3} in BF16 (round to nearest)
-__global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restrict__ Vb, int64_t chains, int C, int F, int ld,
-                               uint4* __restrict__ dst) {
+// P, Vb [NT][ld] (frame-major FP32) -> dst [tile][quad][128 rows] of uint4 {w0, w1, w2, w3}, one 32-bit word per bin:
+//
+//   low  half of w_j : bf16(Vb'_j)                     (round to nearest even)
+//   whole word   w_j : the FP32 number nearest to P'_j among those with that low half (same 2^-9 relative precision
+//                      as a bf16 rounding, but the sampler reads P' with NO unpack instruction and Vb' with one shift)
+//
+// with the layer-3 bias folded into the stream, P'_j = P_j 2^-c_j and Vb'_j = Vb_j 2^-c_j (c = bias in the log2
+// domain): Vx = 2^c (g 2^v + Vb'), so P / Vx = P' / (g 2^v + Vb') and log Vx differs from log(g 2^v + Vb') by a
+// per-bin constant that cancels in l(z) - l(z').  Bins 0,1 of a quad additionally carry the quad scale k = 2^15 on
+// Vb' and bins 2,3 carry 1/k on P' (see loglik16_pv), which saves the explicit scaling multiply.
+__device__ __forceinline__ uint32_t bf16_bits_rn(float x) {
+    const uint32_t b = __float_as_uint(x);
+    return (b + 0x7fffu + ((b >> 16) & 1u)) >> 16;
+}
+__device__ __forceinline__ uint32_t word_with_low_half(float p, uint32_t low16) {
+    long long d = (long long)__float_as_uint(p) - (long long)low16 + 0x8000ll;       // positive floats order like their bits
+    if (d < 0) d = 0;
+    uint32_t w = ((uint32_t)(d >> 16) << 16) | low16;
+    if ((w & 0x7f800000u) == 0x7f800000u) w -= 0x10000u;                               // never Inf / NaN
+    return w;
+}
+__global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restrict__ Vb, const float* __restrict__ bias_log2,
+                               int64_t chains, int C, int F, int ld, uint4* __restrict__ dst) {
     const int64_t n_tiles = (chains + TM - 1) / TM;
     const int64_t total = n_tiles * NQ * TM;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -100,15 +120,20 @@ __global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restr
         const int q = (int)((i / TM) % NQ);
         const int64_t tile = i / ((int64_t)TM * NQ);
         const int64_t m = tile * TM + r;
-        float pv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (m < chains) {
             const int64_t fr = m / C;
             const int f = 4 * q;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (f + j < F) { pv[j] = P[fr * ld + f + j]; pv[4 + j] = Vb[fr * ld + f + j]; }
+                if (f + j < F) {
+                    const float sc = exp2f(-bias_log2[f + j]);
+                    const float pj = P[fr * ld + f + j] * sc * (j < 2 ? 1.0f : 1.0f / kPairScale);
+                    const float vj = Vb[fr * ld + f + j] * sc * (j < 2 ? kPairScale : 1.0f);
+                    w[j] = word_with_low_half(pj, bf16_bits_rn(vj));
+                }
         }
-        dst[i] = make_uint4(pack_bf16x2(pv[0], pv[1]), pack_bf16x2(pv[2], pv[3]), pack_bf16x2(pv[4], pv[5]), pack_bf16x2(pv[6], pv[7]));
+        dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -523,6 +548,43 @@ extern "C" int dvae_tc_pack_decoder(const DvaeMlp* dec, int L, int y_dim, void* 
     return check_launch("pack_decoder_kernel");
 }
 
+// max over bins of log2(e) * sum_k |W3[k][f]|: the layer-3 pre-activation (log2 domain, bias excluded) cannot exceed it
+// because the hidden activations are tanh outputs
+__global__ void exponent_bound_kernel(const float* __restrict__ wt, int K, int F, float* __restrict__ out) {
+    __shared__ float red[256];
+    float m = 0.f;
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < K; ++k) s += fabsf(wt[k * F + f]);
+        m = fmaxf(m, s);
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0] * kLog2e;
+}
+
+extern "C" int dvae_tc_decoder_exponent_bound(const DvaeMlp* dec, int L, int y_dim, float* bound_host, void* stream) {
+    Dims d;
+    int rc = check_dims(dec, L, y_dim, "dvae_tc_decoder_exponent_bound", &d);
+    if (rc) return rc;
+    DVAE_REQUIRE(bound_host, "dvae_tc_decoder_exponent_bound: null pointer");
+    float* dev = nullptr;
+    cudaError_t e = cudaMalloc(&dev, sizeof(float));
+    if (e != cudaSuccess) { set_error("cudaMalloc: %s", cudaGetErrorString(e)); return (int)e; }
+    const bool two = d.n_hidden == 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    exponent_bound_kernel<<<1, 256, 0, st>>>(dec->wt[two ? 2 : 1], HID, d.F, dev);
+    e = cudaMemcpyAsync(bound_host, dev, sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dev);
+    if (e != cudaSuccess) { set_error("dvae_tc_decoder_exponent_bound: %s", cudaGetErrorString(e)); return (int)e; }
+    return 0;
+}
+
 extern "C" int64_t dvae_tc_packed_floats(int64_t chains) {
     if (chains <= 0) return 0;
     return ((chains + TM - 1) / TM) * (int64_t)NQ * TM * 4;
@@ -533,11 +595,17 @@ extern "C" int64_t dvae_tc_packed_pv_bytes(int64_t chains) {
     return ((chains + TM - 1) / TM) * (int64_t)NQ * TM * 16;
 }
 
-extern "C" int dvae_tc_pack_pv(const float* P, const float* Vb, int64_t NT, int n_chains, int F, int ld, void* dst, void* stream) {
-    DVAE_REQUIRE(P && Vb && dst && NT >= 0 && n_chains >= 1 && F >= 1 && F <= NPAD && ld >= F, "dvae_tc_pack_pv: bad arguments");
+extern "C" int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const float* Vb,
+                               int64_t NT, int n_chains, int F, int ld, void* dst, void* stream) {
+    Dims d;
+    int rc = check_dims(dec, L, y_dim, "dvae_tc_pack_pv", &d);
+    if (rc) return rc;
+    DVAE_REQUIRE(image && P && Vb && dst && NT >= 0 && n_chains >= 1 && F == d.F && ld >= F, "dvae_tc_pack_pv: bad arguments");
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0, "dvae_tc_pack_pv: 16-byte alignment required");
     if (NT == 0) return 0;
-    pack_pv_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(P, Vb, NT * n_chains, n_chains, F, ld, (uint4*)dst);
+    // layer-3 bias (log2 domain) inside the decoder image: after the hidden-2 bias if there is one
+    const float* bias_log2 = reinterpret_cast<const float*>((const unsigned char*)image + d.off_bias) + (d.n_hidden == 2 ? HID : 0);
+    pack_pv_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(P, Vb, bias_log2, NT * n_chains, n_chains, F, ld, (uint4*)dst);
     return check_launch("pack_pv_kernel");
 }
 

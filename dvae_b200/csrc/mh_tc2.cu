@@ -51,7 +51,7 @@ static long long* g_dbg_clocks = nullptr;
     } while (0)
 
 
-template <int L>
+template <int L, bool POLY>
 __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t bars[6];                       // layer 1/2 ready, chunk ready x3, buffer free x2
@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     const uint32_t w1_addr = smem_u32(base), w2_addr = smem_u32(base + d.off_w2), w3_addr = smem_u32(base + d.off_w3);
     const float* biasp = reinterpret_cast<const float*>(base + d.off_bias);
     const float* b2 = (d.n_hidden == 2) ? biasp : nullptr;
-    const float* b3 = biasp + (d.n_hidden == 2 ? HID : 0);
     const int n_iter = p.n_burn + p.n_keep;
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
     const int y_dim = d.y_dim, nkb1 = d.nkb1;
@@ -234,10 +233,9 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                     float v[16];
                     tmem_ld16(tmem + 192 * (c & 1) + lane_off + MH2_COL(t), v);
                     tmem_wait_ld();
-                    const float* b3f = b3 + MH2_BIN(t);
-                    if (t % 3 == 0) loglik16_pv(v, pv0, b3f, g_row, acc, accl);
-                    else if (t % 3 == 1) loglik16_pv(v, pv1, b3f, g_row, acc, accl);
-                    else loglik16_pv(v, pv2, b3f, g_row, acc, accl);
+                    if (t % 3 == 0) loglik16_pv<POLY>(v, pv0, g_row, acc, accl);
+                    else if (t % 3 == 1) loglik16_pv<POLY>(v, pv1, g_row, acc, accl);
+                    else loglik16_pv<POLY>(v, pv2, g_row, acc, accl);
                 }
                 if (t == 5) {                                                   // chunk 0 drained by this thread
                     DBG_STAMP(4, threadIdx.x == 0);
@@ -328,7 +326,7 @@ using namespace dvae::tc;
 extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
                                  const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
                                  int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept,
-                                 float* a_trace, int* status, void* stream) {
+                                 float* a_trace, int flags, int* status, void* stream) {
     Mh2Params p{};
     int rc = check_dims(dec, L, y_dim, "dvae_mh_chain_tc2", &p.d);
     if (rc) return rc;
@@ -353,13 +351,17 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const vo
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
     const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
     cudaStream_t st = (cudaStream_t)stream;
-    if (L == 16) {
-        cudaFuncSetAttribute(mh2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mh2_kernel<16><<<grid, MH2_THREADS, smem, st>>>(p);
-    } else {
-        cudaFuncSetAttribute(mh2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        mh2_kernel<32><<<grid, MH2_THREADS, smem, st>>>(p);
-    }
+    const bool poly = (flags & DVAE_TC_POLY_EX2) != 0;
+#define MH2_LAUNCH(LL, PP)                                                                                   \
+    do {                                                                                                     \
+        cudaFuncSetAttribute(mh2_kernel<LL, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
+        mh2_kernel<LL, PP><<<grid, MH2_THREADS, smem, st>>>(p);                                              \
+    } while (0)
+    if (L == 16 && poly) MH2_LAUNCH(16, true);
+    else if (L == 16) MH2_LAUNCH(16, false);
+    else if (poly) MH2_LAUNCH(32, true);
+    else MH2_LAUNCH(32, false);
+#undef MH2_LAUNCH
     return check_launch("mh2_kernel");
 }
 

@@ -112,7 +112,6 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
     const uint32_t a_addr = smem_u32(A), slot_addr = smem_u32(Wslot);
     const uint32_t w1_addr = smem_u32(base), w2_addr = smem_u32(base + d.off_w2);
     const float* b2 = (d.n_hidden == 2) ? biasp : nullptr;
-    const float* b3 = biasp + (d.n_hidden == 2 ? HID : 0);
     const unsigned char* w3g = p.image + d.off_w3;     // global W3 image: K block kb at kb*NPAD*128, row r at r*128
     const int n_iter = p.n_burn + p.n_keep;
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
@@ -120,7 +119,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
     const bool two_hidden = d.n_hidden == 2;
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
 
-    for (int64_t tile = 2 * (int64_t)blockIdx.x + ctx; tile < n_tiles; tile += 2 * (int64_t)gridDim.x) {
+    // tiles are dealt round by round over the CTAs, alternating between the two contexts: with an odd number of rounds the
+    // extra tile goes to context 0 of EVERY CTA (it then runs alone) instead of a full extra pair on half of the CTAs
+    for (int64_t tile = (int64_t)blockIdx.x + (int64_t)ctx * gridDim.x; tile < n_tiles; tile += 2 * (int64_t)gridDim.x) {
         const int64_t row_g = tile * TM + row;
         const bool valid = row_g < p.rows;
         const int64_t fr = valid ? row_g / p.C : 0;
@@ -256,18 +257,18 @@ __global__ void __launch_bounds__(C3_THREADS, 1) mh3_kernel(Mh3Params p) {
                         float v[16];
                         tmem_ld16(tmem + 128 + lane_off + 64 * h + 16 * sub, v);
                         tmem_wait_ld();
-                        const float* b3f = b3 + 128 * j + 64 * h + 16 * sub;
-                        if (t & 1) loglik16_pv(v, pvB, b3f, g_row, acc, accl);
-                        else loglik16_pv(v, pvA, b3f, g_row, acc, accl);
+                        if (t & 1) loglik16_pv<false>(v, pvB, g_row, acc, accl);
+                        else loglik16_pv<false>(v, pvA, g_row, acc, accl);
                     }
                 } else if (h == 0) {                                            // bin 512
                     float v[4];
                     tmem_ld4(tmem + 128 + lane_off, v);
                     tmem_wait_ld();
                     const uint4 pv = __ldg(PVt + 128 * TM);
-                    const float v0 = fmaf(g_row, ex2_approx(v[0] + b3[512]), bf_lo(pv.z));
-                    acc = fmaf(bf_lo(pv.x) * (1.0f / kQuadScale), rcp_approx(v0), acc);
-                    accl += lg2_approx(v0);
+                    // word 0 of the quad: P'_512 with bf16(k Vb'_512) in its low half (pack_pv_kernel); acc carries sums / k
+                    const float xk = fmaf(g_row * kPairScale, ex2_approx(v[0]), __uint_as_float(pv.x << 16));
+                    acc = fmaf(__uint_as_float(pv.x), rcp_approx(xk), acc);
+                    accl += lg2_approx(xk);
                 }
                 tc_fence_before();
                 if (j == 4 && h == 1) red[row] = fmaf(kLn2, accl, acc * kQuadScale);
@@ -352,8 +353,7 @@ extern "C" int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const vo
     const size_t smem = (size_t)shared_bytes + 2 * C3_CTX_BYTES + 1024;
     DVAE_REQUIRE(smem <= 227 * 1024, "dvae_mh_chain_tc3: shared memory budget exceeded");
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
-    const int64_t pairs = (n_tiles + 1) / 2;
-    const int grid = (int)(pairs < 148 ? pairs : 148);
+    const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
     cudaFuncSetAttribute(mh3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     mh3_kernel<16><<<grid, C3_THREADS, smem, (cudaStream_t)stream>>>(p);
     return check_launch("mh3_kernel");

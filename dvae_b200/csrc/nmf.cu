@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
                                                                  const int64_t* __restrict__ fr_off, int K) {
     constexpr int KT = HG2_KT;
     static_assert(R % 2 == 0 && R <= 32 && ld % 4 == 0 && ld >= 513, "hg5: even R up to 32, row pitch a multiple of 16 bytes");
-    extern __shared__ __align__(128) float sm[];
+    extern __shared__ __align__(16) float sm[];
     float* S = sm;                                  // [R][ld] samples of the current frame
     float* red = S + R * ld;                        // [8][HG3_NV] per-warp partials of the H sums
     __shared__ float2 red2[8];

@@ -298,21 +298,46 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 // l(z) - l(z').  -> 1.5 MUFU operations per bin instead of 2.
 constexpr float kPairScale = 32768.0f;
 constexpr float kQuadScale = 32768.0f;
-__device__ __forceinline__ void loglik16_pv(const float* v, const uint4* pv, const float* b3f, float g_row, float& acc, float& accl) {
-    // Packed FP32 pairs: A = (Vx0, Vx1), B = (Vx2, Vx3).  M = k A * B = (k Vx0 Vx2, k Vx1 Vx3),
-    // N = P_A * B + P_B * A = (P0 Vx2 + P2 Vx0, P1 Vx3 + P3 Vx1), so that
-    // sum_i P_i / Vx_i = (N.lo M.hi + N.hi M.lo) / (M.lo M.hi) / k  and  sum_i log2 Vx_i = log2(M.lo M.hi) - 30.
-    const f32x2 g2 = pk2(g_row, g_row), k2 = pk2(kPairScale, kPairScale);
+// 2^x for a packed pair on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f through the 1.5 * 2^23 magic
+// add, degree-3 minimax polynomial for 2^f on [-1/2, 1/2] (max relative error 7.5e-5, far inside the BF16 noise of the
+// layer-3 pre-activation), exponent patched with an integer add.  Valid for |x| < 125: callers must know the range
+// (DVAE_TC_POLY_EX2, dvae_tc_decoder_exponent_bound).
+__device__ __forceinline__ f32x2 ex2_poly2(f32x2 x) {
+    const f32x2 t = add2(x, pk2(12582912.0f, 12582912.0f));
+    const f32x2 n = add2(t, pk2(-12582912.0f, -12582912.0f));
+    const f32x2 f = fma2(n, pk2(-1.0f, -1.0f), x);
+    f32x2 p = fma2(pk2(0.0551716685f, 0.0551716685f), f, pk2(0.242611125f, 0.242611125f));
+    p = fma2(p, f, pk2(0.693260968f, 0.693260968f));
+    p = fma2(p, f, pk2(0.999928057f, 0.999928057f));
+    float plo, phi, tlo, thi;
+    upk2(p, plo, phi);
+    upk2(t, tlo, thi);
+    return pk2(__uint_as_float(__float_as_uint(plo) + (__float_as_uint(tlo) << 23)),
+               __uint_as_float(__float_as_uint(phi) + (__float_as_uint(thi) << 23)));
+}
+
+// POLY: bins 2,3 of every quad take 2^v from ex2_poly2 instead of MUFU.EX2.  The sampler is bound by the MUFU pipe
+// (4 lanes / clk / scheduler: profiles/r01_tc_ncu_mh2.txt shows XU at 51 % with the issue slots at 28 %), so moving a
+// third of its transcendental work to the idle FMA pipe shortens the layer-3 epilogue.
+template <bool POLY>
+__device__ __forceinline__ void loglik16_pv(const float* v, const uint4* pv, float g_row, float& acc, float& accl) {
+    // Stream format: see pack_pv_kernel (bias folded in, word j = P'_j with bf16(Vb'_j) in its low half, quad scale k
+    // pre-applied to Vb' of bins 0,1 and 1/k to P' of bins 2,3).  Packed FP32 pairs:
+    //   A = k (X0, X1),  B = (X2, X3),  X_j = g 2^v_j + Vb'_j
+    //   M = A * B = (k X0 X2, k X1 X3)
+    //   N = P_A * B + (P_B / k) * A = (P0 X2 + P2 X0, P1 X3 + P3 X1)
+    // so that  sum_j P'_j / X_j = (N.lo M.hi + N.hi M.lo) / (M.lo M.hi) / k  and  sum_j log2 X_j = log2(M.lo M.hi) - 30.
+    const f32x2 g2 = pk2(g_row, g_row), g2k = pk2(g_row * kPairScale, g_row * kPairScale);
 #pragma unroll
     for (int qd = 0; qd < 4; ++qd) {
-        const float4 bb = *reinterpret_cast<const float4*>(b3f + 4 * qd);
-        float e0, e1, e2, e3;
-        upk2(add2(pk2(v[4 * qd + 0], v[4 * qd + 1]), pk2(bb.x, bb.y)), e0, e1);
-        upk2(add2(pk2(v[4 * qd + 2], v[4 * qd + 3]), pk2(bb.z, bb.w)), e2, e3);
-        const f32x2 A = fma2(g2, pk2(ex2_approx(e0), ex2_approx(e1)), bf16x2_to_f32x2(pv[qd].z));
-        const f32x2 B = fma2(g2, pk2(ex2_approx(e2), ex2_approx(e3)), bf16x2_to_f32x2(pv[qd].w));
-        const f32x2 M = mul2(mul2(A, k2), B);
-        const f32x2 N = fma2(bf16x2_to_f32x2(pv[qd].x), B, mul2(bf16x2_to_f32x2(pv[qd].y), A));
+        const uint4 w = pv[qd];
+        const f32x2 A = fma2(g2k, pk2(ex2_approx(v[4 * qd + 0]), ex2_approx(v[4 * qd + 1])),
+                             pk2(__uint_as_float(w.x << 16), __uint_as_float(w.y << 16)));
+        const f32x2 e23 = POLY ? ex2_poly2(pk2(v[4 * qd + 2], v[4 * qd + 3])) : pk2(ex2_approx(v[4 * qd + 2]), ex2_approx(v[4 * qd + 3]));
+        const f32x2 B = fma2(g2, e23, pk2(__uint_as_float(w.z << 16), __uint_as_float(w.w << 16)));
+        const f32x2 M = mul2(A, B);
+        const f32x2 N = fma2(pk2(__uint_as_float(w.x), __uint_as_float(w.y)), B,
+                             mul2(pk2(__uint_as_float(w.z), __uint_as_float(w.w)), A));
         float mlo, mhi, nlo, nhi;
         upk2(M, mlo, mhi);
         upk2(N, nlo, nhi);

@@ -22,6 +22,10 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+POLY_EX2 = 1            # DVAE_TC_POLY_EX2
+POLY_EX2_LIMIT = 120.0  # DVAE_TC_POLY_EX2_LIMIT
+
+
 def decoder_image(weights):
     """The UMMA-ready image of ``weights.dec`` (cached on the weights object)."""
     img = getattr(weights, "_tc_image", None)
@@ -33,6 +37,10 @@ def decoder_image(weights):
         img = torch.empty(int(n), dtype=torch.uint8, device=weights.device)
         _lib.call("dvae_tc_pack_decoder", weights.dec.ref, weights.z_dim, weights.y_dim, _p(img), _stream())
         weights._tc_image = img
+        # one-off range query: may the sampler use the polynomial 2^x (see DVAE_TC_POLY_EX2 in include/dvae_b200.h)?
+        bound = C.c_float(0.0)
+        _lib.call("dvae_tc_decoder_exponent_bound", weights.dec.ref, weights.z_dim, weights.y_dim, C.byref(bound), _stream())
+        weights._tc_flags = POLY_EX2 if bound.value < POLY_EX2_LIMIT and os.environ.get("DVAE_TC_POLY", "1") != "0" else 0
     return img
 
 
@@ -90,12 +98,16 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
     fn = "dvae_mh_chain_tc3" if (gen == "v3" and w.z_dim == 16) else "dvae_mh_chain_tc2"
     nb = int(_lib.load().dvae_tc_packed_pv_bytes(chains))
     pv = eng._get("PVpk", (max(nb, 16),), torch.uint8)
-    _lib.call("dvae_tc_pack_pv", _p(eng.P), _p(eng.Vb), b.NT, cfg.n_chains, eng.F, eng.ld, _p(pv), _stream())
+    _lib.call("dvae_tc_pack_pv", w.dec.ref, _p(img), w.z_dim, w.y_dim, _p(eng.P), _p(eng.Vb), b.NT, cfg.n_chains, eng.F, eng.ld,
+              _p(pv), _stream())
     eng.kernel_launches += 1
     with eng.stage("mh_kernel"):
-        _lib.call(fn, w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, _p(eng.Z),
-                  _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep, float(cfg.var_rw), eps_ptr, u_ptr, _p(eng.n_accept),
-                  _p(a_trace), _p(_status(eng)), _stream())
+        args = (w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains,
+                burn, keep, float(cfg.var_rw), eps_ptr, u_ptr, _p(eng.n_accept), _p(a_trace))
+        if fn == "dvae_mh_chain_tc2":
+            _lib.call(fn, *args, int(w._tc_flags), _p(_status(eng)), _stream())
+        else:
+            _lib.call(fn, *args, _p(_status(eng)), _stream())
     eng.kernel_launches += 1
 
 

@@ -159,14 +159,23 @@ int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64
 /* second-generation schedule of the same sampler (software-pipelined P / Vb stream, mbarrier chunk hand-over,
  * register-resident chain state); L in {16, 32}, y_dim <= 3.  The draws always come from global memory:
  * eps[n_iter][NT*C][L], u[n_iter][NT*C] (16-byte aligned), either injected by the caller or produced by
- * dvae_rng_dump with the Philox counters every sampler of this library uses.  P and Vb are streamed as BF16
- * (dvae_tc_pack_pv: [tile][bin quad][128 chains] x {P0P1, P2P3, V0V1, V2V3}, dvae_tc_packed_pv_bytes bytes). */
+ * dvae_rng_dump with the Philox counters every sampler of this library uses.  P and Vb are streamed at BF16 precision
+ * (dvae_tc_pack_pv: [tile][bin quad][128 chains] x 4 words, word j = P'_j with bf16(Vb'_j) as its low half, the
+ * layer-3 bias of `image` folded in as a per-bin scale; dvae_tc_packed_pv_bytes bytes). */
 int64_t dvae_tc_packed_pv_bytes(int64_t chains);
-int dvae_tc_pack_pv(const float* P, const float* Vb, int64_t NT, int n_chains, int F, int ld, void* dst, void* stream);
+int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const float* Vb, int64_t NT,
+                    int n_chains, int F, int ld, void* dst, void* stream);
+/* flags: DVAE_TC_POLY_EX2 lets the sampler evaluate half of the layer-3 exponentials with a polynomial on the FMA pipe
+ * (relative error 7.5e-5) instead of MUFU.EX2; only valid when the pre-activation stays inside +-120 in the log2
+ * domain, i.e. when dvae_tc_decoder_exponent_bound (a one-off, synchronising query: log2(e) * max_f sum_k |W3[k][f]|)
+ * reports less than DVAE_TC_POLY_EX2_LIMIT for the decoder. */
+#define DVAE_TC_POLY_EX2 1
+#define DVAE_TC_POLY_EX2_LIMIT 120.0f
+int dvae_tc_decoder_exponent_bound(const DvaeMlp* dec, int L, int y_dim, float* bound_host, void* stream);
 int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
                       const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
                       int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
-                      int* status, void* stream);
+                      int flags, int* status, void* stream);
 
 /* Warp-specialised decode with per-frame statistics (R in {10,30}): writes Vs[NT][R][ld], A1[n][f] = sum_r 1/Vx and
  * A2[n][f] = sum_r 1/Vx^2; dvae_nmf_mstep takes them as wstat = A1 (A2 = A1 + NT*ld) with n_parts = 0. */
