@@ -15,7 +15,7 @@ timeout 900 python bench.py --sampler $SAMPLER > $OUT/bench_$TAG.json 2> $OUT/be
 echo "bench exit $?"
 cat $OUT/bench_$TAG.json
 tail -3 $OUT/bench_$TAG.err
-SMALL="python bench.py --sampler $SAMPLER --batch 64 --niter 2 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"
+SMALL="python bench.py --sampler $SAMPLER --batch 64 --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"   # full 100-iteration schedule: kernel shares comparable with the bench line
 timeout 300 $SMALL > $OUT/plain_$TAG.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $OUT/launches_$TAG.csv $SMALL > $OUT/ncu_list_$TAG.log 2>&1
 echo "ncu list exit $?"
