@@ -95,7 +95,7 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
         eng.kernel_launches += 1
         eps_ptr, u_ptr = _p(eps), _p(u)
     gen = os.environ.get("DVAE_TC_SAMPLER", "v2")
-    fn = "dvae_mh_chain_tc3" if (gen == "v3" and w.z_dim == 16) else "dvae_mh_chain_tc2"
+    fn = "dvae_mh_chain_tc3" if (gen == "v3" and w.z_dim == 16) else ("dvae_mh_chain_tc4" if gen == "v4" else "dvae_mh_chain_tc2")
     nb = int(_lib.load().dvae_tc_packed_pv_bytes(chains))
     pv = eng._get("PVpk", (max(nb, 16),), torch.uint8)
     _lib.call("dvae_tc_pack_pv", w.dec.ref, _p(img), w.z_dim, w.y_dim, _p(eng.P), _p(eng.Vb), b.NT, cfg.n_chains, eng.F, eng.ld,
@@ -104,7 +104,7 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
     with eng.stage("mh_kernel"):
         args = (w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains,
                 burn, keep, float(cfg.var_rw), eps_ptr, u_ptr, _p(eng.n_accept), _p(a_trace))
-        if fn == "dvae_mh_chain_tc2":
+        if fn != "dvae_mh_chain_tc3":
             _lib.call(fn, *args, int(w._tc_flags), _p(_status(eng)), _stream())
         else:
             _lib.call(fn, *args, _p(_status(eng)), _stream())

@@ -176,6 +176,12 @@ int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, c
                       const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
                       int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
                       int flags, int* status, void* stream);
+/* fourth-generation schedule, same arguments and results as dvae_mh_chain_tc2: two tiles in flight per CTA (front warps:
+ * accept / propose / layers 1-2, back warps: layer-3 likelihood), the layer-3 A operand held in tensor memory */
+int dvae_mh_chain_tc4(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
+                      const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
+                      int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
+                      int flags, int* status, void* stream);
 
 /* Warp-specialised decode with per-frame statistics (R in {10,30}): writes Vs[NT][R][ld], A1[n][f] = sum_r 1/Vx and
  * A2[n][f] = sum_r 1/Vx^2; dvae_nmf_mstep takes them as wstat = A1 (A2 = A1 + NT*ld) with n_parts = 0. */
@@ -194,6 +200,7 @@ int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const void* PVpk, c
 int dvae_debug_set_clock_buffer3(void* dev_buffer);
 int dvae_debug_set_clock_buffer_ws(void* dev_buffer);
 int dvae_debug_set_clock_buffer_ds(void* dev_buffer);
+int dvae_debug_set_clock_buffer4(void* dev_buffer);
 
 /* debug aid: register a device buffer of 64 int64; the tc2 sampler's CTA 0 stamps clock64() at its phase boundaries */
 int dvae_debug_set_clock_buffer(void* dev_buffer);
