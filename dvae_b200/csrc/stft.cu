@@ -20,8 +20,13 @@ namespace dvae {
 
 constexpr int kNfft = 1024;
 constexpr int kHalf = 512;
-constexpr int kRow = 65;                       // padded row stride (float2) of the 8 x 64 exchange buffer
+constexpr int kRow = 64;                       // row stride (float2) of the 8 x 64 exchange buffer
 constexpr int kBuf = 8 * kRow;                 // float2 per frame group
+// Exchange-buffer slot of element (row k1, column c): the column is XOR-swizzled with k1 + 8 (k1 & 1).  With 16 float2
+// banks this makes all three access patterns of the FFT conflict-free per half-warp: stage-1 stores (row fixed, 16
+// consecutive columns), stage-2 loads / stores (rows 2a, 2a+1 x columns 8 m1 + 0..7: the rows differ in bank bit 3)
+// and stage-3 loads (rows 0..7 x columns 8 j1 + m2, j1 in {2b, 2b+1}: bank = (8 j1 + m2) ^ (k1 + 8 (k1 & 1)), distinct).
+__device__ __forceinline__ int xslot(int k1, int c) { return k1 * kRow + (c ^ (k1 | ((k1 & 1) << 3))); }
 
 __device__ float2 g_tw[kNfft];                 // exp(-2*pi*i*k/1024)
 __device__ float g_win[kNfft];                 // periodic Hann
@@ -80,36 +85,72 @@ __device__ __forceinline__ void fft8(float2* a) {
     a[3] = cadd(e3, t3); a[7] = csub(e3, t3);
 }
 
-// 512-point forward complex FFT by the 64 threads of a frame group.
+// 512-point forward complex FFT by the 64 threads (two warps) of frame group `grp`.
 // in : a[n1] = z[t + 64*n1]            (t = thread in group)
 // out: a[j2] = Z[t + 64*j2]
-// `buf` is the group's kBuf-float2 exchange buffer, `tw` the shared twiddle table.  Contains three CTA barriers:
-// every thread of the CTA must call it the same number of times.
-__device__ __forceinline__ void fft512(float2* a, float2* buf, const float2* tw, int t) {
+// `buf` is the group's kBuf-float2 exchange buffer, `tw` the shared twiddle table.  The groups of a CTA are independent:
+// they synchronise on their own named barrier (id 1 + grp, 64 threads), not on the CTA barrier.  The inter-stage
+// twiddles w^k (k = 1..7) are powers of ONE table entry formed in registers: the first version fetched all of them from
+// the table, and those strided shared-memory reads (up to 8-way bank conflicts) kept the shared-memory pipe 73 % busy
+// (ncu, round 1) - the actual bound of the kernel.
+__device__ __forceinline__ void group_bar(int grp) {                        // immediate ids: a register id makes ptxas reserve all 16 barriers
+    switch (grp) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
+
+__device__ __forceinline__ void twiddle_powers(float2 w, float2* wp) {     // wp[k] = w^k, k = 1..7 (wp[0] unused)
+    wp[1] = w;
+    wp[2] = cmul(w, w);
+    wp[3] = cmul(wp[2], w);
+    wp[4] = cmul(wp[2], wp[2]);
+    wp[5] = cmul(wp[4], w);
+    wp[6] = cmul(wp[4], wp[2]);
+    wp[7] = cmul(wp[4], wp[3]);
+}
+
+__device__ __forceinline__ void fft512(float2* a, float2* buf, const float2* tw, int t, int grp) {
     fft8(a);
+    {
+        float2 wp[8];
+        twiddle_powers(tw[2 * t], wp);             // exp(-2 pi i t k1 / 512)
+        buf[xslot(0, t)] = a[0];
 #pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) buf[k1 * kRow + t] = cmul(a[k1], tw[(2 * t * k1) & (kNfft - 1)]);
-    __syncthreads();
+        for (int k1 = 1; k1 < 8; ++k1) buf[xslot(k1, t)] = cmul(a[k1], wp[k1]);
+    }
+    group_bar(grp);
     {
         const int k1 = t >> 3, m2 = t & 7;
 #pragma unroll
-        for (int m1 = 0; m1 < 8; ++m1) a[m1] = buf[k1 * kRow + 8 * m1 + m2];
+        for (int m1 = 0; m1 < 8; ++m1) a[m1] = buf[xslot(k1, 8 * m1 + m2)];
         fft8(a);
+        float2 wp[8];
+        twiddle_powers(tw[16 * m2], wp);           // exp(-2 pi i m2 j1 / 64)
         // in place: this thread rewrites exactly the eight slots it has just read
+        buf[xslot(k1, m2)] = a[0];
 #pragma unroll
-        for (int j1 = 0; j1 < 8; ++j1) buf[k1 * kRow + 8 * j1 + m2] = cmul(a[j1], tw[(16 * m2 * j1) & (kNfft - 1)]);
+        for (int j1 = 1; j1 < 8; ++j1) buf[xslot(k1, 8 * j1 + m2)] = cmul(a[j1], wp[j1]);
     }
-    __syncthreads();
+    group_bar(grp);
     {
         const int k1 = t & 7, j1 = t >> 3;
 #pragma unroll
-        for (int m2 = 0; m2 < 8; ++m2) a[m2] = buf[k1 * kRow + 8 * j1 + m2];
+        for (int m2 = 0; m2 < 8; ++m2) a[m2] = buf[xslot(k1, 8 * j1 + m2)];
         fft8(a);                                   // a[j2] = Z[k1 + 8*j1 + 64*j2] = Z[t + 64*j2]
     }
-    __syncthreads();                               // buf may be reused by the caller
+    group_bar(grp);                                // buf may be reused by the caller
 }
 
 __device__ __forceinline__ int find_utt(const int64_t* __restrict__ fr_off, int B, int64_t n) {
+    {   // equal-length batches (the common case): the proportional guess is right and costs one round of two loads
+        // instead of a chain of log2(B) dependent ones
+        const int64_t NT = fr_off[B];
+        const int g = (int)min((int64_t)B - 1, (n * B) / (NT > 0 ? NT : 1));
+        if (fr_off[g] <= n && n < fr_off[g + 1]) return g;
+    }
     int lo = 0, hi = B;                            // largest u with fr_off[u] <= n
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -119,13 +160,14 @@ __device__ __forceinline__ int find_utt(const int64_t* __restrict__ fr_off, int 
 }
 
 // ----------------------------------------------------------------------------- STFT
-__global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, const int64_t* __restrict__ x_off,
+__global__ void __launch_bounds__(256, 6) stft_kernel(const float* __restrict__ x, const int64_t* __restrict__ x_off,
                                                    const int32_t* __restrict__ x_len, int B, float2* __restrict__ X,
                                                    float* __restrict__ P, const int64_t* __restrict__ fr_off,
                                                    int64_t NT, int hop, int ld) {
     __shared__ float2 tw[kNfft];
+    __shared__ __align__(8) float win[kNfft];
     __shared__ float2 bufs[4][kBuf];
-    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) tw[i] = g_tw[i];
+    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) { tw[i] = g_tw[i]; win[i] = g_win[i]; }
     __syncthreads();
 
     const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
@@ -141,22 +183,31 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, 
             const float* xu = x + x_off[u];
             const int64_t len = x_len[u];
             const int64_t s0 = j * (int64_t)hop;
+            // the frame is read as even / odd sample pairs: one 8-byte load each when the frame start is 8-byte aligned
+            // and the whole frame lies inside the signal
+            const bool fast = ((reinterpret_cast<uintptr_t>(xu + s0) & 7) == 0) && (s0 + kNfft <= len);
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
                 const int p = 2 * (t + 64 * n1);
                 const int64_t q = s0 + p;
-                const float v0 = (q < len) ? __ldg(xu + q) : 0.f;
-                const float v1 = (q + 1 < len) ? __ldg(xu + q + 1) : 0.f;
-                a[n1] = make_float2(v0 * (0.5f - 0.5f * tw[p].x), v1 * (0.5f - 0.5f * tw[p + 1].x));
+                float2 v;
+                if (fast) {
+                    v = __ldg(reinterpret_cast<const float2*>(xu + q));
+                } else {
+                    v.x = (q < len) ? __ldg(xu + q) : 0.f;
+                    v.y = (q + 1 < len) ? __ldg(xu + q + 1) : 0.f;
+                }
+                const float2 w2 = *reinterpret_cast<const float2*>(win + p);
+                a[n1] = make_float2(v.x * w2.x, v.y * w2.y);
             }
         } else {
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) a[n1] = make_float2(0.f, 0.f);
         }
-        fft512(a, buf, tw, t);
+        fft512(a, buf, tw, t, grp);
 #pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2) buf[j2 * kRow + t] = a[j2];          // natural order Z[k] at (k>>6, k&63)
-        __syncthreads();
+        for (int j2 = 0; j2 < 8; ++j2) buf[j2 * kRow + t] = a[j2];          // natural order: Z[k] at slot k
+        group_bar(grp);
         if (live) {
             float2* Xn = X + n * (int64_t)ld;
             float* Pn = P ? P + n * (int64_t)ld : nullptr;
@@ -165,8 +216,8 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, 
                 const int k = t + 64 * j;
                 if (k > kHalf) break;
                 const int km = (kHalf - k) & (kHalf - 1);
-                const float2 zk = buf[((k & (kHalf - 1)) >> 6) * kRow + (k & 63)];
-                float2 zm = buf[(km >> 6) * kRow + (km & 63)];
+                const float2 zk = buf[k & (kHalf - 1)];
+                float2 zm = buf[km];
                 zm.y = -zm.y;                                               // conj(Z[512-k])
                 const float2 s = cadd(zk, zm), d = csub(zk, zm);
                 const float2 wd = cmul(tw[k], d);                           // W^k (Zk - conj Zm)
@@ -176,7 +227,7 @@ __global__ void __launch_bounds__(256) stft_kernel(const float* __restrict__ x, 
                 if (Pn) Pn[k] = r.x * r.x + r.y * r.y;
             }
         }
-        __syncthreads();
+        group_bar(grp);
     }
 }
 
@@ -234,7 +285,7 @@ __global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ X
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) a[n1] = make_float2(0.f, 0.f);
         }
-        fft512(a, buf, tw, t);
+        fft512(a, buf, tw, t, grp);
         if (live) {
             float2* fb = reinterpret_cast<float2*>(fbuf + grp * kNfft);
 #pragma unroll
@@ -289,7 +340,7 @@ extern "C" int dvae_stft_f32(const float* x, const int64_t* x_off, const int32_t
     int rc = ensure_tables(st);
     if (rc) return rc;
     const int64_t n_pass = (NT + 3) / 4;
-    const int grid = (int)(n_pass < 148 * 8 ? n_pass : 148 * 8);
+    const int grid = (int)(n_pass < 148 * 6 ? n_pass : 148 * 6);          // six resident CTAs per SM (40 registers, 28 KB)
     stft_kernel<<<grid, 256, 0, st>>>(x, x_off, x_len, B, (float2*)X, P, fr_off, NT, hop, ld);
     return check_launch("stft_kernel");
 }
