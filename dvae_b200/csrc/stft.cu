@@ -31,6 +31,11 @@ __device__ __forceinline__ int xslot(int k1, int c) { return k1 * kRow + (c ^ (k
 __device__ float2 g_tw[kNfft];                 // exp(-2*pi*i*k/1024)
 __device__ float g_win[kNfft];                 // periodic Hann
 __device__ double g_win2[kNfft];               // Hann^2 in double (librosa window_sumsquare accumulates these into f32)
+// Window-sum-square values for hop = 256 (four frames overlap a sample).  A sample s covered by the frames jlo..jhi gets
+// wss = (((0 + w2[o]) + w2[o - 256]) + ...) with o = s - jlo * 256, accumulated in ascending frame order into float32
+// exactly like librosa's window_sumsquare; that value only depends on q = o / 256, r = o % 256 and the number of frames
+// cnt = jhi - jlo + 1 <= q + 1, so all of them fit a 10 x 256 table: entry (q (q + 1) / 2 + cnt - 1, r).
+__device__ float g_wss[10 * 256];
 
 __global__ void init_tables_kernel() {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,6 +46,19 @@ __global__ void init_tables_kernel() {
     const double w = 0.5 - 0.5 * c;
     g_win[k] = (float)w;
     g_win2[k] = w * w;
+    if (k < 256) {
+        for (int q = 0; q < 4; ++q)
+            for (int cnt = 1; cnt <= q + 1; ++cnt) {
+                float wss = 0.f;
+                for (int i = 0; i < cnt; ++i) {
+                    double s2, c2;
+                    sincospi(2.0 * (double)((q - i) * 256 + k) / (double)kNfft, &s2, &c2);
+                    const double wi = 0.5 - 0.5 * c2;
+                    wss = (float)((double)wss + wi * wi);
+                }
+                g_wss[(q * (q + 1) / 2 + cnt - 1) * 256 + k] = wss;
+            }
+    }
 }
 
 static std::mutex g_init_mutex;
@@ -62,10 +80,19 @@ int ensure_tables(cudaStream_t stream) {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }    // a * (-i)
-__device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }    // a * (+i)
+// complex add / subtract as ONE packed FP32 instruction (FADD2 / FFMA2 on the (re, im) register pair)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) {
+    float2 o;
+    upk2(add2(pk2(a.x, a.y), pk2(b.x, b.y)), o.x, o.y);
+    return o;
+}
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    float2 o;
+    upk2(fma2(pk2(b.x, b.y), pk2(-1.0f, -1.0f), pk2(a.x, a.y)), o.x, o.y);
+    return o;
+}
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b) { return make_float2(a.x + b.y, a.y - b.x); }    // a + b * (-i)
+__device__ __forceinline__ float2 cadd_pi(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }    // a + b * (+i)
 
 // 8-point forward DFT (e^{-2 pi i nk/8}), natural order in and out, in registers.
 __device__ __forceinline__ void fft8(float2* a) {
@@ -74,14 +101,13 @@ __device__ __forceinline__ void fft8(float2* a) {
     const float2 b2 = cadd(a[2], a[6]), b3 = csub(a[2], a[6]);
     const float2 b4 = cadd(a[1], a[5]), b5 = csub(a[1], a[5]);
     const float2 b6 = cadd(a[3], a[7]), b7 = csub(a[3], a[7]);
-    const float2 e0 = cadd(b0, b2), e1 = cadd(b1, mul_mi(b3)), e2 = csub(b0, b2), e3 = cadd(b1, mul_pi(b3));
-    const float2 o0 = cadd(b4, b6), o1 = cadd(b5, mul_mi(b7)), o2 = csub(b4, b6), o3 = cadd(b5, mul_pi(b7));
+    const float2 e0 = cadd(b0, b2), e1 = cadd_mi(b1, b3), e2 = csub(b0, b2), e3 = cadd_pi(b1, b3);
+    const float2 o0 = cadd(b4, b6), o1 = cadd_mi(b5, b7), o2 = csub(b4, b6), o3 = cadd_pi(b5, b7);
     const float2 t1 = make_float2(s * (o1.x + o1.y), s * (o1.y - o1.x));      // o1 * (1-i)/sqrt2
-    const float2 t2 = mul_mi(o2);                                             // o2 * (-i)
     const float2 t3 = make_float2(s * (o3.y - o3.x), -s * (o3.x + o3.y));     // o3 * (-1-i)/sqrt2
     a[0] = cadd(e0, o0); a[4] = csub(e0, o0);
     a[1] = cadd(e1, t1); a[5] = csub(e1, t1);
-    a[2] = cadd(e2, t2); a[6] = csub(e2, t2);
+    a[2] = cadd_mi(e2, o2); a[6] = cadd_pi(e2, o2);                           // e2 -+ i o2
     a[3] = cadd(e3, t3); a[7] = csub(e3, t3);
 }
 
@@ -239,12 +265,13 @@ __global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ X
                                                     const int32_t* __restrict__ y_len, int hop, int ld, int seg_hops) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* tw = reinterpret_cast<float2*>(smem_raw);                         // 1024 float2
-    float2* bufs = tw + kNfft;                                                // 4 * kBuf float2
-    float* fbuf = reinterpret_cast<float*>(bufs + 4 * kBuf);                  // 4 * 1024 floats
-    float* acc = fbuf + 4 * kNfft;                                            // (kSegFrames-1)*hop + 1024 floats
+    float2* bufs = tw + kNfft;                                                // 4 * kBuf float2 (FFT exchange buffers)
+    float* fbuf = reinterpret_cast<float*>(bufs);                             // 4 * 1024 floats: the windowed frames reuse them
+    float* win = fbuf + 4 * kNfft;                                            // 1024 floats
+    float* acc = win + kNfft;                                                 // (kSegFrames-1)*hop + 1024 floats
 
     const int u = blockIdx.y;
-    const int ov = kNfft / hop;                                               // frames overlapping one sample
+    const int ov = kNfft / hop;                                               // frames overlapping one sample (4: hop = 256 = blockDim)
     const int64_t f0 = fr_off[u];
     const int N = (int)(fr_off[u + 1] - f0);
     const int len = y_len[u];
@@ -256,7 +283,7 @@ __global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ X
     const int a0 = jstart * hop;                                              // sample index of acc[0]
     const int span = (kSegFrames - 1) * hop + kNfft;
 
-    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) tw[i] = g_tw[i];
+    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) { tw[i] = g_tw[i]; win[i] = g_win[i]; }
     for (int i = threadIdx.x; i < span; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
 
@@ -271,7 +298,7 @@ __global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ X
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
                 const int k = t + 64 * n1;
-                float2 xk = Xn[k], xm = Xn[kHalf - k];
+                float2 xk = __ldg(Xn + k), xm = __ldg(Xn + kHalf - k);
                 if (k == 0) { xk.y = 0.f; xm.y = 0.f; }                       // irfft ignores Im of DC and Nyquist
                 xm.y = -xm.y;                                                 // conj(X[512-k])
                 const float2 s = cadd(xk, xm), d = csub(xk, xm);
@@ -286,26 +313,35 @@ __global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ X
             for (int n1 = 0; n1 < 8; ++n1) a[n1] = make_float2(0.f, 0.f);
         }
         fft512(a, buf, tw, t, grp);
-        if (live) {
+        {
             float2* fb = reinterpret_cast<float2*>(fbuf + grp * kNfft);
 #pragma unroll
             for (int j2 = 0; j2 < 8; ++j2) {
                 const int m = t + 64 * j2;
+                const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * m);
                 const float xe = a[j2].x * (1.0f / 1024.0f), xo = -a[j2].y * (1.0f / 1024.0f);
-                fb[m] = make_float2(xe * (0.5f - 0.5f * tw[2 * m].x), xo * (0.5f - 0.5f * tw[2 * m + 1].x));
+                fb[m] = live ? make_float2(xe * w2.x, xo * w2.y) : make_float2(0.f, 0.f);
             }
         }
         __syncthreads();
-        // overlap-add the (up to) four frames of this pass in ascending frame order, like the reference's loop
-        const int base = (jp - jstart) * hop;
-        for (int i = threadIdx.x; i < 3 * hop + kNfft; i += blockDim.x) {
-            float v = acc[base + i];
+        // overlap-add the (up to) four frames of this pass in ascending frame order, like the reference's loop.  hop equals
+        // the CTA size, so thread i owns the accumulator positions base + 256 m + i (m = 0..6) in every pass: they are
+        // updated in registers, frame g contributing its sample 256 (m - g) + i for g <= m <= g + 3.
+        {
+            const int base = (jp - jstart) * hop;
+            const int i = threadIdx.x;
+            float v[7];
+#pragma unroll
+            for (int m = 0; m < 7; ++m) v[m] = acc[base + 256 * m + i];
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                const int off = i - g * hop;
-                if (jp + g <= jend && off >= 0 && off < kNfft) v += fbuf[g * kNfft + off];
+                if (jp + g <= jend) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) v[g + c] += fbuf[g * kNfft + 256 * c + i];
+                }
             }
-            acc[base + i] = v;
+#pragma unroll
+            for (int m = 0; m < 7; ++m) acc[base + 256 * m + i] = v[m];
         }
         __syncthreads();
     }
@@ -317,8 +353,8 @@ __global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ X
         if (s < sig_len) {
             v = acc[s - a0];
             const int jlo = max(0, (s - kNfft + hop) / hop), jhi = min(N - 1, s / hop);
-            float wss = 0.f;
-            for (int j = jlo; j <= jhi; ++j) wss = (float)((double)wss + g_win2[s - j * hop]);
+            const int o = s - jlo * hop, q = o >> 8, cnt = jhi - jlo + 1;
+            const float wss = __ldg(g_wss + ((q * (q + 1) / 2 + cnt - 1) << 8) + (o & 255));
             if (wss > FLT_MIN) v /= wss;
         }
         yu[s] = v;
@@ -358,7 +394,7 @@ extern "C" int dvae_istft_f32(const void* X, const int64_t* fr_off, int B, float
     const int ov = kNfft / hop;
     const int seg_hops = kSegFrames - (ov - 1);
     const int n_seg = (max_y_len + seg_hops * hop - 1) / (seg_hops * hop);
-    const size_t smem = sizeof(float2) * (kNfft + 4 * kBuf) + sizeof(float) * (4 * kNfft + (kSegFrames - 1) * hop + kNfft);
+    const size_t smem = sizeof(float2) * (kNfft + 4 * kBuf) + sizeof(float) * (kNfft + (kSegFrames - 1) * hop + kNfft);
     cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     istft_kernel<<<dim3(n_seg, B), 256, smem, st>>>((const float2*)X, fr_off, y, y_off, y_len, hop, ld, seg_hops);
     return check_launch("istft_kernel");
