@@ -77,6 +77,12 @@ PROTOTYPES = {
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr,
                                     c_ptr]),
     "dvae_debug_set_clock_buffer4": (C.c_int, [c_ptr]),
+    "dvae_vad_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "dvae_vad_labels": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr,
+                                  c_ptr]),
+    "dvae_ibm_labels": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, c_ptr, c_ptr,
+                                  c_ptr, c_ptr]),
+    "dvae_energy_ratios": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr]),
     "dvae_tc_decoder_exponent_bound": (C.c_int, [C.POINTER(DvaeMlp), C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_mh_chain_tc3": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

@@ -550,11 +550,13 @@ class Enhancer:
         eng.kernel_launches += 4          # stft, power-free init kernels are counted there; 2 istft + stft + vb
         return s_dev, n_dev, cost
 
-    def enhance(self, x_list, y_list=None, utt_ids=None, max_frames_list=None, draws=None, return_device=False):
+    def enhance(self, x_list, y_list=None, utt_ids=None, max_frames_list=None, draws=None, return_device=False, s_list=None):
         """Enhance a list of 1-D float32 host signals.  Returns ``(s_hat_list, n_hat_list, cost [B][niter])``.
 
         ``y_list``: per-utterance label arrays ``(y_dim, N_u)`` as the reference passes them (M2 variants).
         ``max_frames_list``: optional per-utterance frame caps (the reference truncates to the video length).
+        ``s_list``: clean signals; for a model with one label input and no ``y_list`` the labels are the time-domain VAD
+        of the clean speech (``clean_speech_VAD``, scripts/evaluate_ntcd_M2.py), computed on the device.
         """
         eng, dev = self.engine, self.dev
         B = len(x_list)
@@ -576,7 +578,14 @@ class Enhancer:
         x_len = torch.from_numpy(lens).to(dev)
         batch = RaggedBatch(nfr, dev, utt_ids)
         y = None
-        if self.weights.y_dim:
+        if self.weights.y_dim and y_list is None and s_list is not None:
+            if self.weights.y_dim != 1 or len(s_list) != B or any(len(a) != t for a, t in zip(s_list, lens)):
+                raise ValueError("device VAD labels need one clean signal per utterance and a model with one label input")
+            from .packages.processing.target import vad_batch
+            hs_in = self._pin("s_in", total, torch.float32)
+            self._stage(hs_in.numpy(), s_list, off, lens)
+            y = vad_batch(hs_in.to(dev, non_blocking=True), x_off, x_len, batch, self.n_fft, self.hop).view(batch.NT, 1)
+        elif self.weights.y_dim:
             if y_list is None:
                 raise ValueError("this model needs labels y")
             yc = np.concatenate([np.asarray(yy, np.float32)[:, :n].T for yy, n in zip(y_list, nfr)], axis=0)

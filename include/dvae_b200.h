@@ -202,6 +202,25 @@ int dvae_debug_set_clock_buffer_ws(void* dev_buffer);
 int dvae_debug_set_clock_buffer_ds(void* dev_buffer);
 int dvae_debug_set_clock_buffer4(void* dev_buffer);
 
+/* ---- evaluation metric on the device (packages/metrics.py:12-82: si_sdr_components, energy_ratios, si_sdr_leroux) ----
+ * Ragged batch: utterance u occupies [off[u], off[u] + len[u]) of s_hat / s / n (n nullable).  out[u] = {SI-SDR, SI-SIR,
+ * SI-SAR} in dB (float64, inner products accumulated in double); SI-SIR / SI-SAR are NaN when n is null, SI-SDR then
+ * equals si_sdr_leroux. */
+int dvae_energy_ratios(const float* s_hat, const float* s, const float* n, const int64_t* off, const int32_t* len, int B,
+                       double* out, void* stream);
+
+/* ---- label front end on the device (packages/processing/target.py:5-105; center=False, end-pad rule of the STFT) ----
+ * dvae_vad_labels: vad[n] = 1 where the power of frame n of the zero-padded signal exceeds 10^vad_threshold times the
+ *   utterance's minimum frame power (clean_speech_VAD, target.py:5-56); ws: dvae_vad_workspace_bytes(NT) bytes.
+ * dvae_ibm_labels: mask[n][f] = 20 log10(|S| + eps) > max over the utterance - ibm_threshold_db (clean_speech_IBM,
+ *   target.py:58-70), multiplied by vad[n] when vad is given (noise_robust_clean_speech_IBM, 72-105); ws: 4 B bytes. */
+int64_t dvae_vad_workspace_bytes(int64_t NT);
+int dvae_vad_labels(const float* x, const int64_t* x_off, const int32_t* x_len, int B, const int32_t* frame_utt,
+                    const int64_t* fr_off, int64_t NT, int n_fft, int hop, float vad_threshold, float* vad, void* ws,
+                    void* stream);
+int dvae_ibm_labels(const void* S, const int32_t* frame_utt, const int64_t* fr_off, int B, int64_t NT, int F, int ld,
+                    float eps, float ibm_threshold_db, const float* vad, float* mask, void* ws, void* stream);
+
 /* debug aid: register a device buffer of 64 int64; the tc2 sampler's CTA 0 stamps clock64() at its phase boundaries */
 int dvae_debug_set_clock_buffer(void* dev_buffer);
 

@@ -174,9 +174,77 @@ def run_case(case, seed=7):
           (case["name"], len(rec.log), flat.nbytes / 1024, os.path.getsize(path) / 1024))
 
 
+def run_metrics():
+    """``tests/golden/metrics.npz``: the reference's ``energy_ratios`` / ``si_sdr_leroux`` (packages/metrics.py:39-82) on
+    seeded signals; the port must agree to 1e-10 dB."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_metrics", os.path.join(REF, "packages", "metrics.py"))
+    ref_metrics = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_metrics)
+    rng = np.random.default_rng(77)
+    T, n_case = 2048, 3
+    t = np.arange(T) / 16000.0
+    s_all, n_all, sh_all, ref = [], [], [], []
+    for c in range(n_case):
+        s = (np.sin(2 * np.pi * (150.0 + 40 * c) * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 4 * t)) ** 2 * 0.3).astype(np.float32)
+        n = (0.03 * (c + 1) * rng.standard_normal(T)).astype(np.float32)
+        s_hat = (0.9 * s + 0.2 * n + 0.01 * rng.standard_normal(T)).astype(np.float32)
+        r = ref_metrics.energy_ratios(s_hat.astype(np.float64), s.astype(np.float64), n.astype(np.float64))
+        leroux = ref_metrics.si_sdr_leroux(s_hat.astype(np.float64), s.astype(np.float64))
+        port = mcem_port.energy_ratios(s_hat, s, n)
+        assert max(abs(a - b) for a, b in zip(r, port)) < 1e-10 and abs(mcem_port.si_sdr(s_hat, s) - leroux) < 1e-10
+        assert abs(r[0] - leroux) < 1e-9
+        s_all.append(s); n_all.append(n); sh_all.append(s_hat); ref.append(list(r) + [leroux])
+    path = os.path.join(ROOT, "tests", "golden", "metrics.npz")
+    np.savez_compressed(path, s=np.stack(s_all), n=np.stack(n_all), s_hat=np.stack(sh_all), ref=np.array(ref, np.float64))
+    print("metrics    ok: %d cases, port within 1e-10 dB, file %.0f KB" % (n_case, os.path.getsize(path) / 1024))
+
+
+def run_labels():
+    """``tests/golden/labels.npz``: the reference's ``clean_speech_VAD`` / ``clean_speech_IBM`` /
+    ``noise_robust_clean_speech_IBM`` (packages/processing/target.py:5-105) on a seeded utterance.  target.py imports
+    ``librosa.util`` (absent here) for ``util.frame`` only; a stub module provides that one function (documented librosa
+    semantics: column j = y[j*hop : j*hop + frame_length]), everything else is the reference's own code."""
+    import importlib.util
+    import types
+    stub = types.ModuleType("librosa")
+    stub.util = types.ModuleType("librosa.util")
+
+    def frame(y, frame_length, hop_length):
+        n = 1 + (len(y) - frame_length) // hop_length
+        return y[np.arange(frame_length)[:, None] + hop_length * np.arange(n)[None, :]]
+
+    stub.util.frame = frame
+    sys.modules["librosa"], sys.modules["librosa.util"] = stub, stub.util
+    spec = importlib.util.spec_from_file_location("ref_target", os.path.join(REF, "packages", "processing", "target.py"))
+    ref_target = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_target)
+    del sys.modules["librosa"], sys.modules["librosa.util"]
+    rng = np.random.default_rng(11)
+    T = 9000
+    t = np.arange(T) / 16000.0
+    env = np.clip(np.sin(2 * np.pi * 2.2 * t), 0, None) ** 2                    # speech bursts with silent gaps
+    s = (env * sum(np.sin(2 * np.pi * 210.0 * k * t) / k for k in range(1, 30)) * 0.2 + 1e-4 * rng.standard_normal(T)).astype(np.float32)
+    kw = dict(fs=16000, wlen_sec=64e-3, hop_percent=0.25, center=False, pad_at_end=True)
+    S = stft_np.stft(s, win="hann", **kw)
+    vad = ref_target.clean_speech_VAD(s.astype(np.float64), pad_mode="reflect", vad_threshold=1.70, **kw)
+    ibm = ref_target.clean_speech_IBM(S, eps=1e-8, ibm_threshold=50)
+    nr = ref_target.noise_robust_clean_speech_IBM(s.astype(np.float64), S, pad_mode="reflect", vad_threshold=1.70, eps=1e-8,
+                                                  ibm_threshold=50, **kw)
+    assert np.array_equal(vad, stft_np.clean_speech_vad(s)) and np.array_equal(ibm, stft_np.clean_speech_ibm(S))
+    assert 0.1 < vad.mean() < 0.9 and 0.05 < ibm.mean() < 0.95, (vad.mean(), ibm.mean())
+    path = os.path.join(ROOT, "tests", "golden", "labels.npz")
+    np.savez_compressed(path, s=s, vad=vad, ibm=ibm.astype(np.uint8), nr=nr.astype(np.uint8))      # S = stft_np.stft(s) is recomputed by the tests
+    print("labels     ok: VAD %d/%d frames active, IBM %.1f %% set, port identical, file %.0f KB" %
+          (int(vad.sum()), vad.shape[1], 100 * ibm.mean(), os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("needs the reference at %s (build container only)" % REF)
     torch.set_num_threads(1)
-    for c in CASES:
-        run_case(c)
+    run_metrics()
+    run_labels()
+    if "--metrics-only" not in sys.argv:
+        for c in CASES:
+            run_case(c)

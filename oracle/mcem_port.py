@@ -308,3 +308,16 @@ def si_sdr(s_hat, s):
     alpha = np.dot(s_hat, s) / np.linalg.norm(s) ** 2
     tgt = alpha * s
     return 10 * np.log10(np.linalg.norm(tgt) ** 2 / np.linalg.norm(tgt - s_hat) ** 2)
+
+
+def energy_ratios(s_hat, s, n):
+    """``energy_ratios`` (packages/metrics.py:39-60) in float64 with the vectors of ``si_sdr_components`` (12-37) formed
+    explicitly, exactly as the reference does."""
+    s_hat, s, n = (np.asarray(a, np.float64) for a in (s_hat, s, n))
+    s_target = np.dot(s_hat, s) / np.linalg.norm(s) ** 2 * s
+    e_noise = np.dot(s_hat, n) / np.linalg.norm(n) ** 2 * n
+    e_art = s_hat - s_target - e_noise
+    st = np.linalg.norm(s_target) ** 2
+    return (10 * np.log10(st / np.linalg.norm(e_noise + e_art) ** 2), 10 * np.log10(st / np.linalg.norm(e_noise) ** 2),
+            10 * np.log10(st / np.linalg.norm(e_art) ** 2))
+

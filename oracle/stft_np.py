@@ -121,3 +121,27 @@ def dft_direct(frame: np.ndarray) -> np.ndarray:
     k = np.arange(n // 2 + 1)[:, None]
     t = np.arange(n)[None, :]
     return (frame[None, :] * np.exp(-2j * np.pi * k * t / n)).sum(axis=1)
+
+
+# ---------------------------------------------------------------------------------------------- labels (target.py)
+def clean_speech_vad(speech_t, fs=16000, wlen_sec=64e-3, hop_percent=0.25, pad_at_end=True, vad_threshold=1.70):
+    """``clean_speech_VAD`` (packages/processing/target.py:5-56) with ``center=False``; ``librosa.util.frame`` restated as
+    ``y[j*hop : j*hop + n_fft]`` for ``j < 1 + (len - n_fft) // hop``."""
+    n_fft = int(wlen_sec * fs)
+    hop = int(hop_percent * n_fft)
+    y = np.asarray(speech_t, np.float64)
+    if pad_at_end:
+        utt_len = len(y) / fs
+        if math.ceil(utt_len / wlen_sec / hop_percent) != int(utt_len / wlen_sec / hop_percent):
+            y = np.pad(y, (0, hop), mode="constant")
+    n = 1 + (len(y) - n_fft) // hop
+    frames = y[np.arange(n_fft)[:, None] + hop * np.arange(n)[None, :]]
+    power = np.power(frames, 2).sum(axis=0)
+    return np.float32(power > np.power(10, vad_threshold) * np.min(power))[None]
+
+
+def clean_speech_ibm(speech_tf, eps=1e-8, ibm_threshold=50):
+    """``clean_speech_IBM`` (packages/processing/target.py:58-70)."""
+    power_db = 20 * np.log10(abs(speech_tf) + eps)
+    return np.float32(power_db > np.max(power_db) - ibm_threshold)
+

@@ -131,3 +131,23 @@ def test_multi_chain_pools_samples():
     s, n, c = enh.enhance([x], y_list=[y])
     assert enh.engine.R == 12 and enh.engine.R_wf == 16
     assert np.isfinite(s[0]).all() and np.isfinite(c).all()
+
+
+def test_device_vad_labels_equal_host_labels():
+    """M2-info model: labels from the clean speech on the device (s_list) give the same run as host labels (y_list)."""
+    from dvae_b200.engine import Enhancer, McemConfig
+    lens = [16000, 13000]
+    utts = [synth.synth_utterance(50 + i, l / 16000.0) for i, l in enumerate(lens)]
+    xs, ss = [u[0] for u in utts], [u[1] for u in utts]
+    P0 = np.abs(stft_np.stft(xs[0], **KW)) ** 2
+    sd = synth.xavier_state_dict("M2v3", 513, 16, [128, 128], 1, seed=8, out_bias=float(np.log(P0.mean())))
+    cfg = McemConfig(niter=2, keep_E=3, burn_E=4, keep_WF=4, burn_WF=5, seed=3)
+    enh = Enhancer(sd, "M2v3", cfg, device=0)
+    ys = [synth.energy_vad(s) for s in ss]
+    assert 0 < ys[0].mean() < 1
+    s_host, _, c_host = enh.enhance(xs, y_list=ys, utt_ids=[7, 8])
+    s_host = [a.copy() for a in s_host]
+    s_dev, _, c_dev = enh.enhance(xs, s_list=ss, utt_ids=[7, 8])
+    for a, b in zip(s_host, s_dev):
+        assert np.array_equal(a, b)
+    assert np.array_equal(c_host, c_dev)

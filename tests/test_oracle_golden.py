@@ -49,3 +49,13 @@ def test_draw_count_matches_survey():
     (kE, bE), (kW, bW) = mcem_port.MCEMOracle("M1", g.niter, *g.sched).schedule()
     assert len(g.draws) == 4 + g.niter * 2 * (kE + bE) + 2 * (kW + bW)
     assert [k for k, _ in g.draws[:4]] == ["rand", "rand", "randn", "randn"]
+
+
+def test_energy_ratios_port_matches_reference_golden():
+    """packages/metrics.py:39-82 on the seeded signals of tests/golden/metrics.npz (made by oracle/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics.npz"))
+    for c in range(g["s"].shape[0]):
+        r = mcem_port.energy_ratios(g["s_hat"][c], g["s"][c], g["n"][c])
+        assert np.allclose(r, g["ref"][c, :3], rtol=0, atol=1e-9)
+        assert abs(mcem_port.si_sdr(g["s_hat"][c], g["s"][c]) - g["ref"][c, 3]) < 1e-9

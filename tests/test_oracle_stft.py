@@ -71,3 +71,14 @@ def test_real_recording_vs_torch():
     T = torch.stft(torch.tensor(xp), 1024, 256, window=torch.hann_window(1024, periodic=True, dtype=torch.float64),
                    center=False, return_complex=True).numpy().astype(np.complex64)
     assert X.shape == T.shape and np.max(np.abs(T - X)) <= 1e-6 * np.max(np.abs(X))
+
+
+def test_label_port_matches_reference_golden():
+    """packages/processing/target.py:5-105 on the seeded utterance of tests/golden/labels.npz (oracle/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "labels.npz"))
+    S = stft_np.stft(g["s"], fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False, pad_at_end=True)
+    vad = stft_np.clean_speech_vad(g["s"])
+    ibm = stft_np.clean_speech_ibm(S)
+    assert np.array_equal(vad, g["vad"]) and np.array_equal(ibm, g["ibm"].astype(np.float32))
+    assert np.array_equal(ibm * vad, g["nr"].astype(np.float32))
