@@ -263,27 +263,24 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                         const int fi = s * FS + ff;
                         const int64_t n = t0 + fi;
                         if (n < p.NT) {
-                            float v[RL];
-                            ds_tmem_ld<RL>(tb + lane_off + fi * R, v);
                             const float gg = ggc[ff];
                             const float vb = vbc[ff];
-                            tmem_wait_ld();
                             float* dst = p.Vs + (n * R) * (int64_t)ldv + f;
                             // packed FP32 pairs; four samples share two reciprocals: X = (Vx_r, Vx_r+1), Y = (Vx_r+2, Vx_r+3),
                             // 1 / (X Y) gives 1 / X = Y / (X Y) and 1 / Y = X / (X Y) lane by lane
                             const f32x2 g2 = pk2(gg, gg), vb2 = pk2(vb, vb), bias2 = pk2(bias, bias);
                             f32x2 a1p = 0ull, a2p = 0ull;
-                            constexpr int R4 = R & ~3;
-#pragma unroll
-                            for (int r = 0; r < R4; r += 4) {
+                            float a1 = 0.f, a2 = 0.f;
+                            // CNT samples (rows r0 .. r0 + CNT of the frame) held in v[0 .. CNT)
+                            auto quad = [&](const float* v, int k, int r0) {
                                 float e0, e1, e2, e3;
-                                upk2(add2(pk2(v[r], v[r + 1]), bias2), e0, e1);
-                                upk2(add2(pk2(v[r + 2], v[r + 3]), bias2), e2, e3);
+                                upk2(add2(pk2(v[k], v[k + 1]), bias2), e0, e1);
+                                upk2(add2(pk2(v[k + 2], v[k + 3]), bias2), e2, e3);
                                 const float s0 = ex2_approx(e0), s1 = ex2_approx(e1), s2 = ex2_approx(e2), s3 = ex2_approx(e3);
-                                dst[(int64_t)r * ldv] = s0;
-                                dst[(int64_t)(r + 1) * ldv] = s1;
-                                dst[(int64_t)(r + 2) * ldv] = s2;
-                                dst[(int64_t)(r + 3) * ldv] = s3;
+                                dst[(int64_t)(r0 + k) * ldv] = s0;
+                                dst[(int64_t)(r0 + k + 1) * ldv] = s1;
+                                dst[(int64_t)(r0 + k + 2) * ldv] = s2;
+                                dst[(int64_t)(r0 + k + 3) * ldv] = s3;
                                 const f32x2 X = fma2(g2, pk2(s0, s1), vb2), Y = fma2(g2, pk2(s2, s3), vb2);
                                 float m0, m1;
                                 upk2(mul2(X, Y), m0, m1);
@@ -291,29 +288,38 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                                 const f32x2 i0 = mul2(Y, rr), i1 = mul2(X, rr);
                                 a1p = add2(a1p, add2(i0, i1));
                                 a2p = fma2(i0, i0, fma2(i1, i1, a2p));
-                            }
-                            float a1, a2, a1h, a2h;
-                            upk2(a1p, a1, a1h);
-                            upk2(a2p, a2, a2h);
-                            a1 += a1h;
-                            a2 += a2h;
-#pragma unroll
-                            for (int r = R4; r + 1 < R; r += 2) {
-                                const float s0 = ex2_approx(v[r] + bias), s1 = ex2_approx(v[r + 1] + bias);
-                                dst[(int64_t)r * ldv] = s0;
-                                dst[(int64_t)(r + 1) * ldv] = s1;
+                            };
+                            auto pair = [&](const float* v, int k, int r0) {
+                                const float s0 = ex2_approx(v[k] + bias), s1 = ex2_approx(v[k + 1] + bias);
+                                dst[(int64_t)(r0 + k) * ldv] = s0;
+                                dst[(int64_t)(r0 + k + 1) * ldv] = s1;
                                 const float x0 = fmaf(gg, s0, vb), x1 = fmaf(gg, s1, vb);
                                 const float rr = rcp_approx(x0 * x1);
                                 const float i0 = x1 * rr, i1 = x0 * rr;
                                 a1 += i0 + i1;
                                 a2 = fmaf(i0, i0, fmaf(i1, i1, a2));
+                            };
+                            static_assert(R == 30 || R == 10, "sample count of the back epilogue");
+                            float v0[16];
+                            tmem_ld16(tb + lane_off + fi * R, v0);
+                            tmem_wait_ld();
+                            if (R == 30) {
+                                // second half of the samples: requested now, consumed after the first half has been processed
+                                // (all 16 back warps read TMEM at the same moment: the load queue is ~1 k cycles deep)
+                                float v1[16];
+                                tmem_ld16(tb + lane_off + fi * R + 16, v1);
+                                quad(v0, 0, 0); quad(v0, 4, 0); quad(v0, 8, 0); quad(v0, 12, 0);
+                                tmem_wait_ld();
+                                quad(v1, 0, 16); quad(v1, 4, 16); quad(v1, 8, 16); pair(v1, 12, 16);
+                            } else {
+                                quad(v0, 0, 0); quad(v0, 4, 0); pair(v0, 8, 0);
                             }
-                            if (R & 1) {
-                                const float s0 = ex2_approx(v[R - 1] + bias);
-                                dst[(int64_t)(R - 1) * ldv] = s0;
-                                const float i0 = rcp_approx(fmaf(gg, s0, vb));
-                                a1 += i0;
-                                a2 = fmaf(i0, i0, a2);
+                            {
+                                float lo, hi;
+                                upk2(a1p, lo, hi);
+                                a1 += lo + hi;
+                                upk2(a2p, lo, hi);
+                                a2 += lo + hi;
                             }
                             p.A1[n * ldv + f] = a1;
                             p.A2[n * ldv + f] = a2;
