@@ -111,6 +111,14 @@ __device__ __forceinline__ uint32_t word_with_low_half(float p, uint32_t low16) 
     if ((w & 0x7f800000u) == 0x7f800000u) w -= 0x10000u;                               // never Inf / NaN
     return w;
 }
+__device__ __forceinline__ uint32_t pv_word(float p, float vb, float bias_log2, int j) {
+    const float sc = exp2f(-bias_log2);
+    const float pj = p * sc * (j < 2 ? 1.0f : 1.0f / kPairScale);
+    const float vj = vb * sc * (j < 2 ? kPairScale : 1.0f);
+    return word_with_low_half(pj, bf16_bits_rn(vj));
+}
+
+// generic version: one thread per (tile, quad, row), rows fastest (coalesced stores, strided loads)
 __global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restrict__ Vb, const float* __restrict__ bias_log2,
                                int64_t chains, int C, int F, int ld, uint4* __restrict__ dst) {
     const int64_t n_tiles = (chains + TM - 1) / TM;
@@ -126,14 +134,49 @@ __global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restr
             const int f = 4 * q;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (f + j < F) {
-                    const float sc = exp2f(-bias_log2[f + j]);
-                    const float pj = P[fr * ld + f + j] * sc * (j < 2 ? 1.0f : 1.0f / kPairScale);
-                    const float vj = Vb[fr * ld + f + j] * sc * (j < 2 ? kPairScale : 1.0f);
-                    w[j] = word_with_low_half(pj, bf16_bits_rn(vj));
-                }
+                if (f + j < F) w[j] = pv_word(P[fr * ld + f + j], Vb[fr * ld + f + j], bias_log2[f + j], j);
         }
         dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// ld % 4 == 0: a CTA packs 8 quads x 128 rows of one tile through shared memory, so that both sides are coalesced: the
+// loads run along the bins of a frame (8 quads = 128 contiguous bytes of P and of Vb), the stores along the rows of a quad
+// (2 KB contiguous).  The padded row stride (129) keeps both shared-memory passes conflict-free.
+constexpr int PPV_Q = 8;
+__global__ void __launch_bounds__(256) pack_pv_tiled_kernel(const float* __restrict__ P, const float* __restrict__ Vb,
+                                                            const float* __restrict__ bias_log2, int64_t chains, int C, int F,
+                                                            int ld, uint4* __restrict__ dst) {
+    __shared__ uint4 sm[PPV_Q * (TM + 1)];
+    const int64_t tile = blockIdx.y;
+    const int q0 = blockIdx.x * PPV_Q;
+#pragma unroll
+    for (int k = 0; k < PPV_Q * TM / 256; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        const int row = e / PPV_Q, ql = e % PPV_Q, q = q0 + ql;
+        const int64_t m = tile * TM + row;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (m < chains && q < NQ) {
+            const int64_t fr = m / C;
+            const int f = 4 * q;
+            if (f < F) {
+                const float4 p4 = __ldg(reinterpret_cast<const float4*>(P + fr * ld + f));
+                const float4 v4 = __ldg(reinterpret_cast<const float4*>(Vb + fr * ld + f));
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_log2 + f);
+                w[0] = pv_word(p4.x, v4.x, b4.x, 0);
+                if (f + 1 < F) w[1] = pv_word(p4.y, v4.y, b4.y, 1);
+                if (f + 2 < F) w[2] = pv_word(p4.z, v4.z, b4.z, 2);
+                if (f + 3 < F) w[3] = pv_word(p4.w, v4.w, b4.w, 3);
+            }
+        }
+        sm[ql * (TM + 1) + row] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PPV_Q * TM / 256; ++k) {
+        const int e = threadIdx.x + 256 * k;
+        const int ql = e / TM, row = e % TM, q = q0 + ql;
+        if (q < NQ) dst[(tile * NQ + q) * TM + row] = sm[ql * (TM + 1) + row];
     }
 }
 
@@ -605,7 +648,13 @@ extern "C" int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int
     if (NT == 0) return 0;
     // layer-3 bias (log2 domain) inside the decoder image: after the hidden-2 bias if there is one
     const float* bias_log2 = reinterpret_cast<const float*>((const unsigned char*)image + d.off_bias) + (d.n_hidden == 2 ? HID : 0);
-    pack_pv_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(P, Vb, bias_log2, NT * n_chains, n_chains, F, ld, (uint4*)dst);
+    const int64_t chains = NT * n_chains, n_tiles = (chains + TM - 1) / TM;
+    if ((ld & 3) == 0 && ld >= ((F + 3) & ~3) && ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Vb)) & 15) == 0 && n_tiles < 65536) {
+        pack_pv_tiled_kernel<<<dim3((NQ + PPV_Q - 1) / PPV_Q, (unsigned)n_tiles), 256, 0, (cudaStream_t)stream>>>(P, Vb, bias_log2, chains,
+                                                                                                                n_chains, F, ld, (uint4*)dst);
+        return check_launch("pack_pv_tiled_kernel");
+    }
+    pack_pv_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(P, Vb, bias_log2, chains, n_chains, F, ld, (uint4*)dst);
     return check_launch("pack_pv_kernel");
 }
 

@@ -282,27 +282,27 @@ __global__ void rng_dump_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t ite
 
 // L % 4 == 0: one thread per Philox block (4 normals, one float4 store; consecutive threads write consecutive 16 bytes).
 // Same counters and the same arithmetic as mh_draws, so the numbers are bit-identical to rng_dump_kernel.
+// blockIdx.y = MH iteration, blockIdx.x covers chains * nb blocks: no 64-bit division on the index path.
 __global__ void __launch_bounds__(256) rng_dump4_kernel(uint32_t seed_lo, uint32_t seed_hi, uint32_t iter0,
                                                         const int32_t* __restrict__ frame_utt, const int32_t* __restrict__ frame_idx,
-                                                        int64_t chains, int C, int nb, int n_iter, float4* __restrict__ eps_out,
+                                                        uint32_t chains, uint32_t C, uint32_t nb_shift, float4* __restrict__ eps_out,
                                                         float* __restrict__ u_out) {
-    const int64_t total = chains * n_iter * nb;
-    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < total; j += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = j / nb;
-        const uint32_t b = (uint32_t)(j - i * nb);
-        const int it = (int)(i / chains);
-        const int64_t m = i - (int64_t)it * chains;
-        const int64_t fr = m / C;
-        const uint32_t c = (uint32_t)(m - fr * C);
+    const uint32_t it = blockIdx.y;
+    const uint32_t per_it = chains << nb_shift;
+    const uint32_t nb = 1u << nb_shift;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < per_it; j += gridDim.x * blockDim.x) {
+        const uint32_t m = j >> nb_shift, b = j & (nb - 1);
+        const uint32_t fr = (C == 1) ? m : m / C;
+        const uint32_t c = (C == 1) ? 0u : m - fr * C;
         const uint32_t utt = (uint32_t)__ldg(frame_utt + fr), fc = (uint32_t)__ldg(frame_idx + fr) | (c << 20);
-        const Philox4 r = philox4x32_10(utt, fc, iter0 + (uint32_t)it, b, seed_lo, seed_hi);
+        const Philox4 r = philox4x32_10(utt, fc, iter0 + it, b, seed_lo, seed_hi);
         float4 o;
         box_muller(r.x, r.y, o.x, o.y);
         box_muller(r.z, r.w, o.z, o.w);
-        eps_out[j] = o;
+        eps_out[(size_t)it * per_it + j] = o;
         if (b == 0) {
-            const Philox4 ru = philox4x32_10(utt, fc, iter0 + (uint32_t)it, (uint32_t)nb, seed_lo, seed_hi);
-            u_out[i] = u01(ru.x);
+            const Philox4 ru = philox4x32_10(utt, fc, iter0 + it, nb, seed_lo, seed_hi);
+            u_out[(size_t)it * chains + m] = u01(ru.x);
         }
     }
 }
@@ -415,13 +415,16 @@ extern "C" int dvae_rng_dump(const DvaeRng* rng, const int32_t* frame_utt, const
     DVAE_REQUIRE(NT >= 0 && n_chains >= 1 && L >= 1 && L <= DVAE_MAX_L && n_iter >= 0, "dvae_rng_dump: bad sizes");
     const int64_t total = NT * n_chains * n_iter;
     if (total == 0) return 0;
-    if (L % 4 == 0 && (reinterpret_cast<uintptr_t>(eps) & 15) == 0) {
-        const int nb = L / 4;
-        const int64_t blocks = (total * nb + 255) / 256;
-        const int grid4 = (int)(blocks < 148 * 64 ? blocks : 148 * 64);
-        rng_dump4_kernel<<<grid4, 256, 0, (cudaStream_t)stream>>>((uint32_t)(rng->seed & 0xffffffffu), (uint32_t)(rng->seed >> 32),
-                                                                 rng->iter0, frame_utt, frame_idx, NT * n_chains, n_chains, nb,
-                                                                 n_iter, reinterpret_cast<float4*>(eps), u);
+    if ((L == 4 || L == 8 || L == 16 || L == 32 || L == 64) && (reinterpret_cast<uintptr_t>(eps) & 15) == 0 && n_iter <= 65535 &&
+        NT * n_chains * (L / 4) < (1ll << 31)) {
+        const uint32_t chains = (uint32_t)(NT * n_chains);
+        uint32_t nb_shift = 0;
+        while ((4 << nb_shift) < L) ++nb_shift;
+        const uint32_t per_it = chains << nb_shift;
+        const uint32_t bx = (per_it + 255) / 256;
+        rng_dump4_kernel<<<dim3(bx < 4096 ? bx : 4096, n_iter), 256, 0, (cudaStream_t)stream>>>(
+            (uint32_t)(rng->seed & 0xffffffffu), (uint32_t)(rng->seed >> 32), rng->iter0, frame_utt, frame_idx, chains,
+            (uint32_t)n_chains, nb_shift, reinterpret_cast<float4*>(eps), u);
         return check_launch("rng_dump4_kernel");
     }
     const int grid = (int)((total + 127) / 128 < 148 * 16 ? (total + 127) / 128 : 148 * 16);
