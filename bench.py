@@ -58,6 +58,18 @@ def parse():
     return ap.parse_args()
 
 
+def measured_traffic(B, variant):
+    """DRAM bytes of one sampler launch from the committed ncu capture, when one exists for this workload."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_tc_traffic.json")
+    try:
+        t = json.load(open(path))
+    except (OSError, ValueError):
+        return None
+    if t.get("utterances_per_gpu") == B and t.get("variant") == variant:
+        return t.get("dram_bytes_per_launch")
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -270,15 +282,18 @@ def run_b200(args):
 
     pk = peaks()
     flop_row = DEC_FLOP_PER_ROW[(args.variant, 16)]
-    mh_ms, mh_calls = stages.get("mh", (0.0, 0))
+    # the sampler kernel itself (events around the dvae_mh_chain_* launch); "mh" additionally holds the draw / pack kernels
+    mh_ms, mh_calls = stages.get("mh_kernel", stages.get("mh", (0.0, 0)))
     roof = None
     if mh_calls:
         flops_per_call = flop_row * mh_rows / mh_calls                       # algorithmic: one decoder row per proposal
         achieved = flops_per_call / (mh_ms / mh_calls * 1e-3) / 1e12
         roof = dict(kernel="mh_chain_%s" % args.sampler, bound="tensor", achieved=achieved, peak=pk["tensor"], unit="TFLOP/s",
-                    frac=achieved / pk["tensor"], traffic=None, peak_source=pk["src"],
+                    frac=achieved / pk["tensor"], traffic=measured_traffic(B, args.variant), peak_source=pk["src"],
                     share_of_step=mh_ms / ms_total, launches_per_step=mh_calls / args.steps,
-                    note="sampler time = CUDA events around dvae_mh_chain_* inside the timed region; FLOPs = %d per decoder row x rows" % flop_row)
+                    note="sampler time = CUDA events around dvae_mh_chain_* inside the timed region; FLOPs = %d per decoder row x rows; "
+                         "traffic = dram read+write bytes of one E-step launch from ncu (profiles/r01_tc_traffic.json), null if "
+                         "no capture matches this batch" % flop_row)
     stage_share = {k: round(v[0] / ms_total, 4) for k, v in stages.items()}
 
     cpu = None
