@@ -102,3 +102,23 @@ def test_errors():
         stft(np.zeros(4000, np.float32), fs=16000, wlen_sec=64e-3, center=True)
     with pytest.raises(ValueError):
         istft(np.zeros((513, 4), np.complex64), fs=16000, wlen_sec=50.01e-3)
+
+
+def test_torch_front_end_matches_numpy_wrappers():
+    """stft_pytorch / istft_pytorch (stft.py:102-193): tensors in and out, (F, N, 2) layout, max_len in seconds."""
+    import torch
+    from dvae_b200.packages.processing.stft import istft_pytorch, stft, stft_pytorch
+    kw = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False, pad_at_end=True)
+    x = synth.synth_utterance(3, 1.0)[0].astype(np.float32)
+    ref = stft(x, **kw)
+    for dev in ("cuda:0", "cpu"):
+        S = stft_pytorch(torch.from_numpy(x).to(dev), **kw)
+        assert S.shape == (513, ref.shape[1], 2) and S.dtype == torch.float32 and S.device.type == dev[:4].rstrip(":")
+        assert np.array_equal(torch.view_as_complex(S.contiguous()).cpu().numpy(), ref)
+        y = istft_pytorch(S, fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False, max_len=0.5)
+        assert y.shape == (8000,) and y.dtype == torch.float32
+        assert np.max(np.abs(y.cpu().numpy()[800:] - x[800:8000])) < 1e-5
+    power = (stft_pytorch(torch.from_numpy(x).cuda(), **kw) ** 2).sum(-1)          # packages/data_handling.py:133-136
+    assert np.allclose(power.cpu().numpy(), np.abs(ref) ** 2, rtol=1e-6)
+    with pytest.raises(NotImplementedError):
+        stft_pytorch(torch.zeros(4096), fs=16000, wlen_sec=64e-3, center=True)
