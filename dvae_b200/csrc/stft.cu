@@ -258,106 +258,104 @@ __global__ void __launch_bounds__(256, 6) stft_kernel(const float* __restrict__ 
 }
 
 // ----------------------------------------------------------------------------- ISTFT
-constexpr int kSegFrames = 28;                   // frames touched per CTA (7 passes of 4)
-
-__global__ void __launch_bounds__(256) istft_kernel(const float2* __restrict__ X, const int64_t* __restrict__ fr_off,
-                                                    float* __restrict__ y, const int64_t* __restrict__ y_off,
-                                                    const int32_t* __restrict__ y_len, int hop, int ld, int seg_hops) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* tw = reinterpret_cast<float2*>(smem_raw);                         // 1024 float2
-    float2* bufs = tw + kNfft;                                                // 4 * kBuf float2 (FFT exchange buffers)
-    float* fbuf = reinterpret_cast<float*>(bufs);                             // 4 * 1024 floats: the windowed frames reuse them
-    float* win = fbuf + 4 * kNfft;                                            // 1024 floats
-    float* acc = win + kNfft;                                                 // (kSegFrames-1)*hop + 1024 floats
+// hop = 256 = CTA size: thread i owns sample i of every hop.  A pass inverts four consecutive frames (one per frame
+// group) and overlap-adds them in ascending frame order - the reference's float32 accumulation order - into SEVEN
+// register accumulators per thread (the hops jp .. jp+6 those frames touch).  Hops jp .. jp+3 are final after the pass
+// (no later frame reaches them): they are normalised by the window sum-square table and stored, the other three slide
+// down.  No accumulator lives in shared memory, a CTA can stream a whole utterance (no frame is transformed twice), and
+// only short batches are cut into segments (three lead-in frames each) to fill the GPU.
+__global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict__ X, const int64_t* __restrict__ fr_off,
+                                                       float* __restrict__ y, const int64_t* __restrict__ y_off,
+                                                       const int32_t* __restrict__ y_len, int hop, int ld, int seg_hops) {
+    __shared__ float2 tw[kNfft];
+    __shared__ __align__(8) float win[kNfft];
+    __shared__ __align__(16) float2 bufs[4 * kBuf];                           // FFT exchange buffers; then the windowed frames
+    float* fbuf = reinterpret_cast<float*>(bufs);
 
     const int u = blockIdx.y;
-    const int ov = kNfft / hop;                                               // frames overlapping one sample (4: hop = 256 = blockDim)
     const int64_t f0 = fr_off[u];
     const int N = (int)(fr_off[u + 1] - f0);
     const int len = y_len[u];
     const int h0 = blockIdx.x * seg_hops;                                     // first output hop of this CTA
-    const int out_lo = h0 * hop, out_hi = min(len, (h0 + seg_hops) * hop);
-    if (out_lo >= len) return;
-    const int jstart = max(0, h0 - (ov - 1));
-    const int jend = min(N - 1, h0 + seg_hops - 1);                           // inclusive; may be < jstart
-    const int a0 = jstart * hop;                                              // sample index of acc[0]
-    const int span = (kSegFrames - 1) * hop + kNfft;
+    if (h0 * hop >= len) return;
+    const int h1 = min(h0 + seg_hops, (len + hop - 1) / hop);                 // one past the last output hop
+    const int jstart = max(0, h0 - 3);
+    const int jend = min(N - 1, h1 - 1);                                      // last frame that reaches the segment; may be < jstart
+    const int sig_len = (N > 0) ? kNfft + hop * (N - 1) : 0;
 
     for (int i = threadIdx.x; i < kNfft; i += blockDim.x) { tw[i] = g_tw[i]; win[i] = g_win[i]; }
-    for (int i = threadIdx.x; i < span; i += blockDim.x) acc[i] = 0.f;
     __syncthreads();
 
-    const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
+    const int grp = threadIdx.x >> 6, t = threadIdx.x & 63, i = threadIdx.x;
     float2* buf = bufs + grp * kBuf;
-    for (int jp = jstart; jp <= jend; jp += 4) {
-        const int j = jp + grp;
-        const bool live = j <= jend;
-        float2 a[8];
-        if (live) {
-            const float2* Xn = X + (f0 + j) * (int64_t)ld;
+    float* yu = y + y_off[u];
+    float v[7];
 #pragma unroll
-            for (int n1 = 0; n1 < 8; ++n1) {
-                const int k = t + 64 * n1;
-                float2 xk = __ldg(Xn + k), xm = __ldg(Xn + kHalf - k);
-                if (k == 0) { xk.y = 0.f; xm.y = 0.f; }                       // irfft ignores Im of DC and Nyquist
-                xm.y = -xm.y;                                                 // conj(X[512-k])
-                const float2 s = cadd(xk, xm), d = csub(xk, xm);
-                float2 w = tw[k];
-                w.y = -w.y;                                                   // conj(W^k)
-                const float2 wd = cmul(w, d);
-                const float2 zb = make_float2(s.x - wd.y, s.y + wd.x);        // s + i*wd
-                a[n1] = make_float2(zb.x, -zb.y);                             // conj -> inverse via forward FFT
+    for (int m = 0; m < 7; ++m) v[m] = 0.f;
+    for (int jp = jstart; jp < h1; jp += 4) {
+        if (jp <= jend) {                                                     // CTA-uniform: at least one frame of this pass exists
+            const int j = jp + grp;
+            const bool live = j <= jend;
+            float2 a[8];
+            if (live) {
+                const float2* Xn = X + (f0 + j) * (int64_t)ld;
+#pragma unroll
+                for (int n1 = 0; n1 < 8; ++n1) {
+                    const int k = t + 64 * n1;
+                    float2 xk = __ldg(Xn + k), xm = __ldg(Xn + kHalf - k);
+                    if (k == 0) { xk.y = 0.f; xm.y = 0.f; }                   // irfft ignores Im of DC and Nyquist
+                    xm.y = -xm.y;                                             // conj(X[512-k])
+                    const float2 s = cadd(xk, xm), d = csub(xk, xm);
+                    float2 w = tw[k];
+                    w.y = -w.y;                                               // conj(W^k)
+                    const float2 wd = cmul(w, d);
+                    const float2 zb = make_float2(s.x - wd.y, s.y + wd.x);    // s + i*wd
+                    a[n1] = make_float2(zb.x, -zb.y);                         // conj -> inverse via forward FFT
+                }
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < 8; ++n1) a[n1] = make_float2(0.f, 0.f);
             }
-        } else {
+            fft512(a, buf, tw, t, grp);
+            {
+                float2* fb = reinterpret_cast<float2*>(fbuf + grp * kNfft);
 #pragma unroll
-            for (int n1 = 0; n1 < 8; ++n1) a[n1] = make_float2(0.f, 0.f);
-        }
-        fft512(a, buf, tw, t, grp);
-        {
-            float2* fb = reinterpret_cast<float2*>(fbuf + grp * kNfft);
-#pragma unroll
-            for (int j2 = 0; j2 < 8; ++j2) {
-                const int m = t + 64 * j2;
-                const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * m);
-                const float xe = a[j2].x * (1.0f / 1024.0f), xo = -a[j2].y * (1.0f / 1024.0f);
-                fb[m] = live ? make_float2(xe * w2.x, xo * w2.y) : make_float2(0.f, 0.f);
+                for (int j2 = 0; j2 < 8; ++j2) {
+                    const int m = t + 64 * j2;
+                    const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * m);
+                    const float xe = a[j2].x * (1.0f / 1024.0f), xo = -a[j2].y * (1.0f / 1024.0f);
+                    fb[m] = live ? make_float2(xe * w2.x, xo * w2.y) : make_float2(0.f, 0.f);
+                }
             }
-        }
-        __syncthreads();
-        // overlap-add the (up to) four frames of this pass in ascending frame order, like the reference's loop.  hop equals
-        // the CTA size, so thread i owns the accumulator positions base + 256 m + i (m = 0..6) in every pass: they are
-        // updated in registers, frame g contributing its sample 256 (m - g) + i for g <= m <= g + 3.
-        {
-            const int base = (jp - jstart) * hop;
-            const int i = threadIdx.x;
-            float v[7];
+            __syncthreads();
 #pragma unroll
-            for (int m = 0; m < 7; ++m) v[m] = acc[base + 256 * m + i];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
+            for (int g = 0; g < 4; ++g) {                                     // ascending frame order, like the reference's loop
                 if (jp + g <= jend) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) v[g + c] += fbuf[g * kNfft + 256 * c + i];
                 }
             }
+            __syncthreads();                                                  // fbuf is the next pass's exchange buffer
+        }
+        // hops jp .. jp+3 are complete
 #pragma unroll
-            for (int m = 0; m < 7; ++m) acc[base + 256 * m + i] = v[m];
+        for (int m = 0; m < 4; ++m) {
+            const int hh = jp + m;
+            const int s = hh * hop + i;
+            if (hh >= h0 && hh < h1 && s < len) {
+                float r = 0.f;
+                if (s < sig_len) {
+                    r = v[m];
+                    const int jlo = max(0, (s - kNfft + hop) / hop), jhi = min(N - 1, s / hop);
+                    const int o = s - jlo * hop, q = o >> 8, cnt = jhi - jlo + 1;
+                    const float wss = __ldg(g_wss + ((q * (q + 1) / 2 + cnt - 1) << 8) + (o & 255));
+                    if (wss > FLT_MIN) r /= wss;
+                }
+                yu[s] = r;
+            }
         }
-        __syncthreads();
-    }
-
-    float* yu = y + y_off[u];
-    const int sig_len = (N > 0) ? kNfft + hop * (N - 1) : 0;
-    for (int s = out_lo + threadIdx.x; s < out_hi; s += blockDim.x) {
-        float v = 0.f;
-        if (s < sig_len) {
-            v = acc[s - a0];
-            const int jlo = max(0, (s - kNfft + hop) / hop), jhi = min(N - 1, s / hop);
-            const int o = s - jlo * hop, q = o >> 8, cnt = jhi - jlo + 1;
-            const float wss = __ldg(g_wss + ((q * (q + 1) / 2 + cnt - 1) << 8) + (o & 255));
-            if (wss > FLT_MIN) v /= wss;
-        }
-        yu[s] = v;
+        v[0] = v[4]; v[1] = v[5]; v[2] = v[6];
+        v[3] = 0.f; v[4] = 0.f; v[5] = 0.f; v[6] = 0.f;
     }
 }
 
@@ -385,17 +383,20 @@ extern "C" int dvae_istft_f32(const void* X, const int64_t* fr_off, int B, float
                               const int32_t* y_len, int max_y_len, int n_fft, int hop, int ld, void* stream) {
     DVAE_REQUIRE(n_fft == kNfft, "dvae_istft_f32: only n_fft=1024 is implemented (got %d)", n_fft);
     DVAE_REQUIRE(hop == 256, "dvae_istft_f32: only hop=256 is implemented (got %d)", hop);
-    DVAE_REQUIRE(B >= 1 && max_y_len >= 0 && ld >= kHalf + 1, "dvae_istft_f32: bad sizes");
+    DVAE_REQUIRE(B >= 1 && B <= 65535 && max_y_len >= 0 && ld >= kHalf + 1, "dvae_istft_f32: bad sizes (B <= 65535)");
     DVAE_REQUIRE(X && fr_off && y && y_off && y_len, "dvae_istft_f32: null pointer");
     if (max_y_len == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_tables(st);
     if (rc) return rc;
-    const int ov = kNfft / hop;
-    const int seg_hops = kSegFrames - (ov - 1);
-    const int n_seg = (max_y_len + seg_hops * hop - 1) / (seg_hops * hop);
-    const size_t smem = sizeof(float2) * (kNfft + 4 * kBuf) + sizeof(float) * (kNfft + (kSegFrames - 1) * hop + kNfft);
-    cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    istft_kernel<<<dim3(n_seg, B), 256, smem, st>>>((const float2*)X, fr_off, y, y_off, y_len, hop, ld, seg_hops);
+    // whole utterances per CTA when the batch alone fills the GPU (4 resident CTAs per SM), otherwise segments of at least
+    // 8 hops (each pays three lead-in frames)
+    const int total_hops = (max_y_len + hop - 1) / hop;
+    int n_seg = (148 * 4 + B - 1) / B;
+    if (n_seg > (total_hops + 7) / 8) n_seg = (total_hops + 7) / 8;
+    if (n_seg < 1) n_seg = 1;
+    const int seg_hops = (total_hops + n_seg - 1) / n_seg;
+    n_seg = (total_hops + seg_hops - 1) / seg_hops;
+    istft_kernel<<<dim3(n_seg, B), 256, 0, st>>>((const float2*)X, fr_off, y, y_off, y_len, hop, ld, seg_hops);
     return check_launch("istft_kernel");
 }
