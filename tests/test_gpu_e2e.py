@@ -151,3 +151,31 @@ def test_device_vad_labels_equal_host_labels():
     for a, b in zip(s_host, s_dev):
         assert np.array_equal(a, b)
     assert np.array_equal(c_host, c_dev)
+
+
+def test_process_sublist_replacement(tmp_path):
+    """batch_io.process_sublist: wav files in, *_s_est.wav / *_n_est.wav out, existing outputs skipped (evaluate_ntcd_M1.py:81-214)."""
+    import os
+    from dvae_b200 import batch_io
+    from dvae_b200.engine import Enhancer, McemConfig
+    wav_dir, out_dir = str(tmp_path / "wav") + "/", str(tmp_path / "out") + "/"
+    lens = [16000, 12000, 20000]
+    sub = []
+    for i, l in enumerate(lens):
+        x = synth.synth_utterance(60 + i, l / 16000.0)[0]
+        rel = "spk%d/utt%d.wav" % (i % 2, i)
+        batch_io.write_wav(wav_dir + rel, x, 16000)
+        sub.append((rel, "unused_clean_path"))
+    x0, _ = batch_io.read_wav(wav_dir + sub[0][0])
+    P0 = np.abs(stft_np.stft(x0, **KW)) ** 2
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128], 0, seed=5, out_bias=float(np.log(P0.mean())))
+    enh = Enhancer(sd, "M1", McemConfig(niter=2, keep_E=3, burn_E=4, keep_WF=4, burn_WF=5, seed=2), device=0)
+    done = batch_io.process_sublist(sub, enh, wav_dir, out_dir, batch_size=2)
+    assert len(done) == 3
+    for (rel, _), l in zip(sub, lens):
+        s, fs = batch_io.read_wav(batch_io.output_stem(out_dir, rel) + "_s_est.wav")
+        n, _ = batch_io.read_wav(batch_io.output_stem(out_dir, rel) + "_n_est.wav")
+        x, _ = batch_io.read_wav(wav_dir + rel)
+        assert fs == 16000 and len(s) == l and len(n) == l
+        assert np.max(np.abs((s + n)[800:-800] - x[800:-800])) < 2e-4          # masks sum to one; two 16-bit roundings
+    assert batch_io.process_sublist(sub, enh, wav_dir, out_dir) == []           # everything exists: skipped like the reference

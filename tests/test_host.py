@@ -108,3 +108,28 @@ def test_synthetic_inputs_are_seeded_and_mixed_at_snr():
     assert abs(snr - 0.0) < 1e-3                            # u % 4 == 1 -> 0 dB
     y = synth.energy_vad(s)
     assert y.shape == (1, 185) and set(np.unique(y)) <= {0.0, 1.0}
+
+
+def test_wav_io_round_trip(tmp_path):
+    """batch_io.read_wav / write_wav: 16-bit PCM like sf.write's default, sf.read scaling, other sample formats."""
+    import struct
+    from dvae_b200 import batch_io
+    rng = np.random.default_rng(0)
+    x = np.clip(rng.standard_normal(3000) * 0.2, -0.99, 0.99)
+    p = str(tmp_path / "a" / "x.wav")
+    batch_io.write_wav(p, x, 16000)
+    y, fs = batch_io.read_wav(p)
+    assert fs == 16000 and y.dtype == np.float64 and y.shape == x.shape
+    assert np.max(np.abs(y - x)) <= 0.5 / 32768 + 1e-12
+    assert np.array_equal(y * 32768.0, np.rint(x * 32768.0))
+    # IEEE float32, two channels: first channel is returned
+    st = np.stack([x, -x], 1).astype("<f4").tobytes()
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(st)) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 3, 2, 8000, 8000 * 8, 8, 32) \
+        + b"data" + struct.pack("<I", len(st))
+    q = str(tmp_path / "f.wav")
+    open(q, "wb").write(hdr + st)
+    z, fs2 = batch_io.read_wav(q)
+    assert fs2 == 8000 and np.allclose(z, x.astype(np.float32))
+    with pytest.raises(ValueError):
+        open(q, "wb").write(b"not a wav file")
+        batch_io.read_wav(q)
