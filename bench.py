@@ -294,6 +294,8 @@ def run_b200(args):
                     note="sampler time = CUDA events around dvae_mh_chain_* inside the timed region; FLOPs = %d per decoder row x rows; "
                          "traffic = dram read+write bytes of one E-step launch from ncu (profiles/r01_tc_traffic.json), null if "
                          "no capture matches this batch" % flop_row)
+    cfg_name = "BASELINE.json configs[1]" if (args.variant == "M1" and B == 512) else \
+        "BASELINE.json configs[%d] shape (%s, %d utterances per GPU)" % (2 if args.variant == "M2" else (3 if args.variant == "M2v3" else 1), args.variant, B)
     stage_share = {k: round(v[0] / ms_total, 4) for k, v in stages.items()}
 
     cpu = None
@@ -309,7 +311,7 @@ def run_b200(args):
     out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f32" if args.sampler == "fp32" else "bf16", data="synthetic",
-               config=dict(workload="BASELINE.json configs[1]: %s batch of %d synthetic 3 s 16 kHz utterances per GPU, STFT 1024/256, "
+               config=dict(workload=cfg_name + ": %s batch of %d synthetic 3 s 16 kHz utterances per GPU, STFT 1024/256, "
                                     "NMF rank 10, %d EM iterations, MH schedule %s" % (args.variant, B, args.niter, schedule(args.variant, args.niter)),
                            utterances_per_gpu=B, sampler=args.sampler, chains=args.chains,
                            l2="working set per step (Vs %.1f GB) exceeds the 126 MB L2; no explicit flush" %
