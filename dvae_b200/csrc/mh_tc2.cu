@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     const bool two_hidden = d.n_hidden == 2;
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
 
+    const long long dbg_t0 = clock64();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row_g = tile * TM + row;
         const bool valid = row_g < p.rows;
@@ -309,6 +310,12 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         }
     }
 
+    if (p.dbg && threadIdx.x == 0) {                    // per-CTA duration of the tile loop: min / max / sum over CTAs (slots 56-58)
+        const long long dt = clock64() - dbg_t0;
+        atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 56), (unsigned long long)dt);
+        atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 57), (unsigned long long)dt);
+        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 58), (unsigned long long)dt);
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {

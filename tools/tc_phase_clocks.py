@@ -21,15 +21,18 @@ w = VaeWeights(sd, "M1", DEV)
 eng = McemEngine(w, McemConfig(niter=1, keep_E=30, burn_E=30, sampler="tc"), DEV)
 eng.init_parameters(X, P, RaggedBatch([N] * B, DEV))
 buf = torch.zeros(64, dtype=torch.int64, device=DEV)
+buf[56] = 2 ** 62
 _lib.call("dvae_debug_set_clock_buffer", _p(buf)); _lib.call("dvae_debug_set_clock_buffer3", _p(buf)); _lib.call("dvae_debug_set_clock_buffer4", _p(buf))
 eng.timing = True
 for _ in range(2):
+    buf[56] = 2 ** 62; buf[57] = 0; buf[58] = 0
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record(); eng.sample_posterior(30, 30); t1.record(); torch.cuda.synchronize()
 print("stage events:", eng.stage_times_ms())
 print("sample_posterior(60 iters, %d chains): %.2f ms -> %.0f clk per tile-eval at 1.965 GHz" %
       (B * N, t0.elapsed_time(t1), t0.elapsed_time(t1) * 1e-3 * 1.965e9 / 61 / max(1, (B * N / 128) / 148)))
 c = buf.cpu().numpy()
+print("per-CTA tile-loop clocks (v2 sampler): min %d max %d mean %d" % (c[56], c[57], c[58] / 148))
 _lib.call("dvae_debug_set_clock_buffer", None); _lib.call("dvae_debug_set_clock_buffer3", None); _lib.call("dvae_debug_set_clock_buffer4", None)
 names = {0: "iter start", 1: "after S1 (A1 written)", 20: "warp0 done hidden-1", 2: "after S2", 21: "warp0 done hidden-2", 3: "after S3",
          15: "chunk0 ready", 4: "warp0 done chunk0", 16: "chunk1 ready", 5: "warp0 done chunk1", 17: "chunk2 ready",
