@@ -40,6 +40,7 @@ struct DsParams {
     float* A2;              // [NT][ld]
     int64_t NT;
     int ld;
+    int zs_rtot, zs_r0;     // samples per frame in Zs and the first one this launch decodes (R of them)
     int* status;
     long long* dbg;
 };
@@ -86,12 +87,14 @@ __device__ __forceinline__ void ds_hidden_row(uint32_t tmem, unsigned char* A, i
 }
 
 // LDC: compile-time row pitch of Vs / Vb / A1 / A2 (520 for F = 513: store offsets become immediates), 0 = take p.ld
-template <int R, int L, int LDC>
+// STORE = false: only A1 is produced (no Vs, no A2): the Wiener masks of the final filter follow from A1 alone,
+// mean_r g Vs / Vx = 1 - Vb A1 / R (mcem.py:325-327), so its 75 (25) samples are never written to memory.
+template <int R, int L, int LDC, bool STORE>
 __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p) {
     constexpr int RL = (R <= 16) ? 16 : 32;
-    constexpr int FT = 128 / R;                        // frames per tile
+    constexpr int FT = (R == 25) ? 4 : 128 / R;        // frames per tile (R = 25: 4 x 25 = 100 rows, so that FT stays a multiple of 4)
     constexpr int FS = FT / 4;                         // frames per back warp
-    static_assert(FT % 4 == 0 && (FT - 1) * R + RL <= 128, "tile geometry");
+    static_assert(FT % 4 == 0 && (FT - 1) * R + RL <= 128 && FT * R <= 128, "tile geometry");
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t bars[11];
     __shared__ uint32_t tmem_slot;
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
             float z[L];
             float y0 = 0.f, y1 = 0.f, y2 = 0.f;
             if (valid) {
-                const float4* src = reinterpret_cast<const float4*>(p.Zs + (n * R + r) * (int64_t)L);
+                const float4* src = reinterpret_cast<const float4*>(p.Zs + (n * p.zs_rtot + p.zs_r0 + r) * (int64_t)L);
 #pragma unroll
                 for (int l = 0; l < L / 4; ++l) {
                     const float4 t4 = __ldg(src + l);
@@ -277,10 +280,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                                 upk2(add2(pk2(v[k], v[k + 1]), bias2), e0, e1);
                                 upk2(add2(pk2(v[k + 2], v[k + 3]), bias2), e2, e3);
                                 const float s0 = ex2_approx(e0), s1 = ex2_approx(e1), s2 = ex2_approx(e2), s3 = ex2_approx(e3);
-                                dst[(int64_t)(r0 + k) * ldv] = s0;
-                                dst[(int64_t)(r0 + k + 1) * ldv] = s1;
-                                dst[(int64_t)(r0 + k + 2) * ldv] = s2;
-                                dst[(int64_t)(r0 + k + 3) * ldv] = s3;
+                                if (STORE) {
+                                    dst[(int64_t)(r0 + k) * ldv] = s0;
+                                    dst[(int64_t)(r0 + k + 1) * ldv] = s1;
+                                    dst[(int64_t)(r0 + k + 2) * ldv] = s2;
+                                    dst[(int64_t)(r0 + k + 3) * ldv] = s3;
+                                }
                                 const f32x2 X = fma2(g2, pk2(s0, s1), vb2), Y = fma2(g2, pk2(s2, s3), vb2);
                                 float m0, m1;
                                 upk2(mul2(X, Y), m0, m1);
@@ -291,15 +296,24 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                             };
                             auto pair = [&](const float* v, int k, int r0) {
                                 const float s0 = ex2_approx(v[k] + bias), s1 = ex2_approx(v[k + 1] + bias);
-                                dst[(int64_t)(r0 + k) * ldv] = s0;
-                                dst[(int64_t)(r0 + k + 1) * ldv] = s1;
+                                if (STORE) {
+                                    dst[(int64_t)(r0 + k) * ldv] = s0;
+                                    dst[(int64_t)(r0 + k + 1) * ldv] = s1;
+                                }
                                 const float x0 = fmaf(gg, s0, vb), x1 = fmaf(gg, s1, vb);
                                 const float rr = rcp_approx(x0 * x1);
                                 const float i0 = x1 * rr, i1 = x0 * rr;
                                 a1 += i0 + i1;
                                 a2 = fmaf(i0, i0, fmaf(i1, i1, a2));
                             };
-                            static_assert(R == 30 || R == 10, "sample count of the back epilogue");
+                            auto single = [&](const float* v, int k, int r0) {
+                                const float s0 = ex2_approx(v[k] + bias);
+                                if (STORE) dst[(int64_t)(r0 + k) * ldv] = s0;
+                                const float i0 = rcp_approx(fmaf(gg, s0, vb));
+                                a1 += i0;
+                                a2 = fmaf(i0, i0, a2);
+                            };
+                            static_assert(R == 30 || R == 25 || R == 10, "sample count of the back epilogue");
                             float v0[16];
                             tmem_ld16(tb + lane_off + fi * R, v0);
                             tmem_wait_ld();
@@ -311,6 +325,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                                 quad(v0, 0, 0); quad(v0, 4, 0); quad(v0, 8, 0); quad(v0, 12, 0);
                                 tmem_wait_ld();
                                 quad(v1, 0, 16); quad(v1, 4, 16); quad(v1, 8, 16); pair(v1, 12, 16);
+                            } else if (R == 25) {
+                                float v1[16];
+                                tmem_ld16(tb + lane_off + fi * R + 16, v1);
+                                quad(v0, 0, 0); quad(v0, 4, 0); quad(v0, 8, 0); quad(v0, 12, 0);
+                                tmem_wait_ld();
+                                quad(v1, 0, 16); quad(v1, 4, 16); single(v1, 8, 16);
                             } else {
                                 quad(v0, 0, 0); quad(v0, 4, 0); pair(v0, 8, 0);
                             }
@@ -322,7 +342,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                                 a2 += lo + hi;
                             }
                             p.A1[n * ldv + f] = a1;
-                            p.A2[n * ldv + f] = a2;
+                            if (STORE) p.A2[n * ldv + f] = a2;
                         }
                     }
                 } else if (s == 0) {
@@ -336,7 +356,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                     float inv = 0.f;
                     if (fi < FT && n < p.NT && d.F > 512) {
                         const float vs = ex2_approx(v[0] + b3[512]);
-                        p.Vs[(n * R + r) * (int64_t)ldv + 512] = vs;
+                        if (STORE) p.Vs[(n * R + r) * (int64_t)ldv + 512] = vs;
                         inv = rcp_approx(fmaf(__ldg(p.g + n), vs, __ldg(p.Vb + n * ldv + 512)));
                     }
                     tailS[row] = inv;
@@ -348,7 +368,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                         if (nn < p.NT && d.F > 512) {
                             float sum = 0.f;
                             for (int rr = 0; rr < R; ++rr) sum += tailS[which * 128 + fj * R + rr];
-                            (which ? p.A2 : p.A1)[nn * ldv + 512] = sum;
+                            if (STORE || which == 0) (which ? p.A2 : p.A1)[nn * ldv + 512] = sum;
                         }
                     }
                     ds_bar_tail();
@@ -480,45 +500,92 @@ __global__ void __launch_bounds__(128, 8) w_from_frame_stats_kernel(const float*
 using namespace dvae;
 using namespace dvae::tc;
 
-extern "C" int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y,
-                                    int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1,
-                                    float* A2, int* status, void* stream) {
+static int launch_decode_stats(const char* who, const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R,
+                               int L, const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs,
+                               float* A1, float* A2, int* status, void* stream) {
     DsParams p{};
-    int rc = check_dims(dec, L, y_dim, "dvae_decode_stats_tc", &p.d);
+    int rc = check_dims(dec, L, y_dim, who, &p.d);
     if (rc) return rc;
-    DVAE_REQUIRE(image && Zs && Vb && g && Vs && A1 && A2 && status, "dvae_decode_stats_tc: null pointer");
-    DVAE_REQUIRE(R == 10 || R == 30, "dvae_decode_stats_tc: R must be 10 or 30 (got %d)", R);
-    DVAE_REQUIRE(L == 16 || L == 32, "dvae_decode_stats_tc: latent size must be 16 or 32 (got %d)", L);
-    DVAE_REQUIRE(y_dim <= 3 && (y_dim == 0 || y), "dvae_decode_stats_tc: bad label arguments");
-    DVAE_REQUIRE(NT >= 0 && ld >= p.d.F, "dvae_decode_stats_tc: bad sizes");
+    const bool store = Vs != nullptr;
+    DVAE_REQUIRE(image && Zs && Vb && g && A1 && status && (!store || A2), "%s: null pointer", who);
+    DVAE_REQUIRE(store ? (R == 10 || R == 30) : (R == 10 || R == 25 || R == 30), "%s: unsupported sample count %d", who, R);
+    DVAE_REQUIRE(r0 >= 0 && r0 + R <= R_total, "%s: sample window [%d, %d) outside [0, %d)", who, r0, r0 + R, R_total);
+    DVAE_REQUIRE(L == 16 || L == 32, "%s: latent size must be 16 or 32 (got %d)", who, L);
+    DVAE_REQUIRE(y_dim <= 3 && (y_dim == 0 || y), "%s: bad label arguments", who);
+    DVAE_REQUIRE(NT >= 0 && ld >= p.d.F, "%s: bad sizes", who);
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(Zs) & 15) == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0,
-                 "dvae_decode_stats_tc: Zs and image must be 16-byte aligned");
+                 "%s: Zs and image must be 16-byte aligned", who);
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
     p.Zs = Zs; p.y = y; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status; p.dbg = g_dbg_clocks_ds;
+    p.zs_rtot = R_total; p.zs_r0 = r0;
     const int shared_bytes = (p.d.off_w3 + 4 * ((p.d.n_hidden == 2 ? HID : 0) + NPAD) + 1023) & ~1023;
     const size_t smem = (size_t)shared_bytes + 65536 + 65536 + 1024;
-    DVAE_REQUIRE(smem <= 227 * 1024, "dvae_decode_stats_tc: shared memory budget exceeded");
-    const int FT = 128 / R;
+    DVAE_REQUIRE(smem <= 227 * 1024, "%s: shared memory budget exceeded", who);
+    const int FT = (R == 25) ? 4 : 128 / R;
     const int64_t n_tiles = (NT + FT - 1) / FT;
     const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
     cudaStream_t st = (cudaStream_t)stream;
-#define DS_LAUNCH(RR, LL)                                                                                         \
-    do {                                                                                                          \
-        if (ld == 520) {                                                                                          \
-            cudaFuncSetAttribute(decode_stats_kernel<RR, LL, 520>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            decode_stats_kernel<RR, LL, 520><<<grid, DS_THREADS, smem, st>>>(p);                                  \
-        } else {                                                                                                  \
-            cudaFuncSetAttribute(decode_stats_kernel<RR, LL, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            decode_stats_kernel<RR, LL, 0><<<grid, DS_THREADS, smem, st>>>(p);                                    \
-        }                                                                                                         \
+#define DS_LAUNCH(RR, LL, LD, SS)                                                                                       \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(decode_stats_kernel<RR, LL, LD, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        decode_stats_kernel<RR, LL, LD, SS><<<grid, DS_THREADS, smem, st>>>(p);                                         \
     } while (0)
-    if (R == 10 && L == 16) DS_LAUNCH(10, 16);
-    else if (R == 10) DS_LAUNCH(10, 32);
-    else if (L == 16) DS_LAUNCH(30, 16);
-    else DS_LAUNCH(30, 32);
+#define DS_PICK(RR, SS)                                                 \
+    do {                                                                \
+        if (L == 16 && ld == 520) DS_LAUNCH(RR, 16, 520, SS);           \
+        else if (L == 16) DS_LAUNCH(RR, 16, 0, SS);                     \
+        else if (ld == 520) DS_LAUNCH(RR, 32, 520, SS);                 \
+        else DS_LAUNCH(RR, 32, 0, SS);                                  \
+    } while (0)
+    if (store) {
+        if (R == 10) DS_PICK(10, true);
+        else DS_PICK(30, true);
+    } else {
+        if (R == 10) DS_PICK(10, false);
+        else if (R == 25) DS_PICK(25, false);
+        else DS_PICK(30, false);
+    }
+#undef DS_PICK
 #undef DS_LAUNCH
     return check_launch("decode_stats_kernel");
+}
+
+extern "C" int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y,
+                                    int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1,
+                                    float* A2, int* status, void* stream) {
+    DVAE_REQUIRE(Vs && A2, "dvae_decode_stats_tc: null pointer");
+    return launch_decode_stats("dvae_decode_stats_tc", dec, image, Zs, R, 0, R, L, y, y_dim, Vb, g, NT, ld, Vs, A1, A2, status, stream);
+}
+
+extern "C" int dvae_decode_a1_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R, int L,
+                                 const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* A1,
+                                 int* status, void* stream) {
+    return launch_decode_stats("dvae_decode_a1_tc", dec, image, Zs, R_total, r0, R, L, y, y_dim, Vb, g, NT, ld, nullptr, A1, nullptr,
+                               status, stream);
+}
+
+// WFn (+)= Vb A1, WFs (+)= R - Vb A1: sums over the R samples behind A1 of Vb / Vx and g Vs / Vx = 1 - Vb / Vx (mcem.py:325-327)
+__global__ void wiener_from_a1_kernel(const float* __restrict__ A1, const float* __restrict__ Vb, float R, int64_t NT, int F, int ld,
+                                      float* __restrict__ WFs, float* __restrict__ WFn, int first) {
+    const int64_t total = NT * ld;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i % ld);
+        if (f >= F) continue;
+        const float q = Vb[i] * A1[i];
+        WFn[i] = (first ? 0.f : WFn[i]) + q;
+        WFs[i] = (first ? 0.f : WFs[i]) + (R - q);
+    }
+}
+
+extern "C" int dvae_wiener_from_a1(const float* A1, const float* Vb, int R, int64_t NT, int F, int ld, float* WFs, float* WFn,
+                                   int first, void* stream) {
+    DVAE_REQUIRE(A1 && Vb && WFs && WFn && R >= 1 && NT >= 0 && F >= 1 && ld >= F, "dvae_wiener_from_a1: bad arguments");
+    if (NT == 0) return 0;
+    const int64_t blocks = (NT * ld + 255) / 256;
+    wiener_from_a1_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, (cudaStream_t)stream>>>(A1, Vb, (float)R, NT, F, ld,
+                                                                                                            WFs, WFn, first);
+    return check_launch("wiener_from_a1_kernel");
 }
 
 extern "C" int dvae_nmf_w_from_frame_stats(const float* A1, const float* A2, const float* P, const float* H, const float* W,

@@ -445,15 +445,26 @@ class McemEngine:
         R = Zs.shape[1]
         WFs = self._get("WFs", (b.NT, self.ld))
         WFn = self._get("WFn", (b.NT, self.ld))
-        # decode in frame chunks so the Vs buffer of the E-step (NT * R_E rows) is reused
-        flat = self.Vs_flat
-        step = max(1, min(b.NT, flat.shape[0] // R))
-        for n0 in range(0, b.NT, step):
-            n1 = min(b.NT, n0 + step)
-            self.decode_samples(Zs, n0, n1, flat)
-            _lib.call("dvae_wiener_accum", _p(flat), R, _p(self.Vb[n0:n1]), _p(self.g[n0:n1]), n1 - n0, self.F, self.ld,
-                      _p(WFs[n0:n1]), _p(WFn[n0:n1]), 1, _stream())
-            self.kernel_launches += 1
+        chunk = next((c for c in (30, 25, 10) if R % c == 0), 0)
+        if cfg.sampler == "tc" and chunk and os.environ.get("DVAE_TC_WIENER", "fused") != "v1":
+            # fused: the filter samples are decoded chunk by chunk straight into A1 = sum_r 1 / Vx; the masks follow from
+            # mean_r g Vs / Vx = 1 - Vb A1 / R, so none of the R x F x N variances is written to memory
+            from . import tc
+            for r0 in range(0, R, chunk):
+                A1 = tc.decode_a1_tc(self, Zs, r0, chunk)
+                _lib.call("dvae_wiener_from_a1", _p(A1), _p(self.Vb), chunk, b.NT, self.F, self.ld, _p(WFs), _p(WFn),
+                          1 if r0 == 0 else 0, _stream())
+                self.kernel_launches += 1
+        else:
+            # decode in frame chunks so the Vs buffer of the E-step (NT * R_E rows) is reused
+            flat = self.Vs_flat
+            step = max(1, min(b.NT, flat.shape[0] // R))
+            for n0 in range(0, b.NT, step):
+                n1 = min(b.NT, n0 + step)
+                self.decode_samples(Zs, n0, n1, flat)
+                _lib.call("dvae_wiener_accum", _p(flat), R, _p(self.Vb[n0:n1]), _p(self.g[n0:n1]), n1 - n0, self.F, self.ld,
+                          _p(WFs[n0:n1]), _p(WFn[n0:n1]), 1, _stream())
+                self.kernel_launches += 1
         self.S_hat = self._get("S_hat", (b.NT, self.ld), torch.complex64)
         self.N_hat = self._get("N_hat", (b.NT, self.ld), torch.complex64)
         _lib.call("dvae_wiener_apply", _p(self.X), _p(WFs), _p(WFn), R, b.NT, self.F, self.ld, _p(self.S_hat),

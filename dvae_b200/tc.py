@@ -144,3 +144,15 @@ def decode_stats_tc(eng, Zs, Vs):
               _p(eng.g), b.NT, eng.ld, _p(Vs), _p(A1), _p(A2), _p(_status(eng)), _stream())
     eng.kernel_launches += 1
     return st
+
+
+def decode_a1_tc(eng, Zs, r0, R):
+    """A1 = sum over the samples r0 .. r0+R of 1 / (g Vs + Vb), without storing Vs (dvae_decode_a1_tc); ``[NT][ld]``."""
+    w, b = eng.w, eng.batch
+    img = decoder_image(w)
+    A1 = eng._get("wf_a1", (b.NT * eng.ld,))
+    _lib.call("dvae_decode_a1_tc", w.dec.ref, _p(img), _p(Zs), Zs.shape[1], int(r0), int(R), w.z_dim, _p(eng.y), w.y_dim, _p(eng.Vb),
+              _p(eng.g), b.NT, eng.ld, _p(A1), _p(_status(eng)), _stream())
+    eng.kernel_launches += 1
+    return A1
+

@@ -188,6 +188,13 @@ int dvae_mh_chain_tc4(const DvaeMlp* dec, const void* image, const void* PVpk, c
 int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y, int y_dim,
                          const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1, float* A2, int* status,
                          void* stream);
+/* final filter without materialising its samples: dvae_decode_a1_tc decodes the samples r0 .. r0+R (R in {10, 25, 30}) of
+ * every frame of Zs [NT][R_total][L] and writes only A1 = sum_r 1 / (g Vs + Vb); dvae_wiener_from_a1 then accumulates the
+ * mask sums of compute_WF (mcem.py:325-327): sum_r Vb / Vx = Vb A1 and sum_r g Vs / Vx = R - Vb A1 (first != 0: overwrite) */
+int dvae_decode_a1_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R, int L, const float* y,
+                      int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* A1, int* status, void* stream);
+int dvae_wiener_from_a1(const float* A1, const float* Vb, int R, int64_t NT, int F, int ld, float* WFs, float* WFn, int first,
+                        void* stream);
 int dvae_nmf_w_from_frame_stats(const float* A1, const float* A2, const float* P, const float* H, const float* W,
                                 const int64_t* fr_off, int B, int F, int K, int ld, float* Wtmp, void* stream);
 
