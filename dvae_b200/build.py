@@ -22,8 +22,8 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xptxas=-v",
     "-Xcompiler", "-fPIC",
-    "-shared",
 ]
+OBJ = os.path.join(HERE, "_obj")               # per-source objects (git-ignored); the sources are compiled in parallel
 
 
 def sources():
@@ -44,12 +44,31 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: libdvae_b200.so cannot be built (there is no CPU fallback)")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed (exit %d)" % proc.returncode)
+    os.makedirs(OBJ, exist_ok=True)
+    hdr_t = max(os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(os.path.dirname(HERE), "include", "dvae_b200.h")])
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
+            return obj, 0, ""
+        proc = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src], capture_output=True, text=True)
+        return obj, proc.returncode, proc.stdout + proc.stderr
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(1, min(8, os.cpu_count() or 1))) as pool:
+        results = list(pool.map(compile_one, sources()))
+    log = "".join(r[2] for r in results)
+    failed = [r for r in results if r[1] != 0]
+    if not failed:
+        proc = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + [r[0] for r in results],
+                              capture_output=True, text=True)
+        log += proc.stdout + proc.stderr
+        if proc.returncode != 0:
+            failed = [("link", proc.returncode, "")]
+    if verbose or failed:
+        sys.stderr.write(log)
+    if failed:
+        raise RuntimeError("nvcc failed (%s)" % ", ".join("%s: exit %d" % (os.path.basename(r[0]), r[1]) for r in failed))
     return LIB
 
 
