@@ -773,14 +773,30 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
         const float gnew = gg * sqrtf(t2 / t1s);
         const f32x2 gn2 = pk2(gnew, gnew);
 
-        // ---- cost with Vx = g_new Vs + Vb2: a pair of samples shares one reciprocal and one log2
+        // ---- cost with Vx = g_new Vs + Vb2: FOUR samples share one reciprocal and one log2.  With y_i = c Vx_i (c = 2^8 keeps
+        //      the four-fold products inside FP32 for variances from 1e-10 to 1e7; it rides on g_new and Vb2 for free):
+        //      sum_i log2 Vx_i = log2(y0 y1 y2 y3) - 32,  sum_i 1 / Vx_i = c ((y0 + y1) y2 y3 + (y2 + y3) y0 y1) / (y0 y1 y2 y3)
+        constexpr float kC = 256.0f;
+        const f32x2 gc2 = pk2(gnew * kC, gnew * kC), vc2 = mul2(vb2, pk2(kC, kC));
         f32x2 cl = 0ull, cp = 0ull;
-#pragma unroll 5
-        for (int r = 0; r < R; r += 2) {
-            const f32x2 x0 = fma2(gn2, lds2(S + r * ld + f2), vb2), x1 = fma2(gn2, lds2(S + (r + 1) * ld + f2), vb2);
-            const f32x2 pr = mul2(x0, x1);
+        constexpr int R4 = R & ~3;
+#pragma unroll
+        for (int r = 0; r < R4; r += 4) {
+            const f32x2 y0 = fma2(gc2, lds2(S + r * ld + f2), vc2), y1 = fma2(gc2, lds2(S + (r + 1) * ld + f2), vc2);
+            const f32x2 y2 = fma2(gc2, lds2(S + (r + 2) * ld + f2), vc2), y3 = fma2(gc2, lds2(S + (r + 3) * ld + f2), vc2);
+            const f32x2 p01 = mul2(y0, y1), p23 = mul2(y2, y3);
+            const f32x2 m = mul2(p01, p23);
+            cl = add2(cl, lg22(m));
+            cp = fma2(fma2(add2(y0, y1), p23, mul2(add2(y2, y3), p01)), rcp2(m), cp);
+        }
+        float fix = -8.0f * (float)R4;                 // log2 c per sample
+#pragma unroll
+        for (int r = R4; r < R; r += 2) {              // R is even: one pair left when R % 4 == 2
+            const f32x2 y0 = fma2(gc2, lds2(S + r * ld + f2), vc2), y1 = fma2(gc2, lds2(S + (r + 1) * ld + f2), vc2);
+            const f32x2 pr = mul2(y0, y1);
             cl = add2(cl, lg22(pr));
-            cp = fma2(add2(x0, x1), rcp2(pr), cp);
+            cp = fma2(add2(y0, y1), rcp2(pr), cp);
+            fix -= 16.0f;
         }
         float cX = 0.f;
         if (xl) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
@@ -788,7 +804,8 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
             float cl_lo, cl_hi, pc_lo, pc_hi;
             upk2(cl, cl_lo, cl_hi);
             upk2(mul2(p2, cp), pc_lo, pc_hi);
-            cost_d += (double)(fmaf(0.6931471805599453f, cl_lo + cl_hi, pc_lo + pc_hi) + cX);
+            // both bins of the thread carry the same log2 c offset; the reciprocal sums carry a factor 1 / c
+            cost_d += (double)(fmaf(0.6931471805599453f, (cl_lo + fix) + (cl_hi + fix), kC * (pc_lo + pc_hi)) + cX);
         }
 
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
