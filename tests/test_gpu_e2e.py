@@ -179,3 +179,35 @@ def test_process_sublist_replacement(tmp_path):
         assert fs == 16000 and len(s) == l and len(n) == l
         assert np.max(np.abs((s + n)[800:-800] - x[800:-800])) < 2e-4          # masks sum to one; two 16-bit roundings
     assert batch_io.process_sublist(sub, enh, wav_dir, out_dir) == []           # everything exists: skipped like the reference
+
+
+def test_full_size_properties_configs1():
+    """BASELINE.json configs[1] size (512 x 3 s, M1, full MH schedule, 2 EM iterations): size-independent properties.
+
+    * the two Wiener masks sum to one, so s_hat + n_hat reproduces the mixture (away from the first hop, where the
+      reference's ISTFT divides by a vanishing window sum);
+    * the run is bit-reproducible, and a shard of the batch (rank 1 of 2) gives bit-identical results for its utterances:
+      the Philox counters are keyed by global utterance id, not by position in the batch;
+    * the cost of every utterance is finite and does not increase from the first to the second EM iteration.
+    """
+    from dvae_b200.engine import Enhancer, McemConfig
+    from dvae_b200.shard import shard_range
+    B = 512
+    xs = [np.asarray(x, np.float32) for x in synth.synth_batch(0, B, seconds=3.0)[0]]
+    P0 = np.abs(stft_np.stft(xs[0], **KW)) ** 2
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128], 0, seed=1234, out_bias=float(np.log(P0.mean())))
+    cfg = McemConfig(niter=2, keep_E=30, burn_E=30, keep_WF=75, burn_WF=30, seed=7)
+    enh = Enhancer(sd, "M1", cfg, device=0)
+    ids = list(range(B))
+    s1, n1, c1 = enh.enhance(xs, utt_ids=ids)
+    s1 = [a.copy() for a in s1]
+    n1 = [a.copy() for a in n1]
+    worst = max(float(np.max(np.abs((s + n)[800:-800] - x[800:-800]))) for x, s, n in zip(xs, s1, n1))
+    assert worst <= 1e-4, worst
+    assert np.isfinite(c1).all() and np.all(c1[:, 1] <= c1[:, 0] + 1e-6)
+    s2, _, c2 = enh.enhance(xs, utt_ids=ids)
+    assert all(np.array_equal(a, b) for a, b in zip(s1, s2)) and np.array_equal(c1, c2)
+    lo, hi = shard_range(B, 1, 2)
+    s3, n3, c3 = enh.enhance(xs[lo:hi], utt_ids=ids[lo:hi])
+    assert all(np.array_equal(a, b) for a, b in zip(s1[lo:hi], s3)) and all(np.array_equal(a, b) for a, b in zip(n1[lo:hi], n3))
+    np.testing.assert_allclose(c3, c1[lo:hi], rtol=1e-12)
