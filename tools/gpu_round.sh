@@ -2,7 +2,7 @@
 # One GPU visit: parity suite, smoke, full-size bench, ncu launch list + one full capture of the top kernel.
 # Usage (through gpurun): bash tools/gpu_round.sh <tag> [sampler]
 TAG=${1:-r01}
-SAMPLER=${2:-fp32}
+SAMPLER=${2:-tc}
 OUT=gpurun_out
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q --timeout 600 > $OUT/pytest_$TAG.log 2>&1
