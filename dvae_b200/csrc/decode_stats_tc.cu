@@ -40,7 +40,8 @@ struct DsParams {
     float* A2;              // [NT][ld]
     int64_t NT;
     int ld;
-    int zs_rtot, zs_r0;     // samples per frame in Zs and the first one this launch decodes (R of them)
+    int zs_rtot, zs_r0;     // samples per frame in Zs (and Vs) and the first one this launch decodes (R of them)
+    int acc;                // != 0: add to A1 / A2 instead of overwriting (later sample windows of the same frames)
     int* status;
     long long* dbg;
 };
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                         if (n < p.NT) {
                             const float gg = ggc[ff];
                             const float vb = vbc[ff];
-                            float* dst = p.Vs + (n * R) * (int64_t)ldv + f;
+                            float* dst = p.Vs + (n * p.zs_rtot + p.zs_r0) * (int64_t)ldv + f;
                             // packed FP32 pairs; four samples share two reciprocals: X = (Vx_r, Vx_r+1), Y = (Vx_r+2, Vx_r+3),
                             // 1 / (X Y) gives 1 / X = Y / (X Y) and 1 / Y = X / (X Y) lane by lane
                             const f32x2 g2 = pk2(gg, gg), vb2 = pk2(vb, vb), bias2 = pk2(bias, bias);
@@ -341,6 +342,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                                 upk2(a2p, lo, hi);
                                 a2 += lo + hi;
                             }
+                            if (p.acc) { a1 += p.A1[n * ldv + f]; if (STORE) a2 += p.A2[n * ldv + f]; }
                             p.A1[n * ldv + f] = a1;
                             if (STORE) p.A2[n * ldv + f] = a2;
                         }
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                     float inv = 0.f;
                     if (fi < FT && n < p.NT && d.F > 512) {
                         const float vs = ex2_approx(v[0] + b3[512]);
-                        if (STORE) p.Vs[(n * R + r) * (int64_t)ldv + 512] = vs;
+                        if (STORE) p.Vs[(n * p.zs_rtot + p.zs_r0 + r) * (int64_t)ldv + 512] = vs;
                         inv = rcp_approx(fmaf(__ldg(p.g + n), vs, __ldg(p.Vb + n * ldv + 512)));
                     }
                     tailS[row] = inv;
@@ -368,7 +370,10 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                         if (nn < p.NT && d.F > 512) {
                             float sum = 0.f;
                             for (int rr = 0; rr < R; ++rr) sum += tailS[which * 128 + fj * R + rr];
-                            if (STORE || which == 0) (which ? p.A2 : p.A1)[nn * ldv + 512] = sum;
+                            if (STORE || which == 0) {
+                                float* dst512 = (which ? p.A2 : p.A1) + nn * ldv + 512;
+                                *dst512 = p.acc ? *dst512 + sum : sum;
+                            }
                         }
                     }
                     ds_bar_tail();
@@ -502,7 +507,7 @@ using namespace dvae::tc;
 
 static int launch_decode_stats(const char* who, const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R,
                                int L, const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs,
-                               float* A1, float* A2, int* status, void* stream) {
+                               float* A1, float* A2, int accumulate, int* status, void* stream) {
     DsParams p{};
     int rc = check_dims(dec, L, y_dim, who, &p.d);
     if (rc) return rc;
@@ -518,7 +523,7 @@ static int launch_decode_stats(const char* who, const DvaeMlp* dec, const void* 
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
     p.Zs = Zs; p.y = y; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status; p.dbg = g_dbg_clocks_ds;
-    p.zs_rtot = R_total; p.zs_r0 = r0;
+    p.zs_rtot = R_total; p.zs_r0 = r0; p.acc = accumulate;
     const int shared_bytes = (p.d.off_w3 + 4 * ((p.d.n_hidden == 2 ? HID : 0) + NPAD) + 1023) & ~1023;
     const size_t smem = (size_t)shared_bytes + 65536 + 65536 + 1024;
     DVAE_REQUIRE(smem <= 227 * 1024, "%s: shared memory budget exceeded", who);
@@ -555,14 +560,24 @@ extern "C" int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const
                                     int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1,
                                     float* A2, int* status, void* stream) {
     DVAE_REQUIRE(Vs && A2, "dvae_decode_stats_tc: null pointer");
-    return launch_decode_stats("dvae_decode_stats_tc", dec, image, Zs, R, 0, R, L, y, y_dim, Vb, g, NT, ld, Vs, A1, A2, status, stream);
+    return launch_decode_stats("dvae_decode_stats_tc", dec, image, Zs, R, 0, R, L, y, y_dim, Vb, g, NT, ld, Vs, A1, A2, 0, status, stream);
 }
 
 extern "C" int dvae_decode_a1_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R, int L,
                                  const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* A1,
                                  int* status, void* stream) {
     return launch_decode_stats("dvae_decode_a1_tc", dec, image, Zs, R_total, r0, R, L, y, y_dim, Vb, g, NT, ld, nullptr, A1, nullptr,
-                               status, stream);
+                               0, status, stream);
+}
+
+// sample window [r0, r0 + R) of frames that hold R_total samples each (multi-chain runs): Vs rows n * R_total + r0 + r are
+// written, A1 / A2 are overwritten (accumulate == 0) or added to
+extern "C" int dvae_decode_stats_win_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R, int L,
+                                        const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs,
+                                        float* A1, float* A2, int accumulate, int* status, void* stream) {
+    DVAE_REQUIRE(Vs && A2, "dvae_decode_stats_win_tc: null pointer");
+    return launch_decode_stats("dvae_decode_stats_win_tc", dec, image, Zs, R_total, r0, R, L, y, y_dim, Vb, g, NT, ld, Vs, A1, A2,
+                               accumulate, status, stream);
 }
 
 // WFn (+)= Vb A1, WFs (+)= R - Vb A1: sums over the R samples behind A1 of Vb / Vx and g Vs / Vx = 1 - Vb / Vx (mcem.py:325-327)

@@ -822,6 +822,239 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
     }
 }
 
+// ----------------------------------------------------------------------------- H, g, cost: windowed frame (many samples)
+// Sixth version, for sample counts that do not fit shared memory (multi-chain runs: R = chains x kept samples, e.g. 160):
+// the frame is streamed in windows of RW samples (30 or 10).  Each of the three dependent passes walks all windows and
+// keeps its per-bin partial sums in registers, so the frame is read three times (the first time from HBM, later ones from
+// L2 when it still holds the frame); everything else is hg5: adjacent-bin pairs in packed FP32, bulk-copy staging, pair /
+// quad shared reciprocals, cost reduced once per CTA.
+template <int RW, int ld>
+__global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __restrict__ P, const float* __restrict__ Vs,
+                                                                 const float* __restrict__ Wtmp, const float* __restrict__ norm,
+                                                                 float* __restrict__ H, float* __restrict__ g,
+                                                                 float* __restrict__ Vb, double* __restrict__ cost_part,
+                                                                 const int64_t* __restrict__ fr_off, int K, int R) {
+    constexpr int KT = HG2_KT;
+    static_assert(RW % 2 == 0 && RW <= 32 && ld % 4 == 0 && ld >= 513, "hg6: even window up to 32 samples");
+    extern __shared__ __align__(16) float sm[];
+    float* S = sm;                                  // [RW][ld] samples of the current window
+    float* red = S + RW * ld;                       // [8][HG3_NV] per-warp partials of the H sums
+    __shared__ float2 red2[8];
+    __shared__ double redd[8];
+    __shared__ float hs[KT];
+    __shared__ __align__(8) unsigned long long bar;
+    const int u = blockIdx.y;
+    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
+    const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
+    if (nb >= n1) {
+        if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
+        return;
+    }
+    const int64_t ne = (nb + HG3_FPB < n1) ? nb + HG3_FPB : n1;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int f2 = 2 * t;                           // bins 2t, 2t+1; sample t of a window's bin 512 lives on threads t < RW
+    const bool xl = t < RW;
+    const int NW = R / RW;
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_a), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    f32x2 w2[KT];
+    float wX[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const float* wk = Wtmp + ((int64_t)u * K + k) * ld;
+        w2[k] = (k < K) ? *reinterpret_cast<const f32x2*>(wk + f2) : 0ull;
+        wX[k] = (k < K) ? wk[512] : 0.f;
+    }
+    double cost_d = 0.0;
+    unsigned phase = 0;
+    constexpr unsigned row_bytes = (unsigned)ld * 4u;
+    constexpr float kC = 256.0f;                    // see the cost pass of hg5
+
+    // stage window w of frame n (RW bulk row copies) and wait for it; contains the barrier that frees the buffer
+    auto stage = [&](int64_t n, int w) {
+        __syncthreads();
+        if (wid == 0) {
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(row_bytes * RW) : "memory");
+            __syncwarp();
+            if (lane < RW) {
+                const float* src = Vs + (n * R + (int64_t)w * RW + lane) * (int64_t)ld;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(S + lane * ld);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(dst), "l"(src), "r"(row_bytes), "r"(bar_a) : "memory");
+            }
+        }
+        unsigned done = 0, spins = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+            if (!done && ++spins > (1u << 22)) __trap();
+        }
+        phase ^= 1;
+    };
+
+    for (int64_t n = nb; n < ne; ++n) {
+        const float gg = g[n];
+        const f32x2 gg2 = pk2(gg, gg);
+        const f32x2 p2 = *reinterpret_cast<const f32x2*>(P + n * ld + f2);
+        const float pX = P[n * ld + 512];
+        float h[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
+
+        // ---- H update (Vb1 = W_new H_old)
+        f32x2 vb2 = 0ull;
+        float vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        f32x2 a1 = 0ull, a2 = 0ull;
+        float a1X = 0.f, a2X = 0.f;
+        for (int w = 0; w < NW; ++w) {
+            stage(n, w);
+#pragma unroll 5
+            for (int r = 0; r < RW; r += 2) {
+                const f32x2 x0 = fma2(gg2, lds2(S + r * ld + f2), vb2), x1 = fma2(gg2, lds2(S + (r + 1) * ld + f2), vb2);
+                const f32x2 rr = rcp2(mul2(x0, x1));
+                const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                a1 = add2(a1, add2(i0, i1));
+                a2 = fma2(i0, i0, fma2(i1, i1, a2));
+            }
+            if (xl) { const float ix = rcp_fast(fmaf(gg, S[t * ld + 512], vbX)); a1X += ix; a2X = fmaf(ix, ix, a2X); }
+        }
+        {
+            const f32x2 q2 = mul2(p2, a2);
+            const float qX = pX * a2X;
+            const bool b4 = lane & 16, b3 = lane & 8;
+            float a[10];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float v[10];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int k = 5 * hf + j;
+                    float nlo, nhi, dlo, dhi;
+                    upk2(mul2(w2[k], q2), nlo, nhi);
+                    upk2(mul2(w2[k], a1), dlo, dhi);
+                    v[2 * j] = fmaf(wX[k], qX, nlo + nhi);
+                    v[2 * j + 1] = fmaf(wX[k], a1X, dlo + dhi);
+                }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float send = b4 ? v[j] : v[5 + j], keep = b4 ? v[5 + j] : v[j];
+                    a[5 * hf + j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            }
+            float o5[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float send = b3 ? a[j] : a[5 + j], keep = b3 ? a[5 + j] : a[j];
+                o5[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) o5[j] += __shfl_xor_sync(0xffffffffu, o5[j], o);
+            if ((lane & 7) == 0) {
+                float* dst = red + wid * HG3_NV + 10 * ((lane >> 3) & 1) + 5 * (lane >> 4);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) dst[j] = o5[j];
+            }
+        }
+        __syncthreads();
+        if (t < K) {
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { num += red[w * HG3_NV + 2 * t]; den += red[w * HG3_NV + 2 * t + 1]; }
+            hs[t] = H[n * K + t] * sqrtf(num / den);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? hs[k] : 0.f;
+
+        // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
+        vb2 = 0ull; vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        *reinterpret_cast<f32x2*>(Vb + n * ld + f2) = vb2;
+        if (t == 0) Vb[n * ld + 512] = vbX;
+        f32x2 s1 = 0ull, s2 = 0ull;
+        float s1X = 0.f, s2X = 0.f;
+        for (int w = 0; w < NW; ++w) {
+            stage(n, w);
+#pragma unroll 5
+            for (int r = 0; r < RW; r += 2) {
+                const f32x2 v0 = lds2(S + r * ld + f2), v1 = lds2(S + (r + 1) * ld + f2);
+                const f32x2 x0 = fma2(gg2, v0, vb2), x1 = fma2(gg2, v1, vb2);
+                const f32x2 rr = rcp2(mul2(x0, x1));
+                const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
+                s1 = add2(s1, add2(t0, t1));
+                s2 = fma2(t0, i0, fma2(t1, i1, s2));
+            }
+            if (xl) { const float sx = S[t * ld + 512]; const float ix = rcp_fast(fmaf(gg, sx, vbX)); const float tx = sx * ix; s1X += tx; s2X = fmaf(tx, ix, s2X); }
+        }
+        {
+            float ps_lo, ps_hi, s1lo, s1hi;
+            upk2(mul2(p2, s2), ps_lo, ps_hi);
+            upk2(s1, s1lo, s1hi);
+            const float v2 = warp_sum(fmaf(pX, s2X, ps_lo + ps_hi)), v1 = warp_sum(s1lo + s1hi + s1X);
+            if (lane == 0) red2[wid] = make_float2(v2, v1);
+        }
+        __syncthreads();
+        float t2 = 0.f, t1s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const float2 rr = red2[w]; t2 += rr.x; t1s += rr.y; }
+        const float gnew = gg * sqrtf(t2 / t1s);
+
+        // ---- cost with Vx = g_new Vs + Vb2 (scaled by c = 2^8: four samples share one reciprocal and one log2)
+        const f32x2 gn2c = pk2(gnew * kC, gnew * kC), vc2 = mul2(vb2, pk2(kC, kC));
+        f32x2 cl = 0ull, cp = 0ull;
+        float cX = 0.f;
+        constexpr int RW4 = RW & ~3;
+        for (int w = 0; w < NW; ++w) {
+            stage(n, w);
+#pragma unroll
+            for (int r = 0; r < RW4; r += 4) {
+                const f32x2 y0 = fma2(gn2c, lds2(S + r * ld + f2), vc2), y1 = fma2(gn2c, lds2(S + (r + 1) * ld + f2), vc2);
+                const f32x2 y2 = fma2(gn2c, lds2(S + (r + 2) * ld + f2), vc2), y3 = fma2(gn2c, lds2(S + (r + 3) * ld + f2), vc2);
+                const f32x2 p01 = mul2(y0, y1), p23 = mul2(y2, y3);
+                const f32x2 m = mul2(p01, p23);
+                cl = add2(cl, lg22(m));
+                cp = fma2(fma2(add2(y0, y1), p23, mul2(add2(y2, y3), p01)), rcp2(m), cp);
+            }
+#pragma unroll
+            for (int r = RW4; r < RW; r += 2) {
+                const f32x2 y0 = fma2(gn2c, lds2(S + r * ld + f2), vc2), y1 = fma2(gn2c, lds2(S + (r + 1) * ld + f2), vc2);
+                const f32x2 pr = mul2(y0, y1);
+                cl = add2(cl, lg22(pr));
+                cp = fma2(add2(y0, y1), rcp2(pr), cp);
+            }
+            if (xl) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX += fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
+        }
+        {
+            const float fix = -8.0f * (float)R;     // log2 c per sample and bin
+            float cl_lo, cl_hi, pc_lo, pc_hi;
+            upk2(cl, cl_lo, cl_hi);
+            upk2(mul2(p2, cp), pc_lo, pc_hi);
+            cost_d += (double)(fmaf(0.6931471805599453f, (cl_lo + fix) + (cl_hi + fix), kC * (pc_lo + pc_hi)) + cX);
+        }
+        __syncthreads();                            // hs and the reduction buffers are free for the next frame
+        if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
+        if (t == 0) g[n] = gnew;
+    }
+    cost_d = warp_sum_d(cost_d);
+    if (lane == 0) redd[wid] = cost_d;
+    __syncthreads();
+    if (t == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += redd[w];
+        cost_part[(int64_t)u * gridDim.x + blockIdx.x] = sum / ((double)R * 513.0 * (double)(n1 - n0));
+    }
+}
+
 // cost[u] = sum of the per-CTA partials in block order (deterministic, unlike an atomic accumulation)
 __global__ void cost_reduce_kernel(const double* __restrict__ cost_part, int nblk, double* __restrict__ cost) {
     const int u = blockIdx.x;
@@ -944,7 +1177,22 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
         return 0;
     }
     int nblk_used = nblk;
-    if (F >= 512 && F <= 513 && (ld & 3) == 0 && K <= HG2_KT && (R == 10 || R == 30)) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(Vs) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wtmp) & 7) == 0 &&
+                         (reinterpret_cast<uintptr_t>(P) & 7) == 0 && (reinterpret_cast<uintptr_t>(Vb) & 7) == 0;
+    if (F == 513 && ld == HG5_LD && K <= HG2_KT && R > 30 && R % 10 == 0 && aligned) {
+        // many samples per frame (multi-chain runs): windows of 30 when they divide R, else of 10
+        nblk_used = (max_frames + HG3_FPB - 1) / HG3_FPB;
+        if (R % 30 == 0) {
+            const size_t smem6 = sizeof(float) * ((size_t)30 * ld + (size_t)HG3_NV * 8);
+            cudaFuncSetAttribute(nmf_hg6_kernel<30, HG5_LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6);
+            nmf_hg6_kernel<30, HG5_LD><<<dim3(nblk_used, B), HG3_THREADS, smem6, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, K, R);
+        } else {
+            const size_t smem6 = sizeof(float) * ((size_t)10 * ld + (size_t)HG3_NV * 8);
+            cudaFuncSetAttribute(nmf_hg6_kernel<10, HG5_LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem6);
+            nmf_hg6_kernel<10, HG5_LD><<<dim3(nblk_used, B), HG3_THREADS, smem6, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, K, R);
+        }
+        rc = check_launch("nmf_hg6_kernel");
+    } else if (F >= 512 && F <= 513 && (ld & 3) == 0 && K <= HG2_KT && (R == 10 || R == 30)) {
         nblk_used = (max_frames + HG3_FPB - 1) / HG3_FPB;
         const size_t smem3 = sizeof(float) * ((size_t)R * ld + (size_t)HG3_NV * 8);
         if (F == 513 && ld == HG5_LD && (reinterpret_cast<uintptr_t>(Vs) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wtmp) & 7) == 0 &&

@@ -418,10 +418,10 @@ class McemEngine:
         self.R = Zs.shape[1]
         self.Vs = self.Vs_flat[: self.batch.NT * self.R].view(self.batch.NT, self.R, self.ld)
         self.wstat, self.wstat_parts = None, 0
-        if cfg.sampler == "tc" and self.R in (10, 30) and cfg.nmf_rank <= 10 and cfg.fuse_wstat:
+        if cfg.sampler == "tc" and self.R % 10 == 0 and cfg.nmf_rank <= 10 and cfg.fuse_wstat:
             from . import tc
             with self.stage("decode"):
-                if os.environ.get("DVAE_TC_DECODE", "v3") == "v2":
+                if os.environ.get("DVAE_TC_DECODE", "v3") == "v2" and self.R in (10, 30):
                     self.wstat, self.wstat_parts = tc.decode_wstat_tc(self, Zs, self.Vs), WS_PARTS
                 else:
                     self.wstat = tc.decode_stats_tc(self, Zs, self.Vs)

@@ -135,14 +135,25 @@ def decode_wstat_tc(eng, Zs, Vs):
 
 
 def decode_stats_tc(eng, Zs, Vs):
-    """Warp-specialised decode + per-frame reciprocal sums (dvae_decode_stats_tc); returns the [2][NT][ld] statistics."""
+    """Warp-specialised decode + per-frame reciprocal sums (dvae_decode_stats_tc); returns the [2][NT][ld] statistics.
+
+    Frames with more than 30 samples (multi-chain runs) are decoded in sample windows of 30 or 10 that accumulate into the
+    same statistics (dvae_decode_stats_win_tc)."""
     w, b = eng.w, eng.batch
     img = decoder_image(w)
     st = eng._get("fstat", (2 * b.NT * eng.ld,))
     A1, A2 = st[: b.NT * eng.ld], st[b.NT * eng.ld:]
-    _lib.call("dvae_decode_stats_tc", w.dec.ref, _p(img), _p(Zs), Zs.shape[1], w.z_dim, _p(eng.y), w.y_dim, _p(eng.Vb),
-              _p(eng.g), b.NT, eng.ld, _p(Vs), _p(A1), _p(A2), _p(_status(eng)), _stream())
-    eng.kernel_launches += 1
+    R = Zs.shape[1]
+    if R in (10, 30):
+        _lib.call("dvae_decode_stats_tc", w.dec.ref, _p(img), _p(Zs), R, w.z_dim, _p(eng.y), w.y_dim, _p(eng.Vb),
+                  _p(eng.g), b.NT, eng.ld, _p(Vs), _p(A1), _p(A2), _p(_status(eng)), _stream())
+        eng.kernel_launches += 1
+        return st
+    win = 30 if R % 30 == 0 else 10
+    for r0 in range(0, R, win):
+        _lib.call("dvae_decode_stats_win_tc", w.dec.ref, _p(img), _p(Zs), R, r0, win, w.z_dim, _p(eng.y), w.y_dim, _p(eng.Vb),
+                  _p(eng.g), b.NT, eng.ld, _p(Vs), _p(A1), _p(A2), 0 if r0 == 0 else 1, _p(_status(eng)), _stream())
+        eng.kernel_launches += 1
     return st
 
 

@@ -188,6 +188,11 @@ int dvae_mh_chain_tc4(const DvaeMlp* dec, const void* image, const void* PVpk, c
 int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y, int y_dim,
                          const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1, float* A2, int* status,
                          void* stream);
+/* dvae_decode_stats_tc for frames that hold R_total samples (multi-chain runs): decodes the window r0 .. r0+R (R in {10, 30}),
+ * writes the rows n * R_total + r0 + r of Vs and overwrites (accumulate == 0) or adds to A1 / A2 */
+int dvae_decode_stats_win_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R, int L,
+                             const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1,
+                             float* A2, int accumulate, int* status, void* stream);
 /* final filter without materialising its samples: dvae_decode_a1_tc decodes the samples r0 .. r0+R (R in {10, 25, 30}) of
  * every frame of Zs [NT][R_total][L] and writes only A1 = sum_r 1 / (g Vs + Vb); dvae_wiener_from_a1 then accumulates the
  * mask sums of compute_WF (mcem.py:325-327): sum_r Vb / Vx = Vb A1 and sum_r g Vs / Vx = R - Vb A1 (first != 0: overwrite) */

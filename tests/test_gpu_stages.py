@@ -77,7 +77,8 @@ def _random_mstep_inputs(F, N, K, R, seed):
     return P, Vs, W, H, g
 
 
-@pytest.mark.parametrize("F,N,K,R", [(513, 37, 10, 30), (513, 185, 10, 10), (33, 9, 3, 3), (513, 5, 10, 1)])
+@pytest.mark.parametrize("F,N,K,R", [(513, 37, 10, 30), (513, 185, 10, 10), (33, 9, 3, 3), (513, 5, 10, 1),
+                                     (513, 21, 10, 60), (513, 13, 10, 40), (513, 9, 7, 160)])      # windowed kernel (multi-chain sample counts)
 def test_m_step_matches_oracle(F, N, K, R):
     P, Vs, W, H, g = _random_mstep_inputs(F, N, K, R, seed=F + N)
     ref = mcem_port.m_step_reference(torch.tensor(P), torch.tensor(Vs), torch.tensor(W), torch.tensor(H), torch.tensor(g))
