@@ -190,9 +190,12 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # NCCL prints its version banner to STDOUT at the default / VERSION debug level: keep stdout to the one JSON line
+        # NCCL writes its debug output (the version banner at NCCL_DEBUG=VERSION / WARN / INFO) to STDOUT by default: send it
+        # to stderr so that stdout carries exactly the one JSON line
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so VERSION / unset becomes WARN)
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
