@@ -173,9 +173,13 @@ __device__ __forceinline__ void fft512(float2* a, float2* buf, const float2* tw,
 __device__ __forceinline__ int find_utt(const int64_t* __restrict__ fr_off, int B, int64_t n) {
     {   // equal-length batches (the common case): the proportional guess is right and costs one round of two loads
         // instead of a chain of log2(B) dependent ones
-        const int64_t NT = fr_off[B];
-        const int g = (int)min((int64_t)B - 1, (n * B) / (NT > 0 ? NT : 1));
+        // (single-precision quotient: no 64-bit division; a wrong guess only falls through to the search below)
+        const float NTf = (float)fr_off[B];
+        int g = (int)((float)n * (float)B / fmaxf(NTf, 1.0f));
+        g = min(max(g, 0), B - 1);
         if (fr_off[g] <= n && n < fr_off[g + 1]) return g;
+        if (g + 1 < B && fr_off[g + 1] <= n && n < fr_off[g + 2]) return g + 1;
+        if (g > 0 && fr_off[g - 1] <= n && n < fr_off[g]) return g - 1;
     }
     int lo = 0, hi = B;                            // largest u with fr_off[u] <= n
     while (hi - lo > 1) {
