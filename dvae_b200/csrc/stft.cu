@@ -36,6 +36,7 @@ __device__ double g_win2[kNfft];               // Hann^2 in double (librosa wind
 // exactly like librosa's window_sumsquare; that value only depends on q = o / 256, r = o % 256 and the number of frames
 // cnt = jhi - jlo + 1 <= q + 1, so all of them fit a 10 x 256 table: entry (q (q + 1) / 2 + cnt - 1, r).
 __device__ float g_wss[10 * 256];
+__device__ float g_wss_inv[10 * 256];            // 1 / wss where wss > FLT_MIN (the reference divides only there), else 1
 
 __global__ void init_tables_kernel() {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -57,6 +58,7 @@ __global__ void init_tables_kernel() {
                     wss = (float)((double)wss + wi * wi);
                 }
                 g_wss[(q * (q + 1) / 2 + cnt - 1) * 256 + k] = wss;
+                g_wss_inv[(q * (q + 1) / 2 + cnt - 1) * 256 + k] = (wss > FLT_MIN) ? 1.0f / wss : 1.0f;
             }
     }
 }
@@ -270,7 +272,8 @@ __global__ void __launch_bounds__(256, 6) stft_kernel(const float* __restrict__ 
 // only short batches are cut into segments (three lead-in frames each) to fill the GPU.
 __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict__ X, const int64_t* __restrict__ fr_off,
                                                        float* __restrict__ y, const int64_t* __restrict__ y_off,
-                                                       const int32_t* __restrict__ y_len, int hop, int ld, int seg_hops) {
+                                                       const int32_t* __restrict__ y_len, int /*hop: 256*/, int ld, int seg_hops) {
+    constexpr int hop = 256;                                                  // = CTA size (checked by the host wrapper): index math in shifts
     __shared__ float2 tw[kNfft];
     __shared__ __align__(8) float win[kNfft];
     __shared__ __align__(16) float2 bufs[4 * kBuf];                           // FFT exchange buffers; then the windowed frames
@@ -352,8 +355,8 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
                     r = v[m];
                     const int jlo = max(0, (s - kNfft + hop) / hop), jhi = min(N - 1, s / hop);
                     const int o = s - jlo * hop, q = o >> 8, cnt = jhi - jlo + 1;
-                    const float wss = __ldg(g_wss + ((q * (q + 1) / 2 + cnt - 1) << 8) + (o & 255));
-                    if (wss > FLT_MIN) r /= wss;
+                    // one multiplication by the tabulated reciprocal (<= 1.5 ulp from the reference's division)
+                    r *= __ldg(g_wss_inv + ((q * (q + 1) / 2 + cnt - 1) << 8) + (o & 255));
                 }
                 yu[s] = r;
             }
