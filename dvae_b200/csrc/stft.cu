@@ -192,7 +192,7 @@ __device__ __forceinline__ int find_utt(const int64_t* __restrict__ fr_off, int 
 }
 
 // ----------------------------------------------------------------------------- STFT
-__global__ void __launch_bounds__(256, 6) stft_kernel(const float* __restrict__ x, const int64_t* __restrict__ x_off,
+__global__ void __launch_bounds__(256, 4) stft_kernel(const float* __restrict__ x, const int64_t* __restrict__ x_off,
                                                    const int32_t* __restrict__ x_len, int B, float2* __restrict__ X,
                                                    float* __restrict__ P, const int64_t* __restrict__ fr_off,
                                                    int64_t NT, int hop, int ld) {
@@ -205,37 +205,45 @@ __global__ void __launch_bounds__(256, 6) stft_kernel(const float* __restrict__ 
     const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
     float2* buf = bufs[grp];
     const int64_t n_pass = (NT + 3) / 4;
-    for (int64_t pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
-        const int64_t n = pass * 4 + grp;
-        const bool live = n < NT;
-        float2 a[8];
-        if (live) {
+    // raw samples of frame n (zeros beyond the signal): 8 even / odd pairs per thread.  The frame of the NEXT pass is
+    // requested before the current one is transformed, so its DRAM latency (half of all stall samples in the first
+    // version, profiles/r01_stft_microbench.json) hides behind the FFT.
+    auto fetch = [&](int64_t n, float2* v) {
+        if (n < NT) {
             const int u = find_utt(fr_off, B, n);
             const int64_t j = n - fr_off[u];
             const float* xu = x + x_off[u];
             const int64_t len = x_len[u];
             const int64_t s0 = j * (int64_t)hop;
-            // the frame is read as even / odd sample pairs: one 8-byte load each when the frame start is 8-byte aligned
-            // and the whole frame lies inside the signal
+            // one 8-byte load per pair when the frame start is 8-byte aligned and the whole frame lies inside the signal
             const bool fast = ((reinterpret_cast<uintptr_t>(xu + s0) & 7) == 0) && (s0 + kNfft <= len);
 #pragma unroll
             for (int n1 = 0; n1 < 8; ++n1) {
-                const int p = 2 * (t + 64 * n1);
-                const int64_t q = s0 + p;
-                float2 v;
+                const int64_t q = s0 + 2 * (t + 64 * n1);
                 if (fast) {
-                    v = __ldg(reinterpret_cast<const float2*>(xu + q));
+                    v[n1] = __ldg(reinterpret_cast<const float2*>(xu + q));
                 } else {
-                    v.x = (q < len) ? __ldg(xu + q) : 0.f;
-                    v.y = (q + 1 < len) ? __ldg(xu + q + 1) : 0.f;
+                    v[n1].x = (q < len) ? __ldg(xu + q) : 0.f;
+                    v[n1].y = (q + 1 < len) ? __ldg(xu + q + 1) : 0.f;
                 }
-                const float2 w2 = *reinterpret_cast<const float2*>(win + p);
-                a[n1] = make_float2(v.x * w2.x, v.y * w2.y);
             }
         } else {
 #pragma unroll
-            for (int n1 = 0; n1 < 8; ++n1) a[n1] = make_float2(0.f, 0.f);
+            for (int n1 = 0; n1 < 8; ++n1) v[n1] = make_float2(0.f, 0.f);
         }
+    };
+    float2 nxt[8];
+    fetch((int64_t)blockIdx.x * 4 + grp, nxt);
+    for (int64_t pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+        const int64_t n = pass * 4 + grp;
+        const bool live = n < NT;
+        float2 a[8];
+#pragma unroll
+        for (int n1 = 0; n1 < 8; ++n1) {
+            const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * (t + 64 * n1));
+            a[n1] = make_float2(nxt[n1].x * w2.x, nxt[n1].y * w2.y);
+        }
+        fetch((pass + gridDim.x) * 4 + grp, nxt);
         fft512(a, buf, tw, t, grp);
 #pragma unroll
         for (int j2 = 0; j2 < 8; ++j2) buf[j2 * kRow + t] = a[j2];          // natural order: Z[k] at slot k
@@ -381,7 +389,7 @@ extern "C" int dvae_stft_f32(const float* x, const int64_t* x_off, const int32_t
     int rc = ensure_tables(st);
     if (rc) return rc;
     const int64_t n_pass = (NT + 3) / 4;
-    const int grid = (int)(n_pass < 148 * 6 ? n_pass : 148 * 6);          // six resident CTAs per SM (40 registers, 28 KB)
+    const int grid = (int)(n_pass < 148 * 4 ? n_pass : 148 * 4);          // four resident CTAs per SM (64 registers, 28 KB)
     stft_kernel<<<grid, 256, 0, st>>>(x, x_off, x_len, B, (float2*)X, P, fr_off, NT, hop, ld);
     return check_launch("stft_kernel");
 }
