@@ -613,7 +613,7 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
     __shared__ float2 red2[8];
     __shared__ double redd[8];
     __shared__ float hs[KT];
-    __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bars2[2];
     const int u = blockIdx.y;
     const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
     const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
@@ -625,9 +625,14 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int f2 = 2 * t;                           // bins 2t, 2t+1; sample t of bin 512 lives on threads t < R
     const bool xl = t < R;
-    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar);
+    // The frame is staged in two parts, rows [0, RA) and [RA, R), each completing on its own mbarrier: part A of the NEXT
+    // frame is requested as soon as the cost pass has left it, part B at the end of the frame, so most of the copy runs
+    // under arithmetic (the single-buffer version spent 24 % of its warp time waiting for the frame, profiles/r01_tc_ncu_hg5.txt)
+    constexpr int RA = (R >= 30) ? 16 : R;
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bars2[0]), bar_b = (unsigned)__cvta_generic_to_shared(&bars2[1]);
     if (t == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_a), "r"(1));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar_b), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     f32x2 w2[KT];
@@ -639,22 +644,34 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
         wX[k] = (k < K) ? wk[512] : 0.f;
     }
     double cost_d = 0.0;                            // per-thread partial, reduced once per CTA
-    unsigned phase = 0;
+    unsigned phase_a = 0, phase_b = 0;
     constexpr unsigned row_bytes = (unsigned)ld * 4u;
-
-    for (int64_t n = nb; n < ne; ++n) {
-        // ---- stage the frame: R bulk row copies completing on the mbarrier
-        __syncthreads();                            // previous frame fully consumed (and the mbarrier initialised)
+    auto issue_rows = [&](int64_t n, int lo, int hi, unsigned bar) {      // warp 0: bulk copies of rows [lo, hi) of frame n
         if (wid == 0) {
-            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_a), "r"(row_bytes * R) : "memory");
+            if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(row_bytes * (unsigned)(hi - lo)) : "memory");
             __syncwarp();
-            if (lane < R) {
+            if (lane >= lo && lane < hi) {
                 const float* src = Vs + (n * R + lane) * (int64_t)ld;
                 const unsigned dst = (unsigned)__cvta_generic_to_shared(S + lane * ld);
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(dst), "l"(src), "r"(row_bytes), "r"(bar_a) : "memory");
+                             :: "r"(dst), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
             }
         }
+    };
+    auto wait_rows = [&](unsigned bar, unsigned& ph) {
+        unsigned done = 0, spins = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar), "r"(ph) : "memory");
+            if (!done && ++spins > (1u << 22)) __trap();                // a lost copy must not hang the device
+        }
+        ph ^= 1;
+    };
+    __syncthreads();                                                    // mbarriers initialised
+    issue_rows(nb, 0, RA, bar_a);
+    if (RA < R) issue_rows(nb, RA, R, bar_b);
+
+    for (int64_t n = nb; n < ne; ++n) {
         const float gg = g[n];
         const f32x2 gg2 = pk2(gg, gg);
         const f32x2 p2 = *reinterpret_cast<const f32x2*>(P + n * ld + f2);
@@ -662,24 +679,24 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
         float h[KT];
 #pragma unroll
         for (int k = 0; k < KT; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
-        {
-            unsigned done = 0, spins = 0;
-            while (!done) {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
-                if (!done && ++spins > (1u << 22)) __trap();        // a lost copy must not hang the device
-            }
-            phase ^= 1;
-        }
-
         // ---- H update (Vb1 = W_new H_old)
         f32x2 vb2 = 0ull;
         float vbX = 0.f;
 #pragma unroll
         for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
         f32x2 a1 = 0ull, a2 = 0ull;
-#pragma unroll 5
-        for (int r = 0; r < R; r += 2) {
+        wait_rows(bar_a, phase_a);
+#pragma unroll 4
+        for (int r = 0; r < RA; r += 2) {
+            const f32x2 x0 = fma2(gg2, lds2(S + r * ld + f2), vb2), x1 = fma2(gg2, lds2(S + (r + 1) * ld + f2), vb2);
+            const f32x2 rr = rcp2(mul2(x0, x1));
+            const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+            a1 = add2(a1, add2(i0, i1));
+            a2 = fma2(i0, i0, fma2(i1, i1, a2));
+        }
+        if (RA < R) wait_rows(bar_b, phase_b);
+#pragma unroll
+        for (int r = RA; r < R; r += 2) {
             const f32x2 x0 = fma2(gg2, lds2(S + r * ld + f2), vb2), x1 = fma2(gg2, lds2(S + (r + 1) * ld + f2), vb2);
             const f32x2 rr = rcp2(mul2(x0, x1));
             const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
@@ -780,8 +797,26 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
         const f32x2 gc2 = pk2(gnew * kC, gnew * kC), vc2 = mul2(vb2, pk2(kC, kC));
         f32x2 cl = 0ull, cp = 0ull;
         constexpr int R4 = R & ~3;
+        constexpr int RA4 = (RA < R) ? RA : 0;          // rows [0, RA4) are released to the next frame's copy half-way
+        static_assert(RA4 % 4 == 0, "part A must hold whole quads");
 #pragma unroll
-        for (int r = 0; r < R4; r += 4) {
+        for (int r = 0; r < RA4; r += 4) {
+            const f32x2 y0 = fma2(gc2, lds2(S + r * ld + f2), vc2), y1 = fma2(gc2, lds2(S + (r + 1) * ld + f2), vc2);
+            const f32x2 y2 = fma2(gc2, lds2(S + (r + 2) * ld + f2), vc2), y3 = fma2(gc2, lds2(S + (r + 3) * ld + f2), vc2);
+            const f32x2 p01 = mul2(y0, y1), p23 = mul2(y2, y3);
+            const f32x2 m = mul2(p01, p23);
+            cl = add2(cl, lg22(m));
+            cp = fma2(fma2(add2(y0, y1), p23, mul2(add2(y2, y3), p01)), rcp2(m), cp);
+        }
+        float cX = 0.f;
+        if (RA4 > 0) {
+            // bin 512 of rows < RA4 before part A is handed over
+            if (xl && t < RA4) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
+            __syncthreads();                            // every thread has left rows [0, RA)
+            if (n + 1 < ne) issue_rows(n + 1, 0, RA, bar_a);
+        }
+#pragma unroll
+        for (int r = RA4; r < R4; r += 4) {
             const f32x2 y0 = fma2(gc2, lds2(S + r * ld + f2), vc2), y1 = fma2(gc2, lds2(S + (r + 1) * ld + f2), vc2);
             const f32x2 y2 = fma2(gc2, lds2(S + (r + 2) * ld + f2), vc2), y3 = fma2(gc2, lds2(S + (r + 3) * ld + f2), vc2);
             const f32x2 p01 = mul2(y0, y1), p23 = mul2(y2, y3);
@@ -798,8 +833,7 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
             cp = fma2(add2(y0, y1), rcp2(pr), cp);
             fix -= 16.0f;
         }
-        float cX = 0.f;
-        if (xl) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
+        if (xl && t >= RA4) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
         {
             float cl_lo, cl_hi, pc_lo, pc_hi;
             upk2(cl, cl_lo, cl_hi);
@@ -810,6 +844,11 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
 
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
         if (t == 0) g[n] = gnew;
+        __syncthreads();                                // the frame is fully consumed: the rest of the buffer may be refilled
+        if (n + 1 < ne) {
+            if (RA4 > 0) issue_rows(n + 1, RA, R, bar_b);
+            else issue_rows(n + 1, 0, RA, bar_a);
+        }
     }
     cost_d = warp_sum_d(cost_d);
     if (lane == 0) redd[wid] = cost_d;
