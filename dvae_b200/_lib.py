@@ -38,6 +38,8 @@ PROTOTYPES = {
     "dvae_last_error": (C.c_char_p, []),
     "dvae_stft_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr]),
     "dvae_istft_f32": (C.c_int, [c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr]),
+    "dvae_istft_masked_f32": (C.c_int, [c_ptr, c_ptr, C.c_float, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, c_ptr]),
     "dvae_mlp_workspace_floats": (C.c_int64, [C.POINTER(DvaeMlp), C.c_int64]),
     "dvae_mlp_fwd": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int64,
                                C.c_int, c_ptr, C.c_int, c_ptr, c_ptr]),

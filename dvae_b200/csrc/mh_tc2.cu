@@ -219,29 +219,44 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     } while (0)
             MH2_LOAD(0, pv0);
             MH2_LOAD(1, pv1);
+            // The TMEM reads are double-buffered: the 16 columns of sub-chunk t+1 are requested right after those of t have
+            // arrived, so their latency runs under the arithmetic of t (with two warps per scheduler the other warp alone
+            // cannot cover it: the single-buffer version spent half of the layer-3 phase with neither XU nor issue slots busy).
+            float va[16], vb[16];
+            mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); DBG_STAMP(15, threadIdx.x == 0);
+            tmem_ld16(tmem + lane_off + MH2_COL(0), va);
 #pragma unroll
             for (int t = 0; t < 17; ++t) {
-                const int c = MH2_CH(t);
                 const bool live = (t < 16) || (h == 0);                         // bins 528..543 do not exist
                 if (t + 2 < 17 && ((t + 2 < 16) || (h == 0))) {
                     if ((t + 2) % 3 == 0) MH2_LOAD(t + 2, pv0);
                     else if ((t + 2) % 3 == 1) MH2_LOAD(t + 2, pv1);
                     else MH2_LOAD(t + 2, pv2);
                 }
-                if (t == 0 || t == 12) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); DBG_STAMP(15 + c, threadIdx.x == 0); }
-                if (t == 6) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; tc_fence_after(); DBG_STAMP(15 + c, threadIdx.x == 0); }
-                if (live) {
-                    float v[16];
-                    tmem_ld16(tmem + 192 * (c & 1) + lane_off + MH2_COL(t), v);
-                    tmem_wait_ld();
-                    if (t % 3 == 0) loglik16_pv<POLY>(v, pv0, g_row, acc, accl);
-                    else if (t % 3 == 1) loglik16_pv<POLY>(v, pv1, g_row, acc, accl);
-                    else loglik16_pv<POLY>(v, pv2, g_row, acc, accl);
-                }
+                if (live) tmem_wait_ld();                                       // sub-chunk t is in registers
                 if (t == 5) {                                                   // chunk 0 drained by this thread
                     DBG_STAMP(4, threadIdx.x == 0);
                     tc_fence_before();
                     mbar_arrive2(barf_0);
+                }
+                if (t + 1 < 17 && ((t + 1 < 16) || (h == 0))) {
+                    if (t + 1 == 6) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; tc_fence_after(); DBG_STAMP(16, threadIdx.x == 0); }
+                    if (t + 1 == 12) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); DBG_STAMP(17, threadIdx.x == 0); }
+                    if ((t + 1) % 2 == 0) tmem_ld16(tmem + 192 * (MH2_CH(t + 1) & 1) + lane_off + MH2_COL(t + 1), va);
+                    else tmem_ld16(tmem + 192 * (MH2_CH(t + 1) & 1) + lane_off + MH2_COL(t + 1), vb);
+                }
+                if (live) {
+                    if (t % 2 == 0) {
+                        if (t % 3 == 0) loglik16_pv<POLY>(va, pv0, g_row, acc, accl);
+                        else if (t % 3 == 1) loglik16_pv<POLY>(va, pv1, g_row, acc, accl);
+                        else loglik16_pv<POLY>(va, pv2, g_row, acc, accl);
+                    } else {
+                        if (t % 3 == 0) loglik16_pv<POLY>(vb, pv0, g_row, acc, accl);
+                        else if (t % 3 == 1) loglik16_pv<POLY>(vb, pv1, g_row, acc, accl);
+                        else loglik16_pv<POLY>(vb, pv2, g_row, acc, accl);
+                    }
+                }
+                if (t == 5) {
                     if (warp == 5) {
                         if (lead) {
                             mbar_wait(barf_0, phf_0, dead, p.status);

@@ -278,7 +278,11 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const float* __restrict__ 
 // (no later frame reaches them): they are normalised by the window sum-square table and stored, the other three slide
 // down.  No accumulator lives in shared memory, a CTA can stream a whole utterance (no frame is transformed twice), and
 // only short batches are cut into segments (three lead-in frames each) to fill the GPU.
-__global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict__ X, const int64_t* __restrict__ fr_off,
+// MASKED: the frame is multiplied by a real per-bin mask (mask * mask_scale, the Wiener filter of mcem.py:176-177) as it is
+// loaded, so that S_hat / N_hat need not be materialised between the filter and the inverse transform.
+template <bool MASKED>
+__global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict__ X, const float* __restrict__ mask, float mask_scale,
+                                                       const int64_t* __restrict__ fr_off,
                                                        float* __restrict__ y, const int64_t* __restrict__ y_off,
                                                        const int32_t* __restrict__ y_len, int /*hop: 256*/, int ld, int seg_hops) {
     constexpr int hop = 256;                                                  // = CTA size (checked by the host wrapper): index math in shifts
@@ -318,6 +322,12 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
                 for (int n1 = 0; n1 < 8; ++n1) {
                     const int k = t + 64 * n1;
                     float2 xk = __ldg(Xn + k), xm = __ldg(Xn + kHalf - k);
+                    if (MASKED) {                                             // same products as wiener_apply_kernel
+                        const float* Mn = mask + (f0 + j) * (int64_t)ld;
+                        const float mk = __ldg(Mn + k) * mask_scale, mm = __ldg(Mn + kHalf - k) * mask_scale;
+                        xk = make_float2(mk * xk.x, mk * xk.y);
+                        xm = make_float2(mm * xm.x, mm * xm.y);
+                    }
                     if (k == 0) { xk.y = 0.f; xm.y = 0.f; }                   // irfft ignores Im of DC and Nyquist
                     xm.y = -xm.y;                                             // conj(X[512-k])
                     const float2 s = cadd(xk, xm), d = csub(xk, xm);
@@ -394,12 +404,12 @@ extern "C" int dvae_stft_f32(const float* x, const int64_t* x_off, const int32_t
     return check_launch("stft_kernel");
 }
 
-extern "C" int dvae_istft_f32(const void* X, const int64_t* fr_off, int B, float* y, const int64_t* y_off,
-                              const int32_t* y_len, int max_y_len, int n_fft, int hop, int ld, void* stream) {
-    DVAE_REQUIRE(n_fft == kNfft, "dvae_istft_f32: only n_fft=1024 is implemented (got %d)", n_fft);
-    DVAE_REQUIRE(hop == 256, "dvae_istft_f32: only hop=256 is implemented (got %d)", hop);
-    DVAE_REQUIRE(B >= 1 && B <= 65535 && max_y_len >= 0 && ld >= kHalf + 1, "dvae_istft_f32: bad sizes (B <= 65535)");
-    DVAE_REQUIRE(X && fr_off && y && y_off && y_len, "dvae_istft_f32: null pointer");
+static int istft_launch(const char* who, const void* X, const float* mask, float mask_scale, const int64_t* fr_off, int B, float* y,
+                        const int64_t* y_off, const int32_t* y_len, int max_y_len, int n_fft, int hop, int ld, void* stream) {
+    DVAE_REQUIRE(n_fft == kNfft, "%s: only n_fft=1024 is implemented (got %d)", who, n_fft);
+    DVAE_REQUIRE(hop == 256, "%s: only hop=256 is implemented (got %d)", who, hop);
+    DVAE_REQUIRE(B >= 1 && B <= 65535 && max_y_len >= 0 && ld >= kHalf + 1, "%s: bad sizes (B <= 65535)", who);
+    DVAE_REQUIRE(X && fr_off && y && y_off && y_len, "%s: null pointer", who);
     if (max_y_len == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     int rc = ensure_tables(st);
@@ -412,6 +422,21 @@ extern "C" int dvae_istft_f32(const void* X, const int64_t* fr_off, int B, float
     if (n_seg < 1) n_seg = 1;
     const int seg_hops = (total_hops + n_seg - 1) / n_seg;
     n_seg = (total_hops + seg_hops - 1) / seg_hops;
-    istft_kernel<<<dim3(n_seg, B), 256, 0, st>>>((const float2*)X, fr_off, y, y_off, y_len, hop, ld, seg_hops);
+    if (mask)
+        istft_kernel<true><<<dim3(n_seg, B), 256, 0, st>>>((const float2*)X, mask, mask_scale, fr_off, y, y_off, y_len, hop, ld, seg_hops);
+    else
+        istft_kernel<false><<<dim3(n_seg, B), 256, 0, st>>>((const float2*)X, nullptr, 1.0f, fr_off, y, y_off, y_len, hop, ld, seg_hops);
     return check_launch("istft_kernel");
+}
+
+extern "C" int dvae_istft_f32(const void* X, const int64_t* fr_off, int B, float* y, const int64_t* y_off,
+                              const int32_t* y_len, int max_y_len, int n_fft, int hop, int ld, void* stream) {
+    return istft_launch("dvae_istft_f32", X, nullptr, 1.0f, fr_off, B, y, y_off, y_len, max_y_len, n_fft, hop, ld, stream);
+}
+
+extern "C" int dvae_istft_masked_f32(const void* X, const float* mask, float mask_scale, const int64_t* fr_off, int B, float* y,
+                                     const int64_t* y_off, const int32_t* y_len, int max_y_len, int n_fft, int hop, int ld,
+                                     void* stream) {
+    DVAE_REQUIRE(mask, "dvae_istft_masked_f32: null mask");
+    return istft_launch("dvae_istft_masked_f32", X, mask, mask_scale, fr_off, B, y, y_off, y_len, max_y_len, n_fft, hop, ld, stream);
 }

@@ -352,26 +352,32 @@ __device__ __forceinline__ void loglik16_pv(const float* v, const uint4* pv, flo
 // (tanh.approx.bf16x2) yields both activations already in the operand's storage format -> half the MUFU work of the
 // hidden layers.  Used by the samplers (the decode keeps FP32 tanh).
 __device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) { uint32_t y; asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
-__device__ __forceinline__ void hidden_epilogue_rows_bf(uint32_t tmem, unsigned char* A, int q, int h, int row, const float* bias) {
-    float v[32];
+__device__ __forceinline__ void hidden_rows_bf_part(const float* v, unsigned char* A, int h, int row, int part, const float* bias) {
+    const int col0 = 64 * h + 32 * part;
 #pragma unroll
-    for (int part = 0; part < 2; ++part) {
-        const int col0 = 64 * h + 32 * part;
-        tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + col0, v);
-        tmem_wait_ld();
+    for (int cc = 0; cc < 4; ++cc) {
+        uint32_t w[4];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float x0 = v[8 * cc + 2 * e], x1 = v[8 * cc + 2 * e + 1];
-                if (bias) { x0 += bias[col0 + 8 * cc + 2 * e]; x1 += bias[col0 + 8 * cc + 2 * e + 1]; }
-                w[e] = tanh_bf16x2(pack_bf16x2(x0, x1));
-            }
-            const int chunk = 4 * part + cc;
-            *reinterpret_cast<uint4*>(A + h * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int e = 0; e < 4; ++e) {
+            float x0 = v[8 * cc + 2 * e], x1 = v[8 * cc + 2 * e + 1];
+            if (bias) { x0 += bias[col0 + 8 * cc + 2 * e]; x1 += bias[col0 + 8 * cc + 2 * e + 1]; }
+            w[e] = tanh_bf16x2(pack_bf16x2(x0, x1));
         }
+        const int chunk = 4 * part + cc;
+        *reinterpret_cast<uint4*>(A + h * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
     }
+}
+// The second half of the thread's columns is requested as soon as the first has arrived: its TMEM latency runs under the
+// tanh / pack / store work of the first half.
+__device__ __forceinline__ void hidden_epilogue_rows_bf(uint32_t tmem, unsigned char* A, int q, int h, int row, const float* bias) {
+    float v0[32], v1[32];
+    const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + 64 * h;
+    tmem_ld32(t0, v0);
+    tmem_wait_ld();
+    tmem_ld32(t0 + 32, v1);
+    hidden_rows_bf_part(v0, A, h, row, 0, bias);
+    tmem_wait_ld();
+    hidden_rows_bf_part(v1, A, h, row, 1, bias);
 }
 
 size_t smem_bytes(const Dims& d);

@@ -184,6 +184,19 @@ def istft_batch(X: torch.Tensor, batch: RaggedBatch, y_off: torch.Tensor, y_len:
     return y
 
 
+def istft_masked_batch(X: torch.Tensor, mask: torch.Tensor, batch: RaggedBatch, y_off: torch.Tensor, y_len: torch.Tensor,
+                       total_len: int, max_len: int, mask_scale: float = 1.0, n_fft=N_FFT, hop=HOP,
+                       out: Optional[torch.Tensor] = None):
+    """ISTFT of ``(mask * mask_scale) * X`` (real ``mask [NT][ld]``): the Wiener filter of mcem.py:176-177 applied while the
+    frames are loaded, bit-identical to ``dvae_wiener_apply`` + ``istft_batch`` without materialising the product."""
+    if mask.shape != X.shape or mask.dtype != torch.float32 or not mask.is_contiguous():
+        raise ValueError("mask must be a contiguous float32 tensor of the spectrum's shape")
+    y = out if out is not None else torch.empty(total_len, dtype=torch.float32, device=X.device)
+    _lib.call("dvae_istft_masked_f32", _p(X), _p(mask), float(mask_scale), _p(batch.fr_off), batch.B, _p(y), _p(y_off), _p(y_len),
+              int(max_len), n_fft, hop, X.shape[1], _stream())
+    return y
+
+
 def mlp_forward(mlp: PackedMlp, x: torch.Tensor, act_last: int, x2: Optional[torch.Tensor] = None, x2_row_div: int = 1,
                 out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None):
     """Run a packed tanh MLP on the rows of ``x`` (2-D, last dim contiguous) [+ label columns ``x2``]."""

@@ -79,6 +79,14 @@ int dvae_stft_f32(const float* x, const int64_t* x_off, const int32_t* x_len, in
 int dvae_istft_f32(const void* X /* float2 */, const int64_t* fr_off, int B, float* y, const int64_t* y_off,
                    const int32_t* y_len, int max_y_len, int n_fft, int hop, int ld, void* stream);
 
+/* ---- Wiener filter fused into the ISTFT: mcem.py:176-177 (S_hat = WFs * X) followed by stft.py:63-99 ----
+ * Same as dvae_istft_f32 on the spectrum (mask[n][f] * mask_scale) * X[n][f] (real mask, row pitch ld), formed in
+ * registers while the frame is loaded: bit-identical to dvae_wiener_apply + dvae_istft_f32 without the S_hat / N_hat
+ * round trip through HBM (BASELINE.json configs[4]). */
+int dvae_istft_masked_f32(const void* X /* float2 */, const float* mask, float mask_scale, const int64_t* fr_off, int B,
+                          float* y, const int64_t* y_off, const int32_t* y_len, int max_y_len, int n_fft, int hop, int ld,
+                          void* stream);
+
 /* ---- dense tanh MLP: models.py:102-105 (Encoder trunk + head) and 119-122 (Decoder) ----
  * out[r][0..dims[n_layers]) = act_last(Linear_n(tanh(... tanh(Linear_1([x[r] ; x2[r / x2_row_div]])))))
  * x: rows x k1 (row stride ldx); x2 (nullable): k2 extra input columns (labels y), row r uses x2 row r / x2_row_div.

@@ -122,3 +122,41 @@ def test_torch_front_end_matches_numpy_wrappers():
     assert np.allclose(power.cpu().numpy(), np.abs(ref) ** 2, rtol=1e-6)
     with pytest.raises(NotImplementedError):
         stft_pytorch(torch.zeros(4096), fs=16000, wlen_sec=64e-3, center=True)
+
+
+def test_istft_masked_equals_wiener_apply_then_istft():
+    """Fused Wiener mask + ISTFT (dvae_istft_masked_f32) against the two-kernel path and against the oracle."""
+    from dvae_b200 import _lib
+    from dvae_b200.engine import RaggedBatch, _p, _stream, istft_batch, istft_masked_batch, stft_batch
+    lens = [48000, 16000, 20000, 1024, 33333]
+    xs = [synth.synth_utterance(30 + i, l / 16000.0)[0][:l] for i, l in enumerate(lens)]
+    off = np.zeros(len(lens) + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    flat = torch.from_numpy(np.concatenate(xs)).to(DEV)
+    nfr = [synth.num_frames(l) for l in lens]
+    batch = RaggedBatch(nfr, DEV)
+    x_off = torch.from_numpy(off[:-1].copy()).to(DEV)
+    x_len = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    X, _ = stft_batch(flat, x_off, x_len, batch)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    R = 25
+    ws = torch.rand(X.shape, device=DEV, generator=g) * R          # un-normalised sums over R samples, like WFs / WFn
+    wn = R - ws
+    S, Nn = torch.empty_like(X), torch.empty_like(X)
+    _lib.call("dvae_wiener_apply", _p(X), _p(ws), _p(wn), R, batch.NT, 513, X.shape[1], _p(S), _p(Nn), _stream())
+    total = int(off[-1])
+    for mask, spec in ((ws, S), (wn, Nn)):
+        two = istft_batch(spec, batch, x_off, x_len, total, max(lens))
+        one = istft_masked_batch(X, mask, batch, x_off, x_len, total, max(lens), mask_scale=1.0 / R)
+        assert torch.equal(one, two)                               # same products, same transform: bit-identical
+    # oracle: mask the spectrum on the host, invert with the numpy restatement
+    Xh, wh = X.cpu().numpy(), (ws / R).cpu().numpy()
+    one = istft_masked_batch(X, ws, batch, x_off, x_len, total, max(lens), mask_scale=1.0 / R).cpu().numpy()
+    for u, l in enumerate(lens):
+        a, b = batch.fr_off_host[u], batch.fr_off_host[u + 1]
+        ref = stft_np.istft((Xh[a:b, :513] * wh[a:b, :513]).T.astype(np.complex64), max_len=l, **IKW)
+        got = one[off[u]:off[u] + l]
+        if l > 4000:
+            assert relerr(got[800:-800], ref[800:-800]) <= 1e-4     # north-star tolerance, interior samples
+    with pytest.raises(ValueError):
+        istft_masked_batch(X, ws[:, :512], batch, x_off, x_len, total, max(lens))

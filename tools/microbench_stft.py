@@ -17,7 +17,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from dvae_b200 import _lib, synth                                                   # noqa: E402
-from dvae_b200.engine import RaggedBatch, _p, _stream, istft_batch, stft_batch        # noqa: E402
+from dvae_b200.engine import RaggedBatch, _p, _stream, istft_batch, istft_masked_batch, stft_batch        # noqa: E402
 
 DEV = torch.device("cuda:0")
 T, N, F, LD = 48000, 185, 513, 520
@@ -55,13 +55,18 @@ def run(B_total, chunk=8192):
     t_stft = timed(lambda: _lib.call("dvae_stft_f32", _p(x), _p(off), _p(lens), Bc, _p(X), _p(P), _p(batch.fr_off), batch.NT, 1024, 256, LD, _stream()))
     t_wf = timed(lambda: _lib.call("dvae_wiener_apply", _p(X), _p(mask), _p(inv), 1, batch.NT, F, LD, _p(S), _p(Nn), _stream()))
     t_istft = timed(lambda: istft_batch(S, batch, off, lens, Bc * T, T, out=y))
+    t_fused = timed(lambda: istft_masked_batch(X, mask, batch, off, lens, Bc * T, T, out=y))      # Wiener mask applied in the ISTFT load
     yy = istft_batch(X, batch, off, lens, Bc * T, T).view(Bc, T)
     err = (yy[:, 800:-800] - x[:, 800:-800]).abs().max().item()
     b_stft, b_wf, b_istft = 4 * T + 12 * F * N, 24 * F * N + 8 * F * N, 8 * F * N + 4 * T
     tot_ms = (t_stft + t_wf + 2 * t_istft) * n_chunks
+    b_fused = 12 * F * N + 4 * T
+    fused_ms = (t_stft + 2 * t_fused) * n_chunks
     out = dict(workload="configs[4] STFT->Wiener->ISTFT", utterances=B_total, chunk=Bc, round_trip_max_err=err,
                ms=dict(stft=t_stft, wiener=t_wf, istft=t_istft), total_ms=tot_ms,
                audio_s_per_s=B_total * 3.0 / (tot_ms * 1e-3),
+               fused=dict(istft_masked_ms=t_fused, total_ms=fused_ms, audio_s_per_s=B_total * 3.0 / (fused_ms * 1e-3),
+                          gbs=Bc * b_fused / t_fused / 1e6, frac_of_hbm_peak=Bc * b_fused / t_fused / 1e6 / PEAK),
                gbs=dict(stft=Bc * b_stft / t_stft / 1e6, wiener=Bc * b_wf / t_wf / 1e6, istft=Bc * b_istft / t_istft / 1e6),
                frac_of_hbm_peak=dict(stft=Bc * b_stft / t_stft / 1e6 / PEAK, wiener=Bc * b_wf / t_wf / 1e6 / PEAK,
                                      istft=Bc * b_istft / t_istft / 1e6 / PEAK), hbm_peak_gbs=PEAK)
