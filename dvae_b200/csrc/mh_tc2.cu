@@ -51,7 +51,7 @@ static long long* g_dbg_clocks = nullptr;
     } while (0)
 
 
-template <int L, bool POLY>
+template <int L, int POLY>
 __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint64_t bars[6];                       // layer 1/2 ready, chunk ready x3, buffer free x2
@@ -61,16 +61,15 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     const Dims& d = p.d;
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* A = base + ((d.image_bytes + 1023) & ~1023);
-    float* red = reinterpret_cast<float*>(A + A_BYTES);          // [128] partial l(z') of the upper column half
-    float* zpS = red + TM;                                       // [128][L] proposals (written and read by the row's owner)
+    float2* red2 = reinterpret_cast<float2*>(A + A_BYTES);       // [2][128] {partial l(z'), partial prior term} of each column half
     const uint32_t bar12 = smem_u32(&bars[0]);
     const uint32_t bar3_0 = smem_u32(&bars[1]), bar3_1 = smem_u32(&bars[2]);
     const uint32_t barf_0 = smem_u32(&bars[3]);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3, h = warp >> 2;             // TMEM lane quadrant, column half
-    const bool owner = h == 0;                         // warps 0-3 carry the chain of row 32q + lane
+    const bool owner = h == 0;                         // warps 0-3 also write the label / constant chunk, the trace and the accept count
     // tcgen05.mma issue is spread over lane 0 of different warps so that no single warp pays for all of it:
-    // layer 1: warp 1, layer 2: warp 2, layer-3 chunks 0 / 1 / 2: warps 3 / 4 / 5
+    // layer 1: warp 1, layer 2: warp 2, layer-3 chunks 0 + 1: warp 3, chunk 2: warp 5
     const bool lead = lane == 0;
     const int row = 32 * q + lane;
     uint32_t ph12 = 0, ph3_0 = 0, ph3_1 = 0, phf_0 = 0;
@@ -116,48 +115,46 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         const float g_row = valid ? p.g[fr] : 1.f;
         const uint4* PVt = p.PVpk + (tile * NQ) * TM + row;
 
-        // chain state (owner threads only; dead code in the other warps)
-        float z[L];
-        float4 en[L / 4];                                  // draws of the next proposal (live only around the accept step)
-        float y0 = 0.f, y1 = 0.f, y2 = 0.f, ll_cur = 0.f, u_cur = 0.5f, u_nxt = 0.5f, prior = 0.f;
+        // Chain state, split over the two column halves: thread (row, h) carries latent dimensions [h L/2, (h+1) L/2) of its
+        // row's chain plus a copy of the scalars.  The proposal / accept code is a chain of dependent operations that runs
+        // with one warp per scheduler, so halving its length matters more than the duplicated scalar work (the single-owner
+        // version spent 1.0 k + 0.8 k of 15 k cycles per evaluation there: tools/tc_phase_clocks.py).  Both halves take the
+        // accept decision from the same shared-memory operands in the same order, so they always agree bit for bit.
+        constexpr int LH = L / 2;
+        float zh[LH], zph[LH];
+        float4 enn[LH / 4];                                // this half's draws of the next proposal
+        float y0 = 0.f, y1 = 0.f, y2 = 0.f, ll_cur = 0.f, u_cur = 0.5f, u_nxt = 0.5f, prior_h = 0.f;
         uint32_t n_acc = 0;
-        if (owner) {
 #pragma unroll
-            for (int l = 0; l < L; ++l) z[l] = valid ? p.Z[row_g * L + l] : 0.f;
+        for (int l = 0; l < LH; ++l) { zh[l] = valid ? p.Z[row_g * L + h * LH + l] : 0.f; zph[l] = 0.f; }
 #pragma unroll
-            for (int l = 0; l < L / 4; ++l) en[l] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-                if (y_dim > 0) y0 = p.y[fr * y_dim];
-                if (y_dim > 1) y1 = p.y[fr * y_dim + 1];
-                if (y_dim > 2) y2 = p.y[fr * y_dim + 2];
-            }
+        for (int l = 0; l < LH / 4; ++l) enn[l] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (owner && valid) {
+            if (y_dim > 0) y0 = p.y[fr * y_dim];
+            if (y_dim > 1) y1 = p.y[fr * y_dim + 1];
+            if (y_dim > 2) y2 = p.y[fr * y_dim + 2];
         }
 
         // eval -1 scores the start state, eval it >= 0 scores proposal `it`
         for (int it = -1; it < n_iter; ++it) {
             DBG_STAMP(0, threadIdx.x == 0);
-            if (owner) {
-                if (it >= 0) {
-                    u_cur = u_nxt;
-                    float zp[L];
-                    prior = 0.f;
+            if (it >= 0) {
+                u_cur = u_nxt;
+                prior_h = 0.f;
 #pragma unroll
-                    for (int l = 0; l < L / 4; ++l) {
-                        zp[4 * l + 0] = __fadd_rn(z[4 * l + 0], __fmul_rn(p.sd, en[l].x));
-                        zp[4 * l + 1] = __fadd_rn(z[4 * l + 1], __fmul_rn(p.sd, en[l].y));
-                        zp[4 * l + 2] = __fadd_rn(z[4 * l + 2], __fmul_rn(p.sd, en[l].z));
-                        zp[4 * l + 3] = __fadd_rn(z[4 * l + 3], __fmul_rn(p.sd, en[l].w));
-                    }
-#pragma unroll
-                    for (int l = 0; l < L; ++l) prior += __fsub_rn(__fmul_rn(z[l], z[l]), __fmul_rn(zp[l], zp[l]));
-#pragma unroll
-                    for (int l = 0; l < L / 4; ++l)
-                        *reinterpret_cast<float4*>(zpS + row * L + 4 * l) = make_float4(zp[4 * l], zp[4 * l + 1], zp[4 * l + 2], zp[4 * l + 3]);
-                    write_a1_static<L>(y_dim, nkb1, A, row, zp, y0, y1, y2, valid);
-                } else {
-                    write_a1_static<L>(y_dim, nkb1, A, row, z, y0, y1, y2, valid);
+                for (int l = 0; l < LH / 4; ++l) {
+                    zph[4 * l + 0] = __fadd_rn(zh[4 * l + 0], __fmul_rn(p.sd, enn[l].x));
+                    zph[4 * l + 1] = __fadd_rn(zh[4 * l + 1], __fmul_rn(p.sd, enn[l].y));
+                    zph[4 * l + 2] = __fadd_rn(zh[4 * l + 2], __fmul_rn(p.sd, enn[l].z));
+                    zph[4 * l + 3] = __fadd_rn(zh[4 * l + 3], __fmul_rn(p.sd, enn[l].w));
                 }
+#pragma unroll
+                for (int l = 0; l < LH; ++l) prior_h += __fsub_rn(__fmul_rn(zh[l], zh[l]), __fmul_rn(zph[l], zph[l]));
+                write_a1_half<L>(y_dim, nkb1, A, row, h, zph, y0, y1, y2, valid);
+            } else {
+                write_a1_half<L>(y_dim, nkb1, A, row, h, zh, y0, y1, y2, valid);
             }
+            DBG_STAMP(26, threadIdx.x == 0);
             fence_async_smem();
             __syncthreads();                                                    // S1: layer-1 operand ready
             DBG_STAMP(1, threadIdx.x == 0);
@@ -167,9 +164,23 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 issue_gemm2(a_addr, 16384, w1_addr, 16384, nkb1, tmem + 384, HID);
                 umma_commit(bar12);
             }
+            if (two_hidden) {
+                // Layer-2 bias preloaded into the layer-2 accumulator, TMEM columns [0, 128), while the layer-1 GEMM runs (every
+                // warp would only spin on its mbarrier here; the stores take ~0.6 k cycles).  Every thread writes the 64 columns
+                // it will read back in the layer-2 epilogue.  The columns are free (the previous evaluation's reads of them
+                // completed before its S4; the first layer-3 chunk is issued after S3), the layer-2 GEMM, issued after S2,
+                // accumulates onto the bias, and its epilogue needs no bias loads / adds (0.5 k of its 1.7 k cycles,
+                // tools/tc_phase_clocks.py).
+                tc_fence_after();
+                tmem_preload_bias64(tmem + lane_off + 64 * h, b2 + 64 * h);
+                tmem_wait_st();
+                tc_fence_before();
+                DBG_STAMP(27, threadIdx.x == 0);
+            }
             mbar_wait(bar12, ph12, dead, p.status);
             ph12 ^= 1;
             tc_fence_after();
+            DBG_STAMP(24, threadIdx.x == 0);
             hidden_epilogue_rows_bf(tmem + 384, A, q, h, row, nullptr);              // bias rides on the constant-one column
             fence_async_smem();
             tc_fence_before();
@@ -179,13 +190,14 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             if (two_hidden) {
                 if (warp == 2 && lead) {
                     tc_fence_after();
-                    issue_gemm2(a_addr, 16384, w2_addr, 16384, 2, tmem + 384, HID);
+                    issue_gemm2(a_addr, 16384, w2_addr, 16384, 2, tmem, HID, 1);
                     umma_commit(bar12);
                 }
                 mbar_wait(bar12, ph12, dead, p.status);
                 ph12 ^= 1;
                 tc_fence_after();
-                hidden_epilogue_rows_bf(tmem + 384, A, q, h, row, b2);
+                DBG_STAMP(25, threadIdx.x == 0);
+                hidden_epilogue_rows_bf(tmem, A, q, h, row, nullptr);
                 fence_async_smem();
                 tc_fence_before();
                 DBG_STAMP(21, threadIdx.x == 0);
@@ -194,13 +206,12 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             }
             // ---- layer 3 as three chunks of 192 / 192 / 160 bins (the last one over-reads 16 rows of padding):
             // chunk 0 -> TMEM columns [0,192), chunk 1 -> [192,384), chunk 2 -> [0,160) once chunk 0 is drained
+            // one thread issues chunk 0 and then chunk 1: issued from two warps at once the two GEMMs interleaved in the tensor
+            // pipe and chunk 0 (the one the epilogue is waiting for) completed 0.6 k cycles later
             if (warp == 3 && lead) {
                 tc_fence_after();
                 issue_gemm2(a_addr, 16384, w3_addr, NPAD * 128, 2, tmem, 192);
                 umma_commit(bar3_0);
-            }
-            if (warp == 4 && lead) {
-                tc_fence_after();
                 issue_gemm2(a_addr, 16384, w3_addr + 192 * 128, NPAD * 128, 2, tmem + 192, 192);
                 umma_commit(bar3_1);
             }
@@ -270,15 +281,13 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 }
                 if (t == 11) {
                     DBG_STAMP(5, threadIdx.x == 0);
-                    if (owner) {
-                        // draws of the next proposal: requested here, consumed right after the accept step
-                        const int nxt = it + 1;
-                        if (nxt < n_iter && valid) {
-                            const float4* e = reinterpret_cast<const float4*>(p.eps + ((int64_t)nxt * p.rows + row_g) * L);
+                    // draws of the next proposal: requested here, consumed at the top of the next evaluation
+                    const int nxt = it + 1;
+                    if (nxt < n_iter && valid) {
+                        const float4* e = reinterpret_cast<const float4*>(p.eps + ((int64_t)nxt * p.rows + row_g) * L + h * LH);
 #pragma unroll
-                            for (int l = 0; l < L / 4; ++l) en[l] = __ldg(e + l);
-                            u_nxt = __ldg(p.u + (int64_t)nxt * p.rows + row_g);
-                        }
+                        for (int l = 0; l < LH / 4; ++l) enn[l] = __ldg(e + l);
+                        u_nxt = __ldg(p.u + (int64_t)nxt * p.rows + row_g);
                     }
                 }
             }
@@ -288,40 +297,37 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
 #undef MH2_CH
             tc_fence_before();
             const float part = fmaf(kLn2, accl, acc * kQuadScale);
-            if (h == 1) red[row] = part;
+            red2[h * TM + row] = make_float2(part, prior_h);
             DBG_STAMP(8, threadIdx.x == 0);
-            __syncthreads();                                                    // S4: both halves of l(z') available
+            __syncthreads();                                                    // S4: both halves of l(z') and of the prior term
             DBG_STAMP(9, threadIdx.x == 0);
-
-            if (owner) {
-                const float ll_prop = part + red[row];
+            {
+                const float2 r0 = red2[row], r1 = red2[TM + row];
+                const float ll_prop = r0.x + r1.x;
                 if (it < 0) {
                     ll_cur = ll_prop;
                 } else if (valid) {
-                    const float a = (ll_cur - ll_prop) + 0.5f * prior;
-                    if (p.a_trace) p.a_trace[(int64_t)it * p.rows + row_g] = a;
+                    const float a = (ll_cur - ll_prop) + 0.5f * (r0.y + r1.y);
+                    if (owner && p.a_trace) p.a_trace[(int64_t)it * p.rows + row_g] = a;
                     if (__logf(u_cur) < a) {
 #pragma unroll
-                        for (int l = 0; l < L / 4; ++l) {
-                            const float4 t4 = *reinterpret_cast<const float4*>(zpS + row * L + 4 * l);
-                            z[4 * l] = t4.x; z[4 * l + 1] = t4.y; z[4 * l + 2] = t4.z; z[4 * l + 3] = t4.w;
-                        }
+                        for (int l = 0; l < LH; ++l) zh[l] = zph[l];
                         ll_cur = ll_prop;
                         ++n_acc;
                     }
                     if (it >= p.n_burn) {
-                        float4* dst = reinterpret_cast<float4*>(p.Zs + (row_g * p.n_keep + (it - p.n_burn)) * L);
+                        float4* dst = reinterpret_cast<float4*>(p.Zs + (row_g * p.n_keep + (it - p.n_burn)) * L + h * LH);
 #pragma unroll
-                        for (int l = 0; l < L / 4; ++l) dst[l] = make_float4(z[4 * l], z[4 * l + 1], z[4 * l + 2], z[4 * l + 3]);
+                        for (int l = 0; l < LH / 4; ++l) dst[l] = make_float4(zh[4 * l], zh[4 * l + 1], zh[4 * l + 2], zh[4 * l + 3]);
                     }
                 }
             }
             DBG_STAMP(23, threadIdx.x == 0);
         }
-        if (owner && valid) {
+        if (valid) {
 #pragma unroll
-            for (int l = 0; l < L; ++l) p.Z[row_g * L + l] = z[l];
-            if (p.n_accept) p.n_accept[row_g] += n_acc;
+            for (int l = 0; l < LH; ++l) p.Z[row_g * L + h * LH + l] = zh[l];
+            if (owner && p.n_accept) p.n_accept[row_g] += n_acc;
         }
     }
 
@@ -373,16 +379,18 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const vo
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
     const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool poly = (flags & DVAE_TC_POLY_EX2) != 0;
+    const int poly = (flags & DVAE_TC_POLY_EX2_ALL) ? 2 : ((flags & DVAE_TC_POLY_EX2) ? 1 : 0);
 #define MH2_LAUNCH(LL, PP)                                                                                   \
     do {                                                                                                     \
         cudaFuncSetAttribute(mh2_kernel<LL, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
         mh2_kernel<LL, PP><<<grid, MH2_THREADS, smem, st>>>(p);                                              \
     } while (0)
-    if (L == 16 && poly) MH2_LAUNCH(16, true);
-    else if (L == 16) MH2_LAUNCH(16, false);
-    else if (poly) MH2_LAUNCH(32, true);
-    else MH2_LAUNCH(32, false);
+    if (L == 16 && poly == 2) MH2_LAUNCH(16, 2);
+    else if (L == 16 && poly == 1) MH2_LAUNCH(16, 1);
+    else if (L == 16) MH2_LAUNCH(16, 0);
+    else if (poly == 2) MH2_LAUNCH(32, 2);
+    else if (poly == 1) MH2_LAUNCH(32, 1);
+    else MH2_LAUNCH(32, 0);
 #undef MH2_LAUNCH
     return check_launch("mh2_kernel");
 }

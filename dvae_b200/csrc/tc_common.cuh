@@ -125,10 +125,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 // D[tmem] (+)= A[128 x 64*nkb] * B[N x 64*nkb]^T as 4*nkb tcgen05.mma of K=16; both operands K-major SWIZZLE_128B,
 // K block kb of A / B starts a_kb_stride / b_kb_stride bytes after block kb-1.
+// acc0 = 1 accumulates onto what the accumulator already holds (a bias preloaded with tcgen05.st).
 __device__ __forceinline__ void issue_gemm2(uint32_t a_addr, int a_kb_stride, uint32_t b_addr, int b_kb_stride, int nkb,
-                                            uint32_t d_tmem, int N) {
+                                            uint32_t d_tmem, int N, uint32_t acc0 = 0) {
     const uint32_t idesc = umma_idesc(N);
-    uint32_t acc = 0;
+    uint32_t acc = acc0;
     for (int kb = 0; kb < nkb; ++kb) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -231,6 +232,51 @@ __device__ __forceinline__ void write_a1_static(int y_dim, int nkb1, unsigned ch
     }
 }
 
+// The same operand row written by two threads: half h holds the latent dimensions [h L/2, (h+1) L/2) in zh and writes their
+// hi and lo chunks; half 0 adds the label / constant chunk, half 1 the zero chunks.
+template <int L>
+__device__ __forceinline__ void write_a1_half(int y_dim, int nkb1, unsigned char* A, int row, int h, const float (&zh)[L / 2], float y0,
+                                              float y1, float y2, bool valid) {
+    constexpr int CH = L / 8, CHH = CH / 2;    // chunks of hi (and of lo) per row / per half
+    static_assert(L % 16 == 0, "write_a1_half: whole 8-element chunks per half");
+    const int sw = row & 7;
+#pragma unroll
+    for (int j = 0; j < 2 * CHH; ++j) {
+        const bool lo = j >= CHH;
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float zz = valid ? zh[(j % CHH) * 8 + i] : 0.f;
+            const float hi = bf16_hi(zz);
+            e[i] = lo ? (zz - hi) : hi;
+        }
+        const int c = (lo ? CH : 0) + h * CHH + (j % CHH);
+        const int kb = c >> 3, cc = c & 7;
+        uint4 pk = make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+        *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((cc ^ sw) << 4)) = pk;
+    }
+    if (h == 0) {   // chunk 2*CH: labels (hi, lo pairs, y_dim <= 3) and the constant one
+        const float h0 = bf16_hi(y0), h1 = bf16_hi(y1), h2 = bf16_hi(y2);
+        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, e4 = 0.f, e5 = 0.f, e6 = 0.f;
+        if (valid) {
+            if (y_dim == 0) { e0 = 1.f; }
+            else if (y_dim == 1) { e0 = h0; e1 = y0 - h0; e2 = 1.f; }
+            else if (y_dim == 2) { e0 = h0; e1 = y0 - h0; e2 = h1; e3 = y1 - h1; e4 = 1.f; }
+            else { e0 = h0; e1 = y0 - h0; e2 = h1; e3 = y1 - h1; e4 = h2; e5 = y2 - h2; e6 = 1.f; }
+        }
+        constexpr int c = 2 * CH;
+        const int kb = c >> 3, cc = c & 7;
+        uint4 pk = make_uint4(pack_bf16x2(e0, e1), pack_bf16x2(e2, e3), pack_bf16x2(e4, e5), pack_bf16x2(e6, 0.f));
+        *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((cc ^ sw) << 4)) = pk;
+    } else {
+        const int K1c = 8 * nkb1;              // remaining chunks of the K blocks in use are zero
+        for (int c = 2 * CH + 1; c < K1c; ++c) {
+            const int kb = c >> 3, cc = c & 7;
+            *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + ((cc ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
 __device__ __forceinline__ void mbar_arrive2(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
@@ -319,7 +365,8 @@ __device__ __forceinline__ f32x2 ex2_poly2(f32x2 x) {
 // POLY: bins 2,3 of every quad take 2^v from ex2_poly2 instead of MUFU.EX2.  The sampler is bound by the MUFU pipe
 // (4 lanes / clk / scheduler: profiles/r01_tc_ncu_mh2.txt shows XU at 51 % with the issue slots at 28 %), so moving a
 // third of its transcendental work to the idle FMA pipe shortens the layer-3 epilogue.
-template <bool POLY>
+// POLY = 2 (DVAE_TC_POLY_EX2_ALL): all four bins of a quad from the polynomial -> 0.5 MUFU operations per bin (rcp, lg2 only).
+template <int POLY>
 __device__ __forceinline__ void loglik16_pv(const float* v, const uint4* pv, float g_row, float& acc, float& accl) {
     // Stream format: see pack_pv_kernel (bias folded in, word j = P'_j with bf16(Vb'_j) in its low half, quad scale k
     // pre-applied to Vb' of bins 0,1 and 1/k to P' of bins 2,3).  Packed FP32 pairs:
@@ -331,8 +378,8 @@ __device__ __forceinline__ void loglik16_pv(const float* v, const uint4* pv, flo
 #pragma unroll
     for (int qd = 0; qd < 4; ++qd) {
         const uint4 w = pv[qd];
-        const f32x2 A = fma2(g2k, pk2(ex2_approx(v[4 * qd + 0]), ex2_approx(v[4 * qd + 1])),
-                             pk2(__uint_as_float(w.x << 16), __uint_as_float(w.y << 16)));
+        const f32x2 e01 = (POLY >= 2) ? ex2_poly2(pk2(v[4 * qd + 0], v[4 * qd + 1])) : pk2(ex2_approx(v[4 * qd + 0]), ex2_approx(v[4 * qd + 1]));
+        const f32x2 A = fma2(g2k, e01, pk2(__uint_as_float(w.x << 16), __uint_as_float(w.y << 16)));
         const f32x2 e23 = POLY ? ex2_poly2(pk2(v[4 * qd + 2], v[4 * qd + 3])) : pk2(ex2_approx(v[4 * qd + 2]), ex2_approx(v[4 * qd + 3]));
         const f32x2 B = fma2(g2, e23, pk2(__uint_as_float(w.z << 16), __uint_as_float(w.w << 16)));
         const f32x2 M = mul2(A, B);
@@ -379,6 +426,32 @@ __device__ __forceinline__ void hidden_epilogue_rows_bf(uint32_t tmem, unsigned 
     tmem_wait_ld();
     hidden_rows_bf_part(v1, A, h, row, 1, bias);
 }
+
+// Preload of a layer's bias into the thread's own 64 accumulator columns (lanes 32q.., columns 64h..): the following
+// GEMM accumulates onto it, so the epilogue has no bias loads / adds (they cost the layer-2 epilogue of the sampler 0.5 k of
+// its 1.7 k cycles: tools/tc_phase_clocks.py).  bias64: 64 floats in shared memory, 16-byte aligned.  Asynchronous: the caller
+// runs tmem_wait_st() (and the tcgen05 fence) before handing the columns over.
+__device__ __forceinline__ void tmem_preload_bias64(uint32_t taddr, const float* bias64) {
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        uint32_t r[32];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 b = *reinterpret_cast<const uint4*>(bias64 + 32 * part + 4 * i);
+            r[4 * i] = b.x; r[4 * i + 1] = b.y; r[4 * i + 2] = b.z; r[4 * i + 3] = b.w;
+        }
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+            :: "r"(taddr + 32 * part), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+               "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+               "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+               "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 size_t smem_bytes(const Dims& d);
 int check_dims(const DvaeMlp* dec, int L, int y_dim, const char* who, Dims* out);

@@ -23,6 +23,7 @@ def _stream():
 
 
 POLY_EX2 = 1            # DVAE_TC_POLY_EX2
+POLY_EX2_ALL = 2        # DVAE_TC_POLY_EX2_ALL
 POLY_EX2_LIMIT = 120.0  # DVAE_TC_POLY_EX2_LIMIT
 
 
@@ -40,7 +41,8 @@ def decoder_image(weights):
         # one-off range query: may the sampler use the polynomial 2^x (see DVAE_TC_POLY_EX2 in include/dvae_b200.h)?
         bound = C.c_float(0.0)
         _lib.call("dvae_tc_decoder_exponent_bound", weights.dec.ref, weights.z_dim, weights.y_dim, C.byref(bound), _stream())
-        weights._tc_flags = POLY_EX2 if bound.value < POLY_EX2_LIMIT and os.environ.get("DVAE_TC_POLY", "1") != "0" else 0
+        mode = os.environ.get("DVAE_TC_POLY", "1")          # 0: MUFU only, 1: half of the exponentials, 2: all of them (tc2 sampler)
+        weights._tc_flags = ({"0": 0, "2": POLY_EX2 | POLY_EX2_ALL}.get(mode, POLY_EX2)) if bound.value < POLY_EX2_LIMIT else 0
     return img
 
 

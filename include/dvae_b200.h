@@ -178,6 +178,7 @@ int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int y_dim, con
  * domain, i.e. when dvae_tc_decoder_exponent_bound (a one-off, synchronising query: log2(e) * max_f sum_k |W3[k][f]|)
  * reports less than DVAE_TC_POLY_EX2_LIMIT for the decoder. */
 #define DVAE_TC_POLY_EX2 1
+#define DVAE_TC_POLY_EX2_ALL 2      /* dvae_mh_chain_tc2 only: all layer-3 exponentials from the polynomial (same validity condition) */
 #define DVAE_TC_POLY_EX2_LIMIT 120.0f
 int dvae_tc_decoder_exponent_bound(const DvaeMlp* dec, int L, int y_dim, float* bound_host, void* stream);
 int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,

@@ -34,7 +34,7 @@ print("sample_posterior(60 iters, %d chains): %.2f ms -> %.0f clk per tile-eval 
 c = buf.cpu().numpy()
 print("per-CTA tile-loop clocks (v2 sampler): min %d max %d mean %d" % (c[56], c[57], c[58] / 148))
 _lib.call("dvae_debug_set_clock_buffer", None); _lib.call("dvae_debug_set_clock_buffer3", None); _lib.call("dvae_debug_set_clock_buffer4", None)
-names = {0: "iter start", 1: "after S1 (A1 written)", 20: "warp0 done hidden-1", 2: "after S2", 21: "warp0 done hidden-2", 3: "after S3",
+names = {0: "iter start", 1: "after S1 (A1 written)", 26: "proposal written (thread 0)", 27: "bias preload complete", 24: "layer-1 accumulator ready", 25: "layer-2 accumulator ready", 20: "warp0 done hidden-1", 2: "after S2", 21: "warp0 done hidden-2", 3: "after S3",
          15: "chunk0 ready", 4: "warp0 done chunk0", 16: "chunk1 ready", 5: "warp0 done chunk1", 17: "chunk2 ready",
          6: "warp0 done chunk2 (v3)", 18: "chunk3 ready (v3)", 7: "warp0 done chunk3 (v3)", 19: "chunk4 ready (v3)",
          8: "warp0 done last chunk", 9: "after S4", 23: "accept done (end of iteration)"}
