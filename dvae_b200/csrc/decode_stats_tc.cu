@@ -27,6 +27,10 @@ namespace tc {
 
 constexpr int DS_THREADS = 672;                       // 4 front warps + 16 back warps + 1 issue warp
 constexpr int DS_BACK = 512;
+// Depth of the layer-3 ring (W3 chunk slot in shared memory + accumulator buffer in TMEM per stage).  With two stages the GEMM
+// of chunk c+2 could only be issued once chunk c was drained and every chunk hand-over cost the back warps ~0.5 k cycles of
+// waiting (tools/ws_phase_clocks.py); with three, it is issued one chunk earlier.
+constexpr int DS_NS = 3;
 
 struct DsParams {
     Dims d;
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
     constexpr int FS = FT / 4;                         // frames per back warp
     static_assert(FT % 4 == 0 && (FT - 1) * R + RL <= 128 && FT * R <= 128, "tile geometry");
     extern __shared__ unsigned char smem_raw[];
-    __shared__ uint64_t bars[11];
+    __shared__ uint64_t bars[5 + 3 * DS_NS];
     __shared__ uint32_t tmem_slot;
     __shared__ int dead_flag;
     __shared__ float tailS[256];
@@ -110,13 +114,12 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
     const int shared_bytes = (d.off_w3 + 4 * ((d.n_hidden == 2 ? HID : 0) + NPAD) + 1023) & ~1023;
     float* biasp = reinterpret_cast<float*>(base + d.off_w3);
     unsigned char* Abuf = base + shared_bytes;                       // 2 x 32 KB
-    unsigned char* Wslot = Abuf + 65536;                             // 2 x 32 KB
+    unsigned char* Wslot = Abuf + 65536;                             // DS_NS x 32 KB
     const uint32_t bar12 = smem_u32(&bars[0]);
     const uint32_t a_full0 = smem_u32(&bars[1]), a_full1 = smem_u32(&bars[2]);
     const uint32_t a_free0 = smem_u32(&bars[3]), a_free1 = smem_u32(&bars[4]);
-    const uint32_t w_full0 = smem_u32(&bars[5]), w_full1 = smem_u32(&bars[6]);
-    const uint32_t bar3_0 = smem_u32(&bars[7]), bar3_1 = smem_u32(&bars[8]);
-    const uint32_t barf_0 = smem_u32(&bars[9]), barf_1 = smem_u32(&bars[10]);
+    // ring stage sl: W3 slot loaded / layer-3 accumulator ready / accumulator drained (8 bytes apart)
+    const uint32_t w_full = smem_u32(&bars[5]), bar3 = smem_u32(&bars[5 + DS_NS]), barf = smem_u32(&bars[5 + 2 * DS_NS]);
 
     {
         const uint4* src = reinterpret_cast<const uint4*>(p.image);
@@ -131,9 +134,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
         mbar_init(bar12, 1);
         mbar_init(a_full0, 128); mbar_init(a_full1, 128);
         mbar_init(a_free0, 1); mbar_init(a_free1, 1);
-        mbar_init(w_full0, 1); mbar_init(w_full1, 1);
-        mbar_init(bar3_0, 1); mbar_init(bar3_1, 1);
-        mbar_init(barf_0, DS_BACK); mbar_init(barf_1, DS_BACK);
+        for (int i = 0; i < DS_NS; ++i) { mbar_init(w_full + 8 * i, 1); mbar_init(bar3 + 8 * i, 1); mbar_init(barf + 8 * i, DS_BACK); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -226,9 +227,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
         const int bw = warp - 4;
         const int q = bw & 3, s = bw >> 2;              // TMEM lane quadrant (bins 32q..), frame slot
         const uint32_t lane_off = (uint32_t)(32 * q) << 16;
-        uint32_t ph3_0 = 0, ph3_1 = 0;
-
-        int64_t c = 0;
+        int sl = 0;                                     // ring stage of the current chunk and the parity of its use count
+        uint32_t par = 0;
         int k = 0;
         // Vb and g of the NEXT chunk are fetched while the current one is processed (their DRAM latency otherwise sits in
         // front of every chunk: 18 % of the stall samples in profiles/r01_tc_ncu_decode_stats.txt)
@@ -246,10 +246,8 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
             const int64_t t0 = tile * FT;
 #pragma unroll 1
-            for (int j = 0; j < 5; ++j, ++c) {
-                const int sl = (int)(c & 1);
-                if (sl == 0) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; }
-                else { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; }
+            for (int j = 0; j < 5; ++j) {
+                mbar_wait(bar3 + 8 * sl, par, dead, p.status);
                 tc_fence_after();
                 DBGD(10 + j, threadIdx.x == 128);
                 DBGD(30 + j, threadIdx.x == 608);
@@ -379,59 +377,55 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                     ds_bar_tail();
                 }
                 tc_fence_before();
-                mbar_arrive2(sl ? barf_1 : barf_0);
+                mbar_arrive2(barf + 8 * sl);
                 DBGD(20 + j, threadIdx.x == 128);
                 DBGD(40 + j, threadIdx.x == 608);
+                if (++sl == DS_NS) { sl = 0; par ^= 1; }
             }
         }
     } else if (lane == 0) {
         // =========================================== issue warp: W3 stream + layer-3 MMAs ===========================================
-        uint32_t ph3_0 = 0, ph3_1 = 0, phf_0 = 0, phf_1 = 0, phw_0 = 0, phw_1 = 0, phfull0 = 0, phfull1 = 0;
+        uint32_t phfull0 = 0, phfull1 = 0;
         const uint32_t slot_addr = smem_u32(Wslot);
-        // chunk c of the CTA's stream: tile k = c / 5, j = c % 5; W3 slot and TMEM buffer = c & 1
+        // chunk c of the CTA's stream: tile k = c / 5, j = c % 5; ring stage sl = c % DS_NS, used for the (c / DS_NS)-th time
         auto load_chunk = [&](int j, int sl) {          // issuer only
             const uint32_t bytes = (j < 4) ? 16384u : 2048u;
-            const uint32_t bar = sl ? w_full1 : w_full0;
+            const uint32_t bar = w_full + 8 * sl;
             ds_expect_tx(bar, 2 * bytes);
             ds_bulk_g2s(slot_addr + sl * 32768, w3g + (size_t)j * 128 * 128, bytes, bar);
             ds_bulk_g2s(slot_addr + sl * 32768 + 16384, w3g + NPAD * 128 + (size_t)j * 128 * 128, bytes, bar);
         };
-        auto issue_chunk = [&](int kk, int j, int sl, bool first_use) {   // issuer only
+        auto issue_chunk = [&](int64_t c2, int sl, bool first_use) {   // issuer only
+            const int kk = (int)(c2 / 5), j = (int)(c2 % 5);
+            const uint32_t use = (uint32_t)((c2 / DS_NS) & 1);
             const int buf = kk & 1;
             const uint32_t a_addr = smem_u32(Abuf + buf * 32768);
-            if (sl == 0) { mbar_wait(w_full0, phw_0, dead, p.status); phw_0 ^= 1; }
-            else { mbar_wait(w_full1, phw_1, dead, p.status); phw_1 ^= 1; }
+            mbar_wait(w_full + 8 * sl, use, dead, p.status);
             if (j == 0) {
                 if (buf == 0) { mbar_wait(a_full0, phfull0, dead, p.status); phfull0 ^= 1; }
                 else { mbar_wait(a_full1, phfull1, dead, p.status); phfull1 ^= 1; }
             }
-            if (!first_use) {                           // the TMEM buffer was drained by the chunk two steps earlier
-                if (sl == 0) { mbar_wait(barf_0, phf_0, dead, p.status); phf_0 ^= 1; }
-                else { mbar_wait(barf_1, phf_1, dead, p.status); phf_1 ^= 1; }
-            }
+            if (!first_use) mbar_wait(barf + 8 * sl, use ^ 1u, dead, p.status);      // the accumulator was drained by chunk c2 - DS_NS
             tc_fence_after();
             const uint32_t tb = tmem + 128 + 128 * sl;
             if (j < 4) issue_gemm2(slot_addr + sl * 32768, 16384, a_addr, 16384, 2, tb, 128);      // D^T = W3 chunk x h2^T
             else issue_gemm2(a_addr, 16384, slot_addr + sl * 32768, 16384, 2, tb, 16);             // bin 512: D = h2 x w^T
-            umma_commit(sl ? bar3_1 : bar3_0);
+            umma_commit(bar3 + 8 * sl);
             if (j == 4) umma_commit(buf ? a_free1 : a_free0);                                       // A[buf] may be rewritten
         };
 
         const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t n_chunks = my_tiles * 5;
-        if (n_chunks > 0) {
-            load_chunk(0, 0);
-            load_chunk(1, 1);
-            issue_chunk(0, 0, 0, true);
-            issue_chunk(0, 1, 1, true);
-        }
-        for (int64_t c = 0; c + 2 < n_chunks; ++c) {
-            const int sl = (int)(c & 1);
-            if (sl == 0) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; }      // MMAs of chunk c done: W slot free
-            else { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; }
-            const int64_t c2 = c + 2;
+        for (int i = 0; i < DS_NS && i < n_chunks; ++i) load_chunk(i % 5, i);
+        for (int i = 0; i < DS_NS && i < n_chunks; ++i) issue_chunk(i, i, true);
+        int sl = 0;
+        uint32_t par = 0;
+        for (int64_t c = 0; c + DS_NS < n_chunks; ++c) {
+            mbar_wait(bar3 + 8 * sl, par, dead, p.status);                                          // GEMM of chunk c done: W slot free
+            const int64_t c2 = c + DS_NS;
             load_chunk((int)(c2 % 5), sl);
-            issue_chunk((int)(c2 / 5), (int)(c2 % 5), sl, false);
+            issue_chunk(c2, sl, false);
+            if (++sl == DS_NS) { sl = 0; par ^= 1; }
         }
     }
 
@@ -525,7 +519,7 @@ static int launch_decode_stats(const char* who, const DvaeMlp* dec, const void* 
     p.Zs = Zs; p.y = y; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status; p.dbg = g_dbg_clocks_ds;
     p.zs_rtot = R_total; p.zs_r0 = r0; p.acc = accumulate;
     const int shared_bytes = (p.d.off_w3 + 4 * ((p.d.n_hidden == 2 ? HID : 0) + NPAD) + 1023) & ~1023;
-    const size_t smem = (size_t)shared_bytes + 65536 + 65536 + 1024;
+    const size_t smem = (size_t)shared_bytes + 65536 + (size_t)DS_NS * 32768 + 1024;
     DVAE_REQUIRE(smem <= 227 * 1024, "%s: shared memory budget exceeded", who);
     const int FT = (R == 25) ? 4 : 128 / R;
     const int64_t n_tiles = (NT + FT - 1) / FT;
