@@ -187,6 +187,20 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             DBG_STAMP(20, threadIdx.x == 0);
             __syncthreads();                                                    // S2
             DBG_STAMP(2, threadIdx.x == 0);
+            float acc = 0.f, accl = 0.f;
+            uint4 pv0[4], pv1[4], pv2[4];
+            // sub-chunk t: chunk c = t/6 (capped at 2), column inside the chunk = h*W_c + 16*(t - 6c), W = 96, 96, 80
+#define MH2_CH(t) ((t) < 6 ? 0 : ((t) < 12 ? 1 : 2))
+#define MH2_COL(t) (h * (MH2_CH(t) == 2 ? 80 : 96) + 16 * ((t) - 6 * MH2_CH(t)))
+#define MH2_BIN(t) (192 * MH2_CH(t) + MH2_COL(t))
+#define MH2_LOAD(t, PV)                                                                              \
+    do {                                                                                             \
+        _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) PV[qd] = __ldg(PVt + ((MH2_BIN(t) >> 2) + qd) * TM); \
+    } while (0)
+            // the first two sub-chunks of the P / Vb stream are requested here, two phases ahead of their use (the wait for
+            // them at the start of the layer-3 loop was 3.6 % of the kernel's stall samples: profiles/r01_tc_ncu_mh2.txt)
+            MH2_LOAD(0, pv0);
+            MH2_LOAD(1, pv1);
             if (two_hidden) {
                 if (warp == 2 && lead) {
                     tc_fence_after();
@@ -218,18 +232,6 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
 
             // per thread 17 (h = 0) or 16 (h = 1) sub-chunks of 16 bins; the P / Vb quads of sub-chunk t+2 are requested
             // while sub-chunk t is evaluated (three rotating register buffers, everything statically indexed)
-            float acc = 0.f, accl = 0.f;
-            uint4 pv0[4], pv1[4], pv2[4];
-            // sub-chunk t: chunk c = t/6 (capped at 2), column inside the chunk = h*W_c + 16*(t - 6c), W = 96, 96, 80
-#define MH2_CH(t) ((t) < 6 ? 0 : ((t) < 12 ? 1 : 2))
-#define MH2_COL(t) (h * (MH2_CH(t) == 2 ? 80 : 96) + 16 * ((t) - 6 * MH2_CH(t)))
-#define MH2_BIN(t) (192 * MH2_CH(t) + MH2_COL(t))
-#define MH2_LOAD(t, PV)                                                                              \
-    do {                                                                                             \
-        _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) PV[qd] = __ldg(PVt + ((MH2_BIN(t) >> 2) + qd) * TM); \
-    } while (0)
-            MH2_LOAD(0, pv0);
-            MH2_LOAD(1, pv1);
             // The TMEM reads are double-buffered: the 16 columns of sub-chunk t+1 are requested right after those of t have
             // arrived, so their latency runs under the arithmetic of t (with two warps per scheduler the other warp alone
             // cannot cover it: the single-buffer version spent half of the layer-3 phase with neither XU nor issue slots busy).

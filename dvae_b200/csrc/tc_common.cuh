@@ -432,13 +432,16 @@ __device__ __forceinline__ void hidden_epilogue_rows_bf(uint32_t tmem, unsigned 
 // its 1.7 k cycles: tools/tc_phase_clocks.py).  bias64: 64 floats in shared memory, 16-byte aligned.  Asynchronous: the caller
 // runs tmem_wait_st() (and the tcgen05 fence) before handing the columns over.
 __device__ __forceinline__ void tmem_preload_bias64(uint32_t taddr, const float* bias64) {
+    const uint32_t bias_s = smem_u32(bias64);
 #pragma unroll
     for (int part = 0; part < 2; ++part) {
         uint32_t r[32];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const uint4 b = *reinterpret_cast<const uint4*>(bias64 + 32 * part + 4 * i);
-            r[4 * i] = b.x; r[4 * i + 1] = b.y; r[4 * i + 2] = b.z; r[4 * i + 3] = b.w;
+            // explicit shared-space loads (through the generic pointer they compiled to LD.E and queued behind global traffic)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(r[4 * i]), "=r"(r[4 * i + 1]), "=r"(r[4 * i + 2]), "=r"(r[4 * i + 3])
+                         : "r"(bias_s + 16u * (uint32_t)(8 * part + i)));
         }
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
