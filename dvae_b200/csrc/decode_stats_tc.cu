@@ -243,6 +243,11 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
             }
         };
         prefetch(blockIdx.x, 0);
+        // The thread's four layer-3 biases (one per 128-bin chunk) live in registers: read from shared memory at the start of
+        // every chunk, the load queued behind the chunk's 30 stores per thread and its first consumer collected 29 % of the
+        // kernel's stall samples (profiles/r01_tc_ncu_decode_stats.txt).
+        const float bias_c0 = b3[32 * q + lane], bias_c1 = b3[128 + 32 * q + lane], bias_c2 = b3[256 + 32 * q + lane],
+                    bias_c3 = b3[384 + 32 * q + lane];
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
             const int64_t t0 = tile * FT;
 #pragma unroll 1
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                 const uint32_t tb = tmem + 128 + 128 * sl;
                 if (j < 4) {
                     const int f = 128 * j + 32 * q + lane;
-                    const float bias = b3[f];
+                    const float bias = (j == 0) ? bias_c0 : ((j == 1) ? bias_c1 : ((j == 2) ? bias_c2 : bias_c3));
                     float vbc[FS], ggc[FS];
 #pragma unroll
                     for (int ff = 0; ff < FS; ++ff) { vbc[ff] = vbn[ff]; ggc[ff] = ggn[ff]; }
