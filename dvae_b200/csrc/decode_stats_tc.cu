@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
 // One thread per bin; the utterance's H rows are staged in shared memory (12 floats per frame, read back as three
 // 16-byte broadcasts) and (num_k, den_k) is one packed FP32 pair updated by a single FFMA2 per rank.
 constexpr int WFS_MAXFR = 256;                     // frames staged per pass (12 KB)
-__global__ void __launch_bounds__(128, 8) w_from_frame_stats_kernel(const float* __restrict__ A1, const float* __restrict__ A2,
+__global__ void __launch_bounds__(128, 6) w_from_frame_stats_kernel(const float* __restrict__ A1, const float* __restrict__ A2,
                                                                  const float* __restrict__ P, const float* __restrict__ H,
                                                                  const float* __restrict__ W, const int64_t* __restrict__ fr_off,
                                                                  int F, int K, int ld, float* __restrict__ Wtmp) {
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(128, 8) w_from_frame_stats_kernel(const float*
             const float* a1p = A1 + base * ld + f;
             const float* a2p = A2 + base * ld + f;
             const float* pp = P + base * ld + f;
-#pragma unroll 4
+#pragma unroll 8                            // 24 loads in flight per thread: the kernel is a pure HBM stream (3 x 4 x ld x N bytes per utterance)
             for (int i = 0; i < cnt; ++i) {
                 const float a1 = __ldg(a1p + (int64_t)i * ld);
                 const float pa2 = __ldg(pp + (int64_t)i * ld) * __ldg(a2p + (int64_t)i * ld);
