@@ -133,3 +133,25 @@ def test_wav_io_round_trip(tmp_path):
     with pytest.raises(ValueError):
         open(q, "wb").write(b"not a wav file")
         batch_io.read_wav(q)
+
+
+def test_argument_errors_are_reported_before_any_launch():
+    """Negative status + message for bad arguments (checked before the first CUDA call, so this runs without a GPU)."""
+    lib = _lib.load()
+    buf = (ctypes.c_float * 8)()
+    off = (ctypes.c_int64 * 2)(0, 1)
+    ln = (ctypes.c_int32 * 1)(8)
+    p = lambda a: ctypes.cast(a, ctypes.c_void_p)
+    # n_fft other than 1024
+    rc = lib.dvae_stft_f32(p(buf), p(off), p(ln), 1, p(buf), None, p(off), 1, 512, 128, 520, None)
+    assert rc < 0 and b"n_fft" in lib.dvae_last_error()
+    # hop other than 256
+    rc = lib.dvae_istft_f32(p(buf), p(off), 1, p(buf), p(off), p(ln), 8, 1024, 128, 520, None)
+    assert rc < 0 and b"hop" in lib.dvae_last_error()
+    # fused Wiener mask + ISTFT: the mask is mandatory, the row pitch must hold 513 bins
+    rc = lib.dvae_istft_masked_f32(p(buf), None, 1.0, p(off), 1, p(buf), p(off), p(ln), 8, 1024, 256, 520, None)
+    assert rc < 0 and b"mask" in lib.dvae_last_error()
+    rc = lib.dvae_istft_masked_f32(p(buf), p(buf), 1.0, p(off), 1, p(buf), p(off), p(ln), 8, 1024, 256, 512, None)
+    assert rc < 0 and b"bad sizes" in lib.dvae_last_error()
+    with pytest.raises(ValueError):
+        _lib.call("dvae_istft_masked_f32", p(buf), None, 1.0, p(off), 1, p(buf), p(off), p(ln), 8, 1024, 256, 520, None)
