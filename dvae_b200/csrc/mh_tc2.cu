@@ -15,7 +15,12 @@
 //     arrivals), no CTA barrier inside the chunk loop;
 //   * the random draws are read from global memory (either injected by the caller or produced beforehand by the
 //     Philox dump kernel with the same counters as every other sampler), prefetched one iteration ahead;
-//   * warp 0 lane 0 issues every tcgen05.mma; warps 0-3 own the chain state of row 32*w + lane in registers.
+//   * the tcgen05.mma groups are issued by lane 0 of warps 1 / 2 / 3 / 5 (layer 1, layer 2, layer-3 chunks 0 + 1, chunk 2);
+//   * the chain state of row 32*q + lane is split over the two threads (column halves) that share the row: each carries
+//     half of the latent dimensions and takes the same accept decision from the same shared-memory partial sums;
+//   * every TMEM read is double-buffered, the layer-2 bias is preloaded into the layer-2 accumulator (tcgen05.st) while
+//     the layer-1 GEMM runs, and the first P / Vb sub-chunks are requested two phases before the layer-3 loop
+//     (phase clocks before / after in DESIGN.md section 4).
 #include "tc_common.cuh"
 
 namespace dvae {
