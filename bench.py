@@ -320,8 +320,8 @@ def run_b200(args):
                config=dict(workload=cfg_name + ": %s batch of %d synthetic 3 s 16 kHz utterances per GPU, STFT 1024/256, "
                                     "NMF rank 10, %d EM iterations, MH schedule %s" % (args.variant, B, args.niter, schedule(args.variant, args.niter)),
                            utterances_per_gpu=B, sampler=args.sampler, chains=args.chains,
-                           l2="working set per step (Vs %.1f GB) exceeds the 126 MB L2; no explicit flush" %
-                              (eng.Vs_flat.numel() * 4 / 1e9),
+                           l2="working set per EM iteration (kept-sample variances %.1f GB) exceeds the 126 MB L2; no explicit flush" %
+                              ((eng.VsT.numel() if getattr(eng, "VsT", None) is not None else eng.Vs_flat.numel() * 4) / 1e9),
                            parallelism="utterance shards, %d rank(s), no data-path collective" % world),
                clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu,
                stage_share=stage_share, mean_final_cost=float(all_cost.mean().item()))

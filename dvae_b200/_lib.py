@@ -17,6 +17,8 @@ MAX_LAYERS = 6
 MAX_L = 64
 MAX_K = 16
 ACT_NONE, ACT_TANH, ACT_EXP = 0, 1, 2
+ABI_VERSION = 2
+STATUS_TIMEOUT, STATUS_NONFINITE = 1, 2
 
 c_f32p = C.c_void_p      # device pointers are passed as integers
 c_ptr = C.c_void_p
@@ -48,14 +50,10 @@ PROTOTYPES = {
     "dvae_nmf_vb": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_nmf_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dvae_nmf_mstep": (C.c_int, [c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64,
-                                 C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr]),
-    "dvae_decode_ws_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
-    "dvae_decode_ws_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
-                                    C.c_int, c_ptr, C.c_int, C.c_int64, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr]),
+                                 C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "dvae_decode_stats_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
                                        C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "dvae_nmf_w_from_frame_stats": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
-    "dvae_nmf_w_from_stats": (C.c_int, [c_ptr, C.c_int, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_mh_workspace_floats": (C.c_int64, [C.POINTER(DvaeMlp), C.c_int64, C.c_int]),
     "dvae_mh_chain_f32": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
                                     C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
@@ -65,20 +63,8 @@ PROTOTYPES = {
     "dvae_wiener_apply": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
     "dvae_tc_image_bytes": (C.c_int64, [C.POINTER(DvaeMlp), C.c_int, C.c_int]),
     "dvae_tc_pack_decoder": (C.c_int, [C.POINTER(DvaeMlp), C.c_int, C.c_int, c_ptr, c_ptr]),
-    "dvae_tc_packed_floats": (C.c_int64, [C.c_int64]),
-    "dvae_tc_pack_rows": (C.c_int, [c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
-    "dvae_mh_chain_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
-                                   C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(DvaeRng), c_ptr, c_ptr,
-                                   c_ptr, c_ptr]),
     "dvae_tc_packed_pv_bytes": (C.c_int64, [C.c_int64]),
     "dvae_tc_pack_pv": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
-    "dvae_mh_chain_tc2": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
-                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr,
-                                    c_ptr]),
-    "dvae_mh_chain_tc4": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
-                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr,
-                                    c_ptr]),
-    "dvae_debug_set_clock_buffer4": (C.c_int, [c_ptr]),
     "dvae_vad_workspace_bytes": (C.c_int64, [C.c_int64]),
     "dvae_vad_labels": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr,
                                   c_ptr]),
@@ -91,14 +77,18 @@ PROTOTYPES = {
     "dvae_wiener_from_a1": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr]),
     "dvae_energy_ratios": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr]),
     "dvae_tc_decoder_exponent_bound": (C.c_int, [C.POINTER(DvaeMlp), C.c_int, C.c_int, c_ptr, c_ptr]),
-    "dvae_mh_chain_tc3": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
-                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "dvae_debug_set_clock_buffer3": (C.c_int, [c_ptr]),
-    "dvae_debug_set_clock_buffer_ws": (C.c_int, [c_ptr]),
-    "dvae_debug_set_clock_buffer_ds": (C.c_int, [c_ptr]),
-    "dvae_debug_set_clock_buffer": (C.c_int, [c_ptr]),
     "dvae_decode_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int,
                                  c_ptr, c_ptr]),
+    "dvae_vst_bytes": (C.c_int64, [C.c_int64, C.c_int]),
+    "dvae_mh_chain_tc2": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(DvaeRng), c_ptr, c_ptr, c_ptr, c_ptr,
+                                    C.c_int, c_ptr, c_ptr]),
+    "dvae_vst_frame_stats": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
+                                       C.c_int, c_ptr, c_ptr, c_ptr]),
+    "dvae_nmf_mstep_vst": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
+                                     c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "dvae_vst_unpack": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, c_ptr, c_ptr]),
+    "dvae_vst_pack": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr]),
     "dvae_nmf_init": (C.c_int, [C.c_uint64, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float,
                                 c_ptr, c_ptr, c_ptr, c_ptr]),
 }
@@ -126,8 +116,8 @@ def load(path: str | None = None):
             fn = getattr(lib, name)          # AttributeError if the header and the library disagree
             fn.restype = res
             fn.argtypes = args
-        if lib.dvae_version() != 1:
-            raise DvaeError("libdvae_b200 ABI version %d, expected 1" % lib.dvae_version())
+        if lib.dvae_version() != ABI_VERSION:
+            raise DvaeError("libdvae_b200 ABI version %d, expected %d" % (lib.dvae_version(), ABI_VERSION))
         _lib = lib
         return lib
 

@@ -77,15 +77,25 @@ def output_stem(output_data_dir, proc_noisy_file_path):
     return os.path.splitext(output_data_dir + proc_noisy_file_path)[0]
 
 
+def utterance_id(path: str) -> int:
+    """A stable 31-bit id of an utterance (CRC-32 of its path): word 0 of the Philox counters, so an utterance's random draws do
+    not depend on the batch it lands in, its position in the batch or the rank that processes it."""
+    import zlib
+    return zlib.crc32(path.encode("utf-8")) & 0x7FFFFFFF
+
+
 def process_sublist(sublist, enhancer, processed_wav_dir, output_data_dir, batch_size=512, max_frames=None, labels=None,
-                    io_threads=8, fs=16000):
+                    io_threads=8, fs=16000, utt_ids=None):
     """Batched replacement of ``process_sublist`` / ``process_utt`` (scripts/evaluate_ntcd_M1.py:81-214).
 
     ``sublist``: ``(proc_noisy_file_path, clean_file_path)`` pairs as the reference builds them.  Files whose
     ``*_s_est.wav`` exists are skipped, like the reference.  ``max_frames(noisy_path, clean_path) -> int | None`` supplies the
     video-length frame cap the reference reads from HDF5; ``labels(noisy_path, clean_path) -> (y_dim, N) array`` supplies the
-    labels of the M2 models.  Returns the list of written stems.
+    labels of the M2 models.  ``utt_ids(noisy_path) -> int`` names the utterances for the random number generator
+    (default: ``utterance_id``, a hash of the path), so every utterance gets its own draws whatever ``batch_size`` and
+    sharding are - the reference draws fresh numbers per utterance too.  Returns the list of written stems.
     """
+    utt_ids = utt_ids or utterance_id
     todo = [(a, b) for a, b in sublist if not os.path.exists(output_stem(output_data_dir, a) + "_s_est.wav")]
     written = []
     with ThreadPoolExecutor(max(1, io_threads)) as pool:
@@ -102,14 +112,14 @@ def process_sublist(sublist, enhancer, processed_wav_dir, output_data_dir, batch
                 big = np.iinfo(np.int64).max
                 caps = [big if c is None else c for c in caps]
             ys = [labels(*ab) for ab in part] if labels else None
-            s_hat, n_hat, _ = enhancer.enhance(xs, y_list=ys, max_frames_list=caps)
+            s_hat, n_hat, _ = enhancer.enhance(xs, y_list=ys, max_frames_list=caps, utt_ids=[utt_ids(ab[0]) for ab in part])
             if pending:
                 for fut in pending:
                     fut.result()
             pending = []
             for ab, s, n in zip(part, s_hat, n_hat):
                 stem = output_stem(output_data_dir, ab[0])
-                # the enhancer's result buffers are recycled once these arrays are dropped: the writers hold them until done
+                # the result arrays lease the enhancer's pinned buffers (Enhancer._pin_out): the writers hold them until done
                 pending.append(pool.submit(write_wav, stem + "_s_est.wav", s, fs))
                 pending.append(pool.submit(write_wav, stem + "_n_est.wav", n, fs))
                 written.append(stem)

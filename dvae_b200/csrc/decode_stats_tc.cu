@@ -8,7 +8,7 @@
 // The W update then only needs  num[f,k] = sum_n P A2 H,  den[f,k] = sum_n A1 H  (w_from_frame_stats_kernel): no per-bin
 // accumulators have to live in registers across tiles, which is what allows the schedule below.
 //
-// Phase timing of the previous kernel (decode_ws_tc.cu, tools/ws_phase_clocks.py): 26 k cycles per 120-row tile, of
+// Phase timing of the previous, unpipelined kernel (round 1): 26 k cycles per 120-row tile, of
 // which the serial front (operand write, layers 1-2) took 10 k and each layer-3 chunk epilogue 5 k with two warps per
 // scheduler.  Here the CTA is a two-stage pipeline over tiles:
 //
@@ -29,7 +29,7 @@ constexpr int DS_THREADS = 672;                       // 4 front warps + 16 back
 constexpr int DS_BACK = 512;
 // Depth of the layer-3 ring (W3 chunk slot in shared memory + accumulator buffer in TMEM per stage).  With two stages the GEMM
 // of chunk c+2 could only be issued once chunk c was drained and every chunk hand-over cost the back warps ~0.5 k cycles of
-// waiting (tools/ws_phase_clocks.py); with three, it is issued one chunk earlier.
+// waiting; with three, it is issued one chunk earlier.
 constexpr int DS_NS = 3;
 
 struct DsParams {
@@ -47,11 +47,7 @@ struct DsParams {
     int zs_rtot, zs_r0;     // samples per frame in Zs (and Vs) and the first one this launch decodes (R of them)
     int acc;                // != 0: add to A1 / A2 instead of overwriting (later sample windows of the same frames)
     int* status;
-    long long* dbg;
 };
-
-static long long* g_dbg_clocks_ds = nullptr;
-#define DBGD(slot, cond) do { if (p.dbg && blockIdx.x == 0 && k == 3 && (cond)) p.dbg[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ void ds_bar_front() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void ds_bar_tail() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
@@ -162,7 +158,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
         uint32_t ph12 = 0, phfree0 = 0, phfree1 = 0;
         int k = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
-            DBGD(0, threadIdx.x == 0);
             const int buf = k & 1;
             unsigned char* A = Abuf + buf * 32768;
             const uint32_t a_addr = smem_u32(A);
@@ -188,11 +183,9 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                 if (buf == 0) { mbar_wait(a_free0, phfree0, dead, p.status); phfree0 ^= 1; }
                 else { mbar_wait(a_free1, phfree1, dead, p.status); phfree1 ^= 1; }
             }
-            DBGD(1, threadIdx.x == 0);
             write_a1_static<L>(y_dim, nkb1, A, row, z, y0, y1, y2, valid);
             fence_async_smem();
             ds_bar_front();
-            DBGD(2, threadIdx.x == 0);
             if (threadIdx.x == 0) {
                 tc_fence_after();
                 issue_gemm2(a_addr, 16384, w1_addr, 16384, nkb1, tmem, HID);
@@ -205,7 +198,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
             fence_async_smem();
             tc_fence_before();
             ds_bar_front();
-            DBGD(3, threadIdx.x == 0);
             if (two_hidden) {
                 if (threadIdx.x == 0) {
                     tc_fence_after();
@@ -219,7 +211,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                 fence_async_smem();
                 tc_fence_before();
             }
-            DBGD(4, threadIdx.x == 0);
             mbar_arrive2(buf ? a_full1 : a_full0);      // h2 of this tile is in A[buf]
         }
     } else if (warp < 20) {
@@ -254,8 +245,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
             for (int j = 0; j < 5; ++j) {
                 mbar_wait(bar3 + 8 * sl, par, dead, p.status);
                 tc_fence_after();
-                DBGD(10 + j, threadIdx.x == 128);
-                DBGD(30 + j, threadIdx.x == 608);
                 const uint32_t tb = tmem + 128 + 128 * sl;
                 if (j < 4) {
                     const int f = 128 * j + 32 * q + lane;
@@ -383,8 +372,6 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
                 }
                 tc_fence_before();
                 mbar_arrive2(barf + 8 * sl);
-                DBGD(20 + j, threadIdx.x == 128);
-                DBGD(40 + j, threadIdx.x == 608);
                 if (++sl == DS_NS) { sl = 0; par ^= 1; }
             }
         }
@@ -521,7 +508,7 @@ static int launch_decode_stats(const char* who, const DvaeMlp* dec, const void* 
                  "%s: Zs and image must be 16-byte aligned", who);
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
-    p.Zs = Zs; p.y = y; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status; p.dbg = g_dbg_clocks_ds;
+    p.Zs = Zs; p.y = y; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status;
     p.zs_rtot = R_total; p.zs_r0 = r0; p.acc = accumulate;
     const int shared_bytes = (p.d.off_w3 + 4 * ((p.d.n_hidden == 2 ? HID : 0) + NPAD) + 1023) & ~1023;
     const size_t smem = (size_t)shared_bytes + 65536 + (size_t)DS_NS * 32768 + 1024;
@@ -608,9 +595,4 @@ extern "C" int dvae_nmf_w_from_frame_stats(const float* A1, const float* A2, con
                  "dvae_nmf_w_from_frame_stats: bad arguments");
     w_from_frame_stats_kernel<<<dim3((F + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(A1, A2, P, H, W, fr_off, F, K, ld, Wtmp);
     return check_launch("w_from_frame_stats_kernel");
-}
-
-extern "C" int dvae_debug_set_clock_buffer_ds(void* dev_buffer) {
-    g_dbg_clocks_ds = reinterpret_cast<long long*>(dev_buffer);
-    return 0;
 }

@@ -13,8 +13,12 @@
 //     while sub-chunk t is evaluated (three rotating register buffers);
 //   * the layer-3 chunks are handed over with mbarriers only (chunk ready: tcgen05.commit; buffer free: 256 thread
 //     arrivals), no CTA barrier inside the chunk loop;
-//   * the random draws are read from global memory (either injected by the caller or produced beforehand by the
-//     Philox dump kernel with the same counters as every other sampler), prefetched one iteration ahead;
+//   * the random draws of the next proposal are produced inside the kernel, Philox-4x32-10 with the counters every sampler of
+//     this library uses (utterance id, frame | chain << 20, global iteration, block), under the layer-2 GEMM, where all
+//     warps would otherwise wait on an mbarrier; injected draws (parity runs) are read from global memory instead;
+//   * on kept iterations the decoder output of the proposal, 2^v without the output-layer bias, is written to global
+//     memory in BF16 (tiled layout, see Mh2Params::VsT) together with, per chain and kept sample, the index of the slot
+//     that holds the chain's state: the E-step needs no second decode of the kept samples (mcem.py:280-290);
 //   * the tcgen05.mma groups are issued by lane 0 of warps 1 / 2 / 3 / 5 (layer 1, layer 2, layer-3 chunks 0 + 1, chunk 2);
 //   * the chain state of row 32*q + lane is split over the two threads (column halves) that share the row: each carries
 //     half of the latent dimensions and takes the same accept decision from the same shared-memory partial sums;
@@ -38,23 +42,63 @@ struct Mh2Params {
     const float* g;
     float* Z;
     float* Zs;
-    const float* eps;             // [n_iter][rows][L] standard normals
-    const float* u;               // [n_iter][rows] uniforms
+    const float* eps;             // injected draws [n_iter][rows][L] standard normals, or null: Philox inside the kernel
+    const float* u;               // injected draws [n_iter][rows] uniforms
+    const int32_t* frame_gid;     // Philox counter words per frame: global utterance id, frame index inside the utterance
+    const int32_t* frame_idx;
+    uint32_t seed_lo, seed_hi, iter0;
     uint32_t* n_accept;
     float* a_trace;
     int n_burn, n_keep;
     float sd;
     int* status;
-    long long* dbg;               // optional [64] clock stamps of CTA 0 (see dvae_debug_set_clock_buffer)
+    // Emission of the kept samples' variances (null: off).  VsT[tile][slot][bg][row][16] in BF16: tile = chain / 128,
+    // row = chain % 128, bg = bin / 16 (33 groups, bins 513..527 are padding), slot 0 = the state at the end of the burn-in,
+    // slot 1 + r = the proposal of kept iteration r.  vs_idx[chain][32]: byte r = slot holding kept sample r.
+    uint4* VsT;
+    uint8_t* vs_idx;
 };
 
-static long long* g_dbg_clocks = nullptr;
 
-#define DBG_STAMP(slot, cond)                                                        \
-    do {                                                                             \
-        if (p.dbg && blockIdx.x == 0 && tile == 0 && it == 4 && (cond)) p.dbg[slot] = clock64(); \
-    } while (0)
+// 16 bins of the log-likelihood (loglik16_pv of tc_common.cuh) that also hands back 2^v of the 16 bins as eight bf16x2
+// words (bin 2j in the low half of word j): the sampler's emission of the kept samples' variances.
+template <int POLY>
+__device__ __forceinline__ void loglik16_pv_emit(const float* v, const uint4* pv, float g_row, float& acc, float& accl, uint32_t* out) {
+    const f32x2 g2 = pk2(g_row, g_row), g2k = pk2(g_row * kPairScale, g_row * kPairScale);
+#pragma unroll
+    for (int qd = 0; qd < 4; ++qd) {
+        const uint4 w = pv[qd];
+        const f32x2 e01 = (POLY >= 2) ? ex2_poly2(pk2(v[4 * qd + 0], v[4 * qd + 1])) : pk2(ex2_approx(v[4 * qd + 0]), ex2_approx(v[4 * qd + 1]));
+        const f32x2 A = fma2(g2k, e01, pk2(__uint_as_float(w.x << 16), __uint_as_float(w.y << 16)));
+        const f32x2 e23 = POLY ? ex2_poly2(pk2(v[4 * qd + 2], v[4 * qd + 3])) : pk2(ex2_approx(v[4 * qd + 2]), ex2_approx(v[4 * qd + 3]));
+        const f32x2 B = fma2(g2, e23, pk2(__uint_as_float(w.z << 16), __uint_as_float(w.w << 16)));
+        {
+            float e0, e1, e2, e3;
+            upk2(e01, e0, e1);
+            upk2(e23, e2, e3);
+            out[2 * qd] = pack_bf16x2(e0, e1);
+            out[2 * qd + 1] = pack_bf16x2(e2, e3);
+        }
+        const f32x2 M = mul2(A, B);
+        const f32x2 N = fma2(pk2(__uint_as_float(w.x), __uint_as_float(w.y)), B,
+                             mul2(pk2(__uint_as_float(w.z), __uint_as_float(w.w)), A));
+        float mlo, mhi, nlo, nhi;
+        upk2(M, mlo, mhi);
+        upk2(N, nlo, nhi);
+        const float pq = mlo * mhi;
+        acc = fmaf(fmaf(nlo, mhi, nhi * mlo), rcp_approx(pq), acc);
+        accl += lg2_approx(pq);
+    }
+}
 
+// One Philox block -> four standard normals (the arithmetic of mh_draws / rng_dump4_kernel: bit-identical draws)
+__device__ __forceinline__ float4 philox_normals4(uint32_t utt, uint32_t fc, uint32_t iter, uint32_t b, uint32_t k0, uint32_t k1) {
+    const Philox4 r = philox4x32_10(utt, fc, iter, b, k0, k1);
+    float4 o;
+    box_muller(r.x, r.y, o.x, o.y);
+    box_muller(r.z, r.w, o.z, o.w);
+    return o;
+}
 
 template <int L, int POLY>
 __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
@@ -111,25 +155,37 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     const int y_dim = d.y_dim, nkb1 = d.nkb1;
     const bool two_hidden = d.n_hidden == 2;
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
+    const bool emit = p.VsT != nullptr;
+    // evaluations of a tile: the start state, the burn-in proposals, [the state again: its variances become slot 0 of the
+    // emission], the kept proposals
+    const int n_eval = n_iter + 1 + (emit ? 1 : 0);
+    const int ev_rescore = emit ? p.n_burn + 1 : -1;
+    const int n_slots = p.n_keep + 1;
 
-    const long long dbg_t0 = clock64();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row_g = tile * TM + row;
         const bool valid = row_g < p.rows;
         const int64_t fr = valid ? row_g / p.C : 0;
         const float g_row = valid ? p.g[fr] : 1.f;
         const uint4* PVt = p.PVpk + (tile * NQ) * TM + row;
+        // this thread's 32 bytes of bin group 0 in slot 0 of the tile's emission
+        uint4* VsTt = emit ? p.VsT + ((size_t)tile * n_slots * (NPAD / 16) * TM + row) * 2 : nullptr;
+        uint32_t ph_utt = 0, ph_fc = 0;                 // Philox counter words 0 and 1 of this chain
+        if (!p.eps && valid) {
+            ph_utt = (uint32_t)__ldg(p.frame_gid + fr);
+            ph_fc = (uint32_t)__ldg(p.frame_idx + fr) | ((uint32_t)(row_g - fr * p.C) << 20);
+        }
 
         // Chain state, split over the two column halves: thread (row, h) carries latent dimensions [h L/2, (h+1) L/2) of its
         // row's chain plus a copy of the scalars.  The proposal / accept code is a chain of dependent operations that runs
-        // with one warp per scheduler, so halving its length matters more than the duplicated scalar work (the single-owner
-        // version spent 1.0 k + 0.8 k of 15 k cycles per evaluation there: tools/tc_phase_clocks.py).  Both halves take the
-        // accept decision from the same shared-memory operands in the same order, so they always agree bit for bit.
+        // with one warp per scheduler, so halving its length matters more than the duplicated scalar work.  Both halves take
+        // the accept decision from the same shared-memory operands in the same order, so they always agree bit for bit.
         constexpr int LH = L / 2;
         float zh[LH], zph[LH];
         float4 enn[LH / 4];                                // this half's draws of the next proposal
         float y0 = 0.f, y1 = 0.f, y2 = 0.f, ll_cur = 0.f, u_cur = 0.5f, u_nxt = 0.5f, prior_h = 0.f;
-        uint32_t n_acc = 0;
+        uint32_t n_acc = 0, state_slot = 0;
+        int prop = 0;                                      // index of the next proposal to draw
 #pragma unroll
         for (int l = 0; l < LH; ++l) { zh[l] = valid ? p.Z[row_g * L + h * LH + l] : 0.f; zph[l] = 0.f; }
 #pragma unroll
@@ -140,10 +196,33 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             if (y_dim > 2) y2 = p.y[fr * y_dim + 2];
         }
 
-        // eval -1 scores the start state, eval it >= 0 scores proposal `it`
-        for (int it = -1; it < n_iter; ++it) {
-            DBG_STAMP(0, threadIdx.x == 0);
-            if (it >= 0) {
+        // draws of the next proposal (if the next evaluation is one): consumed at the top of the next evaluation
+        auto draw_next = [&](int ev) {
+            const int nxt = ev + 1;
+            if (nxt >= n_eval || nxt == ev_rescore) return;
+            if (p.eps) {
+                if (valid) {
+                    const float4* e = reinterpret_cast<const float4*>(p.eps + ((int64_t)prop * p.rows + row_g) * L + h * LH);
+#pragma unroll
+                    for (int l = 0; l < LH / 4; ++l) enn[l] = __ldg(e + l);
+                    u_nxt = __ldg(p.u + (int64_t)prop * p.rows + row_g);
+                }
+            } else {
+                const uint32_t iter = p.iter0 + (uint32_t)prop;
+#pragma unroll
+                for (int l = 0; l < LH / 4; ++l) enn[l] = philox_normals4(ph_utt, ph_fc, iter, (uint32_t)(h * (LH / 4) + l), p.seed_lo, p.seed_hi);
+                u_nxt = u01(philox4x32_10(ph_utt, ph_fc, iter, (uint32_t)(L / 4), p.seed_lo, p.seed_hi).x);
+            }
+            ++prop;
+        };
+
+        for (int ev = 0; ev < n_eval; ++ev) {
+            const bool score_only = (ev == 0) || (ev == ev_rescore);     // evaluates the chain's state, no decision
+            const int it = ev - 1 - ((emit && ev > ev_rescore) ? 1 : 0);  // proposal index (meaningless when score_only)
+            // slot of the emission this evaluation's variances go to, or -1
+            const int store_slot = !emit ? -1 : ((ev == ev_rescore) ? 0 : ((ev > ev_rescore) ? 1 + (it - p.n_burn) : -1));
+            if (ev == 0 && !two_hidden) draw_next(ev);
+            if (!score_only) {
                 u_cur = u_nxt;
                 prior_h = 0.f;
 #pragma unroll
@@ -159,10 +238,8 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             } else {
                 write_a1_half<L>(y_dim, nkb1, A, row, h, zh, y0, y1, y2, valid);
             }
-            DBG_STAMP(26, threadIdx.x == 0);
             fence_async_smem();
             __syncthreads();                                                    // S1: layer-1 operand ready
-            DBG_STAMP(1, threadIdx.x == 0);
 
             if (warp == 1 && lead) {
                 tc_fence_after();
@@ -174,24 +251,19 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 // warp would only spin on its mbarrier here; the stores take ~0.6 k cycles).  Every thread writes the 64 columns
                 // it will read back in the layer-2 epilogue.  The columns are free (the previous evaluation's reads of them
                 // completed before its S4; the first layer-3 chunk is issued after S3), the layer-2 GEMM, issued after S2,
-                // accumulates onto the bias, and its epilogue needs no bias loads / adds (0.5 k of its 1.7 k cycles,
-                // tools/tc_phase_clocks.py).
+                // accumulates onto the bias, and its epilogue needs no bias loads / adds.
                 tc_fence_after();
                 tmem_preload_bias64(tmem + lane_off + 64 * h, b2 + 64 * h);
                 tmem_wait_st();
                 tc_fence_before();
-                DBG_STAMP(27, threadIdx.x == 0);
             }
             mbar_wait(bar12, ph12, dead, p.status);
             ph12 ^= 1;
             tc_fence_after();
-            DBG_STAMP(24, threadIdx.x == 0);
             hidden_epilogue_rows_bf(tmem + 384, A, q, h, row, nullptr);              // bias rides on the constant-one column
             fence_async_smem();
             tc_fence_before();
-            DBG_STAMP(20, threadIdx.x == 0);
             __syncthreads();                                                    // S2
-            DBG_STAMP(2, threadIdx.x == 0);
             float acc = 0.f, accl = 0.f;
             uint4 pv0[4], pv1[4], pv2[4];
             // sub-chunk t: chunk c = t/6 (capped at 2), column inside the chunk = h*W_c + 16*(t - 6c), W = 96, 96, 80
@@ -212,16 +284,15 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                     issue_gemm2(a_addr, 16384, w2_addr, 16384, 2, tmem, HID, 1);
                     umma_commit(bar12);
                 }
+                // the next proposal's draws: ~350 integer / MUFU instructions per thread in the shadow of the layer-2 GEMM
+                draw_next(ev);
                 mbar_wait(bar12, ph12, dead, p.status);
                 ph12 ^= 1;
                 tc_fence_after();
-                DBG_STAMP(25, threadIdx.x == 0);
                 hidden_epilogue_rows_bf(tmem, A, q, h, row, nullptr);
                 fence_async_smem();
                 tc_fence_before();
-                DBG_STAMP(21, threadIdx.x == 0);
                 __syncthreads();                                                // S3
-                DBG_STAMP(3, threadIdx.x == 0);
             }
             // ---- layer 3 as three chunks of 192 / 192 / 160 bins (the last one over-reads 16 rows of padding):
             // chunk 0 -> TMEM columns [0,192), chunk 1 -> [192,384), chunk 2 -> [0,160) once chunk 0 is drained
@@ -234,6 +305,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 issue_gemm2(a_addr, 16384, w3_addr + 192 * 128, NPAD * 128, 2, tmem + 192, 192);
                 umma_commit(bar3_1);
             }
+            if (!two_hidden && ev > 0) draw_next(ev);
 
             // per thread 17 (h = 0) or 16 (h = 1) sub-chunks of 16 bins; the P / Vb quads of sub-chunk t+2 are requested
             // while sub-chunk t is evaluated (three rotating register buffers, everything statically indexed)
@@ -241,8 +313,21 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             // arrived, so their latency runs under the arithmetic of t (with two warps per scheduler the other warp alone
             // cannot cover it: the single-buffer version spent half of the layer-3 phase with neither XU nor issue slots busy).
             float va[16], vb[16];
-            mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); DBG_STAMP(15, threadIdx.x == 0);
+            uint4* vs_dst = (store_slot >= 0) ? VsTt + (size_t)store_slot * ((NPAD / 16) * TM * 2) : nullptr;
+            mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after();
             tmem_ld16(tmem + lane_off + MH2_COL(0), va);
+#define MH2_EVAL(V, PV, t)                                                                    \
+    do {                                                                                      \
+        if (vs_dst) {                                                                         \
+            uint32_t o[8];                                                                    \
+            loglik16_pv_emit<POLY>(V, PV, g_row, acc, accl, o);                               \
+            uint4* dst = vs_dst + (MH2_BIN(t) >> 4) * (TM * 2);                               \
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);                                      \
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);                                      \
+        } else {                                                                              \
+            loglik16_pv<POLY>(V, PV, g_row, acc, accl);                                       \
+        }                                                                                     \
+    } while (0)
 #pragma unroll
             for (int t = 0; t < 17; ++t) {
                 const bool live = (t < 16) || (h == 0);                         // bins 528..543 do not exist
@@ -253,25 +338,24 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 }
                 if (live) tmem_wait_ld();                                       // sub-chunk t is in registers
                 if (t == 5) {                                                   // chunk 0 drained by this thread
-                    DBG_STAMP(4, threadIdx.x == 0);
                     tc_fence_before();
                     mbar_arrive2(barf_0);
                 }
                 if (t + 1 < 17 && ((t + 1 < 16) || (h == 0))) {
-                    if (t + 1 == 6) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; tc_fence_after(); DBG_STAMP(16, threadIdx.x == 0); }
-                    if (t + 1 == 12) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); DBG_STAMP(17, threadIdx.x == 0); }
+                    if (t + 1 == 6) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; tc_fence_after(); }
+                    if (t + 1 == 12) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); }
                     if ((t + 1) % 2 == 0) tmem_ld16(tmem + 192 * (MH2_CH(t + 1) & 1) + lane_off + MH2_COL(t + 1), va);
                     else tmem_ld16(tmem + 192 * (MH2_CH(t + 1) & 1) + lane_off + MH2_COL(t + 1), vb);
                 }
                 if (live) {
                     if (t % 2 == 0) {
-                        if (t % 3 == 0) loglik16_pv<POLY>(va, pv0, g_row, acc, accl);
-                        else if (t % 3 == 1) loglik16_pv<POLY>(va, pv1, g_row, acc, accl);
-                        else loglik16_pv<POLY>(va, pv2, g_row, acc, accl);
+                        if (t % 3 == 0) MH2_EVAL(va, pv0, t);
+                        else if (t % 3 == 1) MH2_EVAL(va, pv1, t);
+                        else MH2_EVAL(va, pv2, t);
                     } else {
-                        if (t % 3 == 0) loglik16_pv<POLY>(vb, pv0, g_row, acc, accl);
-                        else if (t % 3 == 1) loglik16_pv<POLY>(vb, pv1, g_row, acc, accl);
-                        else loglik16_pv<POLY>(vb, pv2, g_row, acc, accl);
+                        if (t % 3 == 0) MH2_EVAL(vb, pv0, t);
+                        else if (t % 3 == 1) MH2_EVAL(vb, pv1, t);
+                        else MH2_EVAL(vb, pv2, t);
                     }
                 }
                 if (t == 5) {
@@ -286,18 +370,8 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                     }
                     phf_0 ^= 1;
                 }
-                if (t == 11) {
-                    DBG_STAMP(5, threadIdx.x == 0);
-                    // draws of the next proposal: requested here, consumed at the top of the next evaluation
-                    const int nxt = it + 1;
-                    if (nxt < n_iter && valid) {
-                        const float4* e = reinterpret_cast<const float4*>(p.eps + ((int64_t)nxt * p.rows + row_g) * L + h * LH);
-#pragma unroll
-                        for (int l = 0; l < LH / 4; ++l) enn[l] = __ldg(e + l);
-                        u_nxt = __ldg(p.u + (int64_t)nxt * p.rows + row_g);
-                    }
-                }
             }
+#undef MH2_EVAL
 #undef MH2_LOAD
 #undef MH2_BIN
 #undef MH2_COL
@@ -305,14 +379,14 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             tc_fence_before();
             const float part = fmaf(kLn2, accl, acc * kQuadScale);
             red2[h * TM + row] = make_float2(part, prior_h);
-            DBG_STAMP(8, threadIdx.x == 0);
             __syncthreads();                                                    // S4: both halves of l(z') and of the prior term
-            DBG_STAMP(9, threadIdx.x == 0);
             {
                 const float2 r0 = red2[row], r1 = red2[TM + row];
                 const float ll_prop = r0.x + r1.x;
-                if (it < 0) {
+                if (valid && !(fabsf(ll_prop) <= 3.0e38f)) atomicOr(p.status, DVAE_STATUS_NONFINITE);     // NaN / Inf likelihood
+                if (score_only) {
                     ll_cur = ll_prop;
+                    state_slot = 0;
                 } else if (valid) {
                     const float a = (ll_cur - ll_prop) + 0.5f * (r0.y + r1.y);
                     if (owner && p.a_trace) p.a_trace[(int64_t)it * p.rows + row_g] = a;
@@ -321,15 +395,16 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                         for (int l = 0; l < LH; ++l) zh[l] = zph[l];
                         ll_cur = ll_prop;
                         ++n_acc;
+                        if (store_slot >= 0) state_slot = (uint32_t)store_slot;
                     }
                     if (it >= p.n_burn) {
                         float4* dst = reinterpret_cast<float4*>(p.Zs + (row_g * p.n_keep + (it - p.n_burn)) * L + h * LH);
 #pragma unroll
                         for (int l = 0; l < LH / 4; ++l) dst[l] = make_float4(zh[4 * l], zh[4 * l + 1], zh[4 * l + 2], zh[4 * l + 3]);
+                        if (emit && owner) p.vs_idx[row_g * 32 + (it - p.n_burn)] = (uint8_t)state_slot;
                     }
                 }
             }
-            DBG_STAMP(23, threadIdx.x == 0);
         }
         if (valid) {
 #pragma unroll
@@ -338,12 +413,6 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         }
     }
 
-    if (p.dbg && threadIdx.x == 0) {                    // per-CTA duration of the tile loop: min / max / sum over CTAs (slots 56-58)
-        const long long dt = clock64() - dbg_t0;
-        atomicMin(reinterpret_cast<unsigned long long*>(p.dbg + 56), (unsigned long long)dt);
-        atomicMax(reinterpret_cast<unsigned long long*>(p.dbg + 57), (unsigned long long)dt);
-        atomicAdd(reinterpret_cast<unsigned long long*>(p.dbg + 58), (unsigned long long)dt);
-    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -358,30 +427,42 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
 using namespace dvae;
 using namespace dvae::tc;
 
+extern "C" int64_t dvae_vst_bytes(int64_t chains, int n_keep) {
+    if (chains <= 0 || n_keep < 1) return 0;
+    return ((chains + TM - 1) / TM) * (int64_t)(n_keep + 1) * (NPAD / 16) * TM * 32;
+}
+
 extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
-                                 const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
-                                 int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept,
-                                 float* a_trace, int flags, int* status, void* stream) {
+                                 const float* y, int y_dim, const int32_t* frame_utt, const int32_t* frame_idx, float* Z, float* Zs,
+                                 int64_t NT, int L, int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng,
+                                 uint32_t* n_accept, float* a_trace, void* VsT, uint8_t* vs_idx, int flags, int* status, void* stream) {
     Mh2Params p{};
     int rc = check_dims(dec, L, y_dim, "dvae_mh_chain_tc2", &p.d);
     if (rc) return rc;
     DVAE_REQUIRE(L == 16 || L == 32, "dvae_mh_chain_tc2: latent size must be 16 or 32 (got %d)", L);
     DVAE_REQUIRE(y_dim <= 3, "dvae_mh_chain_tc2: at most 3 label inputs");
-    DVAE_REQUIRE(image && PVpk && g && Z && Zs && eps && u && status, "dvae_mh_chain_tc2: null pointer");
+    DVAE_REQUIRE(image && PVpk && g && Z && Zs && rng && status, "dvae_mh_chain_tc2: null pointer");
     DVAE_REQUIRE(y_dim == 0 || y, "dvae_mh_chain_tc2: y_dim=%d but y is null", y_dim);
     DVAE_REQUIRE(NT >= 0 && n_chains >= 1 && n_chains < 4096 && n_burn >= 0 && n_keep >= 1 && var_rw > 0.f, "dvae_mh_chain_tc2: bad sizes");
-    DVAE_REQUIRE((reinterpret_cast<uintptr_t>(Zs) & 15) == 0 && (reinterpret_cast<uintptr_t>(eps) & 15) == 0,
+    DVAE_REQUIRE((rng->eps == nullptr) == (rng->u == nullptr), "dvae_mh_chain_tc2: eps and u must be injected together");
+    DVAE_REQUIRE(rng->eps || (frame_utt && frame_idx), "dvae_mh_chain_tc2: Philox mode needs frame_utt / frame_idx");
+    DVAE_REQUIRE((reinterpret_cast<uintptr_t>(Zs) & 15) == 0 && (reinterpret_cast<uintptr_t>(rng->eps) & 15) == 0,
                  "dvae_mh_chain_tc2: Zs and eps must be 16-byte aligned");
+    DVAE_REQUIRE((VsT == nullptr) == (vs_idx == nullptr), "dvae_mh_chain_tc2: VsT and vs_idx go together");
+    DVAE_REQUIRE(!VsT || (n_keep <= 31 && (reinterpret_cast<uintptr_t>(VsT) & 15) == 0),
+                 "dvae_mh_chain_tc2: the emission holds at most 31 kept samples per chain, 16-byte aligned");
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
     p.rows = NT * n_chains; p.C = n_chains; p.y = y;
     p.PVpk = (const uint4*)PVpk; p.g = g; p.Z = Z; p.Zs = Zs;
-    p.eps = eps; p.u = u;
+    p.eps = rng->eps; p.u = rng->u;
+    p.frame_gid = frame_utt; p.frame_idx = frame_idx;
+    p.seed_lo = (uint32_t)(rng->seed & 0xffffffffu); p.seed_hi = (uint32_t)(rng->seed >> 32); p.iter0 = rng->iter0;
     p.n_accept = n_accept; p.a_trace = a_trace; p.n_burn = n_burn; p.n_keep = n_keep;
     p.sd = sqrtf(var_rw);
     p.status = status;
-    p.dbg = g_dbg_clocks;
-    const size_t smem = smem_bytes(p.d) + (size_t)TM * L * 4;
+    p.VsT = (uint4*)VsT; p.vs_idx = vs_idx;
+    const size_t smem = smem_bytes(p.d) + (size_t)TM * 16;
     DVAE_REQUIRE(smem <= 227 * 1024, "dvae_mh_chain_tc2: shared memory budget exceeded");
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
     const int grid = (int)(n_tiles < 148 ? n_tiles : 148);
@@ -400,11 +481,4 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const vo
     else MH2_LAUNCH(32, 0);
 #undef MH2_LAUNCH
     return check_launch("mh2_kernel");
-}
-
-// Debug aid: when a device buffer of 64 int64 is registered, CTA 0 of the sampler stamps clock64() at its phase
-// boundaries during iteration 4 of its first tile (slot map in tools/tc_phase_clocks.py).  Pass NULL to disable.
-extern "C" int dvae_debug_set_clock_buffer(void* dev_buffer) {
-    g_dbg_clocks = reinterpret_cast<long long*>(dev_buffer);
-    return 0;
 }

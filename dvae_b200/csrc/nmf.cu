@@ -10,7 +10,7 @@
 // The order of operations follows the reference exactly: the W update uses the Vb kept from the
 // previous iteration, Vb is refreshed after W and after H, W/H are renormalised WITHOUT refreshing Vb, g uses the
 // un-normalised product, the cost uses the new g.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dvae {
 
@@ -241,354 +241,19 @@ __global__ void __launch_bounds__(256) nmf_hg_kernel(const float* __restrict__ P
     if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = cost_acc * inv_count;
 }
 
-// ----------------------------------------------------------------------------- H, g, cost: register-resident fast path
-// One thread per bin (544 threads >= F = 513), R samples of the current frame in registers: Vs is read from HBM
-// exactly once per EM iteration (coalesced 2 KB rows), the three dependent passes (H, g, cost) run out of registers,
-// and the next frame's rows are prefetched into a second register set while the current frame is reduced.
-// MUFU budget: one reciprocal per (sample, bin) in the H and g passes, one reciprocal + one log2 per PAIR in the cost.
-constexpr int HG2_THREADS = 544;
-constexpr int HG2_FPB = 8;
-constexpr int HG2_KT = 10;                    // NMF ranks up to 10 take the fast path
+// ----------------------------------------------------------------------------- shared constants of the staged-frame kernels
+constexpr int HG2_KT = 10;                    // NMF ranks up to 10 take the fast paths
+constexpr int HG3_THREADS = 256;
+constexpr int HG3_FPB = 8;                    // frames per CTA
+constexpr int HG3_NV = 2 * HG2_KT;
 
 __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_fast(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-// second half of a CTA-wide multi-value sum: red[v][t] holds thread t's term of value v; after the call tot[v] is the
-// total (valid for every thread).  Two barriers.
-__device__ __forceinline__ void block_reduce_tail(int nv, const float* red, float* tot) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __syncthreads();
-    for (int v = wid; v < nv; v += HG2_THREADS / 32) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < HG2_THREADS / 32; ++i) s += red[v * HG2_THREADS + lane + 32 * i];
-        s = warp_sum(s);
-        if (lane == 0) tot[v] = s;
-    }
-    __syncthreads();
-}
-
-template <int R, int KT>
-__global__ void __launch_bounds__(HG2_THREADS, 1) nmf_hg2_kernel(const float* __restrict__ P, const float* __restrict__ Vs,
-                                                                 const float* __restrict__ Wtmp, const float* __restrict__ norm,
-                                                                 float* __restrict__ H, float* __restrict__ g,
-                                                                 float* __restrict__ Vb, double* __restrict__ cost_part,
-                                                                 const int64_t* __restrict__ fr_off, int F, int K, int ld) {
-    extern __shared__ float red[];                 // [2*KT][HG2_THREADS]
-    __shared__ float tot[2 * KT];
-    const int u = blockIdx.y;
-    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
-    const int64_t nb = n0 + (int64_t)blockIdx.x * HG2_FPB;
-    if (nb >= n1) {
-        if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
-        return;
-    }
-    const int64_t ne = (nb + HG2_FPB < n1) ? nb + HG2_FPB : n1;
-    const int t = threadIdx.x;
-    const bool live = t < F;
-    const int fc = live ? t : 0;                   // dead threads shadow bin 0 and contribute zeros
-    float w[KT];
-#pragma unroll
-    for (int k = 0; k < KT; ++k) w[k] = (k < K && live) ? Wtmp[((int64_t)u * K + k) * ld + fc] : 0.f;
-    const double inv_count = 1.0 / ((double)R * (double)F * (double)(n1 - n0));
-    double cost_acc = 0.0;
-
-    float va[R], vn[R];
-    {
-        const float* src = Vs + (nb * R) * (int64_t)ld + fc;
-#pragma unroll
-        for (int r = 0; r < R; ++r) va[r] = src[(int64_t)r * ld];
-    }
-    for (int64_t n = nb; n < ne; ++n) {
-        if (n + 1 < ne) {                          // prefetch the next frame's samples
-            const float* src = Vs + ((n + 1) * R) * (int64_t)ld + fc;
-#pragma unroll
-            for (int r = 0; r < R; ++r) vn[r] = src[(int64_t)r * ld];
-        }
-        const float gg = g[n];
-        const float p = live ? P[n * ld + fc] : 0.f;
-        float h[KT];
-#pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
-
-        // ---- H update (Vb1 = W_new H_old)
-        float vb = 0.f;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) vb = fmaf(w[k], h[k], vb);
-        float a1 = 0.f, a2 = 0.f;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float inv = rcp_fast(fmaf(gg, va[r], vb));
-            a1 += inv;
-            a2 = fmaf(inv, inv, a2);
-        }
-        const float pa2 = p * a2;                  // w == 0 for dead threads, so their terms vanish
-#pragma unroll
-        for (int k = 0; k < KT; ++k) {
-            red[(2 * k) * HG2_THREADS + t] = w[k] * pa2;
-            red[(2 * k + 1) * HG2_THREADS + t] = w[k] * a1;
-        }
-        block_reduce_tail(2 * K, red, tot);
-#pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? h[k] * sqrtf(tot[2 * k] / tot[2 * k + 1]) : 0.f;
-
-        // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
-        vb = 0.f;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) vb = fmaf(w[k], h[k], vb);
-        if (live) Vb[n * ld + t] = vb;
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float inv = rcp_fast(fmaf(gg, va[r], vb));
-            const float q = va[r] * inv;
-            s1 += q;
-            s2 = fmaf(q, inv, s2);
-        }
-        red[t] = live ? p * s2 : 0.f;
-        red[HG2_THREADS + t] = live ? s1 : 0.f;
-        block_reduce_tail(2, red, tot);
-        const float gnew = gg * sqrtf(tot[0] / tot[1]);
-
-        // ---- cost with Vx = g_new Vs + Vb2: pairs share one reciprocal and one log2
-        float cl = 0.f, cp = 0.f;
-#pragma unroll
-        for (int r = 0; r + 1 < R; r += 2) {
-            const float v0 = fmaf(gnew, va[r], vb), v1 = fmaf(gnew, va[r + 1], vb);
-            const float pr = v0 * v1;
-            cl += lg2_fast(pr);
-            cp = fmaf(v0 + v1, rcp_fast(pr), cp);
-        }
-        if (R & 1) {
-            const float v0 = fmaf(gnew, va[R - 1], vb);
-            cl += lg2_fast(v0);
-            cp += rcp_fast(v0);
-        }
-        red[t] = live ? fmaf(0.6931471805599453f, cl, p * cp) : 0.f;
-        block_reduce_tail(1, red, tot);
-        cost_acc += (double)tot[0];
-
-        if (t == 0) {
-#pragma unroll
-            for (int k = 0; k < KT; ++k)
-                if (k < K) H[n * K + k] = h[k] * norm[u * K + k];
-            g[n] = gnew;
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) va[r] = vn[r];
-    }
-    if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = cost_acc * inv_count;
-}
-
-// ----------------------------------------------------------------------------- H, g, cost: shared-memory frame tile
-// Third version (the one dispatched for F <= 513 + slack, K <= 10): a CTA of 256 threads stages one frame's R x F
-// speech variances in shared memory with cp.async (no registers tied up, coalesced 16-byte chunks) and runs the three
-// dependent passes out of shared memory; three CTAs fit per SM (R = 30: 3 x 62 KB), so one CTA's staging overlaps the
-// others' arithmetic.  Each thread owns bins t and t + 256; the R samples of the odd last bin (512) are spread over
-// threads 0..R-1.  H and g passes spend one reciprocal per PAIR of samples, the cost pass one reciprocal + one log2.
-constexpr int HG3_THREADS = 256;
-constexpr int HG3_FPB = 8;
-constexpr int HG3_NV = 2 * HG2_KT;
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <int R>
-__global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg3_kernel(const float* __restrict__ P, const float* __restrict__ Vs,
-                                                                 const float* __restrict__ Wtmp, const float* __restrict__ norm,
-                                                                 float* __restrict__ H, float* __restrict__ g,
-                                                                 float* __restrict__ Vb, double* __restrict__ cost_part,
-                                                                 const int64_t* __restrict__ fr_off, int F, int K, int ld) {
-    constexpr int KT = HG2_KT;
-    extern __shared__ __align__(16) float sm[];
-    float* S = sm;                                  // [R][ld] samples of the current frame
-    float* red = S + R * ld;                        // [8][HG3_NV] per-warp partials of the H sums
-    __shared__ float2 red2[8];
-    __shared__ double redd[8];
-    __shared__ float hs[KT];
-    const int u = blockIdx.y;
-    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
-    const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
-    if (nb >= n1) {
-        if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
-        return;
-    }
-    const int64_t ne = (nb + HG3_FPB < n1) ? nb + HG3_FPB : n1;
-    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const int fA = t, fB = t + 256;                 // the two bins of this thread (F >= 512 is checked by the host)
-    const bool xl = (t < R) && (F > 512);           // this thread also holds sample t of bin 512
-    float wA[KT], wB[KT], wX[KT];
-#pragma unroll
-    for (int k = 0; k < KT; ++k) {
-        const float* wk = Wtmp + ((int64_t)u * K + k) * ld;
-        wA[k] = (k < K) ? wk[fA] : 0.f;
-        wB[k] = (k < K) ? wk[fB] : 0.f;
-        wX[k] = (k < K && F > 512) ? wk[512] : 0.f;
-    }
-    double cost_d = 0.0;                            // per-thread partial, reduced once per CTA
-    const int chunks_per_row = ld / 4;
-
-    for (int64_t n = nb; n < ne; ++n) {
-        // ---- stage the frame: R rows of ld floats, 16-byte cp.async chunks
-        __syncthreads();                            // previous frame fully consumed
-        {
-            const float* src = Vs + (n * R) * (int64_t)ld;
-            for (int i = t; i < R * chunks_per_row; i += HG3_THREADS) cp_async16(S + 4 * i, src + 4 * i);
-        }
-        const float gg = g[n];
-        const float pA = P[n * ld + fA], pB = P[n * ld + fB];
-        const float pX = (F > 512) ? P[n * ld + 512] : 0.f;
-        float h[KT];
-#pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
-        cp_async_wait_all();
-        __syncthreads();
-
-        // ---- H update (Vb1 = W_new H_old)
-        float vbA = 0.f, vbB = 0.f, vbX = 0.f;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) { vbA = fmaf(wA[k], h[k], vbA); vbB = fmaf(wB[k], h[k], vbB); vbX = fmaf(wX[k], h[k], vbX); }
-        float a1A = 0.f, a2A = 0.f, a1B = 0.f, a2B = 0.f;
-#pragma unroll 5
-        for (int r = 0; r + 1 < R; r += 2) {
-            const float x0 = fmaf(gg, S[r * ld + fA], vbA), x1 = fmaf(gg, S[(r + 1) * ld + fA], vbA);
-            const float y0 = fmaf(gg, S[r * ld + fB], vbB), y1 = fmaf(gg, S[(r + 1) * ld + fB], vbB);
-            const float rx = rcp_fast(x0 * x1), ry = rcp_fast(y0 * y1);
-            const float ix0 = x1 * rx, ix1 = x0 * rx, iy0 = y1 * ry, iy1 = y0 * ry;
-            a1A += ix0 + ix1; a2A = fmaf(ix0, ix0, fmaf(ix1, ix1, a2A));
-            a1B += iy0 + iy1; a2B = fmaf(iy0, iy0, fmaf(iy1, iy1, a2B));
-        }
-        if (R & 1) {
-            const float ix = rcp_fast(fmaf(gg, S[(R - 1) * ld + fA], vbA)), iy = rcp_fast(fmaf(gg, S[(R - 1) * ld + fB], vbB));
-            a1A += ix; a2A = fmaf(ix, ix, a2A);
-            a1B += iy; a2B = fmaf(iy, iy, a2B);
-        }
-        float a1X = 0.f, a2X = 0.f;                 // bin 512: this thread's single sample
-        if (xl) { const float ix = rcp_fast(fmaf(gg, S[t * ld + 512], vbX)); a1X = ix; a2X = ix * ix; }
-        const float qA = pA * a2A, qB = pB * a2B, qX = pX * a2X;
-        {
-            // 20 warp sums with 30 shuffles: fold over lane bit 4 (each lane keeps half of the values), then bit 3, then a
-            // butterfly over the remaining 8 lanes; lanes 0, 8, 16, 24 end up with five totals each
-            const bool b4 = lane & 16, b3 = lane & 8;
-            float a[10];
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                float v[10];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const int k = 5 * hf + j;
-                    v[2 * j] = fmaf(wA[k], qA, fmaf(wB[k], qB, wX[k] * qX));
-                    v[2 * j + 1] = fmaf(wA[k], a1A, fmaf(wB[k], a1B, wX[k] * a1X));
-                }
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const float send = b4 ? v[j] : v[5 + j], keep = b4 ? v[5 + j] : v[j];
-                    a[5 * hf + j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
-            }
-            float o5[5];
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float send = b3 ? a[j] : a[5 + j], keep = b3 ? a[5 + j] : a[j];
-                o5[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-#pragma unroll
-            for (int o = 4; o >= 1; o >>= 1)
-#pragma unroll
-                for (int j = 0; j < 5; ++j) o5[j] += __shfl_xor_sync(0xffffffffu, o5[j], o);
-            if ((lane & 7) == 0) {                  // value index = 10 * bit3 + 5 * bit4 + j
-                float* dst = red + wid * HG3_NV + 10 * ((lane >> 3) & 1) + 5 * (lane >> 4);
-#pragma unroll
-                for (int j = 0; j < 5; ++j) dst[j] = o5[j];
-            }
-        }
-        __syncthreads();
-        if (t < K) {
-            float num = 0.f, den = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) { num += red[w * HG3_NV + 2 * t]; den += red[w * HG3_NV + 2 * t + 1]; }
-            hs[t] = H[n * K + t] * sqrtf(num / den);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? hs[k] : 0.f;
-
-        // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
-        vbA = 0.f; vbB = 0.f; vbX = 0.f;
-#pragma unroll
-        for (int k = 0; k < KT; ++k) { vbA = fmaf(wA[k], h[k], vbA); vbB = fmaf(wB[k], h[k], vbB); vbX = fmaf(wX[k], h[k], vbX); }
-        Vb[n * ld + fA] = vbA;
-        Vb[n * ld + fB] = vbB;
-        if (t == 0 && F > 512) Vb[n * ld + 512] = vbX;
-        float s1A = 0.f, s2A = 0.f, s1B = 0.f, s2B = 0.f;
-#pragma unroll 5
-        for (int r = 0; r + 1 < R; r += 2) {
-            const float sa0 = S[r * ld + fA], sa1 = S[(r + 1) * ld + fA], sb0 = S[r * ld + fB], sb1 = S[(r + 1) * ld + fB];
-            const float x0 = fmaf(gg, sa0, vbA), x1 = fmaf(gg, sa1, vbA), y0 = fmaf(gg, sb0, vbB), y1 = fmaf(gg, sb1, vbB);
-            const float rx = rcp_fast(x0 * x1), ry = rcp_fast(y0 * y1);
-            const float ix0 = x1 * rx, ix1 = x0 * rx, iy0 = y1 * ry, iy1 = y0 * ry;
-            const float ta0 = sa0 * ix0, ta1 = sa1 * ix1, tb0 = sb0 * iy0, tb1 = sb1 * iy1;
-            s1A += ta0 + ta1; s2A = fmaf(ta0, ix0, fmaf(ta1, ix1, s2A));
-            s1B += tb0 + tb1; s2B = fmaf(tb0, iy0, fmaf(tb1, iy1, s2B));
-        }
-        if (R & 1) {
-            const float sa = S[(R - 1) * ld + fA], sb = S[(R - 1) * ld + fB];
-            const float ix = rcp_fast(fmaf(gg, sa, vbA)), iy = rcp_fast(fmaf(gg, sb, vbB));
-            s1A += sa * ix; s2A = fmaf(sa * ix, ix, s2A);
-            s1B += sb * iy; s2B = fmaf(sb * iy, iy, s2B);
-        }
-        float s1X = 0.f, s2X = 0.f;
-        if (xl) { const float sx = S[t * ld + 512]; const float ix = rcp_fast(fmaf(gg, sx, vbX)); s1X = sx * ix; s2X = s1X * ix; }
-        {
-            const float v2 = warp_sum(fmaf(pA, s2A, fmaf(pB, s2B, pX * s2X))), v1 = warp_sum(s1A + s1B + s1X);
-            if (lane == 0) red2[wid] = make_float2(v2, v1);
-        }
-        __syncthreads();
-        float t2 = 0.f, t1 = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { const float2 rr = red2[w]; t2 += rr.x; t1 += rr.y; }
-        const float gnew = gg * sqrtf(t2 / t1);
-
-        // ---- cost with Vx = g_new Vs + Vb2: a pair of samples shares one reciprocal and one log2
-        float clA = 0.f, cpA = 0.f, clB = 0.f, cpB = 0.f;
-#pragma unroll 5
-        for (int r = 0; r + 1 < R; r += 2) {
-            const float x0 = fmaf(gnew, S[r * ld + fA], vbA), x1 = fmaf(gnew, S[(r + 1) * ld + fA], vbA);
-            const float y0 = fmaf(gnew, S[r * ld + fB], vbB), y1 = fmaf(gnew, S[(r + 1) * ld + fB], vbB);
-            const float px = x0 * x1, py = y0 * y1;
-            clA += lg2_fast(px); cpA = fmaf(x0 + x1, rcp_fast(px), cpA);
-            clB += lg2_fast(py); cpB = fmaf(y0 + y1, rcp_fast(py), cpB);
-        }
-        if (R & 1) {
-            const float x0 = fmaf(gnew, S[(R - 1) * ld + fA], vbA), y0 = fmaf(gnew, S[(R - 1) * ld + fB], vbB);
-            clA += lg2_fast(x0); cpA += rcp_fast(x0);
-            clB += lg2_fast(y0); cpB += rcp_fast(y0);
-        }
-        float cX = 0.f;
-        if (xl) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
-        cost_d += (double)(fmaf(0.6931471805599453f, clA + clB, fmaf(pA, cpA, pB * cpB)) + cX);
-
-        if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
-        if (t == 0) g[n] = gnew;
-    }
-    cost_d = warp_sum_d(cost_d);
-    if (lane == 0) redd[wid] = cost_d;
-    __syncthreads();
-    if (t == 0) {
-        double sum = 0.0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) sum += redd[w];
-        cost_part[(int64_t)u * gridDim.x + blockIdx.x] = sum / ((double)R * (double)F * (double)(n1 - n0));
-    }
-}
-
 // ----------------------------------------------------------------------------- H, g, cost: packed-math frame tile
-// Fifth version (dispatched for F = 513).  ncu on hg3 (profiles/r01_tc_ncu_hg3.txt) showed the kernel issue-bound: 68 % of
-// the issue slots busy, 16 k warp instructions per frame of which 9 % staged the frame and 45 % were scalar FP32 / LDS
-// of the three passes.  Same schedule as hg3 (one frame in shared memory, three CTAs per SM), three changes:
+// Dispatched for F = 513 with FP32 variances.  ncu on its scalar predecessor (profiles/r01_tc_ncu_hg3.txt) showed that kernel
+// issue-bound: 68 % of the issue slots busy, 16 k warp instructions per frame of which 9 % staged the frame and 45 % were scalar
+// FP32 / LDS of the three passes.  One frame in shared memory, three CTAs per SM, and:
 //   * a thread owns the ADJACENT bins 2t, 2t+1: one 8-byte shared load fetches both, and the pair is processed with the
 //     sm_100 packed instructions fma/mul/add.f32x2 (two FP32 lanes per issue slot);
 //   * the frame is staged by the bulk-copy engine: lanes 0..R-1 of warp 0 each issue one cp.async.bulk row copy that
@@ -1094,13 +759,262 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
     }
 }
 
+// ----------------------------------------------------------------------------- H, g, cost on the sampler's BF16 emission
+// hg5 on the variances the tcgen05 sampler wrote itself (vst.cu: VsT[tile][slot][bin group][row][16] bf16 + the per-sample slot
+// index, values without the decoder's output-layer bias E[f] = exp(b3[f])).  Per frame R x 33 cells of 32 bytes; the frame is
+// staged with 16-byte cp.async into one of TWO shared-memory buffers of R x 1056 bytes (half of hg5's FP32 frame, so two fit in
+// hg5's footprint and three CTAs still share an SM): frame n+1 is in flight while frame n is reduced.  A thread owns the
+// adjacent bins 2t, 2t+1 = one 32-bit word of every row (consecutive lanes, consecutive banks), unpacked with one shift and
+// one mask into a packed FP32 pair; E rides on g in the variance (Vx = (g E) v + Vb) and multiplies the g-update sums once
+// per frame.  The arithmetic of the three passes is hg5's.
+constexpr int HG7_ROWW = 264;                   // 32-bit words per staged row (528 bf16)
+__device__ __forceinline__ void hg7_cp16(unsigned smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gmem_src) : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __restrict__ P, const uint4* __restrict__ VsT,
+                                                                 const uint8_t* __restrict__ vs_idx, const float* __restrict__ bias_log2,
+                                                                 const float* __restrict__ Wtmp, const float* __restrict__ norm,
+                                                                 float* __restrict__ H, float* __restrict__ g,
+                                                                 float* __restrict__ Vb, double* __restrict__ cost_part,
+                                                                 const int64_t* __restrict__ fr_off, int K) {
+    constexpr int KT = HG2_KT;
+    constexpr int ld = HG5_LD;
+    constexpr int NBG = 33, TMR = 128;
+    static_assert(R % 2 == 0 && R <= 30, "hg7: even R up to 30");
+    extern __shared__ __align__(16) uint32_t smw[];
+    uint32_t* S0 = smw;                              // [2][R][HG7_ROWW] staged frames
+    float* red = reinterpret_cast<float*>(smw + 2 * R * HG7_ROWW);      // [8][HG3_NV] per-warp partials of the H sums
+    __shared__ float2 red2[8];
+    __shared__ double redd[8];
+    __shared__ float hs[KT];
+    const int u = blockIdx.y;
+    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
+    const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
+    if (nb >= n1) {
+        if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
+        return;
+    }
+    const int64_t ne = (nb + HG3_FPB < n1) ? nb + HG3_FPB : n1;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int f2 = 2 * t;                           // bins 2t, 2t+1; sample t of bin 512 lives on threads t < R
+    const bool xl = t < R;
+    f32x2 w2[KT];
+    float wX[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const float* wk = Wtmp + ((int64_t)u * K + k) * ld;
+        w2[k] = (k < K) ? *reinterpret_cast<const f32x2*>(wk + f2) : 0ull;
+        wX[k] = (k < K) ? wk[512] : 0.f;
+    }
+    const f32x2 E2 = pk2(exp2f(__ldg(bias_log2 + f2)), exp2f(__ldg(bias_log2 + f2 + 1)));
+    const float EX = exp2f(__ldg(bias_log2 + 512));
+    double cost_d = 0.0;                            // per-thread partial, reduced once per CTA
+
+    // stage frame n into buffer b: piece j = t + 256 k covers 16 bytes: row r = j / 66, piece i = j % 66 of the row
+    auto stage = [&](int64_t n, int b) {
+        const int64_t tile = n / TMR;
+        const int row = (int)(n - tile * TMR);
+        const uint8_t* ib = vs_idx + n * 32;
+        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(S0 + b * R * HG7_ROWW);
+        const unsigned char* src0 = reinterpret_cast<const unsigned char*>(VsT) + ((size_t)tile * (R + 1) * NBG * TMR + row) * 32;
+#pragma unroll
+        for (int k = 0; k < (R * 66 + HG3_THREADS - 1) / HG3_THREADS; ++k) {
+            const int j = t + HG3_THREADS * k;
+            if (j < R * 66) {
+                const int r = j / 66, i = j - 66 * r;
+                const unsigned slot = __ldg(ib + r);
+                hg7_cp16(dst0 + (unsigned)(r * HG7_ROWW * 4 + 16 * i),
+                         src0 + ((size_t)slot * NBG + (i >> 1)) * (TMR * 32) + 16 * (i & 1));
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(nb, 0);
+
+    int buf = 0;
+    for (int64_t n = nb; n < ne; ++n, buf ^= 1) {
+        if (n + 1 < ne) {
+            stage(n + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                                // frame n is staged for every thread
+        const uint32_t* S = S0 + buf * R * HG7_ROWW + t;                // this thread's word of row 0
+        const uint32_t* SX = S0 + buf * R * HG7_ROWW + 256;             // word holding bin 512
+        const float gg = g[n];
+        float elo, ehi;
+        upk2(E2, elo, ehi);
+        const f32x2 gg2 = pk2(gg * elo, gg * ehi);
+        const float ggX = gg * EX;
+        const f32x2 p2 = *reinterpret_cast<const f32x2*>(P + n * ld + f2);
+        const float pX = P[n * ld + 512];
+        float h[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
+        // ---- H update (Vb1 = W_new H_old)
+        f32x2 vb2 = 0ull;
+        float vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        f32x2 a1 = 0ull, a2 = 0ull;
+#pragma unroll 5
+        for (int r = 0; r < R; r += 2) {
+            const f32x2 x0 = fma2(gg2, bf16x2_to_f32x2(S[r * HG7_ROWW]), vb2), x1 = fma2(gg2, bf16x2_to_f32x2(S[(r + 1) * HG7_ROWW]), vb2);
+            const f32x2 rr = rcp2(mul2(x0, x1));
+            const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+            a1 = add2(a1, add2(i0, i1));
+            a2 = fma2(i0, i0, fma2(i1, i1, a2));
+        }
+        float sX = 0.f;                             // bin 512: this thread's single sample (without E)
+        float a1X = 0.f, a2X = 0.f;
+        if (xl) { sX = __uint_as_float(SX[t * HG7_ROWW] << 16); const float ix = rcp_fast(fmaf(ggX, sX, vbX)); a1X = ix; a2X = ix * ix; }
+        {
+            const f32x2 q2 = mul2(p2, a2);
+            const float qX = pX * a2X;
+            // 20 warp sums with 30 shuffles: fold over lane bit 4 (each lane keeps half of the values), then bit 3, then a
+            // butterfly over the remaining 8 lanes; lanes 0, 8, 16, 24 end up with five totals each
+            const bool b4 = lane & 16, b3 = lane & 8;
+            float a[10];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float v[10];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int k = 5 * hf + j;
+                    float nlo, nhi, dlo, dhi;
+                    upk2(mul2(w2[k], q2), nlo, nhi);
+                    upk2(mul2(w2[k], a1), dlo, dhi);
+                    v[2 * j] = fmaf(wX[k], qX, nlo + nhi);
+                    v[2 * j + 1] = fmaf(wX[k], a1X, dlo + dhi);
+                }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float send = b4 ? v[j] : v[5 + j], keep = b4 ? v[5 + j] : v[j];
+                    a[5 * hf + j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            }
+            float o5[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float send = b3 ? a[j] : a[5 + j], keep = b3 ? a[5 + j] : a[j];
+                o5[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) o5[j] += __shfl_xor_sync(0xffffffffu, o5[j], o);
+            if ((lane & 7) == 0) {                  // value index = 10 * bit3 + 5 * bit4 + j
+                float* dst = red + wid * HG3_NV + 10 * ((lane >> 3) & 1) + 5 * (lane >> 4);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) dst[j] = o5[j];
+            }
+        }
+        __syncthreads();
+        if (t < K) {
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { num += red[w * HG3_NV + 2 * t]; den += red[w * HG3_NV + 2 * t + 1]; }
+            hs[t] = H[n * K + t] * sqrtf(num / den);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? hs[k] : 0.f;
+
+        // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
+        vb2 = 0ull; vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        *reinterpret_cast<f32x2*>(Vb + n * ld + f2) = vb2;
+        if (t == 0) Vb[n * ld + 512] = vbX;
+        f32x2 s1 = 0ull, s2 = 0ull;
+#pragma unroll 5
+        for (int r = 0; r < R; r += 2) {
+            const f32x2 v0 = bf16x2_to_f32x2(S[r * HG7_ROWW]), v1 = bf16x2_to_f32x2(S[(r + 1) * HG7_ROWW]);
+            const f32x2 x0 = fma2(gg2, v0, vb2), x1 = fma2(gg2, v1, vb2);
+            const f32x2 rr = rcp2(mul2(x0, x1));
+            const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+            const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
+            s1 = add2(s1, add2(t0, t1));
+            s2 = fma2(t0, i0, fma2(t1, i1, s2));
+        }
+        s1 = mul2(s1, E2);                          // Vs = E v
+        s2 = mul2(s2, E2);
+        float s1X = 0.f, s2X = 0.f;
+        if (xl) { const float ix = rcp_fast(fmaf(ggX, sX, vbX)); s1X = EX * sX * ix; s2X = s1X * ix; }
+        {
+            float ps_lo, ps_hi, s1lo, s1hi;
+            upk2(mul2(p2, s2), ps_lo, ps_hi);
+            upk2(s1, s1lo, s1hi);
+            const float v2 = warp_sum(fmaf(pX, s2X, ps_lo + ps_hi)), v1 = warp_sum(s1lo + s1hi + s1X);
+            if (lane == 0) red2[wid] = make_float2(v2, v1);
+        }
+        __syncthreads();
+        float t2 = 0.f, t1s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const float2 rr = red2[w]; t2 += rr.x; t1s += rr.y; }
+        const float gnew = gg * sqrtf(t2 / t1s);
+
+        // ---- cost with Vx = g_new Vs + Vb2: FOUR samples share one reciprocal and one log2 (see hg5; c = 2^8)
+        constexpr float kC = 256.0f;
+        const f32x2 gc2 = pk2(gnew * kC * elo, gnew * kC * ehi), vc2 = mul2(vb2, pk2(kC, kC));
+        f32x2 cl = 0ull, cp = 0ull;
+        constexpr int R4 = R & ~3;
+#pragma unroll
+        for (int r = 0; r < R4; r += 4) {
+            const f32x2 y0 = fma2(gc2, bf16x2_to_f32x2(S[r * HG7_ROWW]), vc2), y1 = fma2(gc2, bf16x2_to_f32x2(S[(r + 1) * HG7_ROWW]), vc2);
+            const f32x2 y2 = fma2(gc2, bf16x2_to_f32x2(S[(r + 2) * HG7_ROWW]), vc2), y3 = fma2(gc2, bf16x2_to_f32x2(S[(r + 3) * HG7_ROWW]), vc2);
+            const f32x2 p01 = mul2(y0, y1), p23 = mul2(y2, y3);
+            const f32x2 m = mul2(p01, p23);
+            cl = add2(cl, lg22(m));
+            cp = fma2(fma2(add2(y0, y1), p23, mul2(add2(y2, y3), p01)), rcp2(m), cp);
+        }
+        float fix = -8.0f * (float)R4;                 // log2 c per sample
+#pragma unroll
+        for (int r = R4; r < R; r += 2) {              // R is even: one pair left when R % 4 == 2
+            const f32x2 y0 = fma2(gc2, bf16x2_to_f32x2(S[r * HG7_ROWW]), vc2), y1 = fma2(gc2, bf16x2_to_f32x2(S[(r + 1) * HG7_ROWW]), vc2);
+            const f32x2 pr = mul2(y0, y1);
+            cl = add2(cl, lg22(pr));
+            cp = fma2(add2(y0, y1), rcp2(pr), cp);
+            fix -= 16.0f;
+        }
+        float cX = 0.f;
+        if (xl) { const float x0 = fmaf(gnew * EX, sX, vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
+        {
+            float cl_lo, cl_hi, pc_lo, pc_hi;
+            upk2(cl, cl_lo, cl_hi);
+            upk2(mul2(p2, cp), pc_lo, pc_hi);
+            // both bins of the thread carry the same log2 c offset; the reciprocal sums carry a factor 1 / c
+            cost_d += (double)(fmaf(0.6931471805599453f, (cl_lo + fix) + (cl_hi + fix), kC * (pc_lo + pc_hi)) + cX);
+        }
+
+        if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
+        if (t == 0) g[n] = gnew;
+        __syncthreads();                                // the frame is fully consumed: its buffer may be refilled
+    }
+    cost_d = warp_sum_d(cost_d);
+    if (lane == 0) redd[wid] = cost_d;
+    __syncthreads();
+    if (t == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += redd[w];
+        cost_part[(int64_t)u * gridDim.x + blockIdx.x] = sum / ((double)R * 513.0 * (double)(n1 - n0));
+    }
+}
+
 // cost[u] = sum of the per-CTA partials in block order (deterministic, unlike an atomic accumulation)
-__global__ void cost_reduce_kernel(const double* __restrict__ cost_part, int nblk, double* __restrict__ cost) {
+__global__ void cost_reduce_kernel(const double* __restrict__ cost_part, int nblk, double* __restrict__ cost, int* __restrict__ status) {
     const int u = blockIdx.x;
     double s = 0.0;
     for (int i = threadIdx.x; i < nblk; i += 32) s += cost_part[(int64_t)u * nblk + i];
     s = warp_sum_d(s);
-    if (threadIdx.x == 0) cost[u] = s;
+    if (threadIdx.x == 0) {
+        cost[u] = s;
+        if (status && !(fabs(s) <= 1.0e300)) atomicOr(status, DVAE_STATUS_NONFINITE);       // NaN / Inf guard
+    }
 }
 
 // ----------------------------------------------------------------------------- Wiener masks (mcem.py:325-327)
@@ -1184,7 +1098,7 @@ extern "C" int64_t dvae_nmf_workspace_floats(int B, int K, int ld, int max_frame
 
 extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, float* H, float* g, float* Vb,
                               double* cost, const int64_t* fr_off, const int32_t* frame_utt, int B, int64_t NT, int F,
-                              int K, int ld, int max_frames, float* ws, const float* wstat, int n_parts, void* stream) {
+                              int K, int ld, int max_frames, float* ws, const float* wstat, int* status, void* stream) {
     (void)frame_utt;
     DVAE_REQUIRE(P && Vs && W && H && g && Vb && cost && fr_off && ws, "dvae_nmf_mstep: null pointer");
     DVAE_REQUIRE(B >= 1 && NT >= 0 && F >= 1 && ld >= F && R >= 1, "dvae_nmf_mstep: bad sizes");
@@ -1199,10 +1113,8 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(cost_part) & 7) == 0, "dvae_nmf_mstep: workspace must be 8-byte aligned");
     const int nblk = (int)hg_blocks(max_frames);
     int rc;
-    if (wstat && n_parts == 0) {                   // per-frame reciprocal sums A1 | A2 from dvae_decode_stats_tc
+    if (wstat) {                                   // per-frame reciprocal sums A1 | A2 from dvae_decode_stats_tc
         rc = dvae_nmf_w_from_frame_stats(wstat, wstat + NT * (int64_t)ld, P, H, W, fr_off, B, F, K, ld, Wtmp, stream);
-    } else if (wstat) {                            // numerator / denominator already reduced by dvae_decode_ws_tc
-        rc = dvae_nmf_w_from_stats(wstat, n_parts, W, B, F, K, ld, Wtmp, stream);
     } else {
         nmf_w_kernel<<<dim3((F + 127) / 128, B), 128, 0, st>>>(P, Vs, R, W, H, g, Vb, fr_off, F, K, ld, Wtmp);
         rc = check_launch("nmf_w_kernel");
@@ -1231,35 +1143,17 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
             nmf_hg6_kernel<10, HG5_LD><<<dim3(nblk_used, B), HG3_THREADS, smem6, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, K, R);
         }
         rc = check_launch("nmf_hg6_kernel");
-    } else if (F >= 512 && F <= 513 && (ld & 3) == 0 && K <= HG2_KT && (R == 10 || R == 30)) {
+    } else if (F == 513 && ld == HG5_LD && K <= HG2_KT && (R == 10 || R == 30) && aligned) {
         nblk_used = (max_frames + HG3_FPB - 1) / HG3_FPB;
         const size_t smem3 = sizeof(float) * ((size_t)R * ld + (size_t)HG3_NV * 8);
-        if (F == 513 && ld == HG5_LD && (reinterpret_cast<uintptr_t>(Vs) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wtmp) & 7) == 0 &&
-            (reinterpret_cast<uintptr_t>(P) & 7) == 0 && (reinterpret_cast<uintptr_t>(Vb) & 7) == 0) {
-            if (R == 10) {
-                cudaFuncSetAttribute(nmf_hg5_kernel<10, HG5_LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-                nmf_hg5_kernel<10, HG5_LD><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, K);
-            } else {
-                cudaFuncSetAttribute(nmf_hg5_kernel<30, HG5_LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-                nmf_hg5_kernel<30, HG5_LD><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, K);
-            }
-        } else if (R == 10) {
-            cudaFuncSetAttribute(nmf_hg3_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-            nmf_hg3_kernel<10><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
-        } else {
-            cudaFuncSetAttribute(nmf_hg3_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
-            nmf_hg3_kernel<30><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
-        }
-        rc = check_launch("nmf_hg3/hg5_kernel");
-    } else if (F <= HG2_THREADS && K <= HG2_KT && (R == 10 || R == 30)) {
-        nblk_used = (max_frames + HG2_FPB - 1) / HG2_FPB;
-        const size_t smem2 = sizeof(float) * (size_t)2 * HG2_KT * HG2_THREADS;
         if (R == 10) {
-            nmf_hg2_kernel<10, HG2_KT><<<dim3(nblk_used, B), HG2_THREADS, smem2, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
+            cudaFuncSetAttribute(nmf_hg5_kernel<10, HG5_LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+            nmf_hg5_kernel<10, HG5_LD><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, K);
         } else {
-            nmf_hg2_kernel<30, HG2_KT><<<dim3(nblk_used, B), HG2_THREADS, smem2, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, F, K, ld);
+            cudaFuncSetAttribute(nmf_hg5_kernel<30, HG5_LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3);
+            nmf_hg5_kernel<30, HG5_LD><<<dim3(nblk_used, B), HG3_THREADS, smem3, st>>>(P, Vs, Wtmp, norm, H, g, Vb, cost_part, fr_off, K);
         }
-        rc = check_launch("nmf_hg2_kernel");
+        rc = check_launch("nmf_hg5_kernel");
     } else {
         const size_t smem = sizeof(float) * (size_t)K * ld;
         DVAE_REQUIRE(smem <= 200 * 1024, "dvae_nmf_mstep: K*ld too large for shared memory");
@@ -1268,7 +1162,54 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
         rc = check_launch("nmf_hg_kernel");
     }
     if (rc) return rc;
-    cost_reduce_kernel<<<B, 32, 0, st>>>(cost_part, nblk_used, cost);
+    cost_reduce_kernel<<<B, 32, 0, st>>>(cost_part, nblk_used, cost, status);
+    return check_launch("cost_reduce_kernel");
+}
+
+// The same M-step on the sampler's BF16 emission (vst.cu) instead of materialised FP32 variances: F = 513, ld = 520,
+// K <= 10, R in {10, 30}; fstat = A1 | A2 from dvae_vst_frame_stats.
+extern "C" int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const void* VsT,
+                                  const uint8_t* vs_idx, int R, float* W, float* H, float* g, float* Vb, double* cost,
+                                  const int64_t* fr_off, int B, int64_t NT, int K, int ld, int max_frames, float* ws,
+                                  const float* fstat, int* status, void* stream) {
+    tc::Dims d;
+    int rc = tc::check_dims(dec, L, y_dim, "dvae_nmf_mstep_vst", &d);
+    if (rc) return rc;
+    DVAE_REQUIRE(image && P && VsT && vs_idx && W && H && g && Vb && cost && fr_off && ws && fstat, "dvae_nmf_mstep_vst: null pointer");
+    DVAE_REQUIRE(B >= 1 && NT >= 0 && max_frames >= 0, "dvae_nmf_mstep_vst: bad sizes");
+    DVAE_REQUIRE(d.F == 513 && ld == HG5_LD && K >= 1 && K <= HG2_KT && (R == 10 || R == 30),
+                 "dvae_nmf_mstep_vst: needs F = 513, ld = %d, K <= %d, R in {10, 30}", HG5_LD, HG2_KT);
+    const float* bias_log2 = reinterpret_cast<const float*>((const unsigned char*)image + d.off_bias) + (d.n_hidden == 2 ? tc::HID : 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    float* Wtmp = ws;
+    float* norm = ws + (int64_t)B * K * ld;
+    int64_t off = (int64_t)B * K * ld + (int64_t)B * K;
+    off += off & 1;
+    double* cost_part = reinterpret_cast<double*>(ws + off);
+    DVAE_REQUIRE((reinterpret_cast<uintptr_t>(cost_part) & 7) == 0 && (reinterpret_cast<uintptr_t>(VsT) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(P) & 7) == 0 && (reinterpret_cast<uintptr_t>(Vb) & 7) == 0,
+                 "dvae_nmf_mstep_vst: workspace / VsT / P / Vb alignment");
+    rc = dvae_nmf_w_from_frame_stats(fstat, fstat + NT * (int64_t)ld, P, H, W, fr_off, B, d.F, K, ld, Wtmp, stream);
+    if (rc) return rc;
+    nmf_norm_kernel<<<B, 256, 0, st>>>(Wtmp, d.F, K, ld, W, norm);
+    rc = check_launch("nmf_norm_kernel");
+    if (rc) return rc;
+    if (max_frames == 0) {
+        cudaMemsetAsync(cost, 0, sizeof(double) * B, st);
+        return 0;
+    }
+    const int nblk = (max_frames + HG3_FPB - 1) / HG3_FPB;
+    const size_t smem7 = 4 * ((size_t)2 * R * HG7_ROWW + (size_t)HG3_NV * 8);
+    if (R == 10) {
+        cudaFuncSetAttribute(nmf_hg7_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7);
+        nmf_hg7_kernel<10><<<dim3(nblk, B), HG3_THREADS, smem7, st>>>(P, (const uint4*)VsT, vs_idx, bias_log2, Wtmp, norm, H, g, Vb, cost_part, fr_off, K);
+    } else {
+        cudaFuncSetAttribute(nmf_hg7_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7);
+        nmf_hg7_kernel<30><<<dim3(nblk, B), HG3_THREADS, smem7, st>>>(P, (const uint4*)VsT, vs_idx, bias_log2, Wtmp, norm, H, g, Vb, cost_part, fr_off, K);
+    }
+    rc = check_launch("nmf_hg7_kernel");
+    if (rc) return rc;
+    cost_reduce_kernel<<<B, 32, 0, st>>>(cost_part, nblk, cost, status);
     return check_launch("cost_reduce_kernel");
 }
 

@@ -74,8 +74,13 @@ int ensure_tables(cudaStream_t stream) {
     if (dev < 64 && g_inited[dev]) return 0;
     init_tables_kernel<<<kNfft / 256, 256, 0, stream>>>();
     int rc = check_launch("init_tables");
-    if (rc == 0 && dev < 64) g_inited[dev] = true;
-    return rc;
+    if (rc) return rc;
+    // one-off: the tables must be complete before the device is marked initialised, or a later call on ANOTHER stream
+    // could read them half-written
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) { set_error("init_tables: %s", cudaGetErrorString(e)); return (int)e; }
+    if (dev < 64) g_inited[dev] = true;
+    return 0;
 }
 
 // ----------------------------------------------------------------------------- complex helpers

@@ -1,5 +1,5 @@
-// Shared pieces of the tcgen05 kernels (sampler, decode, decode + W statistics): operand layout, PTX wrappers,
-// the hidden-layer epilogue and the MMA issue loop.  See mh_tc.cu for the design notes.
+// Shared pieces of the tcgen05 kernels (sampler, decode, decode + frame statistics): operand layout, PTX wrappers,
+// the hidden-layer epilogue and the MMA issue loop.  See tc_decode.cu / mh_tc2.cu for the design notes.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -16,8 +16,6 @@ constexpr int NTHREADS = 288;
 constexpr int A_BYTES = 32768;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
-
-enum { MODE_MH = 0, MODE_DECODE = 1 };
 
 struct Dims {
     int L, y_dim, n_hidden, F, nkb1;
@@ -75,11 +73,14 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
 }
 
-// Bounded wait: a broken pipeline must never hang the GPU. On timeout the CTA-wide `dead` flag makes every later
-// wait fall through and the host sees status != 0.
+// Bounded wait: a broken pipeline must never hang the GPU.  The bound is wall time (2 s on the global timer, polled every
+// 4096 failed probes), not a probe count, so time slicing or an attached profiler cannot produce a false timeout.  On
+// timeout the CTA-wide `dead` flag makes every later wait fall through and the host sees DVAE_STATUS_TIMEOUT.
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int* dead, int* status) {
     if (*dead) return;
-    for (int spin = 0; spin < (1 << 22); ++spin) {
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 1;; ++spin) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -87,9 +88,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatil
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
+        if ((spin & 4095u) == 0) {
+            if (*dead) return;
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) break;
+        }
     }
     *dead = 1;
-    atomicExch(status, 1);
+    atomicOr(status, DVAE_STATUS_TIMEOUT);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -291,49 +298,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         : "r"(taddr) : "memory");
 }
 
-// hidden-layer epilogue, 32 columns per thread: D12[row][32s .. 32s+32) -> tanh(+bias) -> bf16 -> A operand
-__device__ __forceinline__ void hidden_epilogue32(uint32_t tmem, unsigned char* A, int q, int s, int row, const float* bias) {
-    float v[32];
-    const int col0 = 32 * s;
-    tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + col0, v);
-    tmem_wait_ld();
-    const int kb = s >> 1, cbase = 4 * (s & 1);
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        float t[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float x = v[8 * cc + e];
-            if (bias) x += bias[col0 + 8 * cc + e];
-            t[e] = tanh_approx(x);
-        }
-        uint4 pk = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
-        *reinterpret_cast<uint4*>(A + kb * 16384 + row * 128 + (((cbase + cc) ^ (row & 7)) << 4)) = pk;
-    }
-}
-
-// 16 bins of the log-likelihood: v = TMEM accumulators, pp / vb = observation and noise variance quads
-__device__ __forceinline__ void loglik16(const float* v, const float4* pp, const float4* vb, const float* b3f, float g_row,
-                                         float& acc, float& accl) {
-#pragma unroll
-    for (int qd = 0; qd < 4; ++qd) {
-        const float4 bb = *reinterpret_cast<const float4*>(b3f + 4 * qd);
-        const float v0 = fmaf(g_row, ex2_approx(v[4 * qd + 0] + bb.x), vb[qd].x);
-        const float v1 = fmaf(g_row, ex2_approx(v[4 * qd + 1] + bb.y), vb[qd].y);
-        const float v2 = fmaf(g_row, ex2_approx(v[4 * qd + 2] + bb.z), vb[qd].z);
-        const float v3 = fmaf(g_row, ex2_approx(v[4 * qd + 3] + bb.w), vb[qd].w);
-        const float p01 = v0 * v1, p23 = v2 * v3;
-        const float n01 = fmaf(pp[qd].y, v0, pp[qd].x * v1), n23 = fmaf(pp[qd].w, v2, pp[qd].z * v3);
-        acc = fmaf(n01, rcp_approx(p01), acc);
-        acc = fmaf(n23, rcp_approx(p23), acc);
-        accl += lg2_approx(p01) + lg2_approx(p23);
-    }
-}
-
-
-// Same with the observation / noise variance streamed as BF16: pv[qd] = {P0P1, P2P3, V0V1, V2V3} (bf16x2 words) of
-// four consecutive bins.  Half the L2 traffic and half the L2 working set of the FP32 stream; the rounding (2^-9
-// relative, identical for l(z) and l(z')) perturbs the log ratio far less than the BF16 decoder weights do.
+// 16 bins of the log-likelihood with the observation / noise variance streamed at BF16 precision (pack_pv_kernel): half
+// the L2 traffic and half the L2 working set of an FP32 stream; the rounding (2^-9 relative, identical for l(z) and
+// l(z')) perturbs the log ratio far less than the BF16 decoder weights do.
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 // Four bins share ONE reciprocal and ONE logarithm:

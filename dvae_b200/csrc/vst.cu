@@ -1,0 +1,248 @@
+// The E-step's kept-sample variances in the sampler's own format ("VsT": BF16, chain tiles) and the kernels that read it.
+//
+// The tcgen05 sampler (mh_tc2.cu) evaluates the decoder for every proposal; on kept iterations it writes the proposal's
+// output 2^v (= Vs without the output-layer bias) straight to global memory, so compute_Vs (mcem.py:280-290) needs no
+// second decode.  Layout (one 32-byte cell = 16 consecutive bins of one chain in one slot):
+//
+//     VsT[tile = chain / 128][slot 0 .. R][bg = bin / 16 (33 groups)][row = chain % 128][16]   bf16
+//     vs_idx[chain][32] bytes: byte r = slot holding kept sample r  (0 = the state the kept phase started from,
+//                                                                     1 + j = the proposal of kept iteration j)
+//
+// A rejected proposal leaves its slot unreferenced; a sample whose proposal was rejected points at the slot of the last
+// accepted one, so nothing is ever copied.  Vs[n][r][f] = E[f] * VsT[...][vs_idx[n][r]][...] with E[f] = exp(b3[f]), the
+// output-layer bias the sampler folds into its P / Vb stream instead (pack_pv_kernel).
+//
+//   vst_frame_stats_kernel   A1[n][f] = sum_r 1 / Vx, A2[n][f] = sum_r 1 / Vx^2 (inner sums of mcem.py:108-110) with the
+//                            E-step's g and Vb: thread = (chain, 16 bins), a warp reads 1 KB contiguous per slot.
+//   vst_unpack / vst_pack    conversion to / from the dense FP32 layout Vs[NT][R][ld] (the `.Vs` attribute of the MCEM
+//                            shims, parity tests).
+// The H / g / cost kernel on this format is nmf_hg7_kernel (nmf.cu).
+#include "tc_common.cuh"
+
+namespace dvae {
+namespace tc {
+
+constexpr int NBG = NPAD / 16;                  // 33 bin groups
+constexpr int VST_IDX_PITCH = 32;
+
+__device__ __forceinline__ f32x2 vst_rcp2(f32x2 a) { float lo, hi; upk2(a, lo, hi); return pk2(rcp_approx(lo), rcp_approx(hi)); }
+
+// RT > 0: compile-time sample count (even), slot indices held in registers; RT = 0: run-time count r_rt (any parity)
+template <int RT>
+__global__ void __launch_bounds__(128, 4) vst_frame_stats_kernel(const uint4* __restrict__ VsT, const uint8_t* __restrict__ idx, int r_rt,
+                                                                 const float* __restrict__ bias_log2, const float* __restrict__ Vb,
+                                                                 const float* __restrict__ g, int64_t rows, int F, int ld,
+                                                                 float* __restrict__ A1, float* __restrict__ A2) {
+    const int R = RT > 0 ? RT : r_rt;
+    const int64_t tile = blockIdx.x;
+    const int bg = blockIdx.y, row = threadIdx.x;
+    const int64_t m = tile * TM + row;
+    if (m >= rows) return;
+    const int f0 = 16 * bg;
+    const float gg = __ldg(g + m);
+    f32x2 ge2[8], vb2[8], a1[8], a2[8];
+    {
+        float vb[16];
+        if (f0 + 16 <= ld) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(Vb + m * ld + f0) + j);
+                vb[4 * j] = t.x; vb[4 * j + 1] = t.y; vb[4 * j + 2] = t.z; vb[4 * j + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) vb[j] = (f0 + j < F) ? __ldg(Vb + m * ld + f0 + j) : 1.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int f = f0 + 2 * j;
+            const float e0 = (f < F) ? exp2f(__ldg(bias_log2 + f)) : 0.f, e1 = (f + 1 < F) ? exp2f(__ldg(bias_log2 + f + 1)) : 0.f;
+            ge2[j] = pk2(gg * e0, gg * e1);
+            vb2[j] = pk2((f < F) ? vb[2 * j] : 1.f, (f + 1 < F) ? vb[2 * j + 1] : 1.f);      // padding bins: Vx = 1, never stored
+            a1[j] = 0ull;
+            a2[j] = 0ull;
+        }
+    }
+    const size_t slot_stride = (size_t)NBG * TM * 2;
+    const uint4* cell = VsT + ((size_t)tile * (R + 1) * NBG + bg) * (TM * 2) + row * 2;
+    const uint8_t* ib = idx + m * VST_IDX_PITCH;
+    uint32_t iw[8];
+    if (RT > 0) {
+        const uint4 i0 = __ldg(reinterpret_cast<const uint4*>(ib)), i1 = __ldg(reinterpret_cast<const uint4*>(ib) + 1);
+        iw[0] = i0.x; iw[1] = i0.y; iw[2] = i0.z; iw[3] = i0.w; iw[4] = i1.x; iw[5] = i1.y; iw[6] = i1.z; iw[7] = i1.w;
+    }
+    auto slot_of = [&](int r) -> uint32_t {
+        if (RT > 0) return (iw[r >> 2] >> (8 * (r & 3))) & 255u;
+        return (uint32_t)__ldg(ib + r);
+    };
+    auto pair = [&](const uint4& p0, const uint4& p1, const uint4& q0, const uint4& q1) {
+        const uint32_t w0[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+        const uint32_t w1[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            // two samples share one reciprocal: 1 / X0 = X1 / (X0 X1)
+            const f32x2 x0 = fma2(ge2[j], bf16x2_to_f32x2(w0[j]), vb2[j]), x1 = fma2(ge2[j], bf16x2_to_f32x2(w1[j]), vb2[j]);
+            const f32x2 rr = vst_rcp2(mul2(x0, x1));
+            const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+            a1[j] = add2(a1[j], add2(i0, i1));
+            a2[j] = fma2(i0, i0, fma2(i1, i1, a2[j]));
+        }
+    };
+    const int R2 = R & ~1;
+    if (RT > 0) {
+        // software pipeline over sample pairs: the cells of pair k+1 are in flight while pair k is reduced
+        uint4 c[4], nx[4];
+        {
+            const uint4* s0 = cell + slot_of(0) * slot_stride;
+            const uint4* s1 = cell + slot_of(1) * slot_stride;
+            c[0] = __ldcs(s0); c[1] = __ldcs(s0 + 1); c[2] = __ldcs(s1); c[3] = __ldcs(s1 + 1);
+        }
+#pragma unroll
+        for (int r = 0; r < RT; r += 2) {
+            if (r + 2 < RT) {
+                const uint4* s0 = cell + slot_of(r + 2) * slot_stride;
+                const uint4* s1 = cell + slot_of(r + 3) * slot_stride;
+                nx[0] = __ldcs(s0); nx[1] = __ldcs(s0 + 1); nx[2] = __ldcs(s1); nx[3] = __ldcs(s1 + 1);
+            }
+            pair(c[0], c[1], c[2], c[3]);
+            if (r + 2 < RT) { c[0] = nx[0]; c[1] = nx[1]; c[2] = nx[2]; c[3] = nx[3]; }
+        }
+    } else {
+        for (int r = 0; r < R2; r += 2) {
+            const uint4* s0 = cell + slot_of(r) * slot_stride;
+            const uint4* s1 = cell + slot_of(r + 1) * slot_stride;
+            pair(__ldcs(s0), __ldcs(s0 + 1), __ldcs(s1), __ldcs(s1 + 1));
+        }
+        if (R & 1) {
+            const uint4* s0 = cell + slot_of(R - 1) * slot_stride;
+            const uint4 p0 = __ldcs(s0), p1 = __ldcs(s0 + 1);
+            const uint32_t w0[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const f32x2 i0 = vst_rcp2(fma2(ge2[j], bf16x2_to_f32x2(w0[j]), vb2[j]));
+                a1[j] = add2(a1[j], i0);
+                a2[j] = fma2(i0, i0, a2[j]);
+            }
+        }
+    }
+    float o1[16], o2[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { upk2(a1[j], o1[2 * j], o1[2 * j + 1]); upk2(a2[j], o2[2 * j], o2[2 * j + 1]); }
+    if (f0 + 16 <= F) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            reinterpret_cast<float4*>(A1 + m * ld + f0)[j] = make_float4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
+            reinterpret_cast<float4*>(A2 + m * ld + f0)[j] = make_float4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (f0 + j < F) { A1[m * ld + f0 + j] = o1[j]; A2[m * ld + f0 + j] = o2[j]; }
+    }
+}
+
+// Vs[n][r][f] = E[f] * VsT[..][vs_idx[n][r]][..]   (one thread per (frame, sample, bin pair))
+__global__ void vst_unpack_kernel(const uint32_t* __restrict__ VsT, const uint8_t* __restrict__ idx, int R, const float* __restrict__ bias_log2,
+                                  int64_t rows, int F, int ld, float* __restrict__ Vs) {
+    const int64_t total = rows * R * (NPAD / 2);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int pw = (int)(i % (NPAD / 2));
+        const int64_t mr = i / (NPAD / 2);
+        const int r = (int)(mr % R);
+        const int64_t m = mr / R;
+        const int f = 2 * pw;
+        if (f >= F) continue;
+        const int64_t tile = m / TM;
+        const int row = (int)(m % TM), slot = idx[m * VST_IDX_PITCH + r], bg = f >> 4;
+        const uint32_t w = VsT[((((size_t)tile * (R + 1) + slot) * NBG + bg) * TM + row) * 8 + ((f & 15) >> 1)];
+        float* dst = Vs + (m * R + r) * (int64_t)ld + f;
+        dst[0] = exp2f(bias_log2[f]) * __uint_as_float(w << 16);
+        if (f + 1 < F) dst[1] = exp2f(bias_log2[f + 1]) * __uint_as_float(w & 0xffff0000u);
+    }
+}
+
+// the inverse: sample r of frame n goes to slot 1 + r (slot 0 and the padding bins are zero), vs_idx[n][r] = 1 + r
+__global__ void vst_pack_kernel(const float* __restrict__ Vs, int R, const float* __restrict__ bias_log2, int64_t rows, int F, int ld,
+                                uint32_t* __restrict__ VsT, uint8_t* __restrict__ idx) {
+    const int64_t n_tiles = (rows + TM - 1) / TM;
+    const int64_t total = n_tiles * (R + 1) * NBG * TM * 8;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int wd = (int)(i & 7);
+        const int row = (int)((i >> 3) % TM);
+        const int bg = (int)((i / (8 * TM)) % NBG);
+        const int slot = (int)((i / (8 * TM * NBG)) % (R + 1));
+        const int64_t tile = i / ((int64_t)8 * TM * NBG * (R + 1));
+        const int64_t m = tile * TM + row;
+        const int f = 16 * bg + 2 * wd;
+        uint32_t w = 0u;
+        if (m < rows && slot > 0 && f < F) {
+            const float* src = Vs + (m * R + slot - 1) * (int64_t)ld + f;
+            const float lo = src[0] * exp2f(-bias_log2[f]);
+            const float hi = (f + 1 < F) ? src[1] * exp2f(-bias_log2[f + 1]) : 0.f;
+            w = pack_bf16x2(lo, hi);
+        }
+        VsT[i] = w;
+        if (bg == 0 && wd == 0 && m < rows && slot > 0) idx[m * VST_IDX_PITCH + slot - 1] = (uint8_t)slot;
+    }
+}
+
+}  // namespace tc
+}  // namespace dvae
+
+using namespace dvae;
+using namespace dvae::tc;
+
+static const float* vst_bias(const DvaeMlp* dec, const void* image, int L, int y_dim, const char* who, Dims* d, int* rc) {
+    *rc = check_dims(dec, L, y_dim, who, d);
+    if (*rc) return nullptr;
+    // layer-3 bias (log2 domain) inside the decoder image: after the hidden-2 bias if there is one
+    return reinterpret_cast<const float*>((const unsigned char*)image + d->off_bias) + (d->n_hidden == 2 ? HID : 0);
+}
+
+extern "C" int dvae_vst_frame_stats(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx,
+                                    int R, const float* Vb, const float* g, int64_t NT, int ld, float* A1, float* A2, void* stream) {
+    Dims d;
+    int rc;
+    DVAE_REQUIRE(image != nullptr, "dvae_vst_frame_stats: null pointer");
+    const float* bias_log2 = vst_bias(dec, image, L, y_dim, "dvae_vst_frame_stats", &d, &rc);
+    if (rc) return rc;
+    DVAE_REQUIRE(VsT && vs_idx && Vb && g && A1 && A2, "dvae_vst_frame_stats: null pointer");
+    DVAE_REQUIRE(R >= 1 && R <= 31 && NT >= 0 && ld >= d.F && (ld & 3) == 0, "dvae_vst_frame_stats: bad sizes (1 <= R <= 31, ld %% 4 == 0)");
+    DVAE_REQUIRE(((reinterpret_cast<uintptr_t>(VsT) | reinterpret_cast<uintptr_t>(vs_idx) | reinterpret_cast<uintptr_t>(Vb) |
+                   reinterpret_cast<uintptr_t>(A1) | reinterpret_cast<uintptr_t>(A2)) & 15) == 0, "dvae_vst_frame_stats: 16-byte alignment required");
+    if (NT == 0) return 0;
+    const int64_t n_tiles = (NT + TM - 1) / TM;
+    DVAE_REQUIRE(n_tiles < (1ll << 31), "dvae_vst_frame_stats: too many frames");
+    const dim3 grid((unsigned)n_tiles, NBG);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (R == 30) vst_frame_stats_kernel<30><<<grid, TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
+    else if (R == 10) vst_frame_stats_kernel<10><<<grid, TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
+    else vst_frame_stats_kernel<0><<<grid, TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
+    return check_launch("vst_frame_stats_kernel");
+}
+
+extern "C" int dvae_vst_unpack(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx, int R,
+                               int64_t NT, int ld, float* Vs, void* stream) {
+    Dims d;
+    int rc;
+    DVAE_REQUIRE(image != nullptr, "dvae_vst_unpack: null pointer");
+    const float* bias_log2 = vst_bias(dec, image, L, y_dim, "dvae_vst_unpack", &d, &rc);
+    if (rc) return rc;
+    DVAE_REQUIRE(VsT && vs_idx && Vs && R >= 1 && R <= 31 && NT >= 0 && ld >= d.F, "dvae_vst_unpack: bad arguments");
+    if (NT == 0) return 0;
+    vst_unpack_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)VsT, vs_idx, R, bias_log2, NT, d.F, ld, Vs);
+    return check_launch("vst_unpack_kernel");
+}
+
+extern "C" int dvae_vst_pack(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* Vs, int R, int64_t NT, int ld,
+                             void* VsT, uint8_t* vs_idx, void* stream) {
+    Dims d;
+    int rc;
+    DVAE_REQUIRE(image != nullptr, "dvae_vst_pack: null pointer");
+    const float* bias_log2 = vst_bias(dec, image, L, y_dim, "dvae_vst_pack", &d, &rc);
+    if (rc) return rc;
+    DVAE_REQUIRE(VsT && vs_idx && Vs && R >= 1 && R <= 31 && NT >= 0 && ld >= d.F, "dvae_vst_pack: bad arguments");
+    if (NT == 0) return 0;
+    vst_pack_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(Vs, R, bias_log2, NT, d.F, ld, (uint32_t*)VsT, vs_idx);
+    return check_launch("vst_pack_kernel");
+}

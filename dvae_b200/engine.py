@@ -26,7 +26,6 @@ from . import _lib
 from .synth import FS, HOP, N_FFT, num_frames
 
 LD_ALIGN = 8
-WS_PARTS = 2                     # work items per utterance of the fused decode + W-statistics kernel
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -35,6 +34,19 @@ def _p(t: Optional[torch.Tensor]):
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_device(fn):
+    """Run a method with the object's CUDA device current: the kernels of libdvae_b200 launch on the calling thread's current
+    device and ``_stream()`` is that device's current stream, while the reference's scripts hand a device INDEX to every
+    worker and never call ``set_device`` (scripts/evaluate_ntcd_M1.py:69,252)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **kw):
+        with torch.cuda.device(self.dev):
+            return fn(self, *a, **kw)
+    return wrapper
 
 
 def _require_cuda(device):
@@ -170,8 +182,9 @@ def stft_batch(x_flat: torch.Tensor, x_off: torch.Tensor, x_len: torch.Tensor, b
     ld = _ld_for(n_fft // 2 + 1)
     X = torch.empty((batch.NT, ld), dtype=torch.complex64, device=x_flat.device)
     P = torch.empty((batch.NT, ld), dtype=torch.float32, device=x_flat.device) if want_power else None
-    _lib.call("dvae_stft_f32", _p(x_flat), _p(x_off), _p(x_len), batch.B, _p(X), _p(P), _p(batch.fr_off), batch.NT,
-              n_fft, hop, ld, _stream())
+    with torch.cuda.device(x_flat.device):
+        _lib.call("dvae_stft_f32", _p(x_flat), _p(x_off), _p(x_len), batch.B, _p(X), _p(P), _p(batch.fr_off), batch.NT,
+                  n_fft, hop, ld, _stream())
     return X, P
 
 
@@ -179,8 +192,9 @@ def istft_batch(X: torch.Tensor, batch: RaggedBatch, y_off: torch.Tensor, y_len:
                 max_len: int, n_fft=N_FFT, hop=HOP, out: Optional[torch.Tensor] = None):
     """ISTFT of ``X [NT][ld]`` into a concatenated float32 signal of ``total_len`` samples."""
     y = out if out is not None else torch.empty(total_len, dtype=torch.float32, device=X.device)
-    _lib.call("dvae_istft_f32", _p(X), _p(batch.fr_off), batch.B, _p(y), _p(y_off), _p(y_len), int(max_len), n_fft, hop,
-              X.shape[1], _stream())
+    with torch.cuda.device(X.device):
+        _lib.call("dvae_istft_f32", _p(X), _p(batch.fr_off), batch.B, _p(y), _p(y_off), _p(y_len), int(max_len), n_fft, hop,
+                  X.shape[1], _stream())
     return y
 
 
@@ -192,8 +206,9 @@ def istft_masked_batch(X: torch.Tensor, mask: torch.Tensor, batch: RaggedBatch, 
     if mask.shape != X.shape or mask.dtype != torch.float32 or not mask.is_contiguous():
         raise ValueError("mask must be a contiguous float32 tensor of the spectrum's shape")
     y = out if out is not None else torch.empty(total_len, dtype=torch.float32, device=X.device)
-    _lib.call("dvae_istft_masked_f32", _p(X), _p(mask), float(mask_scale), _p(batch.fr_off), batch.B, _p(y), _p(y_off), _p(y_len),
-              int(max_len), n_fft, hop, X.shape[1], _stream())
+    with torch.cuda.device(X.device):
+        _lib.call("dvae_istft_masked_f32", _p(X), _p(mask), float(mask_scale), _p(batch.fr_off), batch.B, _p(y), _p(y_off), _p(y_len),
+                  int(max_len), n_fft, hop, X.shape[1], _stream())
     return y
 
 
@@ -204,11 +219,12 @@ def mlp_forward(mlp: PackedMlp, x: torch.Tensor, act_last: int, x2: Optional[tor
     k2 = 0 if x2 is None else x2.shape[1]
     if out is None:
         out = torch.empty((rows, mlp.out_dim), dtype=torch.float32, device=x.device)
-    need = _lib.load().dvae_mlp_workspace_floats(mlp.ref, rows)
+    need = _lib.load().dvae_mlp_workspace_floats(mlp.ref, rows)          # a host-side size formula, no device work
     if ws is None or ws.numel() < need:
         ws = torch.empty(max(need, 1), dtype=torch.float32, device=x.device)
-    _lib.call("dvae_mlp_fwd", mlp.ref, _p(x), x.stride(0), k1, _p(x2), 0 if x2 is None else x2.stride(0), k2,
-              max(1, x2_row_div), rows, act_last, _p(out), out.stride(0), _p(ws), _stream())
+    with torch.cuda.device(x.device):
+        _lib.call("dvae_mlp_fwd", mlp.ref, _p(x), x.stride(0), k1, _p(x2), 0 if x2 is None else x2.stride(0), k2,
+                  max(1, x2_row_div), rows, act_last, _p(out), out.stride(0), _p(ws), _stream())
     return out
 
 
@@ -226,7 +242,8 @@ class McemConfig:
     n_chains: int = 1
     seed: int = 0
     sampler: str = "fp32"        # "fp32": CUDA-core exact mode; "tc": tcgen05 BF16 kernels; "auto": tc when supported
-    fuse_wstat: bool = True      # tc only: fold the W-update reductions into the kept-sample decode
+    fuse_wstat: bool = True      # tc only: per-frame statistics of the W update instead of a pass over Vs
+    emit_vs: bool = True         # tc only: the sampler writes the kept samples' variances itself (BF16); False: FP32 decode
 
 
 class InjectedDraws:
@@ -316,7 +333,7 @@ class McemEngine:
 
     def stage_times_ms(self, reset=True):
         """Sum of device time per stage (ms) and number of bracketed calls, from the recorded CUDA events."""
-        torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(self.dev).synchronize()
         out = {}
         for name, t0, t1 in self._events:
             ms, n = out.get(name, (0.0, 0))
@@ -336,6 +353,7 @@ class McemEngine:
             self._buf[key] = t
         return t
 
+    @_on_device
     def init_parameters(self, X: torch.Tensor, P: torch.Tensor, batch: RaggedBatch, y: Optional[torch.Tensor] = None,
                         draws: Optional[InjectedDraws] = None):
         """``EM.init_parameters`` + ``MCEM_*.init_parameters`` (mcem.py:36-58, 195-205, 358-370) for the batch."""
@@ -370,14 +388,37 @@ class McemEngine:
         self.n_accept.zero_()
         self.mh_calls = 0
         self.mh_iter0 = 0
-        self._Ppk_for = None
-        # speech variances of the kept samples: NT * R_E rows, and at least one frame's worth of Wiener samples
-        self.Vs_flat = self._get("Vs", (max(NT * C_ * cfg.keep_E, C_ * cfg.keep_WF), ld))
+        self.vst_R = 0                    # > 0: the last E-step's variances live in the sampler's emission (VsT / vs_idx)
+        self._Vs = None
+        self._last_Zs = None
         self.cost = self._get("cost", (cfg.niter, B), torch.float64)
         self.kernel_launches = 0
 
+    @property
+    def Vs_flat(self):
+        """Dense FP32 buffer for materialised speech variances: NT * R_E rows, and at least one frame's worth of Wiener
+        samples.  Allocated on first use (the tensor-core path with one chain per frame never needs it)."""
+        b, cfg = self.batch, self.cfg
+        return self._get("Vs", (max(b.NT * cfg.n_chains * cfg.keep_E, cfg.n_chains * cfg.keep_WF), self.ld))
+
+    @property
+    def Vs(self):
+        """Speech variances of the last E-step's kept samples, ``[NT][R][ld]`` FP32 (the reference's ``self.Vs`` (R,F,N) up
+        to layout).  When they only exist in the sampler's BF16 emission they are unpacked on demand."""
+        if self._Vs is None and self.vst_R:
+            with torch.cuda.device(self.dev):
+                from . import tc
+                self._Vs = tc.vst_unpack(self, self.vst_R)
+        elif self._Vs is None and getattr(self, "_last_Zs", None) is not None:
+            Zs = self._last_Zs                     # the final filter never materialises its samples: decode them on demand
+            out = torch.zeros((self.batch.NT, Zs.shape[1], self.ld), dtype=torch.float32, device=self.dev)
+            self.decode_samples(Zs, 0, self.batch.NT, out)
+            self._Vs = out
+        return self._Vs
+
     # -- one sample_posterior call (mcem.py:207-277): returns kept samples [NT][C*keep][L]
-    def sample_posterior(self, keep: int, burn: int, draws: Optional[InjectedDraws] = None, a_trace=None):
+    @_on_device
+    def sample_posterior(self, keep: int, burn: int, draws: Optional[InjectedDraws] = None, a_trace=None, emit: bool = False):
         cfg, w, b = self.cfg, self.w, self.batch
         C_, L = cfg.n_chains, w.z_dim
         chains = b.NT * C_
@@ -396,7 +437,7 @@ class McemEngine:
         with self.stage("mh"):
             if cfg.sampler == "tc":
                 from . import tc
-                tc.mh_chain_tc(self, Zs, keep, burn, rng, a_trace)
+                tc.mh_chain_tc(self, Zs, keep, burn, rng, a_trace, emit)
             else:
                 need = _lib.load().dvae_mh_workspace_floats(w.dec.ref, chains, self.F)
                 ws = self._get("mh_ws", (max(int(need), 1),))
@@ -409,6 +450,7 @@ class McemEngine:
         self.mh_iter0 += keep + burn
         return Zs
 
+    @_on_device
     def decode_samples(self, Zs: torch.Tensor, n0: int, n1: int, Vs: torch.Tensor):
         """``compute_Vs`` (mcem.py:280-290) for frames [n0, n1): Vs[(n-n0)][r][ld] = decoder([Zs[n][r]; y[n]])."""
         R, L = Zs.shape[1], Zs.shape[2]
@@ -425,41 +467,62 @@ class McemEngine:
                 mlp_forward(self.w.dec, x, _lib.ACT_EXP, x2=x2, x2_row_div=R, out=out, ws=ws)
                 self.kernel_launches += len(self.w.dec.dims) - 1
 
+    @_on_device
     def e_step(self, draws=None):
+        """E-step (mcem.py:292-308): sample, keep the last state, decode the kept samples.  On the tensor-core path with one
+        chain per frame the sampler emits the variances itself (BF16) and only the per-frame statistics of the W update are
+        computed here; otherwise the kept samples are decoded into FP32 ``Vs``."""
         cfg = self.cfg
+        self.wstat, self._Vs, self.vst_R = None, None, 0
+        if cfg.sampler == "tc":
+            from . import tc
+            if tc.vst_supported(self, cfg.keep_E):
+                self.sample_posterior(cfg.keep_E, cfg.burn_E, draws, emit=True)
+                self.R = self.vst_R = cfg.keep_E
+                with self.stage("decode"):
+                    self.wstat = tc.vst_frame_stats(self, self.R)
+                return
         Zs = self.sample_posterior(cfg.keep_E, cfg.burn_E, draws)
         self.R = Zs.shape[1]
-        self.Vs = self.Vs_flat[: self.batch.NT * self.R].view(self.batch.NT, self.R, self.ld)
-        self.wstat, self.wstat_parts = None, 0
+        self._Vs = self.Vs_flat[: self.batch.NT * self.R].view(self.batch.NT, self.R, self.ld)
         if cfg.sampler == "tc" and self.R % 10 == 0 and cfg.nmf_rank <= 10 and cfg.fuse_wstat:
             from . import tc
             with self.stage("decode"):
-                if os.environ.get("DVAE_TC_DECODE", "v3") == "v2" and self.R in (10, 30):
-                    self.wstat, self.wstat_parts = tc.decode_wstat_tc(self, Zs, self.Vs), WS_PARTS
-                else:
-                    self.wstat = tc.decode_stats_tc(self, Zs, self.Vs)
+                self.wstat = tc.decode_stats_tc(self, Zs, self._Vs)
         else:
-            self.decode_samples(Zs, 0, self.batch.NT, self.Vs)
+            self.decode_samples(Zs, 0, self.batch.NT, self._Vs)
 
+    @_on_device
     def m_step(self, it: int):
         b, cfg = self.batch, self.cfg
         need = _lib.load().dvae_nmf_workspace_floats(b.B, cfg.nmf_rank, self.ld, b.max_frames)
         ws = self._get("nmf_ws", (int(need),))
+        st = self._buf.get("tc_status")
         with self.stage("mstep"):
-            _lib.call("dvae_nmf_mstep", _p(self.P), _p(self.Vs), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
-                      C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), _p(b.frame_utt), b.B, b.NT, self.F, cfg.nmf_rank,
-                      self.ld, b.max_frames, _p(ws), _p(getattr(self, "wstat", None)), getattr(self, "wstat_parts", 0), _stream())
+            if self.vst_R:
+                from . import tc
+                w = self.w
+                _lib.call("dvae_nmf_mstep_vst", w.dec.ref, _p(tc.decoder_image(w)), w.z_dim, w.y_dim, _p(self.P), _p(self.VsT),
+                          _p(self.vs_idx), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
+                          C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), b.B, b.NT, cfg.nmf_rank, self.ld, b.max_frames,
+                          _p(ws), _p(self.wstat), _p(st), _stream())
+            else:
+                _lib.call("dvae_nmf_mstep", _p(self.P), _p(self._Vs), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
+                          C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), _p(b.frame_utt), b.B, b.NT, self.F, cfg.nmf_rank,
+                          self.ld, b.max_frames, _p(ws), _p(getattr(self, "wstat", None)), _p(st), _stream())
         self.kernel_launches += 4
 
+    @_on_device
     def wiener(self, draws=None):
         """``compute_WF(sample=True)`` + the mask application of ``EM.run`` (mcem.py:310-329, 176-177)."""
         cfg, b = self.cfg, self.batch
         Zs = self.sample_posterior(cfg.keep_WF, cfg.burn_WF, draws)
+        self._Vs, self.vst_R, self._last_Zs = None, 0, Zs
         R = Zs.shape[1]
         WFs = self._get("WFs", (b.NT, self.ld))
         WFn = self._get("WFn", (b.NT, self.ld))
         chunk = next((c for c in (30, 25, 10) if R % c == 0), 0)
-        if cfg.sampler == "tc" and chunk and os.environ.get("DVAE_TC_WIENER", "fused") != "v1":
+        if cfg.sampler == "tc" and chunk:
             # fused: the filter samples are decoded chunk by chunk straight into A1 = sum_r 1 / Vx; the masks follow from
             # mean_r g Vs / Vx = 1 - Vb A1 / R, so none of the R x F x N variances is written to memory
             from . import tc
@@ -485,6 +548,7 @@ class McemEngine:
         self.kernel_launches += 1
         self.WFs, self.WFn, self.R_wf = WFs, WFn, R
 
+    @_on_device
     def run(self, draws: Optional[InjectedDraws] = None):
         """``EM.run`` (mcem.py:156-179): niter x (E-step, M-step, cost), then the Wiener estimates.
 
@@ -508,7 +572,8 @@ class Enhancer:
         self.engine = McemEngine(self.weights, cfg, self.dev)
         self.fs, self.n_fft, self.hop = fs, n_fft, hop
         self._pinned = {}
-        self._out_pool = []
+        self._out_free = []              # pinned result buffers not leased to any caller (see _pin_out)
+        self._h2d_done = None            # event after the last H2D copy out of the pinned staging buffers
         self._pool = None
         self._stage_threads = max(1, min(8, (os.cpu_count() or 1) // 2))
 
@@ -520,21 +585,25 @@ class Enhancer:
         return t[:n]
 
     def _pin_out(self, n):
-        """A pinned float32 result buffer ``(tensor, ndarray)`` that no earlier result still views.
+        """A pinned float32 result buffer leased to the caller: ``(tensor, ndarray)``.
 
-        Results are returned as views of pinned memory (no host copy).  A buffer is recycled only when every array
-        handed out from it has been dropped (the ndarray's reference count is back to the pool's own), otherwise a
-        new one is pinned, so results never change under the caller.
+        Results are returned as views of pinned memory (no extra host copy).  Ownership is explicit: every lease gets a
+        FRESH ndarray object over the pinned storage, the result views handed out keep that object alive through their
+        ``.base``, and the storage goes back to the free list only when the object is collected (``weakref.finalize``),
+        i.e. when the caller has dropped every array of that call.  Results never change under the caller, and no
+        reference counts are inspected.
         """
-        import sys
-        for t, a in self._out_pool:
-            if t.numel() >= n and sys.getrefcount(a) <= 3:         # tuple + loop variable + getrefcount argument
-                return t, a
-        t = torch.empty(n, dtype=torch.float32).pin_memory()
-        a = t.numpy()
-        self._out_pool.append((t, a))
-        if len(self._out_pool) > 8:                                # drop the oldest unreferenced buffers
-            self._out_pool = [(tt, aa) for tt, aa in self._out_pool if sys.getrefcount(aa) > 3 or tt is t][-8:]
+        import weakref
+        k = next((i for i, t in enumerate(self._out_free) if t.numel() >= n), None)
+        t = self._out_free.pop(k) if k is not None else torch.empty(n, dtype=torch.float32).pin_memory()
+        a = t.numpy()                                              # new ndarray object per lease
+        free = self._out_free
+
+        def give_back(tt=t):
+            if len(free) < 4:                                      # keep a few buffers for reuse, let the rest go
+                free.append(tt)
+
+        weakref.finalize(a, give_back)
         return t, a
 
     def _stage(self, host_np, x_list, off, lens):
@@ -557,6 +626,7 @@ class Enhancer:
         for f in futs:
             f.result()
 
+    @_on_device
     def run_device(self, x_dev, x_off, x_len, batch, y, total, max_len, draws=None):
         """The whole path on device-resident inputs: STFT -> MCEM -> Wiener -> ISTFT.  Nothing touches the host.
 
@@ -574,6 +644,7 @@ class Enhancer:
         eng.kernel_launches += 4          # stft, power-free init kernels are counted there; 2 istft + stft + vb
         return s_dev, n_dev, cost
 
+    @_on_device
     def enhance(self, x_list, y_list=None, utt_ids=None, max_frames_list=None, draws=None, return_device=False, s_list=None):
         """Enhance a list of 1-D float32 host signals.  Returns ``(s_hat_list, n_hat_list, cost [B][niter])``.
 
@@ -581,6 +652,10 @@ class Enhancer:
         ``max_frames_list``: optional per-utterance frame caps (the reference truncates to the video length).
         ``s_list``: clean signals; for a model with one label input and no ``y_list`` the labels are the time-domain VAD
         of the clean speech (``clean_speech_VAD``, scripts/evaluate_ntcd_M2.py), computed on the device.
+        ``utt_ids``: global utterance ids = Philox counter word 0; callers that enhance several batches must pass distinct
+        ids per utterance (``batch_io.process_sublist`` does), or every batch replays the same random draws.
+        ``return_device=True`` returns device tensors that alias the engine's output buffers: they are valid until the
+        next call on this Enhancer (clone them to keep them).
         """
         eng, dev = self.engine, self.dev
         B = len(x_list)
@@ -595,6 +670,8 @@ class Enhancer:
         off = np.zeros(B + 1, np.int64)
         np.cumsum((lens + 1) // 2 * 2, out=off[1:])            # even offsets
         total = int(off[-1])
+        if self._h2d_done is not None:          # the previous call's H2D copies must have left the staging buffers
+            self._h2d_done.synchronize()
         host = self._pin("x", total, torch.float32)
         self._stage(host.numpy(), x_list, off, lens)
         x_dev = host.to(dev, non_blocking=True)
@@ -616,22 +693,22 @@ class Enhancer:
             if yc.shape != (batch.NT, self.weights.y_dim):
                 raise ValueError("labels do not cover the frames")
             y = torch.from_numpy(np.ascontiguousarray(yc)).to(dev)
+        self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record()
         s_dev, n_dev, cost = self.run_device(x_dev, x_off, x_len, batch, y, total, int(lens.max()), draws)
         self.h2d_bytes = total * 4 + (0 if y is None else y.numel() * 4)
         self.d2h_bytes = 2 * total * 4 + cost.numel() * 8
+        from . import tc
         if return_device:
+            tc.check_status(eng)                               # synchronises
             return s_dev, n_dev, cost
         hs, s_np = self._pin_out(total)
-        s_hold = s_np[:0]                                      # marks the buffer as taken while the second one is chosen
         hn, n_np = self._pin_out(total)
-        del s_hold
         hs[:total].copy_(s_dev, non_blocking=True)
         hn[:total].copy_(n_dev, non_blocking=True)
         cost_h = cost.t().contiguous().cpu()                   # synchronises the stream
         torch.cuda.current_stream().synchronize()
-        if self.cfg.sampler == "tc":
-            from . import tc
-            tc.check_status(eng)
+        tc.check_status(eng)
         s_list = [s_np[off[u]:off[u] + lens[u]] for u in range(B)]      # views of pinned memory, see _pin_out
         n_list = [n_np[off[u]:off[u] + lens[u]] for u in range(B)]
         return s_list, n_list, cost_h.numpy()

@@ -77,6 +77,12 @@ class _MCEM:
         if dev.type != "cuda":
             raise _lib.DvaeError("dvae_b200 runs on CUDA devices only (got device=%r); there is no CPU fallback" % (device,))
         self.device = dev
+        with torch.cuda.device(dev):               # the reference's workers never call set_device (evaluate_ntcd_M1.py:69,252)
+            self._setup_on_device(X, S, y, vae, nmf_rank, eps, dev, F, N)
+
+    def _setup_on_device(self, X, S, y, vae, nmf_rank, eps, dev, F, N):
+        from ..processing import stft as _stft_shim
+        _stft_shim.set_device(dev)                  # the numpy-facing stft / istft wrappers follow the MCEM device
         sd = vae.state_dict()
         key = (id(vae), str(dev), tuple(int(p._version) for p in vae.parameters()))
         if self._engine is None or self._weights_key != key or self._cfg_rank != (nmf_rank, eps):
@@ -105,20 +111,17 @@ class _MCEM:
         if self.rng == "torch":
             self._draws = TorchCpuDraws(F, nmf_rank, N, self._weights.z_dim)
         eng.init_parameters(Xd, Pd, batch, yd, self._draws)
-        self.Vs = None
-        self.Vs_scaled = None
-        self.Vx = None
 
     def run(self):
         eng = self._engine
-        cost = eng.run(self._draws)
-        F = eng.F
-        if eng.cfg.sampler == "tc":
+        with torch.cuda.device(eng.dev):
+            cost = eng.run(self._draws)
+            F = eng.F
             from ... import tc
             tc.check_status(eng)
-        self.S_hat = np.ascontiguousarray(eng.S_hat[:, :F].t().cpu().numpy())
-        self.N_hat = np.ascontiguousarray(eng.N_hat[:, :F].t().cpu().numpy())
-        return cost[:, 0].cpu().numpy().astype(np.float64)
+            self.S_hat = np.ascontiguousarray(eng.S_hat[:, :F].t().cpu().numpy())
+            self.N_hat = np.ascontiguousarray(eng.N_hat[:, :F].t().cpu().numpy())
+            return cost[:, 0].cpu().numpy().astype(np.float64)
 
     # ---- state exposed with the reference's shapes
     @property
@@ -141,6 +144,24 @@ class _MCEM:
     @property
     def Vb(self):
         return self._engine.Vb[:, :self._engine.F].t()                    # (F, N)
+
+    # The variances of the last sampled set, with the reference's shapes (mcem.py:29-34, 76-80): (R, F, N).  After ``run()``
+    # these are the filter's samples (mcem.py:316-320).  The engine keeps them in its own formats (BF16 emission of the
+    # sampler / never materialised for the filter), so they are produced on first access.
+    @property
+    def Vs(self):
+        v = self._engine.Vs
+        return None if v is None else v[:, :, :self._engine.F].permute(1, 2, 0)
+
+    @property
+    def Vs_scaled(self):
+        v = self.Vs
+        return None if v is None else self._engine.g[None, None, :] * v
+
+    @property
+    def Vx(self):
+        v = self.Vs_scaled
+        return None if v is None else v + self.Vb[None]
 
     @property
     def X_abs_2(self):

@@ -14,13 +14,19 @@ import torch
 
 from ...engine import RaggedBatch, _require_cuda, istft_batch, stft_batch
 
-_DEVICE = 0
+_DEVICE = None
 
 
 def set_device(device):
-    """CUDA device used by the numpy-facing wrappers (default 0)."""
+    """CUDA device used by the numpy-facing wrappers.  Default: the calling thread's current device; the ``MCEM_*`` shims
+    set it to their own device in ``init_parameters``, so a worker that was handed a device index (the reference's
+    ``process_sublist``) keeps its whole utterance loop on that GPU."""
     global _DEVICE
     _DEVICE = device
+
+
+def _device():
+    return torch.cuda.current_device() if (_DEVICE is None and torch.cuda.is_available()) else (0 if _DEVICE is None else _DEVICE)
 
 
 def _sizes(fs, wlen_sec, hop_percent, what):
@@ -55,7 +61,7 @@ def stft(x, fs=16e3, wlen_sec=50e-3, win='hann', hop_percent=0.25, center=True, 
     if Tp < nfft:
         raise ValueError("input shorter than one frame")
     n_frames = 1 + (Tp - nfft) // hopsamp
-    dev = _require_cuda(_DEVICE)
+    dev = _require_cuda(_device())
     xd = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev)
     batch = RaggedBatch([n_frames], dev)
     X, _ = stft_batch(xd, torch.zeros(1, dtype=torch.int64, device=dev), torch.tensor([T], dtype=torch.int32, device=dev),
@@ -73,7 +79,7 @@ def istft(Sxx, fs=16000, wlen_sec=50e-3, win='hann', hop_percent=0.25, center=Tr
         raise ValueError("spectrogram must be (%d, N)" % F)
     N = Sxx.shape[1]
     T = nfft + hopsamp * (N - 1) if max_len is None else int(max_len)      # max_len is in SAMPLES
-    dev = _require_cuda(_DEVICE)
+    dev = _require_cuda(_device())
     ld = (F + 7) // 8 * 8
     X = torch.zeros((N, ld), dtype=torch.complex64, device=dev)
     X[:, :F] = torch.from_numpy(np.ascontiguousarray(Sxx.T.astype(np.complex64))).to(dev)
@@ -105,7 +111,7 @@ def stft_pytorch(x, fs=16e3, wlen_sec=50e-3, win='hann', hop_percent=0.25, cente
     if Tp < nfft:
         raise ValueError("input shorter than one frame")
     n_frames = 1 + (Tp - nfft) // hopsamp
-    dev = x.device if x.is_cuda else _require_cuda(_DEVICE)
+    dev = x.device if x.is_cuda else _require_cuda(_device())
     xd = x.detach().to(device=dev, dtype=torch.float32).contiguous()
     with torch.cuda.device(dev):
         X, _ = stft_batch(xd, torch.zeros(1, dtype=torch.int64, device=dev), torch.tensor([T], dtype=torch.int32, device=dev),
@@ -128,7 +134,7 @@ def istft_pytorch(Sxx, fs=16000, wlen_sec=50e-3, win='hann', hop_percent=0.25, c
         raise ValueError("spectrogram must be (%d, N)" % F)
     N = int(Sxx.shape[1])
     T = nfft + hopsamp * (N - 1)
-    dev = Sxx.device if Sxx.is_cuda else _require_cuda(_DEVICE)
+    dev = Sxx.device if Sxx.is_cuda else _require_cuda(_device())
     ld = (F + 7) // 8 * 8
     X = torch.zeros((N, ld), dtype=torch.complex64, device=dev)
     X[:, :F] = Sxx.detach().to(device=dev, dtype=torch.complex64).t()

@@ -1,8 +1,8 @@
 """Host glue of the tcgen05 (BF16 tensor-core) sampler and decode: packed operands and the C ABI calls.
 
 ``mh_chain_tc`` / ``decode_tc`` are what ``McemEngine`` runs when ``McemConfig.sampler == "tc"``.  Everything here is
-bookkeeping: building the decoder's shared-memory image once per model, re-tiling P once per batch and Vb once per
-``sample_posterior`` call, and checking the kernel's status word.
+bookkeeping: building the decoder's shared-memory image once per model, re-packing P / Vb once per ``sample_posterior``
+call, sizing the sampler's emission buffers and checking the status word.
 """
 from __future__ import annotations
 
@@ -25,6 +25,8 @@ def _stream():
 POLY_EX2 = 1            # DVAE_TC_POLY_EX2
 POLY_EX2_ALL = 2        # DVAE_TC_POLY_EX2_ALL
 POLY_EX2_LIMIT = 120.0  # DVAE_TC_POLY_EX2_LIMIT
+VST_MAX_KEEP = 31       # kept samples per chain the sampler's emission can index
+VST_IDX_PITCH = 32
 
 
 def decoder_image(weights):
@@ -41,19 +43,9 @@ def decoder_image(weights):
         # one-off range query: may the sampler use the polynomial 2^x (see DVAE_TC_POLY_EX2 in include/dvae_b200.h)?
         bound = C.c_float(0.0)
         _lib.call("dvae_tc_decoder_exponent_bound", weights.dec.ref, weights.z_dim, weights.y_dim, C.byref(bound), _stream())
-        mode = os.environ.get("DVAE_TC_POLY", "1")          # 0: MUFU only, 1: half of the exponentials, 2: all of them (tc2 sampler)
+        mode = os.environ.get("DVAE_TC_POLY", "1")          # 0: MUFU only, 1: half of the exponentials, 2: all of them
         weights._tc_flags = ({"0": 0, "2": POLY_EX2 | POLY_EX2_ALL}.get(mode, POLY_EX2)) if bound.value < POLY_EX2_LIMIT else 0
     return img
-
-
-def pack_rows(eng, name, src):
-    """Frame-major [NT][ld] -> [tile][quad][128 chains][4] (see dvae_tc_pack_rows)."""
-    b, C_ = eng.batch, eng.cfg.n_chains
-    n = int(_lib.load().dvae_tc_packed_floats(b.NT * C_))
-    dst = eng._get(name, (max(n, 4),))
-    _lib.call("dvae_tc_pack_rows", _p(src), b.NT, C_, eng.F, eng.ld, _p(dst), _stream())
-    eng.kernel_launches += 1
-    return dst
 
 
 def _status(eng):
@@ -65,52 +57,72 @@ def _status(eng):
 
 
 def check_status(eng):
-    """Raise if any tensor-core kernel of this engine reported a pipeline timeout (synchronises)."""
+    """Raise if a kernel of this engine reported a pipeline timeout or a non-finite likelihood / cost (synchronises).
+    The status word is cleared when the error is raised, so the engine can be used again."""
     st = eng._buf.get("tc_status")
-    if st is not None and int(st.item()) != 0:
-        raise _lib.DvaeError("tcgen05 kernel reported a pipeline timeout (status %d): results are invalid" % int(st.item()))
+    if st is None:
+        return
+    v = int(st.item())
+    if v == 0:
+        return
+    st.zero_()
+    what = []
+    if v & _lib.STATUS_TIMEOUT:
+        what.append("a tcgen05 pipeline wait timed out")
+    if v & _lib.STATUS_NONFINITE:
+        what.append("a log-likelihood or cost was NaN / Inf")
+    raise _lib.DvaeError("device status %d (%s): results are invalid" % (v, "; ".join(what) or "unknown"))
 
 
-def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace):
+def vst_supported(eng, keep):
+    """The sampler's own emission of the kept samples' variances serves one chain per frame, up to 31 kept samples, and
+    (for the fused M-step kernel) R in {10, 30}, K <= 10, F = 513."""
+    return (eng.cfg.n_chains == 1 and keep in (10, 30) and eng.cfg.nmf_rank <= 10 and eng.F == 513 and eng.ld == 520
+            and eng.cfg.fuse_wstat and eng.cfg.emit_vs)
+
+
+def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace, emit=False):
+    """One ``sample_posterior`` call on the tcgen05 sampler.  ``emit``: also write the kept samples' variances
+    (``eng.VsT`` / ``eng.vs_idx``, see dvae_mh_chain_tc2)."""
     w, b, cfg = eng.w, eng.batch, eng.cfg
     img = decoder_image(w)
-    v2 = w.z_dim in (16, 32) and w.y_dim <= 3 and os.environ.get("DVAE_TC_SAMPLER", "v2") != "v1"
-    if not v2:
-        if getattr(eng, "_Ppk_for", None) is not eng.P:
-            eng._Ppk = pack_rows(eng, "Ppk", eng.P)
-            eng._Ppk_for = eng.P
-        Vbpk = pack_rows(eng, "Vbpk", eng.Vb)
-        _lib.call("dvae_mh_chain_tc", w.dec.ref, _p(img), _p(eng._Ppk), _p(Vbpk), _p(eng.g), _p(eng.y), w.y_dim,
-                  _p(b.frame_gid), _p(b.frame_idx), _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep,
-                  float(cfg.var_rw), C.byref(rng), _p(eng.n_accept), _p(a_trace), _p(_status(eng)), _stream())
-        eng.kernel_launches += 1
-        return
-    # v2 reads its draws from global memory: injected ones as they are, Philox ones dumped by the generator kernel
-    n_iter, chains = keep + burn, b.NT * cfg.n_chains
-    if rng.eps:
-        eps_ptr, u_ptr = C.c_void_p(rng.eps), C.c_void_p(rng.u)
-    else:
-        eps = eng._get("tc_eps", (n_iter * chains * w.z_dim,))
-        u = eng._get("tc_u", (n_iter * chains,))
-        _lib.call("dvae_rng_dump", C.byref(rng), _p(b.frame_gid), _p(b.frame_idx), b.NT, cfg.n_chains, w.z_dim, n_iter,
-                  _p(eps), _p(u), _stream())
-        eng.kernel_launches += 1
-        eps_ptr, u_ptr = _p(eps), _p(u)
-    gen = os.environ.get("DVAE_TC_SAMPLER", "v2")
-    fn = "dvae_mh_chain_tc3" if (gen == "v3" and w.z_dim == 16) else ("dvae_mh_chain_tc4" if gen == "v4" else "dvae_mh_chain_tc2")
-    nb = int(_lib.load().dvae_tc_packed_pv_bytes(chains))
-    pv = eng._get("PVpk", (max(nb, 16),), torch.uint8)
+    chains = b.NT * cfg.n_chains
+    lib = _lib.load()
+    pv = eng._get("PVpk", (max(int(lib.dvae_tc_packed_pv_bytes(chains)), 16),), torch.uint8)
     _lib.call("dvae_tc_pack_pv", w.dec.ref, _p(img), w.z_dim, w.y_dim, _p(eng.P), _p(eng.Vb), b.NT, cfg.n_chains, eng.F, eng.ld,
               _p(pv), _stream())
     eng.kernel_launches += 1
+    vst = idx = None
+    if emit:
+        vst = eng._get("VsT", (max(int(lib.dvae_vst_bytes(chains, keep)), 16),), torch.uint8)
+        idx = eng._get("vs_idx", (max(chains, 1) * VST_IDX_PITCH,), torch.uint8)
     with eng.stage("mh_kernel"):
-        args = (w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains,
-                burn, keep, float(cfg.var_rw), eps_ptr, u_ptr, _p(eng.n_accept), _p(a_trace))
-        if fn != "dvae_mh_chain_tc3":
-            _lib.call(fn, *args, int(w._tc_flags), _p(_status(eng)), _stream())
-        else:
-            _lib.call(fn, *args, _p(_status(eng)), _stream())
+        _lib.call("dvae_mh_chain_tc2", w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, _p(b.frame_gid), _p(b.frame_idx),
+                  _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep, float(cfg.var_rw), C.byref(rng), _p(eng.n_accept),
+                  _p(a_trace), _p(vst), _p(idx), int(w._tc_flags), _p(_status(eng)), _stream())
     eng.kernel_launches += 1
+    eng.VsT, eng.vs_idx = vst, idx
+
+
+def vst_frame_stats(eng, R):
+    """A1 | A2 (``[2][NT][ld]``) of the emitted samples with the E-step's g and Vb (dvae_vst_frame_stats)."""
+    w, b = eng.w, eng.batch
+    st = eng._get("fstat", (2 * b.NT * eng.ld,))
+    A1, A2 = st[: b.NT * eng.ld], st[b.NT * eng.ld:]
+    _lib.call("dvae_vst_frame_stats", w.dec.ref, _p(decoder_image(w)), w.z_dim, w.y_dim, _p(eng.VsT), _p(eng.vs_idx), R, _p(eng.Vb),
+              _p(eng.g), b.NT, eng.ld, _p(A1), _p(A2), _stream())
+    eng.kernel_launches += 1
+    return st
+
+
+def vst_unpack(eng, R, out=None):
+    """Dense FP32 ``Vs [NT][R][ld]`` of the emitted samples (dvae_vst_unpack): the reference's ``self.Vs`` up to layout."""
+    w, b = eng.w, eng.batch
+    if out is None:
+        out = torch.zeros((b.NT, R, eng.ld), dtype=torch.float32, device=eng.dev)
+    _lib.call("dvae_vst_unpack", w.dec.ref, _p(decoder_image(w)), w.z_dim, w.y_dim, _p(eng.VsT), _p(eng.vs_idx), R, b.NT, eng.ld,
+              _p(out), _stream())
+    return out
 
 
 def decode_tc(eng, x, x2, x2_row_div, out):
@@ -120,20 +132,6 @@ def decode_tc(eng, x, x2, x2_row_div, out):
     _lib.call("dvae_decode_tc", w.dec.ref, _p(img), _p(x), x.shape[0], w.z_dim, _p(x2), w.y_dim, max(1, x2_row_div), _p(out),
               out.stride(0), _p(_status(eng)), _stream())
     eng.kernel_launches += 1
-
-
-def decode_wstat_tc(eng, Zs, Vs):
-    """Kept-sample decode fused with the W-update statistics (dvae_decode_ws_tc); returns the statistics buffer."""
-    from .engine import WS_PARTS
-    w, b, cfg = eng.w, eng.batch, eng.cfg
-    img = decoder_image(w)
-    n = int(_lib.load().dvae_decode_ws_workspace_floats(b.B, WS_PARTS, eng.ld))
-    ws = eng._get("wstat", (n,))
-    _lib.call("dvae_decode_ws_tc", w.dec.ref, _p(img), _p(Zs), Zs.shape[1], w.z_dim, _p(eng.y), w.y_dim, _p(eng.P), _p(eng.Vb),
-              _p(eng.g), _p(eng.H), cfg.nmf_rank, _p(b.fr_off), b.B, b.NT, eng.ld, _p(Vs), _p(ws), WS_PARTS, _p(_status(eng)),
-              _stream())
-    eng.kernel_launches += 1
-    return ws
 
 
 def decode_stats_tc(eng, Zs, Vs):
@@ -168,4 +166,3 @@ def decode_a1_tc(eng, Zs, r0, R):
               _p(eng.g), b.NT, eng.ld, _p(A1), _p(_status(eng)), _stream())
     eng.kernel_launches += 1
     return A1
-

@@ -31,11 +31,15 @@
 extern "C" {
 #endif
 
-#define DVAE_ABI_VERSION 1
+#define DVAE_ABI_VERSION 2
 #define DVAE_ERR_ARG (-1)
 #define DVAE_MAX_LAYERS 6
 #define DVAE_MAX_L 64          /* latent dimension limit of the Metropolis-Hastings kernels */
 #define DVAE_MAX_K 16          /* NMF rank limit */
+
+/* bits of the device status word (`int* status`) some entry points take: it is OR-ed into, never cleared by the library */
+#define DVAE_STATUS_TIMEOUT 1      /* a tcgen05 kernel's internal pipeline wait ran out: results invalid */
+#define DVAE_STATUS_NONFINITE 2    /* NaN / Inf guard: a chain's log-likelihood or an utterance's cost was not finite */
 
 /* activation applied after the LAST layer of dvae_mlp_fwd (hidden layers are always tanh, models.py:102-104,119-121) */
 #define DVAE_ACT_NONE 0
@@ -117,7 +121,9 @@ int64_t dvae_nmf_workspace_floats(int B, int K, int ld, int max_frames);
 int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, float* H, float* g, float* Vb, double* cost,
                    const int64_t* fr_off, const int32_t* frame_utt, int B, int64_t NT, int F, int K, int ld,
                    int max_frames /* max_u frames of one utterance, for grid sizing */, float* ws,
-                   const float* wstat /* nullable: W statistics from dvae_decode_ws_tc */, int n_parts, void* stream);
+                   const float* wstat /* nullable: frame statistics A1 | A2 (dvae_decode_stats_tc), replace the pass over Vs of
+                                         the W update */,
+                   int* status /* nullable: DVAE_STATUS_NONFINITE is OR-ed in when a cost is not finite */, void* stream);
 
 /* ---- Metropolis-Hastings E-step sampler: mcem.py:207-277 / 372-448 / 544-620 / 716-792 ----
  * FP32 CUDA-core decoder ("exact" mode).  Runs n_burn + n_keep random-walk iterations on every (frame, chain):
@@ -150,50 +156,60 @@ int dvae_wiener_apply(const void* X, const float* WFs, const float* WFn, int R_t
  * Specialised for F = 513 bins, hidden width 128, 1 or 2 hidden layers, 2L + 2*y_dim + 1 <= 128.
  * dvae_tc_pack_decoder builds the shared-memory image of the decoder (UMMA K-major 128B-swizzled BF16 operands +
  * FP32 biases; W3/b3 pre-scaled by log2 e) into `image` (dvae_tc_image_bytes bytes, 16-byte aligned).
- * dvae_tc_pack_rows re-tiles a frame-major [NT][ld] array (P or Vb) to [tile][bin quad][128 chains][4] for the
- * sampler's coalesced 16-byte loads (dvae_tc_packed_floats floats).
- * dvae_mh_chain_tc: same contract as dvae_mh_chain_f32 with packed P / Vb; *status is set non-zero if the kernel's
- * internal pipeline timed out (results invalid).  dvae_decode_tc: Vs[r][0..F) = decoder([Zs[r]; y[r / x2_row_div]]). */
+ * dvae_decode_tc: Vs[r][0..F) = decoder([Zs[r]; y[r / x2_row_div]]) for any number of rows; *status: DVAE_STATUS_* bits. */
 int64_t dvae_tc_image_bytes(const DvaeMlp* dec, int L, int y_dim);
 int dvae_tc_pack_decoder(const DvaeMlp* dec, int L, int y_dim, void* image, void* stream);
-int64_t dvae_tc_packed_floats(int64_t chains);
-int dvae_tc_pack_rows(const float* src, int64_t NT, int n_chains, int F, int ld, float* dst, void* stream);
-int dvae_mh_chain_tc(const DvaeMlp* dec, const void* image, const float* Ppk, const float* Vbpk, const float* g,
-                     const float* y, int y_dim, const int32_t* frame_utt, const int32_t* frame_idx, float* Z, float* Zs,
-                     int64_t NT, int L, int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng,
-                     uint32_t* n_accept, float* a_trace, int* status, void* stream);
 int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64_t rows, int L, const float* y, int y_dim,
                    int x2_row_div, float* Vs, int ld, int* status, void* stream);
-/* second-generation schedule of the same sampler (software-pipelined P / Vb stream, mbarrier chunk hand-over,
- * register-resident chain state); L in {16, 32}, y_dim <= 3.  The draws always come from global memory:
- * eps[n_iter][NT*C][L], u[n_iter][NT*C] (16-byte aligned), either injected by the caller or produced by
- * dvae_rng_dump with the Philox counters every sampler of this library uses.  P and Vb are streamed at BF16 precision
- * (dvae_tc_pack_pv: [tile][bin quad][128 chains] x 4 words, word j = P'_j with bf16(Vb'_j) as its low half, the
- * layer-3 bias of `image` folded in as a per-bin scale; dvae_tc_packed_pv_bytes bytes). */
+
+/* The Metropolis-Hastings sampler on tensor cores: same contract as dvae_mh_chain_f32 (Z, Zs, frame_utt / frame_idx,
+ * rng, n_accept, a_trace); L in {16, 32}, y_dim <= 3.  Draws: counter-based Philox inside the kernel (rng->eps == NULL,
+ * the counters of every sampler of this library) or injected eps / u (16-byte aligned).  P and Vb are streamed at BF16
+ * precision (dvae_tc_pack_pv: [tile][bin quad][128 chains] x 4 words, word j = P'_j with bf16(Vb'_j) as its low half, the
+ * layer-3 bias of `image` folded in as a per-bin scale; dvae_tc_packed_pv_bytes bytes).
+ * Emission (VsT, vs_idx non-NULL; n_keep <= 31): the decoder output of the kept samples -- compute_Vs, mcem.py:280-290 --
+ * is written by the sampler itself, in BF16 and WITHOUT the output-layer bias E[f] = exp(b3[f]):
+ *   VsT[tile = chain / 128][slot 0..n_keep][bg = bin / 16 (33)][row = chain % 128][16] bf16  (dvae_vst_bytes bytes),
+ *   vs_idx[chain][32] bytes: byte r = slot of kept sample r, i.e. Vs[chain][r][f] = E[f] VsT[..][vs_idx[chain][r]][..].
+ * flags: DVAE_TC_POLY_EX2 lets the sampler evaluate half of the layer-3 exponentials with a polynomial on the FMA pipe
+ * (relative error 7.5e-5) instead of MUFU.EX2; only valid when the pre-activation stays inside +-120 in the log2
+ * domain, i.e. when dvae_tc_decoder_exponent_bound (a one-off, synchronising query: log2(e) * max_f sum_k |W3[k][f]|)
+ * reports less than DVAE_TC_POLY_EX2_LIMIT for the decoder.
+ * *status: DVAE_STATUS_TIMEOUT / DVAE_STATUS_NONFINITE are OR-ed in. */
+#define DVAE_TC_POLY_EX2 1
+#define DVAE_TC_POLY_EX2_ALL 2      /* all layer-3 exponentials from the polynomial (same validity condition) */
+#define DVAE_TC_POLY_EX2_LIMIT 120.0f
 int64_t dvae_tc_packed_pv_bytes(int64_t chains);
 int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const float* Vb, int64_t NT,
                     int n_chains, int F, int ld, void* dst, void* stream);
-/* flags: DVAE_TC_POLY_EX2 lets the sampler evaluate half of the layer-3 exponentials with a polynomial on the FMA pipe
- * (relative error 7.5e-5) instead of MUFU.EX2; only valid when the pre-activation stays inside +-120 in the log2
- * domain, i.e. when dvae_tc_decoder_exponent_bound (a one-off, synchronising query: log2(e) * max_f sum_k |W3[k][f]|)
- * reports less than DVAE_TC_POLY_EX2_LIMIT for the decoder. */
-#define DVAE_TC_POLY_EX2 1
-#define DVAE_TC_POLY_EX2_ALL 2      /* dvae_mh_chain_tc2 only: all layer-3 exponentials from the polynomial (same validity condition) */
-#define DVAE_TC_POLY_EX2_LIMIT 120.0f
 int dvae_tc_decoder_exponent_bound(const DvaeMlp* dec, int L, int y_dim, float* bound_host, void* stream);
-int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
-                      const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
-                      int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
-                      int flags, int* status, void* stream);
-/* fourth-generation schedule, same arguments and results as dvae_mh_chain_tc2: two tiles in flight per CTA (front warps:
- * accept / propose / layers 1-2, back warps: layer-3 likelihood), the layer-3 A operand held in tensor memory */
-int dvae_mh_chain_tc4(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
-                      const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
-                      int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
-                      int flags, int* status, void* stream);
+int64_t dvae_vst_bytes(int64_t chains, int n_keep);
+int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g, const float* y, int y_dim,
+                      const int32_t* frame_utt, const int32_t* frame_idx, float* Z, float* Zs, int64_t NT, int L,
+                      int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng, uint32_t* n_accept,
+                      float* a_trace, void* VsT /* nullable */, uint8_t* vs_idx /* nullable */, int flags, int* status,
+                      void* stream);
 
-/* Warp-specialised decode with per-frame statistics (R in {10,30}): writes Vs[NT][R][ld], A1[n][f] = sum_r 1/Vx and
- * A2[n][f] = sum_r 1/Vx^2; dvae_nmf_mstep takes them as wstat = A1 (A2 = A1 + NT*ld) with n_parts = 0. */
+/* Consumers of the emission (one chain per frame: chain = frame).
+ * dvae_vst_frame_stats: A1[n][f] = sum_r 1/Vx, A2[n][f] = sum_r 1/Vx^2 with Vx = g[n] Vs[n][r][f] + Vb[n][f]: the inner
+ *   sums of the W update (mcem.py:108-110); R <= 31.
+ * dvae_nmf_mstep_vst: dvae_nmf_mstep on the emission (F = 513, ld = 520, K <= 10, R in {10, 30}); fstat = A1 | A2
+ *   (A2 = A1 + NT*ld) from dvae_vst_frame_stats.
+ * dvae_vst_unpack / dvae_vst_pack: conversion to / from dense FP32 Vs[NT][R][ld] (pack: sample r -> slot 1 + r). */
+int dvae_vst_frame_stats(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx,
+                         int R, const float* Vb, const float* g, int64_t NT, int ld, float* A1, float* A2, void* stream);
+int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const void* VsT,
+                       const uint8_t* vs_idx, int R, float* W, float* H, float* g, float* Vb, double* cost,
+                       const int64_t* fr_off, int B, int64_t NT, int K, int ld, int max_frames, float* ws,
+                       const float* fstat, int* status, void* stream);
+int dvae_vst_unpack(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx, int R,
+                    int64_t NT, int ld, float* Vs, void* stream);
+int dvae_vst_pack(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* Vs, int R, int64_t NT, int ld,
+                  void* VsT, uint8_t* vs_idx, void* stream);
+
+/* Warp-specialised decode with per-frame statistics (R in {10,30}): writes FP32 Vs[NT][R][ld], A1[n][f] = sum_r 1/Vx and
+ * A2[n][f] = sum_r 1/Vx^2; dvae_nmf_mstep takes them as wstat = A1 (A2 = A1 + NT*ld).  Used when the sampler's emission
+ * does not apply (several chains per frame, injected kept samples). */
 int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y, int y_dim,
                          const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1, float* A2, int* status,
                          void* stream);
@@ -209,19 +225,9 @@ int dvae_decode_a1_tc(const DvaeMlp* dec, const void* image, const float* Zs, in
                       int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* A1, int* status, void* stream);
 int dvae_wiener_from_a1(const float* A1, const float* Vb, int R, int64_t NT, int F, int ld, float* WFs, float* WFn, int first,
                         void* stream);
+/* W <- W sqrt(num / den), num[f,k] = sum_n P A2 H, den[f,k] = sum_n A1 H (mcem.py:108-111); Wtmp: un-normalised result */
 int dvae_nmf_w_from_frame_stats(const float* A1, const float* A2, const float* P, const float* H, const float* W,
                                 const int64_t* fr_off, int B, int F, int K, int ld, float* Wtmp, void* stream);
-
-/* third-generation schedule: two tile contexts per CTA, W3 streamed chunk-wise with cp.async.bulk (L = 16 only).
- * Same arguments and results as dvae_mh_chain_tc2. */
-int dvae_mh_chain_tc3(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
-                      const float* y, int y_dim, float* Z, float* Zs, int64_t NT, int L, int n_chains, int n_burn,
-                      int n_keep, float var_rw, const float* eps, const float* u, uint32_t* n_accept, float* a_trace,
-                      int* status, void* stream);
-int dvae_debug_set_clock_buffer3(void* dev_buffer);
-int dvae_debug_set_clock_buffer_ws(void* dev_buffer);
-int dvae_debug_set_clock_buffer_ds(void* dev_buffer);
-int dvae_debug_set_clock_buffer4(void* dev_buffer);
 
 /* ---- evaluation metric on the device (packages/metrics.py:12-82: si_sdr_components, energy_ratios, si_sdr_leroux) ----
  * Ragged batch: utterance u occupies [off[u], off[u] + len[u]) of s_hat / s / n (n nullable).  out[u] = {SI-SDR, SI-SIR,
@@ -241,18 +247,6 @@ int dvae_vad_labels(const float* x, const int64_t* x_off, const int32_t* x_len, 
                     void* stream);
 int dvae_ibm_labels(const void* S, const int32_t* frame_utt, const int64_t* fr_off, int B, int64_t NT, int F, int ld,
                     float eps, float ibm_threshold_db, const float* vad, float* mask, void* ws, void* stream);
-
-/* debug aid: register a device buffer of 64 int64; the tc2 sampler's CTA 0 stamps clock64() at its phase boundaries */
-int dvae_debug_set_clock_buffer(void* dev_buffer);
-
-/* Fused decode + W-update statistics (mcem.py:280-290 + the reductions of 108-110), R in {10, 30}, K <= 10:
- * writes Vs[NT][R][ld] and, per (utterance, part), num/den partial sums into ws (dvae_decode_ws_workspace_floats
- * floats); dvae_nmf_mstep consumes them through its wstat argument, dvae_nmf_w_from_stats is the reduction it runs. */
-int64_t dvae_decode_ws_workspace_floats(int B, int n_parts, int ld);
-int dvae_decode_ws_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y, int y_dim,
-                      const float* P, const float* Vb, const float* g, const float* H, int K, const int64_t* fr_off, int B,
-                      int64_t NT, int ld, float* Vs, float* ws, int n_parts, int* status, void* stream);
-int dvae_nmf_w_from_stats(const float* ws, int n_parts, const float* W, int B, int F, int K, int ld, float* Wtmp, void* stream);
 
 /* uniform [eps,1) initialisation of W, H and g = 1 from Philox (mcem.py:42-44: max(rand, eps)) */
 int dvae_nmf_init(uint64_t seed, const int32_t* utt_ids /*[B] global ids*/, const int64_t* fr_off, int B, int64_t NT, int F,

@@ -66,9 +66,12 @@ def test_estep_decode_keeps_pad_columns_and_tail_rows(variant, keep):
     eng = McemEngine(w, McemConfig(niter=1, keep_E=keep, burn_E=4, keep_WF=keep, burn_WF=4, sampler="tc"), DEV)
     y = None if y_dim == 0 else torch.tensor(rng.integers(0, 2, size=(NT, 1)).astype(np.float32)).to(DEV)
     eng.init_parameters(X, P, RaggedBatch(N, DEV), y)
-    eng.Vs_flat.fill_(SENT)
-    eng.e_step()
-    Vs = eng.Vs
+    from dvae_b200 import tc
+    Zs = eng.sample_posterior(keep, 4)
+    flat = torch.full(((NT + 3) * keep, 520), SENT, device=DEV)
+    Vs = flat[: NT * keep].view(NT, keep, 520)
+    tc.decode_stats_tc(eng, Zs, Vs)
+    tc.check_status(eng)
     assert bool((Vs[:, :, 513:] == SENT).all()), "pad columns of Vs were written"
-    assert bool((eng.Vs_flat[NT * eng.R:] == SENT).all()), "rows beyond the batch were written"
+    assert bool((flat[NT * keep:] == SENT).all()), "rows beyond the batch were written"
     assert bool(torch.isfinite(Vs[:, :, :513]).all()) and bool((Vs[:, :, :513] > 0).all())

@@ -102,7 +102,7 @@ def test_m_step_matches_oracle(F, N, K, R):
         cost = torch.zeros(B, dtype=torch.float64, device=DEV)
         ws = torch.empty(int(_lib.load().dvae_nmf_workspace_floats(B, K, ld, batch.max_frames)), device=DEV)
         _lib.call("dvae_nmf_mstep", _p(Pd), _p(Vsd), R, _p(Wd), _p(Hd), _p(gd), _p(Vbd), _p(cost), _p(batch.fr_off),
-                  _p(batch.frame_utt), B, N, F, K, ld, batch.max_frames, _p(ws), None, 0, _stream())
+                  _p(batch.frame_utt), B, N, F, K, ld, batch.max_frames, _p(ws), None, None, _stream())
         assert relerr(Wd[0, :, :F].t().cpu().numpy(), ref["W"].numpy()) <= 1e-4
         assert relerr(Hd.t().cpu().numpy(), ref["H"].numpy()) <= 1e-4
         assert relerr(gd.cpu().numpy(), ref["g"].numpy()) <= 1e-4
@@ -133,7 +133,7 @@ def test_m_step_batch_equals_single():
         cost = torch.zeros(len(idx), dtype=torch.float64, device=DEV)
         ws = torch.empty(int(_lib.load().dvae_nmf_workspace_floats(len(idx), K, ld, batch.max_frames)), device=DEV)
         _lib.call("dvae_nmf_mstep", _p(Pd), _p(Vsd), R, _p(Wd), _p(Hd), _p(gd), _p(Vbd), _p(cost), _p(batch.fr_off),
-                  _p(batch.frame_utt), len(idx), N, F, K, ld, batch.max_frames, _p(ws), None, 0, _stream())
+                  _p(batch.frame_utt), len(idx), N, F, K, ld, batch.max_frames, _p(ws), None, None, _stream())
         return Wd.cpu(), Hd.cpu(), gd.cpu(), cost.cpu(), batch
 
     Wb, Hb, gb, cb, batch = run([0, 1, 2])

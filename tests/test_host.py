@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "libdvae_b200.so does not export %s" % n
     assert set(names) == set(_lib.PROTOTYPES), "ctypes prototypes and header disagree"
-    assert _lib.load().dvae_version() == 1
+    assert _lib.load().dvae_version() == _lib.ABI_VERSION
 
 
 def test_library_is_sm100a_only():
