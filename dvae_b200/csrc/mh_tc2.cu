@@ -25,6 +25,8 @@
 //   * every TMEM read is double-buffered, the layer-2 bias is preloaded into the layer-2 accumulator (tcgen05.st) while
 //     the layer-1 GEMM runs, and the first P / Vb sub-chunks are requested two phases before the layer-3 loop
 //     (phase clocks before / after in DESIGN.md section 4).
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace dvae {
@@ -46,7 +48,8 @@ struct Mh2Params {
     const float* u;               // injected draws [n_iter][rows] uniforms
     const int32_t* frame_gid;     // Philox counter words per frame: global utterance id, frame index inside the utterance
     const int32_t* frame_idx;
-    uint32_t seed_lo, seed_hi, iter0;
+    PhiloxKeys keys;              // round keys of the run seed (read from the parameter bank)
+    uint32_t iter0;
     uint32_t* n_accept;
     float* a_trace;
     int n_burn, n_keep;
@@ -60,8 +63,8 @@ struct Mh2Params {
 };
 
 
-// 16 bins of the log-likelihood (loglik16_pv of tc_common.cuh) that also hands back 2^v of the 16 bins as eight bf16x2
-// words (bin 2j in the low half of word j): the sampler's emission of the kept samples' variances.
+// 16 bins of the log-likelihood (loglik16_pv of tc_common.cuh) that also hands back 2^v of the 16 bins as eight "VsT words"
+// (common.cuh: bin 2j as bf16 in the low half, the whole word nearest to bin 2j+1): the emission of the kept samples' variances.
 template <int POLY>
 __device__ __forceinline__ void loglik16_pv_emit(const float* v, const uint4* pv, float g_row, float& acc, float& accl, uint32_t* out) {
     const f32x2 g2 = pk2(g_row, g_row), g2k = pk2(g_row * kPairScale, g_row * kPairScale);
@@ -76,8 +79,8 @@ __device__ __forceinline__ void loglik16_pv_emit(const float* v, const uint4* pv
             float e0, e1, e2, e3;
             upk2(e01, e0, e1);
             upk2(e23, e2, e3);
-            out[2 * qd] = pack_bf16x2(e0, e1);
-            out[2 * qd + 1] = pack_bf16x2(e2, e3);
+out[2 * qd] = vst_word(e0, e1);
+            out[2 * qd + 1] = vst_word(e2, e3);
         }
         const f32x2 M = mul2(A, B);
         const f32x2 N = fma2(pk2(__uint_as_float(w.x), __uint_as_float(w.y)), B,
@@ -91,13 +94,34 @@ __device__ __forceinline__ void loglik16_pv_emit(const float* v, const uint4* pv
     }
 }
 
-// One Philox block -> four standard normals (the arithmetic of mh_draws / rng_dump4_kernel: bit-identical draws)
-__device__ __forceinline__ float4 philox_normals4(uint32_t utt, uint32_t fc, uint32_t iter, uint32_t b, uint32_t k0, uint32_t k1) {
-    const Philox4 r = philox4x32_10(utt, fc, iter, b, k0, k1);
+// One Philox block -> four standard normals (the arithmetic of mh_draws / rng_dump4_kernel: bit-identical draws); block 0
+// also carries the accept uniform (u01_low_bytes)
+__device__ __forceinline__ float4 philox_normals4(uint32_t utt, uint32_t fc, uint32_t iter, uint32_t b, const PhiloxKeys& keys, float& u) {
+    const Philox4 r = philox4x32_10_rk(utt, fc, iter, b, keys);
+    u = u01_low_bytes(r);
     float4 o;
     box_muller(r.x, r.y, o.x, o.y);
     box_muller(r.z, r.w, o.z, o.w);
     return o;
+}
+
+// One 32-byte cell of the emission as a single 256-bit store (STG.E.ENL2.256: a whole sector per lane, 1 KB contiguous per warp).
+// Measured on the E-step call at B = 512 (tools/bench_sampler.py): two 16-byte st.global.cs (evict-first) stores per cell cost
+// +0.37 ms per call (half-sector writes that leave L2 before their second half arrives), two plain 16-byte stores +0.04 ms,
+// the 256-bit store nothing (2.48 ms with emission against 2.52 ms without).
+// One 32-byte cell of the emission as a single 256-bit store (STG.E.ENL2.256: a whole sector per lane, 1 KB contiguous per warp)
+// with an evict-first L2 policy; the P / Vb stream, which every evaluation re-reads from L2, is loaded with an evict-last
+// policy.  ncu on the E-step call at B = 512 (profiles/r02_ncu_mh2_emit_vs_plain.txt): the 3 GB the kept iterations write
+// push clean lines out of L2 -- part of the P / Vb stream (DRAM reads 208 -> 445 MB) and the kernel's own instructions
+// (no_instruction stalls 0.46 per issued instruction) -- which costs 0.55 ms per call without the policies and 0.3 ms with them.
+__device__ __forceinline__ void st_cell(uint4* p, const uint32_t (&o)[8], uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" :: "l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                 "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint4 ld_pv(const uint4* p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
 }
 
 template <int L, int POLY>
@@ -111,6 +135,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* A = base + ((d.image_bytes + 1023) & ~1023);
     float2* red2 = reinterpret_cast<float2*>(A + A_BYTES);       // [2][128] {partial l(z'), partial prior term} of each column half
+    float* u_sh = reinterpret_cast<float*>(red2 + 2 * TM);       // [128] accept uniform of the next proposal (written by half 0)
     const uint32_t bar12 = smem_u32(&bars[0]);
     const uint32_t bar3_0 = smem_u32(&bars[1]), bar3_1 = smem_u32(&bars[2]);
     const uint32_t barf_0 = smem_u32(&bars[3]);
@@ -156,6 +181,9 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     const bool two_hidden = d.n_hidden == 2;
     const uint32_t lane_off = (uint32_t)(32 * q) << 16;
     const bool emit = p.VsT != nullptr;
+    uint64_t pol_last, pol_first;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
     // evaluations of a tile: the start state, the burn-in proposals, [the state again: its variances become slot 0 of the
     // emission], the kept proposals
     const int n_eval = n_iter + 1 + (emit ? 1 : 0);
@@ -183,7 +211,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         constexpr int LH = L / 2;
         float zh[LH], zph[LH];
         float4 enn[LH / 4];                                // this half's draws of the next proposal
-        float y0 = 0.f, y1 = 0.f, y2 = 0.f, ll_cur = 0.f, u_cur = 0.5f, u_nxt = 0.5f, prior_h = 0.f;
+        float y0 = 0.f, y1 = 0.f, y2 = 0.f, ll_cur = 0.f, u_cur = 0.5f, prior_h = 0.f;
         uint32_t n_acc = 0, state_slot = 0;
         int prop = 0;                                      // index of the next proposal to draw
 #pragma unroll
@@ -196,34 +224,47 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             if (y_dim > 2) y2 = p.y[fr * y_dim + 2];
         }
 
-        // draws of the next proposal (if the next evaluation is one): consumed at the top of the next evaluation
-        auto draw_next = [&](int ev) {
+        // Draws of the next proposal (if the next evaluation is one), consumed at the top of the next evaluation.  Philox mode:
+        // this thread's LH / 4 blocks are produced in two parts that sit under two different GEMM waits (part 0 under the
+        // layer-2 GEMM, part 1 under the first layer-3 chunk; ~150 integer / MUFU instructions per block and thread, which
+        // two warps per scheduler cannot hide under one wait); the accept uniform rides on block 0 and reaches the other
+        // column half through shared memory.
+        auto draw_part = [&](int ev, int part) {
             const int nxt = ev + 1;
             if (nxt >= n_eval || nxt == ev_rescore) return;
             if (p.eps) {
-                if (valid) {
+                if (part == 0 && valid) {
                     const float4* e = reinterpret_cast<const float4*>(p.eps + ((int64_t)prop * p.rows + row_g) * L + h * LH);
 #pragma unroll
                     for (int l = 0; l < LH / 4; ++l) enn[l] = __ldg(e + l);
-                    u_nxt = __ldg(p.u + (int64_t)prop * p.rows + row_g);
+                    if (owner) u_sh[row] = __ldg(p.u + (int64_t)prop * p.rows + row_g);
                 }
             } else {
                 const uint32_t iter = p.iter0 + (uint32_t)prop;
+                constexpr int HALF = (LH / 4 + 1) / 2;              // blocks in part 0
 #pragma unroll
-                for (int l = 0; l < LH / 4; ++l) enn[l] = philox_normals4(ph_utt, ph_fc, iter, (uint32_t)(h * (LH / 4) + l), p.seed_lo, p.seed_hi);
-                u_nxt = u01(philox4x32_10(ph_utt, ph_fc, iter, (uint32_t)(L / 4), p.seed_lo, p.seed_hi).x);
+                for (int l = 0; l < LH / 4; ++l) {
+                    if ((l < HALF) != (part == 0)) continue;
+                    float u;
+                    enn[l] = philox_normals4(ph_utt, ph_fc, iter, (uint32_t)(h * (LH / 4) + l), p.keys, u);
+                    if (l == 0 && owner) u_sh[row] = u;             // block 0 belongs to half 0
+                }
             }
-            ++prop;
+            if (part == 1) ++prop;
         };
 
-        for (int ev = 0; ev < n_eval; ++ev) {
+        // One evaluation.  EMIT (compile time): the evaluation writes its variances to slot `store_slot` of the emission.  The
+        // body exists twice, once per flag, and a tile runs [start + burn-in] through the plain copy and then [state again + kept
+        // proposals] through the emitting copy: with ONE copy that branched around the stores in each of its 17 sub-chunks the
+        // interleaved dead code cost 0.33 ms per call (13 %) even when nothing was emitted (instruction fetch; tools/bench_sampler.py).
+        auto evaluate = [&](auto emit_c, const int ev) {
+            constexpr bool EMIT = decltype(emit_c)::value;
             const bool score_only = (ev == 0) || (ev == ev_rescore);     // evaluates the chain's state, no decision
             const int it = ev - 1 - ((emit && ev > ev_rescore) ? 1 : 0);  // proposal index (meaningless when score_only)
-            // slot of the emission this evaluation's variances go to, or -1
-            const int store_slot = !emit ? -1 : ((ev == ev_rescore) ? 0 : ((ev > ev_rescore) ? 1 + (it - p.n_burn) : -1));
-            if (ev == 0 && !two_hidden) draw_next(ev);
+            // slot of the emission this evaluation's variances go to
+            const int store_slot = (ev == ev_rescore) ? 0 : 1 + (it - p.n_burn);
             if (!score_only) {
-                u_cur = u_nxt;
+                u_cur = u_sh[row];
                 prior_h = 0.f;
 #pragma unroll
                 for (int l = 0; l < LH / 4; ++l) {
@@ -272,7 +313,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
 #define MH2_BIN(t) (192 * MH2_CH(t) + MH2_COL(t))
 #define MH2_LOAD(t, PV)                                                                              \
     do {                                                                                             \
-        _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) PV[qd] = __ldg(PVt + ((MH2_BIN(t) >> 2) + qd) * TM); \
+        _Pragma("unroll") for (int qd = 0; qd < 4; ++qd) PV[qd] = ld_pv(PVt + ((MH2_BIN(t) >> 2) + qd) * TM, pol_last); \
     } while (0)
             // the first two sub-chunks of the P / Vb stream are requested here, two phases ahead of their use (the wait for
             // them at the start of the layer-3 loop was 3.6 % of the kernel's stall samples: profiles/r01_tc_ncu_mh2.txt)
@@ -284,8 +325,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                     issue_gemm2(a_addr, 16384, w2_addr, 16384, 2, tmem, HID, 1);
                     umma_commit(bar12);
                 }
-                // the next proposal's draws: ~350 integer / MUFU instructions per thread in the shadow of the layer-2 GEMM
-                draw_next(ev);
+                draw_part(ev, 0);                                               // in the shadow of the layer-2 GEMM
                 mbar_wait(bar12, ph12, dead, p.status);
                 ph12 ^= 1;
                 tc_fence_after();
@@ -305,7 +345,8 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                 issue_gemm2(a_addr, 16384, w3_addr + 192 * 128, NPAD * 128, 2, tmem + 192, 192);
                 umma_commit(bar3_1);
             }
-            if (!two_hidden && ev > 0) draw_next(ev);
+            if (!two_hidden) draw_part(ev, 0);
+            draw_part(ev, 1);                                                   // in the shadow of the first layer-3 chunk
 
             // per thread 17 (h = 0) or 16 (h = 1) sub-chunks of 16 bins; the P / Vb quads of sub-chunk t+2 are requested
             // while sub-chunk t is evaluated (three rotating register buffers, everything statically indexed)
@@ -313,52 +354,54 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             // arrived, so their latency runs under the arithmetic of t (with two warps per scheduler the other warp alone
             // cannot cover it: the single-buffer version spent half of the layer-3 phase with neither XU nor issue slots busy).
             float va[16], vb[16];
-            uint4* vs_dst = (store_slot >= 0) ? VsTt + (size_t)store_slot * ((NPAD / 16) * TM * 2) : nullptr;
+            uint4* vs_dst = EMIT ? VsTt + (size_t)store_slot * ((NPAD / 16) * TM * 2) : nullptr;
             mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after();
             tmem_ld16(tmem + lane_off + MH2_COL(0), va);
 #define MH2_EVAL(V, PV, t)                                                                    \
     do {                                                                                      \
-        if (vs_dst) {                                                                         \
+        if constexpr (EMIT) {                                                                 \
             uint32_t o[8];                                                                    \
             loglik16_pv_emit<POLY>(V, PV, g_row, acc, accl, o);                               \
             uint4* dst = vs_dst + (MH2_BIN(t) >> 4) * (TM * 2);                               \
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);                                      \
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);                                      \
+            st_cell(dst, o, pol_first);                                                       \
         } else {                                                                              \
             loglik16_pv<POLY>(V, PV, g_row, acc, accl);                                       \
         }                                                                                     \
     } while (0)
-#pragma unroll
-            for (int t = 0; t < 17; ++t) {
+            // The 17 sub-chunks are spelled out through a compile-time index (a `#pragma unroll` loop over this body was left
+            // partly rolled by the compiler once the emission was added, which turned the statically indexed register buffers into
+            // select chains: 1.8 x the instructions)
+            auto step = [&](auto tc_) {
+                constexpr int t = decltype(tc_)::value;
                 const bool live = (t < 16) || (h == 0);                         // bins 528..543 do not exist
                 if (t + 2 < 17 && ((t + 2 < 16) || (h == 0))) {
-                    if ((t + 2) % 3 == 0) MH2_LOAD(t + 2, pv0);
-                    else if ((t + 2) % 3 == 1) MH2_LOAD(t + 2, pv1);
+                    if constexpr ((t + 2) % 3 == 0) MH2_LOAD(t + 2, pv0);
+                    else if constexpr ((t + 2) % 3 == 1) MH2_LOAD(t + 2, pv1);
                     else MH2_LOAD(t + 2, pv2);
                 }
                 if (live) tmem_wait_ld();                                       // sub-chunk t is in registers
-                if (t == 5) {                                                   // chunk 0 drained by this thread
+                if constexpr (t == 5) {                                         // chunk 0 drained by this thread
                     tc_fence_before();
                     mbar_arrive2(barf_0);
                 }
                 if (t + 1 < 17 && ((t + 1 < 16) || (h == 0))) {
-                    if (t + 1 == 6) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; tc_fence_after(); }
-                    if (t + 1 == 12) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); }
-                    if ((t + 1) % 2 == 0) tmem_ld16(tmem + 192 * (MH2_CH(t + 1) & 1) + lane_off + MH2_COL(t + 1), va);
+                    if constexpr (t + 1 == 6) { mbar_wait(bar3_1, ph3_1, dead, p.status); ph3_1 ^= 1; tc_fence_after(); }
+                    if constexpr (t + 1 == 12) { mbar_wait(bar3_0, ph3_0, dead, p.status); ph3_0 ^= 1; tc_fence_after(); }
+                    if constexpr ((t + 1) % 2 == 0) tmem_ld16(tmem + 192 * (MH2_CH(t + 1) & 1) + lane_off + MH2_COL(t + 1), va);
                     else tmem_ld16(tmem + 192 * (MH2_CH(t + 1) & 1) + lane_off + MH2_COL(t + 1), vb);
                 }
                 if (live) {
-                    if (t % 2 == 0) {
-                        if (t % 3 == 0) MH2_EVAL(va, pv0, t);
-                        else if (t % 3 == 1) MH2_EVAL(va, pv1, t);
+                    if constexpr (t % 2 == 0) {
+                        if constexpr (t % 3 == 0) MH2_EVAL(va, pv0, t);
+                        else if constexpr (t % 3 == 1) MH2_EVAL(va, pv1, t);
                         else MH2_EVAL(va, pv2, t);
                     } else {
-                        if (t % 3 == 0) MH2_EVAL(vb, pv0, t);
-                        else if (t % 3 == 1) MH2_EVAL(vb, pv1, t);
+                        if constexpr (t % 3 == 0) MH2_EVAL(vb, pv0, t);
+                        else if constexpr (t % 3 == 1) MH2_EVAL(vb, pv1, t);
                         else MH2_EVAL(vb, pv2, t);
                     }
                 }
-                if (t == 5) {
+                if constexpr (t == 5) {
                     if (warp == 5) {
                         if (lead) {
                             mbar_wait(barf_0, phf_0, dead, p.status);
@@ -370,7 +413,11 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                     }
                     phf_0 ^= 1;
                 }
-            }
+            };
+#define MH2_STEP(T) step(std::integral_constant<int, T>{})
+            MH2_STEP(0); MH2_STEP(1); MH2_STEP(2); MH2_STEP(3); MH2_STEP(4); MH2_STEP(5); MH2_STEP(6); MH2_STEP(7); MH2_STEP(8);
+            MH2_STEP(9); MH2_STEP(10); MH2_STEP(11); MH2_STEP(12); MH2_STEP(13); MH2_STEP(14); MH2_STEP(15); MH2_STEP(16);
+#undef MH2_STEP
 #undef MH2_EVAL
 #undef MH2_LOAD
 #undef MH2_BIN
@@ -395,16 +442,21 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
                         for (int l = 0; l < LH; ++l) zh[l] = zph[l];
                         ll_cur = ll_prop;
                         ++n_acc;
-                        if (store_slot >= 0) state_slot = (uint32_t)store_slot;
+                        if (EMIT) state_slot = (uint32_t)store_slot;
                     }
                     if (it >= p.n_burn) {
                         float4* dst = reinterpret_cast<float4*>(p.Zs + (row_g * p.n_keep + (it - p.n_burn)) * L + h * LH);
 #pragma unroll
                         for (int l = 0; l < LH / 4; ++l) dst[l] = make_float4(zh[4 * l], zh[4 * l + 1], zh[4 * l + 2], zh[4 * l + 3]);
-                        if (emit && owner) p.vs_idx[row_g * 32 + (it - p.n_burn)] = (uint8_t)state_slot;
+                        if (EMIT && owner) p.vs_idx[row_g * 32 + (it - p.n_burn)] = (uint8_t)state_slot;
                     }
                 }
             }
+        };
+        {
+            const int n_plain = emit ? ev_rescore : n_eval;
+            for (int ev = 0; ev < n_plain; ++ev) evaluate(std::false_type{}, ev);
+            for (int ev = n_plain; ev < n_eval; ++ev) evaluate(std::true_type{}, ev);
         }
         if (valid) {
 #pragma unroll
@@ -449,20 +501,20 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const vo
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(Zs) & 15) == 0 && (reinterpret_cast<uintptr_t>(rng->eps) & 15) == 0,
                  "dvae_mh_chain_tc2: Zs and eps must be 16-byte aligned");
     DVAE_REQUIRE((VsT == nullptr) == (vs_idx == nullptr), "dvae_mh_chain_tc2: VsT and vs_idx go together");
-    DVAE_REQUIRE(!VsT || (n_keep <= 31 && (reinterpret_cast<uintptr_t>(VsT) & 15) == 0),
-                 "dvae_mh_chain_tc2: the emission holds at most 31 kept samples per chain, 16-byte aligned");
+    DVAE_REQUIRE(!VsT || (n_keep <= 31 && (reinterpret_cast<uintptr_t>(VsT) & 31) == 0),
+                 "dvae_mh_chain_tc2: the emission holds at most 31 kept samples per chain, 32-byte aligned");
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
     p.rows = NT * n_chains; p.C = n_chains; p.y = y;
     p.PVpk = (const uint4*)PVpk; p.g = g; p.Z = Z; p.Zs = Zs;
     p.eps = rng->eps; p.u = rng->u;
     p.frame_gid = frame_utt; p.frame_idx = frame_idx;
-    p.seed_lo = (uint32_t)(rng->seed & 0xffffffffu); p.seed_hi = (uint32_t)(rng->seed >> 32); p.iter0 = rng->iter0;
+    p.keys = philox_keys((uint32_t)(rng->seed & 0xffffffffu), (uint32_t)(rng->seed >> 32)); p.iter0 = rng->iter0;
     p.n_accept = n_accept; p.a_trace = a_trace; p.n_burn = n_burn; p.n_keep = n_keep;
     p.sd = sqrtf(var_rw);
     p.status = status;
     p.VsT = (uint4*)VsT; p.vs_idx = vs_idx;
-    const size_t smem = smem_bytes(p.d) + (size_t)TM * 16;
+    const size_t smem = smem_bytes(p.d) + (size_t)TM * 20;       // + red2 [2][128] float2 and u_sh [128] behind the activation operand
     DVAE_REQUIRE(smem <= 227 * 1024, "dvae_mh_chain_tc2: shared memory budget exceeded");
     const int64_t n_tiles = (p.rows + TM - 1) / TM;
     const int grid = (int)(n_tiles < 148 ? n_tiles : 148);

@@ -300,15 +300,7 @@ __global__ void __launch_bounds__(256) rng_dump4_kernel(uint32_t seed_lo, uint32
         box_muller(r.x, r.y, o.x, o.y);
         box_muller(r.z, r.w, o.z, o.w);
         eps_out[(size_t)it * per_it + j] = o;
-    }
-    // the uniforms (Philox block nb of every chain) in a dense second pass: inside the loop above only every nb-th lane needed
-    // one, and the divergent branch made the whole warp pay for a second Philox evaluation
-    for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < chains; m += gridDim.x * blockDim.x) {
-        const uint32_t fr = (C == 1) ? m : m / C;
-        const uint32_t c = (C == 1) ? 0u : m - fr * C;
-        const uint32_t utt = (uint32_t)__ldg(frame_utt + fr), fc = (uint32_t)__ldg(frame_idx + fr) | (c << 20);
-        const Philox4 ru = philox4x32_10(utt, fc, iter0 + it, nb, seed_lo, seed_hi);
-        u_out[(size_t)it * chains + m] = u01(ru.x);
+        if (b == 0) u_out[(size_t)it * chains + m] = u01_low_bytes(r);      // the accept uniform rides on block 0 (common.cuh)
     }
 }
 

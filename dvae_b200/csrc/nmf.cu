@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? hs[k] : 0.f;
+        for (int k = 0; k < KT; ++k) h[k] = hs[k];
 
         // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
         vb2 = 0ull; vbX = 0.f;
@@ -675,7 +675,7 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? hs[k] : 0.f;
+        for (int k = 0; k < KT; ++k) h[k] = hs[k];
 
         // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
         vb2 = 0ull; vbX = 0.f;
@@ -747,6 +747,7 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
         __syncthreads();                            // hs and the reduction buffers are free for the next frame
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
         if (t == 0) g[n] = gnew;
+        __syncthreads();                                // the frame is fully consumed: its buffer may be refilled
     }
     cost_d = warp_sum_d(cost_d);
     if (lane == 0) redd[wid] = cost_d;
@@ -760,14 +761,22 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
 }
 
 // ----------------------------------------------------------------------------- H, g, cost on the sampler's BF16 emission
-// hg5 on the variances the tcgen05 sampler wrote itself (vst.cu: VsT[tile][slot][bin group][row][16] bf16 + the per-sample slot
-// index, values without the decoder's output-layer bias E[f] = exp(b3[f])).  Per frame R x 33 cells of 32 bytes; the frame is
-// staged with 16-byte cp.async into one of TWO shared-memory buffers of R x 1056 bytes (half of hg5's FP32 frame, so two fit in
-// hg5's footprint and three CTAs still share an SM): frame n+1 is in flight while frame n is reduced.  A thread owns the
-// adjacent bins 2t, 2t+1 = one 32-bit word of every row (consecutive lanes, consecutive banks), unpacked with one shift and
-// one mask into a packed FP32 pair; E rides on g in the variance (Vx = (g E) v + Vb) and multiplies the g-update sums once
-// per frame.  The arithmetic of the three passes is hg5's.
-constexpr int HG7_ROWW = 264;                   // 32-bit words per staged row (528 bf16)
+// The M-step's frame kernel on the variances the tcgen05 sampler wrote itself (vst.cu: VsT[tile][slot][bin group][row][8 words]
+// + the per-sample slot index; values without the decoder's output-layer bias E[f] = exp(b3[f])).  ncu on the first version
+// (hg5's schedule reading the frame from shared memory in every pass: profiles/r02_ncu_hg7_v1.txt) showed it issue-bound by
+// its own overhead: 12 % of all warp instructions unpacked BF16 pairs, 9 % computed cp.async addresses, 8 % were the three
+// passes' shared-memory loads.  Here:
+//   * a thread owns the adjacent bins 2t, 2t+1 = ONE 32-bit word per sample (consecutive lanes, consecutive banks);
+//   * the packed FP32 lanes are two SAMPLES of one bin, not two bins of one sample: the odd bin's pair (w_r, w_r+1) is the raw
+//     words themselves (adjacent registers, no instruction), the even bin's pair is two shifts;
+//   * the pair trick (two variances share one reciprocal) runs between sample pairs (r, r+1) x (r+2, r+3);
+//   * two shared-memory buffers of R x 1 056 bytes (together hg5's footprint: three CTAs per SM): the next frame is staged
+//     with 16-byte cp.async (a warp copies whole rows: one slot lookup and one 64-bit address per row) under the current
+//     frame's arithmetic.  A variant that kept the frame's words in registers for the three passes (60 shared-memory loads
+//     fewer per thread and frame, but 128 registers = two CTAs per SM) was not faster: the kernel is bound by latency between
+//     its five barriers per frame, i.e. by the number of resident warps (profiles/r02_ncu_v2.txt);
+//   * E rides on g in the variance (Vx = (g E) v + Vb) and multiplies the g-update sums once per frame.
+constexpr int HG7_ROWW = 264;                   // 32-bit words per staged row (528 bins)
 __device__ __forceinline__ void hg7_cp16(unsigned smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_dst), "l"(gmem_src) : "memory");
 }
@@ -782,13 +791,15 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
     constexpr int KT = HG2_KT;
     constexpr int ld = HG5_LD;
     constexpr int NBG = 33, TMR = 128;
+    constexpr int NPC = (R * 66 + HG3_THREADS - 1) / HG3_THREADS;     // 16-byte pieces per thread and frame
     static_assert(R % 2 == 0 && R <= 30, "hg7: even R up to 30");
     extern __shared__ __align__(16) uint32_t smw[];
-    uint32_t* S0 = smw;                              // [2][R][HG7_ROWW] staged frames
+    uint32_t* S0 = smw;                              // [2][R][HG7_ROWW] the current frame and the next one being staged
     float* red = reinterpret_cast<float*>(smw + 2 * R * HG7_ROWW);      // [8][HG3_NV] per-warp partials of the H sums
     __shared__ float2 red2[8];
     __shared__ double redd[8];
     __shared__ float hs[KT];
+    __shared__ float hs_old[KT];
     const int u = blockIdx.y;
     const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
     const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
@@ -808,69 +819,103 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
         w2[k] = (k < K) ? *reinterpret_cast<const f32x2*>(wk + f2) : 0ull;
         wX[k] = (k < K) ? wk[512] : 0.f;
     }
-    const f32x2 E2 = pk2(exp2f(__ldg(bias_log2 + f2)), exp2f(__ldg(bias_log2 + f2 + 1)));
-    const float EX = exp2f(__ldg(bias_log2 + 512));
+    const float E0 = exp2f(__ldg(bias_log2 + f2)), E1 = exp2f(__ldg(bias_log2 + f2 + 1)), EX = exp2f(__ldg(bias_log2 + 512));
     double cost_d = 0.0;                            // per-thread partial, reduced once per CTA
 
-    // stage frame n into buffer b: piece j = t + 256 k covers 16 bytes: row r = j / 66, piece i = j % 66 of the row
+    // staging: warp w copies the rows w, w + 8, w + 16, w + 24 of the frame; a row is 66 pieces of 16 bytes = lanes 0..31 twice
+    // plus lanes 0, 1 once more.  Piece i of a row sits (i >> 1) cells of 4 KB + 16 (i & 1) bytes behind the row's first cell.
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(S0);
+    const unsigned po0 = (unsigned)((lane >> 1) * (TMR * 32) + 16 * (lane & 1));           // piece `lane`; piece lane + 32 is 16 cells on
     auto stage = [&](int64_t n, int b) {
         const int64_t tile = n / TMR;
         const int row = (int)(n - tile * TMR);
         const uint8_t* ib = vs_idx + n * 32;
-        const unsigned dst0 = (unsigned)__cvta_generic_to_shared(S0 + b * R * HG7_ROWW);
         const unsigned char* src0 = reinterpret_cast<const unsigned char*>(VsT) + ((size_t)tile * (R + 1) * NBG * TMR + row) * 32;
 #pragma unroll
-        for (int k = 0; k < (R * 66 + HG3_THREADS - 1) / HG3_THREADS; ++k) {
-            const int j = t + HG3_THREADS * k;
-            if (j < R * 66) {
-                const int r = j / 66, i = j - 66 * r;
-                const unsigned slot = __ldg(ib + r);
-                hg7_cp16(dst0 + (unsigned)(r * HG7_ROWW * 4 + 16 * i),
-                         src0 + ((size_t)slot * NBG + (i >> 1)) * (TMR * 32) + 16 * (i & 1));
+        for (int k = 0; k < (R + 7) / 8; ++k) {
+            const int r = wid + 8 * k;
+            if (r < R) {
+                const unsigned char* src = src0 + (size_t)__ldg(ib + r) * (NBG * TMR * 32) + po0;
+                const unsigned dst = s_base + (unsigned)((b * R + r) * HG7_ROWW * 4 + 16 * lane);
+                hg7_cp16(dst, src);
+                hg7_cp16(dst + 512, src + 16 * (TMR * 32));
+                if (lane < 2) hg7_cp16(dst + 1024, src + 32 * (TMR * 32));
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     stage(nb, 0);
+    if (t >= K && t < KT) { hs_old[t] = 0.f; hs[t] = 0.f; }
 
     int buf = 0;
     for (int64_t n = nb; n < ne; ++n, buf ^= 1) {
+        // per-frame scalars first: their global-memory latency runs under the wait for the staged frame
+        const float gg = g[n];
+        const f32x2 p2 = *reinterpret_cast<const f32x2*>(P + n * ld + f2);
+        const float pX = P[n * ld + 512];
+        if (t < K) hs_old[t] = H[n * K + t];                            // the frame's activations reach every thread through shared memory
         if (n + 1 < ne) {
-            stage(n + 1, buf ^ 1);
+            stage(n + 1, buf ^ 1);                                      // the other buffer was released by the barrier that ended frame n - 1
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();                                                // frame n is staged for every thread
-        const uint32_t* S = S0 + buf * R * HG7_ROWW + t;                // this thread's word of row 0
-        const uint32_t* SX = S0 + buf * R * HG7_ROWW + 256;             // word holding bin 512
-        const float gg = g[n];
-        float elo, ehi;
-        upk2(E2, elo, ehi);
-        const f32x2 gg2 = pk2(gg * elo, gg * ehi);
-        const float ggX = gg * EX;
-        const f32x2 p2 = *reinterpret_cast<const f32x2*>(P + n * ld + f2);
-        const float pX = P[n * ld + 512];
         float h[KT];
 #pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? H[n * K + k] : 0.f;
+        for (int k = 0; k < KT; ++k) h[k] = hs_old[k];
+        const uint32_t* S = S0 + buf * R * HG7_ROWW + t;                // this thread's word of sample 0
+        const float sX = xl ? vst_lo(S0[(buf * R + t) * HG7_ROWW + 256]) : 0.f;     // bin 512: this thread's single sample (without E)
+
+        float p_lo, p_hi;
+        upk2(p2, p_lo, p_hi);
+        const f32x2 ga = pk2(gg * E0, gg * E0), gb = pk2(gg * E1, gg * E1);     // (g E) of bin 2t / 2t+1 for both sample lanes
+        const float ggX = gg * EX;
+        // even bin (a): lanes = samples (r, r+1) from two shifts; odd bin (b): the raw words
+#define HG7_VA(r) pk2(vst_lo(S[(r) * HG7_ROWW]), vst_lo(S[((r) + 1) * HG7_ROWW]))
+#define HG7_VB(r) pk2(vst_hi(S[(r) * HG7_ROWW]), vst_hi(S[((r) + 1) * HG7_ROWW]))
         // ---- H update (Vb1 = W_new H_old)
         f32x2 vb2 = 0ull;
         float vbX = 0.f;
 #pragma unroll
         for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
-        f32x2 a1 = 0ull, a2 = 0ull;
-#pragma unroll 5
-        for (int r = 0; r < R; r += 2) {
-            const f32x2 x0 = fma2(gg2, bf16x2_to_f32x2(S[r * HG7_ROWW]), vb2), x1 = fma2(gg2, bf16x2_to_f32x2(S[(r + 1) * HG7_ROWW]), vb2);
-            const f32x2 rr = rcp2(mul2(x0, x1));
-            const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
-            a1 = add2(a1, add2(i0, i1));
-            a2 = fma2(i0, i0, fma2(i1, i1, a2));
+        float vb_lo, vb_hi;
+        upk2(vb2, vb_lo, vb_hi);
+        f32x2 va2 = pk2(vb_lo, vb_lo), vbb2 = pk2(vb_hi, vb_hi);
+        f32x2 a1a = 0ull, a2a = 0ull, a1b = 0ull, a2b = 0ull;
+        constexpr int R4 = R & ~3;
+#pragma unroll
+        for (int r = 0; r < R4; r += 4) {
+            {
+                const f32x2 x0 = fma2(ga, HG7_VA(r), va2), x1 = fma2(ga, HG7_VA(r + 2), va2);
+                const f32x2 rr = rcp2(mul2(x0, x1));
+                const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                a1a = add2(a1a, add2(i0, i1));
+                a2a = fma2(i0, i0, fma2(i1, i1, a2a));
+            }
+            {
+                const f32x2 x0 = fma2(gb, HG7_VB(r), vbb2), x1 = fma2(gb, HG7_VB(r + 2), vbb2);
+                const f32x2 rr = rcp2(mul2(x0, x1));
+                const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                a1b = add2(a1b, add2(i0, i1));
+                a2b = fma2(i0, i0, fma2(i1, i1, a2b));
+            }
         }
-        float sX = 0.f;                             // bin 512: this thread's single sample (without E)
+        if (R4 < R) {                               // R % 4 == 2: one sample pair left, one reciprocal per lane
+            const f32x2 ia = rcp2(fma2(ga, HG7_VA(R4), va2)), ibb = rcp2(fma2(gb, HG7_VB(R4), vbb2));
+            a1a = add2(a1a, ia); a2a = fma2(ia, ia, a2a);
+            a1b = add2(a1b, ibb); a2b = fma2(ibb, ibb, a2b);
+        }
+        f32x2 a1, a2;                               // back to (bin 2t, bin 2t+1)
+        {
+            float l0, l1, m0, m1;
+            upk2(a1a, l0, l1); upk2(a1b, m0, m1);
+            a1 = pk2(l0 + l1, m0 + m1);
+            upk2(a2a, l0, l1); upk2(a2b, m0, m1);
+            a2 = pk2(l0 + l1, m0 + m1);
+        }
         float a1X = 0.f, a2X = 0.f;
-        if (xl) { sX = __uint_as_float(SX[t * HG7_ROWW] << 16); const float ix = rcp_fast(fmaf(ggX, sX, vbX)); a1X = ix; a2X = ix * ix; }
+        if (xl) { const float ix = rcp_fast(fmaf(ggX, sX, vbX)); a1X = ix; a2X = ix * ix; }
         {
             const f32x2 q2 = mul2(p2, a2);
             const float qX = pX * a2X;
@@ -917,11 +962,11 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
             float num = 0.f, den = 0.f;
 #pragma unroll
             for (int w = 0; w < 8; ++w) { num += red[w * HG3_NV + 2 * t]; den += red[w * HG3_NV + 2 * t + 1]; }
-            hs[t] = H[n * K + t] * sqrtf(num / den);
+            hs[t] = hs_old[t] * sqrtf(num / den);
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = (k < K) ? hs[k] : 0.f;
+        for (int k = 0; k < KT; ++k) h[k] = hs[k];
 
         // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
         vb2 = 0ull; vbX = 0.f;
@@ -929,26 +974,46 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
         for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
         *reinterpret_cast<f32x2*>(Vb + n * ld + f2) = vb2;
         if (t == 0) Vb[n * ld + 512] = vbX;
-        f32x2 s1 = 0ull, s2 = 0ull;
-#pragma unroll 5
-        for (int r = 0; r < R; r += 2) {
-            const f32x2 v0 = bf16x2_to_f32x2(S[r * HG7_ROWW]), v1 = bf16x2_to_f32x2(S[(r + 1) * HG7_ROWW]);
-            const f32x2 x0 = fma2(gg2, v0, vb2), x1 = fma2(gg2, v1, vb2);
-            const f32x2 rr = rcp2(mul2(x0, x1));
-            const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
-            const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
-            s1 = add2(s1, add2(t0, t1));
-            s2 = fma2(t0, i0, fma2(t1, i1, s2));
+        upk2(vb2, vb_lo, vb_hi);
+        va2 = pk2(vb_lo, vb_lo); vbb2 = pk2(vb_hi, vb_hi);
+        f32x2 s1a = 0ull, s2a = 0ull, s1b = 0ull, s2b = 0ull;
+#pragma unroll
+        for (int r = 0; r < R4; r += 4) {
+            {
+                const f32x2 v0 = HG7_VA(r), v1 = HG7_VA(r + 2);
+                const f32x2 x0 = fma2(ga, v0, va2), x1 = fma2(ga, v1, va2);
+                const f32x2 rr = rcp2(mul2(x0, x1));
+                const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
+                s1a = add2(s1a, add2(t0, t1));
+                s2a = fma2(t0, i0, fma2(t1, i1, s2a));
+            }
+            {
+                const f32x2 v0 = HG7_VB(r), v1 = HG7_VB(r + 2);
+                const f32x2 x0 = fma2(gb, v0, vbb2), x1 = fma2(gb, v1, vbb2);
+                const f32x2 rr = rcp2(mul2(x0, x1));
+                const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
+                s1b = add2(s1b, add2(t0, t1));
+                s2b = fma2(t0, i0, fma2(t1, i1, s2b));
+            }
         }
-        s1 = mul2(s1, E2);                          // Vs = E v
-        s2 = mul2(s2, E2);
+        if (R4 < R) {
+            const f32x2 v0 = HG7_VA(R4), v1 = HG7_VB(R4);
+            const f32x2 i0 = rcp2(fma2(ga, v0, va2)), i1 = rcp2(fma2(gb, v1, vbb2));
+            const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
+            s1a = add2(s1a, t0); s2a = fma2(t0, i0, s2a);
+            s1b = add2(s1b, t1); s2b = fma2(t1, i1, s2b);
+        }
         float s1X = 0.f, s2X = 0.f;
         if (xl) { const float ix = rcp_fast(fmaf(ggX, sX, vbX)); s1X = EX * sX * ix; s2X = s1X * ix; }
         {
-            float ps_lo, ps_hi, s1lo, s1hi;
-            upk2(mul2(p2, s2), ps_lo, ps_hi);
-            upk2(s1, s1lo, s1hi);
-            const float v2 = warp_sum(fmaf(pX, s2X, ps_lo + ps_hi)), v1 = warp_sum(s1lo + s1hi + s1X);
+            float l0, l1, m0, m1;
+            upk2(s1a, l0, l1); upk2(s1b, m0, m1);
+            const float s1lo = E0 * (l0 + l1), s1hi = E1 * (m0 + m1);       // Vs = E v
+            upk2(s2a, l0, l1); upk2(s2b, m0, m1);
+            const float s2lo = E0 * (l0 + l1), s2hi = E1 * (m0 + m1);
+            const float v2 = warp_sum(fmaf(pX, s2X, fmaf(p_lo, s2lo, p_hi * s2hi))), v1 = warp_sum(s1lo + s1hi + s1X);
             if (lane == 0) red2[wid] = make_float2(v2, v1);
         }
         __syncthreads();
@@ -957,42 +1022,56 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
         for (int w = 0; w < 8; ++w) { const float2 rr = red2[w]; t2 += rr.x; t1s += rr.y; }
         const float gnew = gg * sqrtf(t2 / t1s);
 
-        // ---- cost with Vx = g_new Vs + Vb2: FOUR samples share one reciprocal and one log2 (see hg5; c = 2^8)
+        // ---- cost with Vx = g_new Vs + Vb2: FOUR samples of a bin share one reciprocal and one log2.  With y_i = c Vx_i
+        //      (c = 2^8 keeps the four-fold products inside FP32 for variances from 1e-10 to 1e7; it rides on g_new and Vb2):
+        //      sum_i log2 Vx_i = log2(y0 y1 y2 y3) - 32,  sum_i 1 / Vx_i = c ((y0 + y2) y1 y3 + (y1 + y3) y0 y2) / (y0 y1 y2 y3)
         constexpr float kC = 256.0f;
-        const f32x2 gc2 = pk2(gnew * kC * elo, gnew * kC * ehi), vc2 = mul2(vb2, pk2(kC, kC));
-        f32x2 cl = 0ull, cp = 0ull;
-        constexpr int R4 = R & ~3;
+        const f32x2 gca = pk2(gnew * kC * E0, gnew * kC * E0), gcb = pk2(gnew * kC * E1, gnew * kC * E1);
+        const f32x2 vca = pk2(vb_lo * kC, vb_lo * kC), vcb = pk2(vb_hi * kC, vb_hi * kC);
+        float cla = 0.f, cpa = 0.f, clb = 0.f, cpb = 0.f;
 #pragma unroll
         for (int r = 0; r < R4; r += 4) {
-            const f32x2 y0 = fma2(gc2, bf16x2_to_f32x2(S[r * HG7_ROWW]), vc2), y1 = fma2(gc2, bf16x2_to_f32x2(S[(r + 1) * HG7_ROWW]), vc2);
-            const f32x2 y2 = fma2(gc2, bf16x2_to_f32x2(S[(r + 2) * HG7_ROWW]), vc2), y3 = fma2(gc2, bf16x2_to_f32x2(S[(r + 3) * HG7_ROWW]), vc2);
-            const f32x2 p01 = mul2(y0, y1), p23 = mul2(y2, y3);
-            const f32x2 m = mul2(p01, p23);
-            cl = add2(cl, lg22(m));
-            cp = fma2(fma2(add2(y0, y1), p23, mul2(add2(y2, y3), p01)), rcp2(m), cp);
+            {
+                const f32x2 y01 = fma2(gca, HG7_VA(r), vca), y23 = fma2(gca, HG7_VA(r + 2), vca);
+                float s_lo, s_hi, q_lo, q_hi;
+                upk2(add2(y01, y23), s_lo, s_hi);
+                upk2(mul2(y01, y23), q_lo, q_hi);
+                const float m = q_lo * q_hi;
+                cla += lg2_fast(m);
+                cpa = fmaf(fmaf(s_lo, q_hi, s_hi * q_lo), rcp_fast(m), cpa);
+            }
+            {
+                const f32x2 y01 = fma2(gcb, HG7_VB(r), vcb), y23 = fma2(gcb, HG7_VB(r + 2), vcb);
+                float s_lo, s_hi, q_lo, q_hi;
+                upk2(add2(y01, y23), s_lo, s_hi);
+                upk2(mul2(y01, y23), q_lo, q_hi);
+                const float m = q_lo * q_hi;
+                clb += lg2_fast(m);
+                cpb = fmaf(fmaf(s_lo, q_hi, s_hi * q_lo), rcp_fast(m), cpb);
+            }
         }
         float fix = -8.0f * (float)R4;                 // log2 c per sample
-#pragma unroll
-        for (int r = R4; r < R; r += 2) {              // R is even: one pair left when R % 4 == 2
-            const f32x2 y0 = fma2(gc2, bf16x2_to_f32x2(S[r * HG7_ROWW]), vc2), y1 = fma2(gc2, bf16x2_to_f32x2(S[(r + 1) * HG7_ROWW]), vc2);
-            const f32x2 pr = mul2(y0, y1);
-            cl = add2(cl, lg22(pr));
-            cp = fma2(add2(y0, y1), rcp2(pr), cp);
+        if (R4 < R) {                                  // one sample pair left: sum 1 / y = (y0 + y1) / (y0 y1)
+            float y0, y1;
+            upk2(fma2(gca, HG7_VA(R4), vca), y0, y1);
+            float m = y0 * y1;
+            cla += lg2_fast(m);
+            cpa = fmaf(y0 + y1, rcp_fast(m), cpa);
+            upk2(fma2(gcb, HG7_VB(R4), vcb), y0, y1);
+            m = y0 * y1;
+            clb += lg2_fast(m);
+            cpb = fmaf(y0 + y1, rcp_fast(m), cpb);
             fix -= 16.0f;
         }
+#undef HG7_VA
+#undef HG7_VB
         float cX = 0.f;
         if (xl) { const float x0 = fmaf(gnew * EX, sX, vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
-        {
-            float cl_lo, cl_hi, pc_lo, pc_hi;
-            upk2(cl, cl_lo, cl_hi);
-            upk2(mul2(p2, cp), pc_lo, pc_hi);
-            // both bins of the thread carry the same log2 c offset; the reciprocal sums carry a factor 1 / c
-            cost_d += (double)(fmaf(0.6931471805599453f, (cl_lo + fix) + (cl_hi + fix), kC * (pc_lo + pc_hi)) + cX);
-        }
+        // both bins of the thread carry the same log2 c offset; the reciprocal sums carry a factor 1 / c
+        cost_d += (double)(fmaf(0.6931471805599453f, (cla + fix) + (clb + fix), kC * fmaf(p_lo, cpa, p_hi * cpb)) + cX);
 
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
         if (t == 0) g[n] = gnew;
-        __syncthreads();                                // the frame is fully consumed: its buffer may be refilled
     }
     cost_d = warp_sum_d(cost_d);
     if (lane == 0) redd[wid] = cost_d;

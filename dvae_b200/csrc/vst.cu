@@ -4,7 +4,9 @@
 // output 2^v (= Vs without the output-layer bias) straight to global memory, so compute_Vs (mcem.py:280-290) needs no
 // second decode.  Layout (one 32-byte cell = 16 consecutive bins of one chain in one slot):
 //
-//     VsT[tile = chain / 128][slot 0 .. R][bg = bin / 16 (33 groups)][row = chain % 128][16]   bf16
+//     VsT[tile = chain / 128][slot 0 .. R][bg = bin / 16 (33 groups)][row = chain % 128][8 words]
+//     one word = the variances of bins 2j, 2j+1 at BF16 precision (common.cuh, "VsT word": bf16(v_2j) in the low half, the
+//     whole word read as FP32 is v_2j+1 to the same precision: one shift unpacks the even bin, nothing the odd one)
 //     vs_idx[chain][32] bytes: byte r = slot holding kept sample r  (0 = the state the kept phase started from,
 //                                                                     1 + j = the proposal of kept iteration j)
 //
@@ -13,7 +15,7 @@
 // output-layer bias the sampler folds into its P / Vb stream instead (pack_pv_kernel).
 //
 //   vst_frame_stats_kernel   A1[n][f] = sum_r 1 / Vx, A2[n][f] = sum_r 1 / Vx^2 (inner sums of mcem.py:108-110) with the
-//                            E-step's g and Vb: thread = (chain, 16 bins), a warp reads 1 KB contiguous per slot.
+//                            E-step's g and Vb: thread = (chain, 8 bins), a warp reads 512 contiguous bytes per slot.
 //   vst_unpack / vst_pack    conversion to / from the dense FP32 layout Vs[NT][R][ld] (the `.Vs` attribute of the MCEM
 //                            shims, parity tests).
 // The H / g / cost kernel on this format is nmf_hg7_kernel (nmf.cu).
@@ -27,34 +29,37 @@ constexpr int VST_IDX_PITCH = 32;
 
 __device__ __forceinline__ f32x2 vst_rcp2(f32x2 a) { float lo, hi; upk2(a, lo, hi); return pk2(rcp_approx(lo), rcp_approx(hi)); }
 
+// Thread = (chain, half of a cell): 8 bins = one 16-byte load per slot; the two threads of a chain are adjacent lanes, so a warp
+// reads 16 chains x 32 bytes = 512 contiguous bytes per slot.  64 registers -> 1 024 threads per SM, each with two sample pairs
+// (64 bytes) in flight ahead of the one it reduces: the kernel is a pure HBM stream (R x 1 056 bytes per frame in, 2 x 2 052 out).
 // RT > 0: compile-time sample count (even), slot indices held in registers; RT = 0: run-time count r_rt (any parity)
 template <int RT>
-__global__ void __launch_bounds__(128, 4) vst_frame_stats_kernel(const uint4* __restrict__ VsT, const uint8_t* __restrict__ idx, int r_rt,
+__global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __restrict__ VsT, const uint8_t* __restrict__ idx, int r_rt,
                                                                  const float* __restrict__ bias_log2, const float* __restrict__ Vb,
                                                                  const float* __restrict__ g, int64_t rows, int F, int ld,
                                                                  float* __restrict__ A1, float* __restrict__ A2) {
     const int R = RT > 0 ? RT : r_rt;
     const int64_t tile = blockIdx.x;
-    const int bg = blockIdx.y, row = threadIdx.x;
+    const int bg = blockIdx.y, row = threadIdx.x >> 1, half = threadIdx.x & 1;
     const int64_t m = tile * TM + row;
     if (m >= rows) return;
-    const int f0 = 16 * bg;
+    const int f0 = 16 * bg + 8 * half;
     const float gg = __ldg(g + m);
-    f32x2 ge2[8], vb2[8], a1[8], a2[8];
+    f32x2 ge2[4], vb2[4], a1[4], a2[4];
     {
-        float vb[16];
-        if (f0 + 16 <= ld) {
+        float vb[8];
+        if (f0 + 8 <= ld) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 const float4 t = __ldg(reinterpret_cast<const float4*>(Vb + m * ld + f0) + j);
                 vb[4 * j] = t.x; vb[4 * j + 1] = t.y; vb[4 * j + 2] = t.z; vb[4 * j + 3] = t.w;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) vb[j] = (f0 + j < F) ? __ldg(Vb + m * ld + f0 + j) : 1.f;
+            for (int j = 0; j < 8; ++j) vb[j] = (f0 + j < F) ? __ldg(Vb + m * ld + f0 + j) : 1.f;
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
             const int f = f0 + 2 * j;
             const float e0 = (f < F) ? exp2f(__ldg(bias_log2 + f)) : 0.f, e1 = (f + 1 < F) ? exp2f(__ldg(bias_log2 + f + 1)) : 0.f;
             ge2[j] = pk2(gg * e0, gg * e1);
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(128, 4) vst_frame_stats_kernel(const uint4* __
         }
     }
     const size_t slot_stride = (size_t)NBG * TM * 2;
-    const uint4* cell = VsT + ((size_t)tile * (R + 1) * NBG + bg) * (TM * 2) + row * 2;
+    const uint4* cell = VsT + ((size_t)tile * (R + 1) * NBG + bg) * (TM * 2) + row * 2 + half;
     const uint8_t* ib = idx + m * VST_IDX_PITCH;
     uint32_t iw[8];
     if (RT > 0) {
@@ -75,68 +80,56 @@ __global__ void __launch_bounds__(128, 4) vst_frame_stats_kernel(const uint4* __
         if (RT > 0) return (iw[r >> 2] >> (8 * (r & 3))) & 255u;
         return (uint32_t)__ldg(ib + r);
     };
-    auto pair = [&](const uint4& p0, const uint4& p1, const uint4& q0, const uint4& q1) {
-        const uint32_t w0[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-        const uint32_t w1[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            // two samples share one reciprocal: 1 / X0 = X1 / (X0 X1)
-            const f32x2 x0 = fma2(ge2[j], bf16x2_to_f32x2(w0[j]), vb2[j]), x1 = fma2(ge2[j], bf16x2_to_f32x2(w1[j]), vb2[j]);
-            const f32x2 rr = vst_rcp2(mul2(x0, x1));
-            const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
-            a1[j] = add2(a1[j], add2(i0, i1));
-            a2[j] = fma2(i0, i0, fma2(i1, i1, a2[j]));
-        }
+    auto word_pair = [&](uint32_t w0, uint32_t w1, int j) {
+        // two samples share one reciprocal: 1 / X0 = X1 / (X0 X1)
+        const f32x2 x0 = fma2(ge2[j], pk2(vst_lo(w0), vst_hi(w0)), vb2[j]), x1 = fma2(ge2[j], pk2(vst_lo(w1), vst_hi(w1)), vb2[j]);
+        const f32x2 rr = vst_rcp2(mul2(x0, x1));
+        const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+        a1[j] = add2(a1[j], add2(i0, i1));
+        a2[j] = fma2(i0, i0, fma2(i1, i1, a2[j]));
     };
-    const int R2 = R & ~1;
+    auto pair = [&](const uint4& p, const uint4& q) {
+        word_pair(p.x, q.x, 0); word_pair(p.y, q.y, 1); word_pair(p.z, q.z, 2); word_pair(p.w, q.w, 3);
+    };
     if (RT > 0) {
-        // software pipeline over sample pairs: the cells of pair k+1 are in flight while pair k is reduced
-        uint4 c[4], nx[4];
-        {
-            const uint4* s0 = cell + slot_of(0) * slot_stride;
-            const uint4* s1 = cell + slot_of(1) * slot_stride;
-            c[0] = __ldcs(s0); c[1] = __ldcs(s0 + 1); c[2] = __ldcs(s1); c[3] = __ldcs(s1 + 1);
-        }
+        // software pipeline over sample pairs: pairs k+1 and k+2 are in flight while pair k is reduced
+        constexpr int NP = RT / 2;
+        uint4 c[2], n1[2], n2[2];
+        c[0] = __ldcs(cell + slot_of(0) * slot_stride); c[1] = __ldcs(cell + slot_of(1) * slot_stride);
+        if (NP > 1) { n1[0] = __ldcs(cell + slot_of(2) * slot_stride); n1[1] = __ldcs(cell + slot_of(3) * slot_stride); }
 #pragma unroll
-        for (int r = 0; r < RT; r += 2) {
-            if (r + 2 < RT) {
-                const uint4* s0 = cell + slot_of(r + 2) * slot_stride;
-                const uint4* s1 = cell + slot_of(r + 3) * slot_stride;
-                nx[0] = __ldcs(s0); nx[1] = __ldcs(s0 + 1); nx[2] = __ldcs(s1); nx[3] = __ldcs(s1 + 1);
-            }
-            pair(c[0], c[1], c[2], c[3]);
-            if (r + 2 < RT) { c[0] = nx[0]; c[1] = nx[1]; c[2] = nx[2]; c[3] = nx[3]; }
+        for (int k = 0; k < NP; ++k) {
+            if (k + 2 < NP) { n2[0] = __ldcs(cell + slot_of(2 * k + 4) * slot_stride); n2[1] = __ldcs(cell + slot_of(2 * k + 5) * slot_stride); }
+            pair(c[0], c[1]);
+            c[0] = n1[0]; c[1] = n1[1];
+            n1[0] = n2[0]; n1[1] = n2[1];
         }
     } else {
-        for (int r = 0; r < R2; r += 2) {
-            const uint4* s0 = cell + slot_of(r) * slot_stride;
-            const uint4* s1 = cell + slot_of(r + 1) * slot_stride;
-            pair(__ldcs(s0), __ldcs(s0 + 1), __ldcs(s1), __ldcs(s1 + 1));
-        }
+        const int R2 = R & ~1;
+        for (int r = 0; r < R2; r += 2) pair(__ldcs(cell + slot_of(r) * slot_stride), __ldcs(cell + slot_of(r + 1) * slot_stride));
         if (R & 1) {
-            const uint4* s0 = cell + slot_of(R - 1) * slot_stride;
-            const uint4 p0 = __ldcs(s0), p1 = __ldcs(s0 + 1);
-            const uint32_t w0[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            const uint4 p = __ldcs(cell + slot_of(R - 1) * slot_stride);
+            const uint32_t w0[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const f32x2 i0 = vst_rcp2(fma2(ge2[j], bf16x2_to_f32x2(w0[j]), vb2[j]));
+            for (int j = 0; j < 4; ++j) {
+                const f32x2 i0 = vst_rcp2(fma2(ge2[j], pk2(vst_lo(w0[j]), vst_hi(w0[j])), vb2[j]));
                 a1[j] = add2(a1[j], i0);
                 a2[j] = fma2(i0, i0, a2[j]);
             }
         }
     }
-    float o1[16], o2[16];
+    float o1[8], o2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { upk2(a1[j], o1[2 * j], o1[2 * j + 1]); upk2(a2[j], o2[2 * j], o2[2 * j + 1]); }
-    if (f0 + 16 <= F) {
+    for (int j = 0; j < 4; ++j) { upk2(a1[j], o1[2 * j], o1[2 * j + 1]); upk2(a2[j], o2[2 * j], o2[2 * j + 1]); }
+    if (f0 + 8 <= F) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 2; ++j) {
             reinterpret_cast<float4*>(A1 + m * ld + f0)[j] = make_float4(o1[4 * j], o1[4 * j + 1], o1[4 * j + 2], o1[4 * j + 3]);
             reinterpret_cast<float4*>(A2 + m * ld + f0)[j] = make_float4(o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
         }
     } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
+        for (int j = 0; j < 8; ++j)
             if (f0 + j < F) { A1[m * ld + f0 + j] = o1[j]; A2[m * ld + f0 + j] = o2[j]; }
     }
 }
@@ -156,8 +149,8 @@ __global__ void vst_unpack_kernel(const uint32_t* __restrict__ VsT, const uint8_
         const int row = (int)(m % TM), slot = idx[m * VST_IDX_PITCH + r], bg = f >> 4;
         const uint32_t w = VsT[((((size_t)tile * (R + 1) + slot) * NBG + bg) * TM + row) * 8 + ((f & 15) >> 1)];
         float* dst = Vs + (m * R + r) * (int64_t)ld + f;
-        dst[0] = exp2f(bias_log2[f]) * __uint_as_float(w << 16);
-        if (f + 1 < F) dst[1] = exp2f(bias_log2[f + 1]) * __uint_as_float(w & 0xffff0000u);
+        dst[0] = exp2f(bias_log2[f]) * vst_lo(w);
+        if (f + 1 < F) dst[1] = exp2f(bias_log2[f + 1]) * vst_hi(w);
     }
 }
 
@@ -178,8 +171,8 @@ __global__ void vst_pack_kernel(const float* __restrict__ Vs, int R, const float
         if (m < rows && slot > 0 && f < F) {
             const float* src = Vs + (m * R + slot - 1) * (int64_t)ld + f;
             const float lo = src[0] * exp2f(-bias_log2[f]);
-            const float hi = (f + 1 < F) ? src[1] * exp2f(-bias_log2[f + 1]) : 0.f;
-            w = pack_bf16x2(lo, hi);
+            const float hi = (f + 1 < F) ? src[1] * exp2f(-bias_log2[f + 1]) : 1.f;
+            w = vst_word(lo, hi);
         }
         VsT[i] = w;
         if (bg == 0 && wd == 0 && m < rows && slot > 0) idx[m * VST_IDX_PITCH + slot - 1] = (uint8_t)slot;
@@ -215,9 +208,9 @@ extern "C" int dvae_vst_frame_stats(const DvaeMlp* dec, const void* image, int L
     DVAE_REQUIRE(n_tiles < (1ll << 31), "dvae_vst_frame_stats: too many frames");
     const dim3 grid((unsigned)n_tiles, NBG);
     cudaStream_t st = (cudaStream_t)stream;
-    if (R == 30) vst_frame_stats_kernel<30><<<grid, TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
-    else if (R == 10) vst_frame_stats_kernel<10><<<grid, TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
-    else vst_frame_stats_kernel<0><<<grid, TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
+    if (R == 30) vst_frame_stats_kernel<30><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
+    else if (R == 10) vst_frame_stats_kernel<10><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
+    else vst_frame_stats_kernel<0><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
     return check_launch("vst_frame_stats_kernel");
 }
 

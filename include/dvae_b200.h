@@ -169,7 +169,7 @@ int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64
  * layer-3 bias of `image` folded in as a per-bin scale; dvae_tc_packed_pv_bytes bytes).
  * Emission (VsT, vs_idx non-NULL; n_keep <= 31): the decoder output of the kept samples -- compute_Vs, mcem.py:280-290 --
  * is written by the sampler itself, in BF16 and WITHOUT the output-layer bias E[f] = exp(b3[f]):
- *   VsT[tile = chain / 128][slot 0..n_keep][bg = bin / 16 (33)][row = chain % 128][16] bf16  (dvae_vst_bytes bytes),
+ *   VsT[tile = chain / 128][slot 0..n_keep][bg = bin / 16 (33)][row = chain % 128][16] bf16  (dvae_vst_bytes bytes, 32-byte aligned),
  *   vs_idx[chain][32] bytes: byte r = slot of kept sample r, i.e. Vs[chain][r][f] = E[f] VsT[..][vs_idx[chain][r]][..].
  * flags: DVAE_TC_POLY_EX2 lets the sampler evaluate half of the layer-3 exponentials with a polynomial on the FMA pipe
  * (relative error 7.5e-5) instead of MUFU.EX2; only valid when the pre-activation stays inside +-120 in the log2

