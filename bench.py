@@ -6,9 +6,11 @@
         bench.py --gpus N --steps K --warmup W
 
 One *step* = one pass of the hot path (STFT -> 100 EM iterations of MH E-step + NMF M-step -> Wiener -> ISTFT) over
-one batch of synthetic 3 s utterances.  Workload at every N: BASELINE.json configs[1] per GPU ("M1 batch of 512
-synthetic utterances on 1 B200"), i.e. weak scaling with 512 utterances per rank and no data-path collective;
-NCCL only gathers per-utterance metrics and the max-over-ranks time.
+one batch of synthetic 3 s utterances.  Headline workload at every N: BASELINE.json configs[1] per GPU ("M1 batch of 512
+synthetic utterances on 1 B200"), i.e. weak scaling with 512 distinct utterances per rank and no data-path collective;
+NCCL only gathers per-utterance metrics (SI-SDR, final cost) and the max-over-ranks time.  The same JSON line carries
+``extra_configs``: BASELINE configs[2] (M2, 4 096 utterances in total split over the ranks: strong scaling) and, on 8 GPUs,
+configs[3] (M2-info / MCEM_M2v3, 4 096 utterances x 16 chains), each with its own ms_per_step, roofline and e2e.
 
 Printed JSON line (rank 0): `value` times the device-resident path with CUDA events; `e2e` times the public host API
 (`dvae_b200.engine.Enhancer.enhance`: pinned host buffers in, host arrays out, copies inside the timed region);
@@ -55,12 +57,14 @@ def parse():
     ap.add_argument("--chains", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs blocks (BASELINE configs[2], configs[3])")
+    ap.add_argument("--config3", action="store_true", help="run the configs[3] block at any GPU count (512 utterances x 16 chains per GPU)")
     return ap.parse_args()
 
 
 def measured_traffic(B, variant):
     """DRAM bytes of one sampler launch from the committed ncu capture, when one exists for this workload."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_tc_traffic.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_tc_traffic.json")
     try:
         t = json.load(open(path))
     except (OSError, ValueError):
@@ -180,10 +184,193 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def run_b200(args):
+# MUFU lane-operations the sampler needs per decoder row (SURVEY section 8d "MUFU ~ 1 795 / row" is the FP32 count; the
+# tcgen05 sampler shares reciprocals / logarithms between four bins and takes half of the exponentials from a polynomial):
+# 2 x 128 / 2 packed tanh + 528 x (0.5 ex2 + 0.25 rcp + 0.25 lg2)
+MUFU_PER_ROW = 128 + 528
+XU_LANES_PER_CLK_SM = 16
+
+
+def synth_set(u0, count, seconds=SECONDS, threads=16):
+    """``count`` distinct synthetic utterances with global ids u0 .. : ``(x, s)`` lists (threads: numpy releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max(1, min(threads, os.cpu_count() or 1))) as pool:
+        trip = list(pool.map(lambda u: synth.synth_utterance(u, seconds), range(u0, u0 + count)))
+    return [t[0] for t in trip], [t[1] for t in trip]
+
+
+def measure(variant, n_total, chains, steps, warmup, want_e2e, scaling, niter, sampler, rank, world, dev, label):
+    """One workload on this rank's shard; returns the JSON block (rank 0) or None.
+
+    ``scaling`` "weak": ``n_total`` utterances PER RANK; "strong": ``n_total`` utterances split over the ranks with
+    ``shard_range`` (the reference's np.array_split over processes, scripts/evaluate_ntcd_M2.py:298-327).
+    """
     import torch.distributed as dist
     from dvae_b200.engine import Enhancer, McemConfig, RaggedBatch
-    from dvae_b200.shard import gather_metrics, max_over_ranks
+    from dvae_b200.packages.metrics import energy_ratios_batch
+    from dvae_b200.packages.processing.target import vad_batch
+    from dvae_b200.shard import gather_metrics, max_over_ranks, shard_range
+
+    if scaling == "weak":
+        lo, hi, n_all = rank * n_total, (rank + 1) * n_total, world * n_total
+    else:
+        lo, hi = shard_range(n_total, rank, world)
+        n_all = n_total
+    B = hi - lo
+    T = int(SECONDS * synth.FS)
+    x_host, s_host = synth_set(1000 + lo, B)                     # every utterance distinct, global ids lo .. hi
+    sd = model_weights(variant, reference_power())
+    cfg = McemConfig(var_rw=0.01, nmf_rank=10, eps=1e-8, n_chains=chains, seed=2024, sampler=sampler, **schedule(variant, niter))
+    enh = Enhancer(sd, variant, cfg, device=dev.index)
+    eng = enh.engine
+    utt_ids = list(range(lo, hi))
+    nfr = [synth.num_frames(T)] * B
+    batch = RaggedBatch(nfr, dev, utt_ids)
+    x_dev = torch.from_numpy(np.stack(x_host)).to(dev).reshape(-1)
+    s_clean = torch.from_numpy(np.stack(s_host)).to(dev).reshape(-1)
+    x_off = (torch.arange(B, dtype=torch.int64) * T).to(dev)
+    x_len = torch.full((B,), T, dtype=torch.int32, device=dev)
+    y_dev = y_host = None
+    if variant != "M1":                                         # speech-activity labels of the clean signal (target.py:5-56), on the device
+        y_dev = vad_batch(s_clean, x_off, x_len, batch).view(batch.NT, 1)
+        yh = y_dev.view(B, -1).cpu().numpy()
+        y_host = [yh[u][None, :] for u in range(B)]
+
+    def step_device():
+        return enh.run_device(x_dev, x_off, x_len, batch, y_dev, B * T, T)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    sampler_clk = ClockSampler(dev.index)
+    if rank == 0:
+        sampler_clk.start()
+    eng.timing = True
+    eng._events = []
+    eng.kernel_launches = 0
+    eng.mh_rows = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s_dev, n_dev, cost = step_device()
+    e1.record()
+    barrier()
+    clocks = sampler_clk.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
+    stages = eng.stage_times_ms()
+    launches = eng.kernel_launches
+    mh_rows = eng.mh_rows
+    eng.timing = False
+    from dvae_b200 import tc
+    tc.check_status(eng)
+    value = n_all * SECONDS * steps / (ms_total * 1e-3)
+
+    # the path's only collective: per-utterance SI-SDR (packages/metrics.py:62-82, computed on the device) and final cost
+    sdr_out = energy_ratios_batch(s_dev, s_clean, None, x_off, x_len)[:, 0]
+    sdr_in = energy_ratios_batch(x_dev, s_clean, None, x_off, x_len)[:, 0]
+    local = torch.stack([sdr_out, sdr_in, cost[-1].to(torch.float64)], dim=1)
+    allm = gather_metrics(local, n_all)
+
+    e2e = None
+    if want_e2e:                                                # public host API: pinned host buffers in, host arrays out
+        for _ in range(2 if steps > 1 else 1):                  # warm the pinned staging / result buffers
+            res = enh.enhance(x_host, y_host, utt_ids=utt_ids)
+        del res
+        barrier()
+        t0 = time.perf_counter()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        n_e2e = max(1, min(steps, 2))
+        for _ in range(n_e2e):
+            res = enh.enhance(x_host, y_host, utt_ids=utt_ids)
+        g1.record()
+        barrier()
+        wall = max_over_ranks(max(time.perf_counter() - t0, g0.elapsed_time(g1) * 1e-3), dev)
+        e2e = dict(value=n_all * SECONDS * n_e2e / wall, unit=UNIT, h2d_bytes_per_step=int(enh.h2d_bytes),
+                   d2h_bytes_per_step=int(enh.d2h_bytes), steps=n_e2e)
+        del res
+    vs_bytes = (eng.VsT.numel() if getattr(eng, "VsT", None) is not None else eng.Vs_flat.numel() * 4)
+    del enh, eng
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+
+    pk = peaks()
+    flop_row = DEC_FLOP_PER_ROW[(variant, 16)]
+    # the sampler kernel itself (events around the dvae_mh_chain_tc2 launch); "mh" additionally holds the P / Vb packing
+    mh_ms, mh_calls = stages.get("mh_kernel", stages.get("mh", (0.0, 0)))
+    roof = None
+    if mh_calls:
+        flops_per_call = flop_row * mh_rows / mh_calls                       # algorithmic: one decoder row per proposal
+        achieved = flops_per_call / (mh_ms / mh_calls * 1e-3) / 1e12
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        xu_peak = XU_LANES_PER_CLK_SM * 148 * sm_hz                          # MUFU lane-operations per second at the clocks seen
+        xu_rate = MUFU_PER_ROW * mh_rows / (mh_ms * 1e-3)
+        roof = dict(kernel="mh2_kernel (dvae_mh_chain_tc2)", bound="tensor", achieved=achieved, peak=pk["tensor"], unit="TFLOP/s",
+                    frac=achieved / pk["tensor"], xu_frac=xu_rate / xu_peak, traffic=measured_traffic(B, variant), peak_source=pk["src"],
+                    share_of_step=mh_ms / ms_total, launches_per_step=mh_calls / steps,
+                    note="sampler time = CUDA events around dvae_mh_chain_tc2 inside the timed region; FLOPs = %d per decoder row x rows "
+                         "(one row per proposal); xu_frac = %d MUFU lane-operations per row against 16 lanes per clock and SM at the SM "
+                         "clock seen; traffic = dram read+write bytes of one E-step launch from ncu (profiles/r02_tc_traffic.json), null "
+                         "if no capture matches this batch" % (flop_row, MUFU_PER_ROW))
+    m = allm.cpu().numpy()
+    return dict(workload=label, value=value, unit=UNIT, ms_per_step=ms_total / steps, steps=steps, warmup=warmup, scaling=scaling,
+                utterances_total=n_all, utterances_this_rank=B, variant=variant, chains=chains, sampler=sampler,
+                schedule=schedule(variant, niter), clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roof,
+                stage_share={k: round(v[0] / ms_total, 4) for k, v in stages.items()},
+                si_sdr_db=dict(mean_out=float(m[:, 0].mean()), mean_in=float(m[:, 1].mean()),
+                               mean_improvement=float((m[:, 0] - m[:, 1]).mean()), n=int(m.shape[0])),
+                mean_final_cost=float(m[:, 2].mean()), kept_sample_bytes=int(vs_bytes))
+
+
+def oracle_si_sdr_delta(variant, niter, u=1000):
+    """|SI-SDR(GPU, sampler="tc") - SI-SDR(CPU oracle)| in dB for one utterance of the workload, both fed the SAME random draws
+    (torch's CPU generator in the reference's consumption order).  Returns (delta, oracle seconds)."""
+    from dvae_b200.packages.models import mcem as shim_mcem
+    from dvae_b200.packages.models import models as shim_models
+    from dvae_b200.packages.processing.stft import istft
+    from oracle import mcem_port, stft_np
+    kw = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False, pad_at_end=True)
+    ikw = dict(fs=16000, wlen_sec=64e-3, win="hann", hop_percent=0.25, center=False)
+    x, s, _ = synth.synth_utterance(u, SECONDS)
+    sd = model_weights(variant, reference_power())
+    y = synth.energy_vad(s) if variant != "M1" else None
+    t0 = time.perf_counter()
+    X, S = stft_np.stft(x, **kw), stft_np.stft(s, **kw)
+    torch.manual_seed(4321)
+    o = mcem_port.MCEMOracle(variant, niter, 10, 30, 25, 75, 0.01)
+    o.init_parameters(X, S, sd, 10, 1e-8, y=y)
+    o.run()
+    s_ref = stft_np.istft(o.S_hat, max_len=len(x), **ikw)
+    stft_np.istft(o.N_hat, max_len=len(x), **ikw)
+    t_cpu = time.perf_counter() - t0
+    if variant == "M1":
+        model = shim_models.VariationalAutoencoder([513, 16, [128, 128]])
+        cls = shim_mcem.MCEM_M1
+    else:
+        model = shim_models.DeepGenerativeModel([513, 1, 16, [128, 128]], None) if variant == "M2" else shim_models.DeepGenerativeModel_v3([513, 1, 16, [128, 128]])
+        cls = shim_mcem.MCEM_M2 if variant == "M2" else shim_mcem.MCEM_M2v3
+    model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()}, strict=False)
+    model.to("cuda:%d" % torch.cuda.current_device()).eval()
+    algo = cls(niter, 10, 30, 25, 75, 0.01, rng="torch", sampler="tc")
+    torch.manual_seed(4321)
+    args = dict(X=X, S=S, vae=model, nmf_rank=10, eps=1e-8, device=torch.cuda.current_device())
+    if variant != "M1":
+        args["y"] = torch.tensor(y, device="cuda:%d" % torch.cuda.current_device())
+    algo.init_parameters(**args)
+    algo.run()
+    s_gpu = istft(algo.S_hat, max_len=len(x), **ikw)
+    a, b = mcem_port.si_sdr(s_gpu[800:-800], s[800:-800]), mcem_port.si_sdr(s_ref[800:-800], s[800:-800])
+    return abs(a - b), b, t_cpu
+
+
+def run_b200(args):
+    import torch.distributed as dist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,131 +387,60 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = args.batch
-    u0 = rank * B                                     # global utterance ids of this rank's shard
-    T = int(SECONDS * synth.FS)
 
-    # synthetic inputs (host); a few distinct waveforms are tiled over the batch to keep set-up time short,
-    # every utterance still gets its own Philox stream (global id) and its own NMF / latent state
-    n_distinct = min(B, 32)
-    base_x, base_s = synth.synth_batch(1000, n_distinct, SECONDS)
-    idx = (np.arange(B) + u0) % n_distinct
-    x_host = [base_x[i] for i in idx]
-    y_host = [synth.energy_vad(base_s[i]) for i in idx] if args.variant != "M1" else None
-    sd = model_weights(args.variant, reference_power())
-    cfg = McemConfig(var_rw=0.01, nmf_rank=10, eps=1e-8, n_chains=args.chains, seed=2024, sampler=args.sampler,
-                     **schedule(args.variant, args.niter))
-    enh = Enhancer(sd, args.variant, cfg, device=local)
-    eng = enh.engine
-    utt_ids = list(range(u0, u0 + B))
+    headline = (args.variant == "M1" and B == 512 and args.chains == 1)
+    cfg_name = "BASELINE.json configs[1]" if headline else \
+        "BASELINE.json configs[%d] shape (%s, %d utterances per GPU)" % (2 if args.variant == "M2" else (3 if args.variant == "M2v3" else 1), args.variant, B)
+    label = cfg_name + ": %s batch of %d synthetic 3 s 16 kHz utterances per GPU (all distinct), STFT 1024/256, NMF rank 10, %d EM iterations" % (
+        args.variant, B, args.niter)
+    main = measure(args.variant, B, args.chains, args.steps, args.warmup, not args.no_e2e, "weak", args.niter, args.sampler, rank, world, dev, label)
 
-    # device-resident copy of the inputs for the `value` measurement
-    nfr = [synth.num_frames(T)] * B
-    batch = RaggedBatch(nfr, dev, utt_ids)
-    x_dev = torch.from_numpy(np.stack(x_host)).to(dev).reshape(-1)
-    x_off = (torch.arange(B, dtype=torch.int64) * T).to(dev)
-    x_len = torch.full((B,), T, dtype=torch.int32, device=dev)
-    y_dev = None
-    if y_host is not None:
-        y_dev = torch.from_numpy(np.ascontiguousarray(np.concatenate([y.T for y in y_host], 0))).to(dev)
-
-    def step_device():
-        return enh.run_device(x_dev, x_off, x_len, batch, y_dev, B * T, T)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    eng.timing = True
-    eng._events = []
-    eng.kernel_launches = 0
-    eng.mh_rows = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        s_dev, n_dev, cost = step_device()
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = max_over_ranks(e0.elapsed_time(e1), dev)
-    stages = eng.stage_times_ms()
-    launches = eng.kernel_launches
-    mh_rows = eng.mh_rows
-    eng.timing = False
-    value = world * B * SECONDS * args.steps / (ms_total * 1e-3)
-
-    # end-to-end through the public host API: pinned host buffers in, host arrays out, copies inside the timed region
-    e2e = None
-    if not args.no_e2e:
-        for _ in range(2):                                           # warm the pinned staging / result buffers (two result sets alternate)
-            s_list, n_list, cost_h = enh.enhance(x_host, y_host, utt_ids=utt_ids)
-        barrier()
-        t0 = time.perf_counter()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        n_e2e = max(1, min(args.steps, 2))
-        for _ in range(n_e2e):
-            s_list, n_list, cost_h = enh.enhance(x_host, y_host, utt_ids=utt_ids)
-        g1.record()
-        barrier()
-        wall = max_over_ranks(max(time.perf_counter() - t0, g0.elapsed_time(g1) * 1e-3), dev)
-        e2e = dict(value=world * B * SECONDS * n_e2e / wall, unit=UNIT, h2d_bytes_per_step=int(enh.h2d_bytes),
-                   d2h_bytes_per_step=int(enh.d2h_bytes), steps=n_e2e)
-
-    # per-utterance metric gathered over ranks (the path's only collective): final cost of each utterance
-    final_cost = cost[-1].to(torch.float64).reshape(B, 1)
-    all_cost = gather_metrics(final_cost, world * B)
+    extra = []
+    if headline and not args.no_extra:
+        # configs[2]: M2, 4 096 utterances sharded over the ranks (strong scaling, scripts/evaluate_ntcd_M2.py:298-327)
+        blk = measure("M2", 4096, 1, min(args.steps, 2), 1, not args.no_e2e, "strong", args.niter, args.sampler, rank, world, dev,
+                      "BASELINE.json configs[2]: M2 speech-activity-conditioned VAE, 4 096 synthetic 3 s utterances in total, sharded over "
+                      "%d GPU(s) with shard_range" % world)
+        if blk:
+            extra.append(blk)
+        if world == 8 or args.config3:
+            # configs[3]: M2-info weights layout (enc_dec_clf of DeepGenerativeModel_v5 = MCEM_M2v3), 4 096 utterances x 16 chains
+            blk = measure("M2v3", 4096 if world == 8 else 512 * world, 16, 1, 1, False, "strong", args.niter, args.sampler, rank, world, dev,
+                          "BASELINE.json configs[3]: M2-info (MCEM_M2v3) with visual-VAD-style label input, %d utterances x 16 MH chains "
+                          "sharded over %d GPU(s)" % (4096 if world == 8 else 512 * world, world))
+            if blk:
+                extra.append(blk)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    pk = peaks()
-    flop_row = DEC_FLOP_PER_ROW[(args.variant, 16)]
-    # the sampler kernel itself (events around the dvae_mh_chain_* launch); "mh" additionally holds the draw / pack kernels
-    mh_ms, mh_calls = stages.get("mh_kernel", stages.get("mh", (0.0, 0)))
-    roof = None
-    if mh_calls:
-        flops_per_call = flop_row * mh_rows / mh_calls                       # algorithmic: one decoder row per proposal
-        achieved = flops_per_call / (mh_ms / mh_calls * 1e-3) / 1e12
-        roof = dict(kernel="mh_chain_%s" % args.sampler, bound="tensor", achieved=achieved, peak=pk["tensor"], unit="TFLOP/s",
-                    frac=achieved / pk["tensor"], traffic=measured_traffic(B, args.variant), peak_source=pk["src"],
-                    share_of_step=mh_ms / ms_total, launches_per_step=mh_calls / args.steps,
-                    note="sampler time = CUDA events around dvae_mh_chain_* inside the timed region; FLOPs = %d per decoder row x rows; "
-                         "traffic = dram read+write bytes of one E-step launch from ncu (profiles/r01_tc_traffic.json), null if "
-                         "no capture matches this batch" % flop_row)
-    cfg_name = "BASELINE.json configs[1]" if (args.variant == "M1" and B == 512) else \
-        "BASELINE.json configs[%d] shape (%s, %d utterances per GPU)" % (2 if args.variant == "M2" else (3 if args.variant == "M2v3" else 1), args.variant, B)
-    stage_share = {k: round(v[0] / ms_total, 4) for k, v in stages.items()}
-
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         cpu_reference_run(args.variant, max(1, args.niter // 20), 0)
-        t_cpu = cpu_reference_run(args.variant, args.niter, 1000)
+        delta, sdr_ref, t_cpu = oracle_si_sdr_delta(args.variant, args.niter, 1000)
         cpu = dict(value=SECONDS / t_cpu, unit=UNIT, cores=cores, kind="port",
                    sample="1 of the %d utterances (3 s, %d EM iterations) through oracle.mcem_port on %d host threads: %.1f s" %
                           (B, args.niter, cores, t_cpu))
+        parity = dict(si_sdr_delta_db=delta, oracle_si_sdr_db=sdr_ref,
+                      how="the CPU oracle run of cpu_baseline and the GPU path (sampler=tc, reference-signature MCEM shim) on the same "
+                          "utterance and the same torch CPU draws (seed 4321); north star: within 0.05 dB")
 
-    out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-               ms_per_step=ms_total / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+    out = dict(metric=METRIC, value=main["value"], unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+               ms_per_step=main["ms_per_step"], higher_is_better=True, scaling="weak", vs_baseline=None,
                dtype="f32" if args.sampler == "fp32" else "bf16", data="synthetic",
-               config=dict(workload=cfg_name + ": %s batch of %d synthetic 3 s 16 kHz utterances per GPU, STFT 1024/256, "
-                                    "NMF rank 10, %d EM iterations, MH schedule %s" % (args.variant, B, args.niter, schedule(args.variant, args.niter)),
-                           utterances_per_gpu=B, sampler=args.sampler, chains=args.chains,
+               config=dict(workload=main["workload"] + ", MH schedule %s" % main["schedule"], utterances_per_gpu=B, sampler=args.sampler,
+                           chains=args.chains,
                            l2="working set per EM iteration (kept-sample variances %.1f GB) exceeds the 126 MB L2; no explicit flush" %
-                              ((eng.VsT.numel() if getattr(eng, "VsT", None) is not None else eng.Vs_flat.numel() * 4) / 1e9),
+                              (main["kept_sample_bytes"] / 1e9),
                            parallelism="utterance shards, %d rank(s), no data-path collective" % world),
-               clocks=clocks, e2e=e2e, gpu_launches=int(launches), roofline=roof, cpu_baseline=cpu,
-               stage_share=stage_share, mean_final_cost=float(all_cost.mean().item()))
+               clocks=main["clocks"], e2e=main["e2e"], gpu_launches=main["gpu_launches"], roofline=main["roofline"], cpu_baseline=cpu,
+               stage_share=main["stage_share"], mean_final_cost=main["mean_final_cost"], si_sdr_db=main["si_sdr_db"], parity=parity,
+               extra_configs=extra)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -30,12 +30,50 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+MANIFEST = os.path.join(HERE, "libdvae_b200.manifest.json")
+
+
+def _sha256(path: str) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()
+
+
+def _deps():
+    return sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(os.path.dirname(HERE), "include", "dvae_b200.h")]
+
+
+def source_hashes() -> dict:
+    return {os.path.relpath(d, os.path.dirname(HERE)): _sha256(d) for d in _deps()}
+
+
+def verify() -> dict:
+    """Check that the shared library on disk is the one built from the sources on disk: the manifest written at link time
+    records the SHA-256 of every source / header and of the library itself (the library travels to the GPU box as a binary).
+    Returns the manifest; raises RuntimeError on any mismatch."""
+    import json
+    if not (os.path.exists(LIB) and os.path.exists(MANIFEST)):
+        raise RuntimeError("libdvae_b200.so or its manifest is missing: run `python -m dvae_b200.build`")
+    with open(MANIFEST) as f:
+        man = json.load(f)
+    if man.get("library_sha256") != _sha256(LIB):
+        raise RuntimeError("libdvae_b200.so does not match its build manifest")
+    if man.get("sources") != source_hashes():
+        raise RuntimeError("libdvae_b200.so was built from different sources than the ones on disk")
+    return man
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    """True unless the library's manifest matches the sources on disk (content hashes, not modification times: the tree is
+    copied to the GPU box, which does not preserve them)."""
+    try:
+        verify()
+        return False
+    except RuntimeError:
         return True
-    t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(os.path.dirname(HERE), "include", "dvae_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -50,7 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t):
-            return obj, 0, ""
+            return obj, 0, ""                      # object cache of the build container (modification times are reliable here)
         proc = subprocess.run([nvcc] + NVCC_FLAGS + ["-c", "-o", obj, src], capture_output=True, text=True)
         return obj, proc.returncode, proc.stdout + proc.stderr
 
@@ -69,6 +107,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(log)
     if failed:
         raise RuntimeError("nvcc failed (%s)" % ", ".join("%s: exit %d" % (os.path.basename(r[0]), r[1]) for r in failed))
+    import json
+    with open(MANIFEST, "w") as f:
+        json.dump({"library_sha256": _sha256(LIB), "sources": source_hashes(), "nvcc_flags": NVCC_FLAGS}, f, indent=1, sort_keys=True)
     return LIB
 
 

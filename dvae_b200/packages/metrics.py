@@ -61,3 +61,48 @@ def si_sdr_components(s_hat, s, n):
     s_target = (np.dot(s_hat, s) / np.dot(s, s)) * s
     e_noise = (np.dot(s_hat, n) / np.dot(n, n)) * n
     return s_target, e_noise, s_hat - s_target - e_noise
+
+
+# ---------------------------------------------------------------------------------------------- statistics table (host)
+def mean_confidence_interval(data, confidence=0.95, round=3):
+    """Mean and half-width of the Student-t confidence interval, both rounded to 3 decimals (packages/metrics.py:5-10)."""
+    import scipy.stats
+    a = np.asarray(data, dtype=np.float64)
+    half = scipy.stats.sem(a) * scipy.stats.t.ppf((1.0 + confidence) / 2.0, len(a) - 1)
+    return np.round(np.mean(a), 3), np.round(half, 3)
+
+
+def compute_stats(metrics_keys, all_metrics, model_data_dir, confidence, all_snr_db=None, all_noise_types=None, all_speakers=None,
+                  all_noise_stationarities=None):
+    """The evaluation table of the reference (packages/metrics.py:84-167): average and confidence interval of every metric
+    over all utterances, then per input SNR / noise type / noise stationarity / speaker when those lists are given.  Prints
+    the same tables (same headings and column format) and additionally RETURNS them:
+    ``{"all": {key: {"avg", "+/-"}}, "snr": {value: {...}}, "noise_type": {...}, "noise_stationarity": {...}, "speaker": {...}}``.
+    ``all_metrics`` is a list of per-utterance tuples in the order of ``metrics_keys`` (``scripts/run_metrics.py:117-129``)."""
+    cols = {key: np.asarray([row[i] for row in all_metrics], dtype=np.float64) for i, key in enumerate(metrics_keys)}
+
+    def table(select):
+        print("{:<10} {:<10} {:<10}".format('METRIC', 'AVERAGE', 'CONF. INT.'))
+        out = {}
+        for key, col in cols.items():
+            m, h = mean_confidence_interval(col[select], confidence=confidence)
+            out[key] = {'avg': m, '+/-': h}
+            print("{:<10} {:<10} {:<10}".format(key, m, h))
+        print('\n')
+        return out
+
+    n = len(all_metrics)
+    result = {"all": table(np.ones(n, dtype=bool))}
+    groups = (("snr", all_snr_db, lambda v: 'Input SNR = {:.2f}'.format(v)),
+              ("noise_type", all_noise_types, lambda v: 'Noise type = {}'.format(v)),
+              ("noise_stationarity", all_noise_stationarities, lambda v: 'Noise type = {}'.format(v)),      # heading as in the reference
+              ("speaker", all_speakers, lambda v: 'Speaker = {}'.format(v)))
+    for name, labels, heading in groups:
+        if labels is None:
+            continue
+        labels = np.asarray(labels)
+        result[name] = {}
+        for v in (np.unique(labels) if name == "snr" else sorted(set(labels.tolist()))):
+            print(heading(v))
+            result[name][v] = table(labels == v)
+    return result

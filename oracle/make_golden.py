@@ -239,12 +239,41 @@ def run_labels():
           (int(vad.sum()), vad.shape[1], 100 * ibm.mean(), os.path.getsize(path) / 1024))
 
 
+def stats_inputs():
+    """Seeded per-utterance metric rows and grouping labels for the ``compute_stats`` fixture (also used by the test)."""
+    rng = np.random.default_rng(5)
+    rows = [tuple(float(v) for v in rng.normal(loc=(8.0, 15.0, 9.0), scale=2.0)) for _ in range(48)]
+    snr = np.array([(-5, 0, 5, 10)[i % 4] for i in range(48)])
+    noise = [("Babble", "Cafe", "Car")[i % 3] for i in range(48)]
+    return ["si_sdr", "si_sir", "si_sar"], rows, snr, noise
+
+
+def run_stats():
+    """``tests/golden/compute_stats.txt``: what the reference's ``compute_stats`` (packages/metrics.py:84-167) prints for seeded
+    metric rows, grouped by input SNR and noise type."""
+    import contextlib
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("ref_metrics", os.path.join(REF, "packages", "metrics.py"))
+    ref_metrics = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_metrics)
+    keys, rows, snr, noise = stats_inputs()
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ref_metrics.compute_stats(keys, rows, "", 0.95, all_snr_db=snr, all_noise_types=noise)
+    path = os.path.join(ROOT, "tests", "golden", "compute_stats.txt")
+    with open(path, "w") as f:
+        f.write(buf.getvalue())
+    print("stats      ok: %d lines" % buf.getvalue().count("\n"))
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("needs the reference at %s (build container only)" % REF)
     torch.set_num_threads(1)
     run_metrics()
     run_labels()
+    run_stats()
     if "--metrics-only" not in sys.argv:
         for c in CASES:
             run_case(c)

@@ -2,7 +2,11 @@
 
 Follows ``packages/processing/stft.py:13-60`` (``stft``) and ``:63-99`` (``istft``), which are
 thin wrappers over ``librosa.core.stft`` / ``librosa.core.istft`` (librosa 0.7-0.9 semantics,
-restated here because librosa is not installed; **parity unpinned**, see ``oracle/__init__.py``).
+restated here because librosa is not installed and the reference holds no vector at this boundary:
+**not pinned by a reference-held vector**, see ``oracle/__init__.py``; pinned against three independent
+implementations instead: ``torch.stft`` in float64 and a direct DFT (forward), ``scipy.signal.stft`` /
+``scipy.signal.istft`` with the same framing (forward bit for bit after the complex64 cast, inverse to
+float32 rounding on plain and on masked spectrograms), ``tests/test_oracle_stft.py``).
 
 librosa semantics restated (for ``center=False``; ``center=True`` adds the reflect padding):
   stft : periodic Hann ``get_window('hann', n_fft, fftbins=True)`` in float64, frames

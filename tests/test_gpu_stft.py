@@ -160,3 +160,26 @@ def test_istft_masked_equals_wiener_apply_then_istft():
             assert relerr(got[800:-800], ref[800:-800]) <= 1e-4     # north-star tolerance, interior samples
     with pytest.raises(ValueError):
         istft_masked_batch(X, ws[:, :512], batch, x_off, x_len, total, max(lens))
+
+
+def test_cuda_stft_istft_against_scipy_signal_directly():
+    """The CUDA kernels against scipy.signal's STFT / ISTFT (no restatement in between): STFT to FP32-FFT accuracy, ISTFT of a
+    Wiener-masked spectrogram in the region where scipy and librosa share semantics (away from the first / last window)."""
+    import warnings
+
+    import scipy.signal
+    from dvae_b200.packages.processing.stft import istft, stft
+    x, _, _ = synth.synth_utterance(8, 3.0)
+    xp = np.pad(x.astype(np.float64), (0, 256))
+    w = scipy.signal.get_window("hann", 1024)
+    _, _, Z = scipy.signal.stft(xp, fs=16000, window="hann", nperseg=1024, noverlap=768, nfft=1024, boundary=None, padded=False,
+                                return_onesided=True, scaling="spectrum")
+    got = stft(x, **KW)
+    assert got.shape == Z.shape and relerr(got, Z * w.sum()) <= 2e-6
+    M = np.random.default_rng(1).uniform(0.0, 1.0, size=Z.shape)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, ym = scipy.signal.istft(M * Z, fs=16000, window="hann", nperseg=1024, noverlap=768, nfft=1024, boundary=False, scaling="spectrum")
+    y = istft((M * Z * w.sum()).astype(np.complex64), max_len=len(xp), **IKW)
+    n = min(len(y), len(ym))
+    assert np.max(np.abs(y[1024:n - 1024] - ym[1024:n - 1024])) <= 5e-6 * max(1.0, np.max(np.abs(ym)))

@@ -149,6 +149,53 @@ def test_tc_si_sdr_within_0p05_db_of_oracle_and_fp32():
     assert abs(sdr["tc"] - ref) <= 0.05 and abs(sdr["fp32"] - ref) <= 0.05, (sdr, ref, base)
 
 
+@pytest.mark.parametrize("variant", ["M1", "M2", "M2v3"])
+def test_tc_at_the_benchmark_configuration_against_the_oracle(variant):
+    """bench.py's workload for one utterance: 3 s, 100 EM iterations, the reference's MH schedule (M1: 60 / 30 and 105 / 75;
+    M2*: 40 / 10 and 100 / 25), sampler="tc" (sampler emission, BF16 variances), against the CPU oracle on the SAME draws
+    (torch CPU generator in the reference's consumption order).  North star: SI-SDR within 0.05 dB; cost curve within 2 %."""
+    from dvae_b200.packages.models import mcem as shim_mcem
+    from dvae_b200.packages.models import models as shim_models
+    from dvae_b200.packages.processing.stft import istft
+    x, s, _ = synth.synth_utterance(1003, 3.0)
+    X_ref, S_ref = stft_np.stft(x, **KW), stft_np.stft(s, **KW)
+    y_dim = 0 if variant == "M1" else 1
+    y = synth.energy_vad(s) if y_dim else None
+    sd = synth.xavier_state_dict(variant, 513, 16, [128, 128], y_dim, seed=1234, out_bias=synth.speech_prior_bias(s))
+    niter = 100
+    torch.manual_seed(2024)
+    o = mcem_port.MCEMOracle(variant, niter, 10, 30, 25, 75, 0.01)
+    o.init_parameters(X_ref, S_ref, sd, 10, 1e-8, y=y)
+    cost_ref = o.run()
+    s_ref = stft_np.istft(o.S_hat, max_len=len(x), **IKW)
+    ref = mcem_port.si_sdr(s_ref[800:-800], s[800:-800])
+    base = mcem_port.si_sdr(x[800:-800], s[800:-800])
+    assert ref > base + 1.0, "the synthetic speech prior should enhance (%.2f -> %.2f dB)" % (base, ref)
+    if variant == "M1":
+        model, cls = shim_models.VariationalAutoencoder([513, 16, [128, 128]]), shim_mcem.MCEM_M1
+    elif variant == "M2":
+        model, cls = shim_models.DeepGenerativeModel([513, 1, 16, [128, 128]], None), shim_mcem.MCEM_M2
+    else:
+        model, cls = shim_models.DeepGenerativeModel_v3([513, 1, 16, [128, 128]]), shim_mcem.MCEM_M2v3
+    model.load_state_dict({k: torch.tensor(v) for k, v in sd.items()}, strict=False)
+    model.to(DEV).eval()
+    algo = cls(niter, 10, 30, 25, 75, 0.01, rng="torch", sampler="tc")
+    torch.manual_seed(2024)
+    kw = dict(X=X_ref, S=S_ref, vae=model, nmf_rank=10, eps=1e-8, device=0)
+    if y_dim:
+        kw["y"] = torch.tensor(y, device=DEV)
+    algo.init_parameters(**kw)
+    cost = algo.run()
+    assert algo._engine.vst_R == 0 and algo._engine.cfg.sampler == "tc" and getattr(algo._engine, "VsT", None) is not None   # the E-steps went through the sampler's emission
+    s_hat = istft(algo.S_hat, max_len=len(x), **IKW)
+    got = mcem_port.si_sdr(s_hat[800:-800], s[800:-800])
+    assert abs(got - ref) <= 0.05, (got, ref, base)
+    np.testing.assert_allclose(cost, cost_ref, rtol=2e-2)
+    # the lazily exposed variances of the filter samples have the reference's shapes (mcem.py:29-34)
+    R_wf = 75 if variant == "M1" else 25
+    assert tuple(algo.Vs.shape) == (R_wf, 513, X_ref.shape[1]) and tuple(algo.Vx.shape) == tuple(algo.Vs.shape)
+
+
 def test_tc_rejects_unsupported_shapes():
     sd = synth.xavier_state_dict("M1", 257, 16, [128, 128], 0)
     w = VaeWeights(sd, "M1", torch.device(DEV))

@@ -155,3 +155,28 @@ def test_argument_errors_are_reported_before_any_launch():
     assert rc < 0 and b"bad sizes" in lib.dvae_last_error()
     with pytest.raises(ValueError):
         _lib.call("dvae_istft_masked_f32", p(buf), None, 1.0, p(off), 1, p(buf), p(off), p(ln), 8, 1024, 256, 520, None)
+
+
+def test_compute_stats_prints_the_reference_tables():
+    """``compute_stats`` of the metrics shim against what the reference's own function printed for the same rows
+    (tests/golden/compute_stats.txt, written by oracle/make_golden.py).  The reference walks the noise types in ``set`` order,
+    so the blocks are compared as a multiset of lines; the returned dictionary is checked against numpy / scipy directly."""
+    import contextlib
+    import io
+
+    import scipy.stats
+    from dvae_b200.packages.metrics import compute_stats, mean_confidence_interval
+    from oracle.make_golden import stats_inputs
+    keys, rows, snr, noise = stats_inputs()
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out = compute_stats(keys, rows, "", 0.95, all_snr_db=snr, all_noise_types=noise)
+    golden = open(os.path.join(os.path.dirname(__file__), "golden", "compute_stats.txt")).read()
+    assert sorted(buf.getvalue().split("\n")) == sorted(golden.split("\n"))
+    col = np.asarray([r[0] for r in rows])
+    half = scipy.stats.sem(col) * scipy.stats.t.ppf(0.975, len(col) - 1)
+    assert out["all"]["si_sdr"] == {"avg": np.round(col.mean(), 3), "+/-": np.round(half, 3)}
+    assert set(out["snr"]) == {-5, 0, 5, 10} and set(out["noise_type"]) == {"Babble", "Cafe", "Car"}
+    sel = col[snr == 5]
+    assert out["snr"][5]["si_sdr"]["avg"] == np.round(sel.mean(), 3)
+    assert mean_confidence_interval([1.0, 2.0, 4.0])[0] == np.round(7.0 / 3.0, 3)

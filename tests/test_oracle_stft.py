@@ -1,4 +1,5 @@
-"""STFT / ISTFT restatement: cross-checks (parity unpinned: librosa is not installable, see oracle/__init__.py)."""
+"""STFT / ISTFT restatement: cross-checks against torch.stft, a direct DFT and scipy.signal (librosa itself is not installable and
+the reference holds no vector at this boundary, see oracle/__init__.py)."""
 import os
 
 import numpy as np
@@ -36,6 +37,47 @@ def test_matches_direct_dft():
     for i in (0, 77, 184):
         fr = np.pad(x.astype(np.float64), (0, 256))[i * 256:i * 256 + 1024] * stft_np.hann_periodic(1024)
         np.testing.assert_allclose(X[:, i], stft_np.dft_direct(fr), rtol=0, atol=1e-5 * np.abs(X[:, i]).max())
+
+
+def _scipy_pair(xp):
+    """scipy.signal's STFT / ISTFT with the reference's framing (no boundary extension, no padding, periodic Hann, hop 256):
+    an implementation that shares no code with the restatement (scipy 1.x ShortTimeFFT machinery)."""
+    import scipy.signal
+    w = scipy.signal.get_window("hann", 1024)
+    _, _, Z = scipy.signal.stft(xp, fs=16000, window="hann", nperseg=1024, noverlap=768, nfft=1024, boundary=None, padded=False,
+                                return_onesided=True, scaling="spectrum")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                                # NOLA warning: the first hop has no full window coverage
+        _, y = scipy.signal.istft(Z, fs=16000, window="hann", nperseg=1024, noverlap=768, nfft=1024, boundary=False, scaling="spectrum")
+    return Z * w.sum(), y
+
+
+def test_stft_and_istft_match_scipy_signal():
+    """Pins both halves of the restatement against an independent implementation: the STFT bit for bit after the cast to
+    complex64, the ISTFT to float32 rounding wherever the two share semantics (away from the first / last window, where
+    librosa divides by the window sum above float32 tiny and scipy above 1e-10)."""
+    x, _, _ = synth.synth_utterance(3)
+    xp = np.pad(x.astype(np.float64), (0, 256))
+    Z, y = _scipy_pair(xp)
+    X = stft_np.stft(x, **KW)
+    assert Z.shape == X.shape and np.array_equal(Z.astype(np.complex64), X)
+    yo = stft_np.istft(X, fs=16000, wlen_sec=64e-3, hop_percent=0.25, center=False, max_len=len(xp))
+    n = min(len(y), len(yo))
+    assert np.max(np.abs(y[1024:n - 1024] - yo[1024:n - 1024])) <= 3e-7
+    # and on a spectrogram that is NOT the STFT of a signal (a Wiener-masked one): the inverse is a genuine least-squares
+    # overlap-add, not just "undo the forward transform"
+    rng = np.random.default_rng(0)
+    M = rng.uniform(0.0, 1.0, size=X.shape).astype(np.float32)
+    import scipy.signal
+    import warnings
+    w = scipy.signal.get_window("hann", 1024)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, ym = scipy.signal.istft((M * X).astype(np.complex128) / w.sum(), fs=16000, window="hann", nperseg=1024, noverlap=768, nfft=1024,
+                                   boundary=False, scaling="spectrum")
+    yom = stft_np.istft((M * X).astype(np.complex64), fs=16000, wlen_sec=64e-3, hop_percent=0.25, center=False, max_len=len(xp))
+    assert np.max(np.abs(ym[1024:n - 1024] - yom[1024:n - 1024])) <= 3e-7
 
 
 def test_round_trip_interior():
