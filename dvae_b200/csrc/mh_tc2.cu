@@ -114,6 +114,8 @@ __device__ __forceinline__ float4 philox_normals4(uint32_t utt, uint32_t fc, uin
 // policy.  ncu on the E-step call at B = 512 (profiles/r02_ncu_mh2_emit_vs_plain.txt): the 3 GB the kept iterations write
 // push clean lines out of L2 -- part of the P / Vb stream (DRAM reads 208 -> 445 MB) and the kernel's own instructions
 // (no_instruction stalls 0.46 per issued instruction) -- which costs 0.55 ms per call without the policies and 0.3 ms with them.
+// (Reserving part of L2 for evict-last lines with cudaLimitPersistingL2CacheSize made it worse: 32 MB +0.02 ms, 64 MB +0.3 ms,
+// and the frame-statistics kernel that follows lost up to 0.6 ms.)
 __device__ __forceinline__ void st_cell(uint4* p, const uint32_t (&o)[8], uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;" :: "l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
                  "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "l"(pol) : "memory");
