@@ -452,7 +452,11 @@ def run_b200(args):
 
 def reference_power():
     """Decoder output bias shared by both arms: log of the mean clean-speech power spectrum of synthetic utterance 1000
-    (random weights around it act as a crude speech prior, so the Wiener filter does real work)."""
+    (random weights around it act as a crude speech prior, so the Wiener filter does real work).  The prior carries that
+    utterance's harmonics: utterance 1000 is genuinely enhanced (the `parity` block compares its SI-SDR with the oracle's),
+    the other utterances of the batch have other pitches, and with untrained weights their SI-SDR (gathered in `si_sdr_db`)
+    is a payload for the metric path, not a quality claim (a pitch-independent envelope prior was tried: the rank-10 NMF
+    then explains the stationary synthetic harmonics as noise for every utterance)."""
     _, s, _ = synth.synth_utterance(1000, SECONDS)
     return synth.speech_prior_bias(s)
 

@@ -51,7 +51,7 @@ PROTOTYPES = {
     "dvae_nmf_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dvae_nmf_mstep": (C.c_int, [c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64,
                                  C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
-    "dvae_decode_stats_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
+    "dvae_decode_stats_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int64,
                                        C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "dvae_nmf_w_from_frame_stats": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_mh_workspace_floats": (C.c_int64, [C.POINTER(DvaeMlp), C.c_int64, C.c_int]),
@@ -70,17 +70,17 @@ PROTOTYPES = {
                                   c_ptr]),
     "dvae_ibm_labels": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_float, c_ptr, c_ptr,
                                   c_ptr, c_ptr]),
-    "dvae_decode_stats_win_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr,
+    "dvae_decode_stats_win_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr,
                                            c_ptr, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr]),
-    "dvae_decode_a1_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr,
+    "dvae_decode_a1_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
                                     C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr]),
     "dvae_wiener_from_a1": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr]),
     "dvae_energy_ratios": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr]),
     "dvae_tc_decoder_exponent_bound": (C.c_int, [C.POINTER(DvaeMlp), C.c_int, C.c_int, c_ptr, c_ptr]),
-    "dvae_decode_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, C.c_int, c_ptr, C.c_int,
+    "dvae_decode_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int,
                                  c_ptr, c_ptr]),
     "dvae_vst_bytes": (C.c_int64, [C.c_int64, C.c_int]),
-    "dvae_mh_chain_tc2": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64,
+    "dvae_mh_chain_tc2": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(DvaeRng), c_ptr, c_ptr, c_ptr, c_ptr,
                                     C.c_int, c_ptr, c_ptr]),
     "dvae_vst_frame_stats": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,

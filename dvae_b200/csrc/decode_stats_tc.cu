@@ -37,6 +37,7 @@ struct DsParams {
     const unsigned char* image;
     const float* Zs;        // [NT][R][L]
     const float* y;         // [NT][y_dim] or null
+    const float* ybias;     // [NT][128] per-frame layer-1 bias or null
     const float* Vb;        // [NT][ld]
     const float* g;         // [NT]
     float* Vs;              // [NT][R][ld]
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(DS_THREADS, 1) decode_stats_kernel(DsParams p)
             mbar_wait(bar12, ph12, dead, p.status);
             ph12 ^= 1;
             tc_fence_after();
-            ds_hidden_row(tmem, A, q, row, nullptr);
+            ds_hidden_row(tmem, A, q, row, (p.ybias && valid) ? p.ybias + n * HID : nullptr);
             fence_async_smem();
             tc_fence_before();
             ds_bar_front();
@@ -492,7 +493,7 @@ using namespace dvae;
 using namespace dvae::tc;
 
 static int launch_decode_stats(const char* who, const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R,
-                               int L, const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs,
+                               int L, const float* y, int y_dim, const float* ybias, const float* Vb, const float* g, int64_t NT, int ld, float* Vs,
                                float* A1, float* A2, int accumulate, int* status, void* stream) {
     DsParams p{};
     int rc = check_dims(dec, L, y_dim, who, &p.d);
@@ -508,7 +509,7 @@ static int launch_decode_stats(const char* who, const DvaeMlp* dec, const void* 
                  "%s: Zs and image must be 16-byte aligned", who);
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
-    p.Zs = Zs; p.y = y; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status;
+    p.Zs = Zs; p.y = y; p.ybias = ybias; p.Vb = Vb; p.g = g; p.Vs = Vs; p.A1 = A1; p.A2 = A2; p.NT = NT; p.ld = ld; p.status = status;
     p.zs_rtot = R_total; p.zs_r0 = r0; p.acc = accumulate;
     const int shared_bytes = (p.d.off_w3 + 4 * ((p.d.n_hidden == 2 ? HID : 0) + NPAD) + 1023) & ~1023;
     const size_t smem = (size_t)shared_bytes + 65536 + (size_t)DS_NS * 32768 + 1024;
@@ -543,26 +544,26 @@ static int launch_decode_stats(const char* who, const DvaeMlp* dec, const void* 
 }
 
 extern "C" int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y,
-                                    int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1,
+                                    int y_dim, const float* ybias, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1,
                                     float* A2, int* status, void* stream) {
     DVAE_REQUIRE(Vs && A2, "dvae_decode_stats_tc: null pointer");
-    return launch_decode_stats("dvae_decode_stats_tc", dec, image, Zs, R, 0, R, L, y, y_dim, Vb, g, NT, ld, Vs, A1, A2, 0, status, stream);
+    return launch_decode_stats("dvae_decode_stats_tc", dec, image, Zs, R, 0, R, L, y, y_dim, ybias, Vb, g, NT, ld, Vs, A1, A2, 0, status, stream);
 }
 
 extern "C" int dvae_decode_a1_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R, int L,
-                                 const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* A1,
+                                 const float* y, int y_dim, const float* ybias, const float* Vb, const float* g, int64_t NT, int ld, float* A1,
                                  int* status, void* stream) {
-    return launch_decode_stats("dvae_decode_a1_tc", dec, image, Zs, R_total, r0, R, L, y, y_dim, Vb, g, NT, ld, nullptr, A1, nullptr,
+    return launch_decode_stats("dvae_decode_a1_tc", dec, image, Zs, R_total, r0, R, L, y, y_dim, ybias, Vb, g, NT, ld, nullptr, A1, nullptr,
                                0, status, stream);
 }
 
 // sample window [r0, r0 + R) of frames that hold R_total samples each (multi-chain runs): Vs rows n * R_total + r0 + r are
 // written, A1 / A2 are overwritten (accumulate == 0) or added to
 extern "C" int dvae_decode_stats_win_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R, int L,
-                                        const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs,
+                                        const float* y, int y_dim, const float* ybias, const float* Vb, const float* g, int64_t NT, int ld, float* Vs,
                                         float* A1, float* A2, int accumulate, int* status, void* stream) {
     DVAE_REQUIRE(Vs && A2, "dvae_decode_stats_win_tc: null pointer");
-    return launch_decode_stats("dvae_decode_stats_win_tc", dec, image, Zs, R_total, r0, R, L, y, y_dim, Vb, g, NT, ld, Vs, A1, A2,
+    return launch_decode_stats("dvae_decode_stats_win_tc", dec, image, Zs, R_total, r0, R, L, y, y_dim, ybias, Vb, g, NT, ld, Vs, A1, A2,
                                accumulate, status, stream);
 }
 

@@ -40,6 +40,7 @@ struct Mh2Params {
     int64_t rows;                 // NT*C chains
     int C;
     const float* y;
+    const float* ybias;           // per-frame layer-1 bias [frames][128] or null (label inputs folded into a bias, see dvae_b200.h)
     const uint4* PVpk;            // [tile][quad][128] {P0P1, P2P3, V0V1, V2V3} in BF16
     const float* g;
     float* Z;
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         const int64_t fr = valid ? row_g / p.C : 0;
         const float g_row = valid ? p.g[fr] : 1.f;
         const uint4* PVt = p.PVpk + (tile * NQ) * TM + row;
+        const float* ybias_row = p.ybias ? p.ybias + fr * HID : nullptr;
         // this thread's 32 bytes of bin group 0 in slot 0 of the tile's emission
         uint4* VsTt = emit ? p.VsT + ((size_t)tile * n_slots * (NPAD / 16) * TM + row) * 2 : nullptr;
         uint32_t ph_utt = 0, ph_fc = 0;                 // Philox counter words 0 and 1 of this chain
@@ -303,7 +305,8 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
             mbar_wait(bar12, ph12, dead, p.status);
             ph12 ^= 1;
             tc_fence_after();
-            hidden_epilogue_rows_bf(tmem + 384, A, q, h, row, nullptr);              // bias rides on the constant-one column
+            if (ybias_row) hidden_epilogue_rows_bf(tmem + 384, A, q, h, row, ybias_row);  // label inputs folded into a per-frame bias
+            else hidden_epilogue_rows_bf(tmem + 384, A, q, h, row, nullptr);         // bias rides on the constant-one column
             fence_async_smem();
             tc_fence_before();
             __syncthreads();                                                    // S2
@@ -487,7 +490,8 @@ extern "C" int64_t dvae_vst_bytes(int64_t chains, int n_keep) {
 }
 
 extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
-                                 const float* y, int y_dim, const int32_t* frame_utt, const int32_t* frame_idx, float* Z, float* Zs,
+                                 const float* y, int y_dim, const float* ybias, const int32_t* frame_utt, const int32_t* frame_idx,
+                                 float* Z, float* Zs,
                                  int64_t NT, int L, int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng,
                                  uint32_t* n_accept, float* a_trace, void* VsT, uint8_t* vs_idx, int flags, int* status, void* stream) {
     Mh2Params p{};
@@ -497,6 +501,7 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const vo
     DVAE_REQUIRE(y_dim <= 3, "dvae_mh_chain_tc2: at most 3 label inputs");
     DVAE_REQUIRE(image && PVpk && g && Z && Zs && rng && status, "dvae_mh_chain_tc2: null pointer");
     DVAE_REQUIRE(y_dim == 0 || y, "dvae_mh_chain_tc2: y_dim=%d but y is null", y_dim);
+    DVAE_REQUIRE(!ybias || (reinterpret_cast<uintptr_t>(ybias) & 15) == 0, "dvae_mh_chain_tc2: ybias must be 16-byte aligned");
     DVAE_REQUIRE(NT >= 0 && n_chains >= 1 && n_chains < 4096 && n_burn >= 0 && n_keep >= 1 && var_rw > 0.f, "dvae_mh_chain_tc2: bad sizes");
     DVAE_REQUIRE((rng->eps == nullptr) == (rng->u == nullptr), "dvae_mh_chain_tc2: eps and u must be injected together");
     DVAE_REQUIRE(rng->eps || (frame_utt && frame_idx), "dvae_mh_chain_tc2: Philox mode needs frame_utt / frame_idx");
@@ -507,7 +512,7 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const vo
                  "dvae_mh_chain_tc2: the emission holds at most 31 kept samples per chain, 32-byte aligned");
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
-    p.rows = NT * n_chains; p.C = n_chains; p.y = y;
+    p.rows = NT * n_chains; p.C = n_chains; p.y = y; p.ybias = ybias;
     p.PVpk = (const uint4*)PVpk; p.g = g; p.Z = Z; p.Zs = Zs;
     p.eps = rng->eps; p.u = rng->u;
     p.frame_gid = frame_utt; p.frame_idx = frame_idx;

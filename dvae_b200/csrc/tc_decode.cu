@@ -157,6 +157,7 @@ struct Params {
     int64_t rows;                 // rows of Zin
     int C;                        // label row divisor: row r uses y[r / C]
     const float* y;               // [rows / C][y_dim] or null
+    const float* ybias;           // [rows / C][128] per-frame layer-1 bias or null
     const float* Zin;             // [rows][L]
     float* Vs;                    // [rows][ld]
     int ld;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) decoder_tc_kernel(Params p) {
         if (epi) {
             mbar_wait(bar12, ph12, dead, p.status);
             tc_fence_after();
-            hidden_epilogue_rows(tmem, A, q, h, row, nullptr);
+            hidden_epilogue_rows(tmem, A, q, h, row, (p.ybias && valid) ? p.ybias + (row_g / p.C) * HID : nullptr);
             fence_async_smem();
             tc_fence_before();
         }
@@ -426,16 +427,16 @@ extern "C" int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int
 }
 
 extern "C" int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64_t rows, int L, const float* y,
-                              int y_dim, int x2_row_div, float* Vs, int ld, int* status, void* stream) {
+                              int y_dim, const float* ybias, int x2_row_div, float* Vs, int ld, int* status, void* stream) {
     Params p{};
     int rc = check_dims(dec, L, y_dim, "dvae_decode_tc", &p.d);
     if (rc) return rc;
     DVAE_REQUIRE(image && Zs && Vs && status, "dvae_decode_tc: null pointer");
-    DVAE_REQUIRE(y_dim == 0 || (y && x2_row_div >= 1), "dvae_decode_tc: bad label arguments");
+    DVAE_REQUIRE((y_dim == 0 || y) && x2_row_div >= 1, "dvae_decode_tc: bad label arguments");
     DVAE_REQUIRE(rows >= 0 && ld >= p.d.F && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(Vs) & 15) == 0, "dvae_decode_tc: bad sizes / alignment");
     if (rows == 0) return 0;
     p.image = (const unsigned char*)image;
-    p.rows = rows; p.C = x2_row_div < 1 ? 1 : x2_row_div; p.y = y;
+    p.rows = rows; p.C = x2_row_div < 1 ? 1 : x2_row_div; p.y = y; p.ybias = ybias;
     p.Zin = Zs; p.Vs = Vs; p.ld = ld; p.status = status;
     const size_t smem = smem_bytes(p.d);
     const int64_t n_tiles = (p.rows + TM - 1) / TM;

@@ -135,6 +135,17 @@ class VaeWeights:
         self.z_dim = int(mu[0].shape[0])
         self.x_dim = self.dec.out_dim
         self.y_dim = self.dec.in_dim - self.z_dim
+        # Tensor-core kernels carry at most three labels in their layer-1 operand.  Wider label vectors (the IBM-conditioned
+        # M2 model: y_dim = 513, scripts/evaluate_ntcd_M2.py:66-73) are folded into a per-frame layer-1 bias: the decoder is
+        # packed without its label columns and without b1, and W1[:, L:] y + b1 is evaluated once per batch.
+        self.tc_label_bias = self.y_dim > 3
+        if self.tc_label_bias:
+            w1, b1 = dec_h[0]
+            self.dec_tc = PackedMlp([(w1[:, :self.z_dim], torch.zeros_like(b1))] + dec_h[1:] + [rec], device)
+            self.ybias_mlp = PackedMlp([(w1[:, self.z_dim:], b1)], device)
+        else:
+            self.dec_tc = self.dec
+        self.tc_y_dim = 0 if self.tc_label_bias else self.y_dim
         self.enc_takes_y = self.enc_mu.in_dim == self.x_dim + self.y_dim and self.y_dim > 0
         if (variant == "M1") != (self.y_dim == 0):
             raise ValueError("variant %s does not match a decoder with %d label inputs" % (variant, self.y_dim))
@@ -283,10 +294,10 @@ class TorchCpuDraws(InjectedDraws):
 
 
 def tc_supported(w: "VaeWeights") -> bool:
-    """True when the decoder fits the tcgen05 kernels: 513 bins, 1-2 hidden layers of 128 units, L in {16, 32}, <= 3 labels."""
+    """True when the decoder fits the tcgen05 kernels: 513 bins, 1-2 hidden layers of 128 units, L in {16, 32}; any number of
+    label inputs (more than three are folded into a per-frame bias, which needs a hidden layer to add it to)."""
     dims = w.dec.dims
-    return (dims[-1] == 513 and len(dims) in (3, 4) and all(d == 128 for d in dims[1:-1]) and w.z_dim in (16, 32)
-            and w.y_dim <= 3)
+    return dims[-1] == 513 and len(dims) in (3, 4) and all(d == 128 for d in dims[1:-1]) and w.z_dim in (16, 32)
 
 
 class McemEngine:
@@ -365,6 +376,11 @@ class McemEngine:
         if y is not None and tuple(y.shape) != (batch.NT, w.y_dim):
             raise ValueError("y must be [NT][y_dim=%d]" % w.y_dim)
         self.batch, self.X, self.P, self.y = batch, X, P, (None if y is None else y.contiguous().float())
+        # what the tensor-core kernels see of the labels: the labels themselves (<= 3) or a per-frame layer-1 bias
+        self.tc_y, self.ybias = self.y, None
+        if cfg.sampler == "tc" and w.tc_label_bias:
+            self.tc_y = None
+            self.ybias = mlp_forward(w.ybias_mlp, self.y, _lib.ACT_NONE, out=self._get("ybias", (batch.NT, 128)))
         B, NT, K, ld, C_ = batch.B, batch.NT, cfg.nmf_rank, self.ld, cfg.n_chains
         self.W = self._get("W", (B, K, ld))
         self.H = self._get("H", (NT, K))
@@ -461,7 +477,7 @@ class McemEngine:
         with self.stage("decode"):
             if self.cfg.sampler == "tc":
                 from . import tc
-                tc.decode_tc(self, x, x2, R, out)
+                tc.decode_tc(self, x, x2, R, out, None if self.ybias is None else self.ybias[n0:n1])
             else:
                 ws = self._get("mlp_ws", (max(int(_lib.load().dvae_mlp_workspace_floats(self.w.dec.ref, rows)), 1),))
                 mlp_forward(self.w.dec, x, _lib.ACT_EXP, x2=x2, x2_row_div=R, out=out, ws=ws)
@@ -502,7 +518,7 @@ class McemEngine:
             if self.vst_R:
                 from . import tc
                 w = self.w
-                _lib.call("dvae_nmf_mstep_vst", w.dec.ref, _p(tc.decoder_image(w)), w.z_dim, w.y_dim, _p(self.P), _p(self.VsT),
+                _lib.call("dvae_nmf_mstep_vst", w.dec_tc.ref, _p(tc.decoder_image(w)), w.z_dim, w.tc_y_dim, _p(self.P), _p(self.VsT),
                           _p(self.vs_idx), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
                           C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), b.B, b.NT, cfg.nmf_rank, self.ld, b.max_frames,
                           _p(ws), _p(self.wstat), _p(st), _stream())

@@ -146,3 +146,4 @@ def speech_prior_bias(s, n_fft: int = N_FFT, hop: int = HOP):
     w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / n_fft)
     P = np.abs(np.fft.rfft(y[idx] * w, axis=1)) ** 2
     return np.log(P.mean(axis=0) + 1e-10).astype(np.float32)
+

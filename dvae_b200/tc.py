@@ -34,15 +34,15 @@ def decoder_image(weights):
     img = getattr(weights, "_tc_image", None)
     if img is None:
         lib = _lib.load()
-        n = lib.dvae_tc_image_bytes(weights.dec.ref, weights.z_dim, weights.y_dim)
+        n = lib.dvae_tc_image_bytes(weights.dec_tc.ref, weights.z_dim, weights.tc_y_dim)
         if n < 0:
             _lib.check(-1, "dvae_tc_image_bytes")
         img = torch.empty(int(n), dtype=torch.uint8, device=weights.device)
-        _lib.call("dvae_tc_pack_decoder", weights.dec.ref, weights.z_dim, weights.y_dim, _p(img), _stream())
+        _lib.call("dvae_tc_pack_decoder", weights.dec_tc.ref, weights.z_dim, weights.tc_y_dim, _p(img), _stream())
         weights._tc_image = img
         # one-off range query: may the sampler use the polynomial 2^x (see DVAE_TC_POLY_EX2 in include/dvae_b200.h)?
         bound = C.c_float(0.0)
-        _lib.call("dvae_tc_decoder_exponent_bound", weights.dec.ref, weights.z_dim, weights.y_dim, C.byref(bound), _stream())
+        _lib.call("dvae_tc_decoder_exponent_bound", weights.dec_tc.ref, weights.z_dim, weights.tc_y_dim, C.byref(bound), _stream())
         mode = os.environ.get("DVAE_TC_POLY", "1")          # 0: MUFU only, 1: half of the exponentials, 2: all of them
         weights._tc_flags = ({"0": 0, "2": POLY_EX2 | POLY_EX2_ALL}.get(mode, POLY_EX2)) if bound.value < POLY_EX2_LIMIT else 0
     return img
@@ -89,7 +89,7 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace, emit=False):
     chains = b.NT * cfg.n_chains
     lib = _lib.load()
     pv = eng._get("PVpk", (max(int(lib.dvae_tc_packed_pv_bytes(chains)), 16),), torch.uint8)
-    _lib.call("dvae_tc_pack_pv", w.dec.ref, _p(img), w.z_dim, w.y_dim, _p(eng.P), _p(eng.Vb), b.NT, cfg.n_chains, eng.F, eng.ld,
+    _lib.call("dvae_tc_pack_pv", w.dec_tc.ref, _p(img), w.z_dim, w.tc_y_dim, _p(eng.P), _p(eng.Vb), b.NT, cfg.n_chains, eng.F, eng.ld,
               _p(pv), _stream())
     eng.kernel_launches += 1
     vst = idx = None
@@ -97,7 +97,7 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace, emit=False):
         vst = eng._get("VsT", (max(int(lib.dvae_vst_bytes(chains, keep)), 16),), torch.uint8)
         idx = eng._get("vs_idx", (max(chains, 1) * VST_IDX_PITCH,), torch.uint8)
     with eng.stage("mh_kernel"):
-        _lib.call("dvae_mh_chain_tc2", w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, _p(b.frame_gid), _p(b.frame_idx),
+        _lib.call("dvae_mh_chain_tc2", w.dec_tc.ref, _p(img), _p(pv), _p(eng.g), _p(eng.tc_y), w.tc_y_dim, _p(eng.ybias), _p(b.frame_gid), _p(b.frame_idx),
                   _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep, float(cfg.var_rw), C.byref(rng), _p(eng.n_accept),
                   _p(a_trace), _p(vst), _p(idx), int(w._tc_flags), _p(_status(eng)), _stream())
     eng.kernel_launches += 1
@@ -109,7 +109,7 @@ def vst_frame_stats(eng, R):
     w, b = eng.w, eng.batch
     st = eng._get("fstat", (2 * b.NT * eng.ld,))
     A1, A2 = st[: b.NT * eng.ld], st[b.NT * eng.ld:]
-    _lib.call("dvae_vst_frame_stats", w.dec.ref, _p(decoder_image(w)), w.z_dim, w.y_dim, _p(eng.VsT), _p(eng.vs_idx), R, _p(eng.Vb),
+    _lib.call("dvae_vst_frame_stats", w.dec_tc.ref, _p(decoder_image(w)), w.z_dim, w.tc_y_dim, _p(eng.VsT), _p(eng.vs_idx), R, _p(eng.Vb),
               _p(eng.g), b.NT, eng.ld, _p(A1), _p(A2), _stream())
     eng.kernel_launches += 1
     return st
@@ -120,17 +120,20 @@ def vst_unpack(eng, R, out=None):
     w, b = eng.w, eng.batch
     if out is None:
         out = torch.zeros((b.NT, R, eng.ld), dtype=torch.float32, device=eng.dev)
-    _lib.call("dvae_vst_unpack", w.dec.ref, _p(decoder_image(w)), w.z_dim, w.y_dim, _p(eng.VsT), _p(eng.vs_idx), R, b.NT, eng.ld,
+    _lib.call("dvae_vst_unpack", w.dec_tc.ref, _p(decoder_image(w)), w.z_dim, w.tc_y_dim, _p(eng.VsT), _p(eng.vs_idx), R, b.NT, eng.ld,
               _p(out), _stream())
     return out
 
 
-def decode_tc(eng, x, x2, x2_row_div, out):
-    """Vs rows for the kept samples ``x [rows][L]`` (+ labels) through the tensor-core decoder."""
+def decode_tc(eng, x, x2, x2_row_div, out, ybias=None):
+    """Vs rows for the kept samples ``x [rows][L]`` (+ labels ``x2`` or the per-frame label bias ``ybias``) through the
+    tensor-core decoder."""
     w = eng.w
     img = decoder_image(w)
-    _lib.call("dvae_decode_tc", w.dec.ref, _p(img), _p(x), x.shape[0], w.z_dim, _p(x2), w.y_dim, max(1, x2_row_div), _p(out),
-              out.stride(0), _p(_status(eng)), _stream())
+    if w.tc_label_bias:
+        x2 = None                                   # the labels arrive as ybias (row r uses frame r / x2_row_div)
+    _lib.call("dvae_decode_tc", w.dec_tc.ref, _p(img), _p(x), x.shape[0], w.z_dim, _p(x2), w.tc_y_dim, _p(ybias), max(1, x2_row_div),
+              _p(out), out.stride(0), _p(_status(eng)), _stream())
     eng.kernel_launches += 1
 
 
@@ -145,13 +148,13 @@ def decode_stats_tc(eng, Zs, Vs):
     A1, A2 = st[: b.NT * eng.ld], st[b.NT * eng.ld:]
     R = Zs.shape[1]
     if R in (10, 30):
-        _lib.call("dvae_decode_stats_tc", w.dec.ref, _p(img), _p(Zs), R, w.z_dim, _p(eng.y), w.y_dim, _p(eng.Vb),
+        _lib.call("dvae_decode_stats_tc", w.dec_tc.ref, _p(img), _p(Zs), R, w.z_dim, _p(eng.tc_y), w.tc_y_dim, _p(eng.ybias), _p(eng.Vb),
                   _p(eng.g), b.NT, eng.ld, _p(Vs), _p(A1), _p(A2), _p(_status(eng)), _stream())
         eng.kernel_launches += 1
         return st
     win = 30 if R % 30 == 0 else 10
     for r0 in range(0, R, win):
-        _lib.call("dvae_decode_stats_win_tc", w.dec.ref, _p(img), _p(Zs), R, r0, win, w.z_dim, _p(eng.y), w.y_dim, _p(eng.Vb),
+        _lib.call("dvae_decode_stats_win_tc", w.dec_tc.ref, _p(img), _p(Zs), R, r0, win, w.z_dim, _p(eng.tc_y), w.tc_y_dim, _p(eng.ybias), _p(eng.Vb),
                   _p(eng.g), b.NT, eng.ld, _p(Vs), _p(A1), _p(A2), 0 if r0 == 0 else 1, _p(_status(eng)), _stream())
         eng.kernel_launches += 1
     return st
@@ -162,7 +165,7 @@ def decode_a1_tc(eng, Zs, r0, R):
     w, b = eng.w, eng.batch
     img = decoder_image(w)
     A1 = eng._get("wf_a1", (b.NT * eng.ld,))
-    _lib.call("dvae_decode_a1_tc", w.dec.ref, _p(img), _p(Zs), Zs.shape[1], int(r0), int(R), w.z_dim, _p(eng.y), w.y_dim, _p(eng.Vb),
+    _lib.call("dvae_decode_a1_tc", w.dec_tc.ref, _p(img), _p(Zs), Zs.shape[1], int(r0), int(R), w.z_dim, _p(eng.tc_y), w.tc_y_dim, _p(eng.ybias), _p(eng.Vb),
               _p(eng.g), b.NT, eng.ld, _p(A1), _p(_status(eng)), _stream())
     eng.kernel_launches += 1
     return A1

@@ -156,11 +156,18 @@ int dvae_wiener_apply(const void* X, const float* WFs, const float* WFn, int R_t
  * Specialised for F = 513 bins, hidden width 128, 1 or 2 hidden layers, 2L + 2*y_dim + 1 <= 128.
  * dvae_tc_pack_decoder builds the shared-memory image of the decoder (UMMA K-major 128B-swizzled BF16 operands +
  * FP32 biases; W3/b3 pre-scaled by log2 e) into `image` (dvae_tc_image_bytes bytes, 16-byte aligned).
- * dvae_decode_tc: Vs[r][0..F) = decoder([Zs[r]; y[r / x2_row_div]]) for any number of rows; *status: DVAE_STATUS_* bits. */
+ * dvae_decode_tc: Vs[r][0..F) = decoder([Zs[r]; y[r / x2_row_div]]) for any number of rows; *status: DVAE_STATUS_* bits.
+ *
+ * Label inputs.  Up to three labels per frame ride in the layer-1 operand (y, y_dim <= 3).  Wider label vectors -- the
+ * IBM-conditioned M2 model has y_dim = 513 (scripts/evaluate_ntcd_M2.py:66-73) -- are folded into a PER-FRAME layer-1 bias
+ * instead: the caller packs the decoder WITHOUT its label columns and without its layer-1 bias (dims[0] = L, y_dim = 0) and
+ * passes ybias[frame][128] = W1[:, L:] y[frame] + b1 (one dvae_mlp_fwd over the frames; the labels do not change during a
+ * run), which every tensor-core kernel adds to the layer-1 pre-activation of the frame's rows.  ybias == NULL: no such bias. */
 int64_t dvae_tc_image_bytes(const DvaeMlp* dec, int L, int y_dim);
 int dvae_tc_pack_decoder(const DvaeMlp* dec, int L, int y_dim, void* image, void* stream);
 int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64_t rows, int L, const float* y, int y_dim,
-                   int x2_row_div, float* Vs, int ld, int* status, void* stream);
+                   const float* ybias /* nullable: [rows / x2_row_div][128] */, int x2_row_div, float* Vs, int ld, int* status,
+                   void* stream);
 
 /* The Metropolis-Hastings sampler on tensor cores: same contract as dvae_mh_chain_f32 (Z, Zs, frame_utt / frame_idx,
  * rng, n_accept, a_trace); L in {16, 32}, y_dim <= 3.  Draws: counter-based Philox inside the kernel (rng->eps == NULL,
@@ -185,7 +192,8 @@ int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int y_dim, con
 int dvae_tc_decoder_exponent_bound(const DvaeMlp* dec, int L, int y_dim, float* bound_host, void* stream);
 int64_t dvae_vst_bytes(int64_t chains, int n_keep);
 int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g, const float* y, int y_dim,
-                      const int32_t* frame_utt, const int32_t* frame_idx, float* Z, float* Zs, int64_t NT, int L,
+                      const float* ybias /* nullable: [NT][128] */, const int32_t* frame_utt, const int32_t* frame_idx, float* Z,
+                      float* Zs, int64_t NT, int L,
                       int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng, uint32_t* n_accept,
                       float* a_trace, void* VsT /* nullable */, uint8_t* vs_idx /* nullable */, int flags, int* status,
                       void* stream);
@@ -211,18 +219,18 @@ int dvae_vst_pack(const DvaeMlp* dec, const void* image, int L, int y_dim, const
  * A2[n][f] = sum_r 1/Vx^2; dvae_nmf_mstep takes them as wstat = A1 (A2 = A1 + NT*ld).  Used when the sampler's emission
  * does not apply (several chains per frame, injected kept samples). */
 int dvae_decode_stats_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R, int L, const float* y, int y_dim,
-                         const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1, float* A2, int* status,
+                         const float* ybias /* nullable */, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1, float* A2, int* status,
                          void* stream);
 /* dvae_decode_stats_tc for frames that hold R_total samples (multi-chain runs): decodes the window r0 .. r0+R (R in {10, 30}),
  * writes the rows n * R_total + r0 + r of Vs and overwrites (accumulate == 0) or adds to A1 / A2 */
 int dvae_decode_stats_win_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R, int L,
-                             const float* y, int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1,
+                             const float* y, int y_dim, const float* ybias /* nullable */, const float* Vb, const float* g, int64_t NT, int ld, float* Vs, float* A1,
                              float* A2, int accumulate, int* status, void* stream);
 /* final filter without materialising its samples: dvae_decode_a1_tc decodes the samples r0 .. r0+R (R in {10, 25, 30}) of
  * every frame of Zs [NT][R_total][L] and writes only A1 = sum_r 1 / (g Vs + Vb); dvae_wiener_from_a1 then accumulates the
  * mask sums of compute_WF (mcem.py:325-327): sum_r Vb / Vx = Vb A1 and sum_r g Vs / Vx = R - Vb A1 (first != 0: overwrite) */
 int dvae_decode_a1_tc(const DvaeMlp* dec, const void* image, const float* Zs, int R_total, int r0, int R, int L, const float* y,
-                      int y_dim, const float* Vb, const float* g, int64_t NT, int ld, float* A1, int* status, void* stream);
+                      int y_dim, const float* ybias /* nullable */, const float* Vb, const float* g, int64_t NT, int ld, float* A1, int* status, void* stream);
 int dvae_wiener_from_a1(const float* A1, const float* Vb, int R, int64_t NT, int F, int ld, float* WFs, float* WFn, int first,
                         void* stream);
 /* W <- W sqrt(num / den), num[f,k] = sum_n P A2 H, den[f,k] = sum_n A1 H (mcem.py:108-111); Wtmp: un-normalised result */

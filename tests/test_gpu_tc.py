@@ -65,7 +65,7 @@ def test_decode_tc_within_one_percent_of_fp32(variant, L, h):
     ref = mlp_forward(w.dec, x, _lib.ACT_EXP, x2=y, x2_row_div=div)
     out = torch.full((rows + 3, 520), -1.0, device=DEV)
     st = torch.zeros(1, dtype=torch.int32, device=DEV)
-    _lib.call("dvae_decode_tc", w.dec.ref, _p(tc.decoder_image(w)), _p(x), rows, L, _p(y), y_dim, div, _p(out), 520, _p(st), _stream())
+    _lib.call("dvae_decode_tc", w.dec.ref, _p(tc.decoder_image(w)), _p(x), rows, L, _p(y), y_dim, None, div, _p(out), 520, _p(st), _stream())
     assert int(st.item()) == 0
     rel = ((out[:rows, :513] - ref) / ref).abs()
     assert rel.max().item() <= 1e-2 and rel.mean().item() <= 2e-3

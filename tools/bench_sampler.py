@@ -105,7 +105,7 @@ for tag in "BCDEFG":
             rng.eps, rng.u = inj.eps.data_ptr(), inj.u.data_ptr()
 
         def var():
-            rc = fv(w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, _p(batch.frame_gid), _p(batch.frame_idx), _p(eng.Z), _p(Zs), NT, L,
+            rc = fv(w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, None, _p(batch.frame_gid), _p(batch.frame_idx), _p(eng.Z), _p(Zs), NT, L,
                     1, burn, keep, 0.01, C.byref(rng), _p(eng.n_accept), None, _p(eng.VsT), _p(eng.vs_idx), int(w._tc_flags), _p(st), _stream())
             assert rc == 0
         out["v%s %s+emit" % (tag, mode)] = timed(var)

@@ -37,7 +37,7 @@ def decode(w, x, y=None, div=1):
     img = tc.decoder_image(w)
     out = torch.zeros((x.shape[0], 520), device=DEV)
     st = torch.zeros(1, dtype=torch.int32, device=DEV)
-    _lib.call("dvae_decode_tc", w.dec.ref, _p(img), _p(x), x.shape[0], w.z_dim, _p(y), w.y_dim, div, _p(out), 520, _p(st), _stream())
+    _lib.call("dvae_decode_tc", w.dec.ref, _p(img), _p(x), x.shape[0], w.z_dim, _p(y), w.y_dim, None, div, _p(out), 520, _p(st), _stream())
     status(st)
     return out
 
