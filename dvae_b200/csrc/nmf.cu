@@ -1250,11 +1250,13 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
 extern "C" int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const void* VsT,
                                   const uint8_t* vs_idx, int R, float* W, float* H, float* g, float* Vb, double* cost,
                                   const int64_t* fr_off, int B, int64_t NT, int K, int ld, int max_frames, float* ws,
-                                  const float* fstat, int* status, void* stream) {
+                                  const float* fstat, const float* wpart, const int32_t* utt_seg, int* status, void* stream) {
     tc::Dims d;
     int rc = tc::check_dims(dec, L, y_dim, "dvae_nmf_mstep_vst", &d);
     if (rc) return rc;
-    DVAE_REQUIRE(image && P && VsT && vs_idx && W && H && g && Vb && cost && fr_off && ws && fstat, "dvae_nmf_mstep_vst: null pointer");
+    DVAE_REQUIRE(image && P && VsT && vs_idx && W && H && g && Vb && cost && fr_off && ws, "dvae_nmf_mstep_vst: null pointer");
+    DVAE_REQUIRE((fstat != nullptr) != (wpart != nullptr) && (!wpart || utt_seg),
+                 "dvae_nmf_mstep_vst: exactly one of fstat (A1 | A2) and wpart (+ utt_seg) must be given");
     DVAE_REQUIRE(B >= 1 && NT >= 0 && max_frames >= 0, "dvae_nmf_mstep_vst: bad sizes");
     DVAE_REQUIRE(d.F == 513 && ld == HG5_LD && K >= 1 && K <= HG2_KT && (R == 10 || R == 30),
                  "dvae_nmf_mstep_vst: needs F = 513, ld = %d, K <= %d, R in {10, 30}", HG5_LD, HG2_KT);
@@ -1268,7 +1270,8 @@ extern "C" int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, 
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(cost_part) & 7) == 0 && (reinterpret_cast<uintptr_t>(VsT) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(P) & 7) == 0 && (reinterpret_cast<uintptr_t>(Vb) & 7) == 0,
                  "dvae_nmf_mstep_vst: workspace / VsT / P / Vb alignment");
-    rc = dvae_nmf_w_from_frame_stats(fstat, fstat + NT * (int64_t)ld, P, H, W, fr_off, B, d.F, K, ld, Wtmp, stream);
+    if (fstat) rc = dvae_nmf_w_from_frame_stats(fstat, fstat + NT * (int64_t)ld, P, H, W, fr_off, B, d.F, K, ld, Wtmp, stream);
+    else rc = dvae_nmf_w_from_partials(wpart, utt_seg, W, B, d.F, K, ld, Wtmp, stream);
     if (rc) return rc;
     nmf_norm_kernel<<<B, 256, 0, st>>>(Wtmp, d.F, K, ld, W, norm);
     rc = check_launch("nmf_norm_kernel");

@@ -33,30 +33,58 @@ __device__ __forceinline__ f32x2 vst_rcp2(f32x2 a) { float lo, hi; upk2(a, lo, h
 // reads 16 chains x 32 bytes = 512 contiguous bytes per slot.  64 registers -> 1 024 threads per SM, each with two sample pairs
 // (64 bytes) in flight ahead of the one it reduces: the kernel is a pure HBM stream (R x 1 056 bytes per frame in, 2 x 2 052 out).
 // RT > 0: compile-time sample count (even), slot indices held in registers; RT = 0: run-time count r_rt (any parity)
-template <int RT>
+// WPART: instead of writing A1 / A2, the CTA multiplies them with the frames' activations and reduces over the frames of each
+// utterance segment inside its tile: Wpart[seg][k][0][f] = sum_n P A2 H[n][k], Wpart[seg][k][1][f] = sum_n A1 H[n][k] (the sums of
+// the W update, mcem.py:108-110).  A segment is a maximal run of frames that lies in one tile AND one utterance (host table);
+// every (segment, bin) has exactly one writer and the final sum over an utterance's <= 3-4 segments runs in a fixed order, so
+// the result is deterministic.  Saves the A1 / A2 round trip (2 x 4 x ld x NT bytes out, 3 x in) and the separate W kernel.
+struct WPartArgs {
+    const float* P;            // [NT][ld]
+    const float* H;            // [NT][K]
+    int K;
+    const int64_t* seg_start;  // [S + 1] frame boundaries of the segments (ascending)
+    const int32_t* tile_seg;   // [n_tiles + 1] first segment of every tile
+    float* Wpart;              // [S][K][2][ld]
+};
+
+template <int RT, bool WPART>
 __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __restrict__ VsT, const uint8_t* __restrict__ idx, int r_rt,
                                                                  const float* __restrict__ bias_log2, const float* __restrict__ Vb,
                                                                  const float* __restrict__ g, int64_t rows, int F, int ld,
-                                                                 float* __restrict__ A1, float* __restrict__ A2) {
+                                                                 float* __restrict__ A1, float* __restrict__ A2, WPartArgs wp) {
+    __shared__ float sA1[WPART ? TM : 1][17], sPA2[WPART ? TM : 1][17], sH[WPART ? TM : 1][12];
     const int R = RT > 0 ? RT : r_rt;
     const int64_t tile = blockIdx.x;
     const int bg = blockIdx.y, row = threadIdx.x >> 1, half = threadIdx.x & 1;
     const int64_t m = tile * TM + row;
-    if (m >= rows) return;
+    if (WPART) {
+        for (int i = threadIdx.x; i < TM * 12; i += 256) {
+            const int r = i / 12, k = i - 12 * r;
+            const int64_t n = tile * TM + r;
+            sH[r][k] = (n < rows && k < wp.K) ? __ldg(wp.H + n * wp.K + k) : 0.f;
+        }
+    }
+    if (m >= rows) {
+        if (!WPART) return;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sA1[row][8 * half + j] = 0.f; sPA2[row][8 * half + j] = 0.f; }
+    }
+    const bool rowlive = m < rows;
+    const int64_t mm = rowlive ? m : 0;
     const int f0 = 16 * bg + 8 * half;
-    const float gg = __ldg(g + m);
+    const float gg = __ldg(g + mm);
     f32x2 ge2[4], vb2[4], a1[4], a2[4];
     {
         float vb[8];
         if (f0 + 8 <= ld) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(Vb + m * ld + f0) + j);
+                const float4 t = __ldg(reinterpret_cast<const float4*>(Vb + mm * ld + f0) + j);
                 vb[4 * j] = t.x; vb[4 * j + 1] = t.y; vb[4 * j + 2] = t.z; vb[4 * j + 3] = t.w;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vb[j] = (f0 + j < F) ? __ldg(Vb + m * ld + f0 + j) : 1.f;
+            for (int j = 0; j < 8; ++j) vb[j] = (f0 + j < F) ? __ldg(Vb + mm * ld + f0 + j) : 1.f;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -70,7 +98,7 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
     }
     const size_t slot_stride = (size_t)NBG * TM * 2;
     const uint4* cell = VsT + ((size_t)tile * (R + 1) * NBG + bg) * (TM * 2) + row * 2 + half;
-    const uint8_t* ib = idx + m * VST_IDX_PITCH;
+    const uint8_t* ib = idx + mm * VST_IDX_PITCH;
     uint32_t iw[8];
     if (RT > 0) {
         const uint4 i0 = __ldg(reinterpret_cast<const uint4*>(ib)), i1 = __ldg(reinterpret_cast<const uint4*>(ib) + 1);
@@ -121,6 +149,59 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
     float o1[8], o2[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { upk2(a1[j], o1[2 * j], o1[2 * j + 1]); upk2(a2[j], o2[2 * j], o2[2 * j + 1]); }
+    if (WPART) {
+        if (rowlive) {
+            float pp[8];
+            if (f0 + 8 <= ld) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(wp.P + m * ld + f0) + j);
+                    pp[4 * j] = t.x; pp[4 * j + 1] = t.y; pp[4 * j + 2] = t.z; pp[4 * j + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pp[j] = (f0 + j < F) ? __ldg(wp.P + m * ld + f0 + j) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool ok = f0 + j < F;
+                sA1[row][8 * half + j] = ok ? o1[j] : 0.f;
+                sPA2[row][8 * half + j] = ok ? pp[j] * o2[j] : 0.f;
+            }
+        }
+        __syncthreads();
+        const int j = threadIdx.x & 15, k = threadIdx.x >> 4;               // threads 0 .. 16 K - 1: (bin of the group, rank)
+        const int f = 16 * bg + j;
+        if (k < wp.K && f < F) {
+            const int64_t tile0 = tile * TM;
+            for (int sg = wp.tile_seg[tile]; sg < wp.tile_seg[tile + 1]; ++sg) {
+                const int lo = (int)(wp.seg_start[sg] - tile0), hi = (int)(wp.seg_start[sg + 1] - tile0);
+                float num = 0.f, den = 0.f, num1 = 0.f, den1 = 0.f;      // two accumulator pairs: the loads of 8 frames in flight
+                int n = lo;
+                for (; n + 8 <= hi; n += 8) {
+#pragma unroll
+                    for (int i = 0; i < 8; i += 2) {
+                        const float h0 = sH[n + i][k], h1 = sH[n + i + 1][k];
+                        num = fmaf(sPA2[n + i][j], h0, num);
+                        den = fmaf(sA1[n + i][j], h0, den);
+                        num1 = fmaf(sPA2[n + i + 1][j], h1, num1);
+                        den1 = fmaf(sA1[n + i + 1][j], h1, den1);
+                    }
+                }
+                for (; n < hi; ++n) {
+                    const float hk = sH[n][k];
+                    num = fmaf(sPA2[n][j], hk, num);
+                    den = fmaf(sA1[n][j], hk, den);
+                }
+                num += num1;
+                den += den1;
+                float* dst = wp.Wpart + ((size_t)sg * wp.K + k) * 2 * ld + f;
+                dst[0] = num;
+                dst[ld] = den;
+            }
+        }
+        return;
+    }
     if (f0 + 8 <= F) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
@@ -131,6 +212,24 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             if (f0 + j < F) { A1[m * ld + f0 + j] = o1[j]; A2[m * ld + f0 + j] = o2[j]; }
+    }
+}
+
+// W <- W sqrt(num / den) from the per-segment partial sums (mcem.py:108-111); one thread per bin, an utterance's segments in order
+__global__ void __launch_bounds__(128) w_from_partials_kernel(const float* __restrict__ Wpart, const int32_t* __restrict__ utt_seg,
+                                                              const float* __restrict__ W, int F, int K, int ld, float* __restrict__ Wtmp) {
+    const int u = blockIdx.y, f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const int s0 = utt_seg[u], s1 = utt_seg[u + 1];
+    for (int k = 0; k < K; ++k) {
+        float num = 0.f, den = 0.f;
+        for (int sg = s0; sg < s1; ++sg) {
+            const float* src = Wpart + ((size_t)sg * K + k) * 2 * ld + f;
+            num += src[0];
+            den += src[ld];
+        }
+        const int64_t i = ((int64_t)u * K + k) * ld + f;
+        Wtmp[i] = W[i] * sqrtf(num / den);
     }
 }
 
@@ -208,10 +307,48 @@ extern "C" int dvae_vst_frame_stats(const DvaeMlp* dec, const void* image, int L
     DVAE_REQUIRE(n_tiles < (1ll << 31), "dvae_vst_frame_stats: too many frames");
     const dim3 grid((unsigned)n_tiles, NBG);
     cudaStream_t st = (cudaStream_t)stream;
-    if (R == 30) vst_frame_stats_kernel<30><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
-    else if (R == 10) vst_frame_stats_kernel<10><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
-    else vst_frame_stats_kernel<0><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2);
+    const WPartArgs none{};
+    if (R == 30) vst_frame_stats_kernel<30, false><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2, none);
+    else if (R == 10) vst_frame_stats_kernel<10, false><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2, none);
+    else vst_frame_stats_kernel<0, false><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2, none);
     return check_launch("vst_frame_stats_kernel");
+}
+
+extern "C" int64_t dvae_vst_w_partial_floats(int64_t n_segments, int K, int ld) {
+    if (n_segments <= 0 || K <= 0 || ld <= 0) return 0;
+    return n_segments * K * 2 * (int64_t)ld;
+}
+
+extern "C" int dvae_vst_w_partials(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx,
+                                   int R, const float* P, const float* Vb, const float* g, const float* H, int K, int64_t NT, int ld,
+                                   const int64_t* seg_start, const int32_t* tile_seg, float* Wpart, void* stream) {
+    Dims d;
+    int rc;
+    DVAE_REQUIRE(image != nullptr, "dvae_vst_w_partials: null pointer");
+    const float* bias_log2 = vst_bias(dec, image, L, y_dim, "dvae_vst_w_partials", &d, &rc);
+    if (rc) return rc;
+    DVAE_REQUIRE(VsT && vs_idx && P && Vb && g && H && seg_start && tile_seg && Wpart, "dvae_vst_w_partials: null pointer");
+    DVAE_REQUIRE(R >= 1 && R <= 31 && K >= 1 && K <= 12 && NT >= 0 && ld >= d.F && (ld & 3) == 0,
+                 "dvae_vst_w_partials: bad sizes (1 <= R <= 31, K <= 12, ld %% 4 == 0)");
+    DVAE_REQUIRE(((reinterpret_cast<uintptr_t>(VsT) | reinterpret_cast<uintptr_t>(vs_idx) | reinterpret_cast<uintptr_t>(Vb) |
+                   reinterpret_cast<uintptr_t>(P)) & 15) == 0, "dvae_vst_w_partials: 16-byte alignment required");
+    if (NT == 0) return 0;
+    const int64_t n_tiles = (NT + TM - 1) / TM;
+    DVAE_REQUIRE(n_tiles < (1ll << 31), "dvae_vst_w_partials: too many frames");
+    const dim3 grid((unsigned)n_tiles, NBG);
+    cudaStream_t st = (cudaStream_t)stream;
+    const WPartArgs wp{P, H, K, seg_start, tile_seg, Wpart};
+    if (R == 30) vst_frame_stats_kernel<30, true><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, nullptr, nullptr, wp);
+    else if (R == 10) vst_frame_stats_kernel<10, true><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, nullptr, nullptr, wp);
+    else vst_frame_stats_kernel<0, true><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, nullptr, nullptr, wp);
+    return check_launch("vst_frame_stats_kernel<wpart>");
+}
+
+extern "C" int dvae_nmf_w_from_partials(const float* Wpart, const int32_t* utt_seg, const float* W, int B, int F, int K, int ld,
+                                        float* Wtmp, void* stream) {
+    DVAE_REQUIRE(Wpart && utt_seg && W && Wtmp && B >= 1 && K >= 1 && ld >= F, "dvae_nmf_w_from_partials: bad arguments");
+    w_from_partials_kernel<<<dim3((F + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>(Wpart, utt_seg, W, F, K, ld, Wtmp);
+    return check_launch("w_from_partials_kernel");
 }
 
 extern "C" int dvae_vst_unpack(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx, int R,

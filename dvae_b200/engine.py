@@ -180,6 +180,26 @@ class RaggedBatch:
         self.frame_gid = torch.from_numpy(ids[local] if self.NT else np.zeros(0, np.int32)).to(device)
         idx = (np.arange(self.NT, dtype=np.int64) - off[:-1][local]).astype(np.int32) if self.NT else np.zeros(0, np.int32)
         self.frame_idx = torch.from_numpy(idx).to(device)
+        self._segments = None
+        self._device = device
+
+    def segments(self, tile: int = 128):
+        """Segment tables of the fused W-update reduction (dvae_vst_w_partials): a segment is a maximal run of frames inside
+        one ``tile``-frame tile AND one utterance.  Returns device tensors ``(seg_start [S+1] int64, tile_seg [n_tiles+1]
+        int32, utt_seg [B+1] int32)`` and ``S``; utterance ``u`` owns the segments ``utt_seg[u] .. utt_seg[u+1]``."""
+        if self._segments is None:
+            n_tiles = (self.NT + tile - 1) // tile
+            cuts = np.unique(np.concatenate([np.arange(0, n_tiles + 1, dtype=np.int64) * tile, self.fr_off_host]))
+            cuts = cuts[cuts <= self.NT]
+            if len(cuts) == 0 or cuts[-1] != self.NT:
+                cuts = np.append(cuts, self.NT)
+            S = len(cuts) - 1
+            tile_seg = np.searchsorted(cuts[:-1], np.arange(0, n_tiles + 1, dtype=np.int64) * tile, side="left").astype(np.int32)
+            utt_seg = np.searchsorted(cuts[:-1], self.fr_off_host, side="left").astype(np.int32)
+            dev = self._device
+            self._segments = (torch.from_numpy(cuts.astype(np.int64)).to(dev), torch.from_numpy(tile_seg).to(dev),
+                              torch.from_numpy(utt_seg).to(dev), S)
+        return self._segments
 
 
 # --------------------------------------------------------------------------------------------- STFT / ISTFT
@@ -255,6 +275,7 @@ class McemConfig:
     sampler: str = "fp32"        # "fp32": CUDA-core exact mode; "tc": tcgen05 BF16 kernels; "auto": tc when supported
     fuse_wstat: bool = True      # tc only: per-frame statistics of the W update instead of a pass over Vs
     emit_vs: bool = True         # tc only: the sampler writes the kept samples' variances itself (BF16); False: FP32 decode
+    w_partials: bool = True      # with emit_vs: reduce the W-update sums inside the statistics kernel (no A1 / A2 round trip)
 
 
 class InjectedDraws:
@@ -489,14 +510,17 @@ class McemEngine:
         chain per frame the sampler emits the variances itself (BF16) and only the per-frame statistics of the W update are
         computed here; otherwise the kept samples are decoded into FP32 ``Vs``."""
         cfg = self.cfg
-        self.wstat, self._Vs, self.vst_R = None, None, 0
+        self.wstat, self.wpart, self._Vs, self.vst_R = None, None, None, 0
         if cfg.sampler == "tc":
             from . import tc
             if tc.vst_supported(self, cfg.keep_E):
                 self.sample_posterior(cfg.keep_E, cfg.burn_E, draws, emit=True)
                 self.R = self.vst_R = cfg.keep_E
                 with self.stage("decode"):
-                    self.wstat = tc.vst_frame_stats(self, self.R)
+                    if cfg.w_partials:
+                        self.wpart = tc.vst_w_partials(self, self.R)
+                    else:
+                        self.wstat = tc.vst_frame_stats(self, self.R)
                 return
         Zs = self.sample_posterior(cfg.keep_E, cfg.burn_E, draws)
         self.R = Zs.shape[1]
@@ -521,7 +545,8 @@ class McemEngine:
                 _lib.call("dvae_nmf_mstep_vst", w.dec_tc.ref, _p(tc.decoder_image(w)), w.z_dim, w.tc_y_dim, _p(self.P), _p(self.VsT),
                           _p(self.vs_idx), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
                           C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), b.B, b.NT, cfg.nmf_rank, self.ld, b.max_frames,
-                          _p(ws), _p(self.wstat), _p(st), _stream())
+                          _p(ws), _p(self.wstat), _p(self.wpart), _p(b.segments()[2]) if self.wpart is not None else None, _p(st),
+                          _stream())
             else:
                 _lib.call("dvae_nmf_mstep", _p(self.P), _p(self._Vs), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
                           C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), _p(b.frame_utt), b.B, b.NT, self.F, cfg.nmf_rank,

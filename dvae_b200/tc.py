@@ -115,6 +115,17 @@ def vst_frame_stats(eng, R):
     return st
 
 
+def vst_w_partials(eng, R):
+    """Per-segment partial sums of the W update, reduced inside the statistics pass (dvae_vst_w_partials); ``[S][K][2][ld]``."""
+    w, b, K = eng.w, eng.batch, eng.cfg.nmf_rank
+    seg_start, tile_seg, _, S = b.segments()
+    wp = eng._get("wpart", (max(int(_lib.load().dvae_vst_w_partial_floats(S, K, eng.ld)), 1),))
+    _lib.call("dvae_vst_w_partials", w.dec_tc.ref, _p(decoder_image(w)), w.z_dim, w.tc_y_dim, _p(eng.VsT), _p(eng.vs_idx), R, _p(eng.P),
+              _p(eng.Vb), _p(eng.g), _p(eng.H), K, b.NT, eng.ld, _p(seg_start), _p(tile_seg), _p(wp), _stream())
+    eng.kernel_launches += 1
+    return wp
+
+
 def vst_unpack(eng, R, out=None):
     """Dense FP32 ``Vs [NT][R][ld]`` of the emitted samples (dvae_vst_unpack): the reference's ``self.Vs`` up to layout."""
     w, b = eng.w, eng.batch

@@ -201,15 +201,27 @@ int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, c
 /* Consumers of the emission (one chain per frame: chain = frame).
  * dvae_vst_frame_stats: A1[n][f] = sum_r 1/Vx, A2[n][f] = sum_r 1/Vx^2 with Vx = g[n] Vs[n][r][f] + Vb[n][f]: the inner
  *   sums of the W update (mcem.py:108-110); R <= 31.
- * dvae_nmf_mstep_vst: dvae_nmf_mstep on the emission (F = 513, ld = 520, K <= 10, R in {10, 30}); fstat = A1 | A2
- *   (A2 = A1 + NT*ld) from dvae_vst_frame_stats.
+ * dvae_vst_w_partials: the same pass, but instead of writing A1 / A2 it multiplies them with the activations H and reduces over
+ *   the frames of every SEGMENT (a maximal run of frames inside one 128-frame tile and one utterance; seg_start[S+1] ascending
+ *   frame boundaries, tile_seg[n_tiles+1] first segment per tile): Wpart[seg][k][0|1][f] = sum_n P A2 H | sum_n A1 H
+ *   (dvae_vst_w_partial_floats floats).  dvae_nmf_w_from_partials sums an utterance's segments (utt_seg[B+1]) in order and
+ *   applies the W update; deterministic, and the A1 / A2 round trip through memory disappears.
+ * dvae_nmf_mstep_vst: dvae_nmf_mstep on the emission (F = 513, ld = 520, K <= 10, R in {10, 30}); exactly one of
+ *   fstat = A1 | A2 (A2 = A1 + NT*ld, from dvae_vst_frame_stats) and wpart (+ utt_seg, from dvae_vst_w_partials).
  * dvae_vst_unpack / dvae_vst_pack: conversion to / from dense FP32 Vs[NT][R][ld] (pack: sample r -> slot 1 + r). */
 int dvae_vst_frame_stats(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx,
                          int R, const float* Vb, const float* g, int64_t NT, int ld, float* A1, float* A2, void* stream);
 int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const void* VsT,
                        const uint8_t* vs_idx, int R, float* W, float* H, float* g, float* Vb, double* cost,
                        const int64_t* fr_off, int B, int64_t NT, int K, int ld, int max_frames, float* ws,
-                       const float* fstat, int* status, void* stream);
+                       const float* fstat /* nullable */, const float* wpart /* nullable */, const int32_t* utt_seg, int* status,
+                       void* stream);
+int64_t dvae_vst_w_partial_floats(int64_t n_segments, int K, int ld);
+int dvae_vst_w_partials(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx, int R,
+                        const float* P, const float* Vb, const float* g, const float* H, int K, int64_t NT, int ld,
+                        const int64_t* seg_start, const int32_t* tile_seg, float* Wpart, void* stream);
+int dvae_nmf_w_from_partials(const float* Wpart, const int32_t* utt_seg, const float* W, int B, int F, int K, int ld, float* Wtmp,
+                             void* stream);
 int dvae_vst_unpack(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx, int R,
                     int64_t NT, int ld, float* Vs, void* stream);
 int dvae_vst_pack(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* Vs, int R, int64_t NT, int ld,

@@ -224,19 +224,22 @@ def test_fused_decode_stats_and_emission_match_unfused(variant, keep):
     sd = synth.xavier_state_dict(variant, 513, 16, [128, 128], y_dim, seed=9, out_bias=float(np.log(0.05)))
     w = VaeWeights(sd, variant, torch.device(DEV))
     out = {}
-    for mode, fuse, emit in (("unfused", False, False), ("stats", True, False), ("emit", True, True)):
-        cfg = McemConfig(niter=2, keep_E=keep, burn_E=5, keep_WF=3, burn_WF=3, sampler="tc", seed=3, fuse_wstat=fuse, emit_vs=emit)
+    for mode, fuse, emit in (("unfused", False, False), ("stats", True, False), ("emit", True, True), ("emit_a1a2", True, True)):
+        cfg = McemConfig(niter=2, keep_E=keep, burn_E=5, keep_WF=3, burn_WF=3, sampler="tc", seed=3, fuse_wstat=fuse, emit_vs=emit,
+                         w_partials=(mode == "emit"))
         eng = McemEngine(w, cfg, DEV)
         eng.init_parameters(X, P, RaggedBatch(lens, DEV), y)
         for it in range(2):
             eng.e_step()
-            assert (eng.wstat is not None) == fuse and (eng.vst_R > 0) == emit
+            assert ((eng.wstat is not None) or (eng.wpart is not None)) == fuse and (eng.vst_R > 0) == emit and (eng.wpart is not None) == (mode == "emit")
             if it == 0:
                 vs = eng.Vs.clone()
             eng.m_step(it)
         tc.check_status(eng)
         out[mode] = (vs.cpu(), eng.W.cpu().clone(), eng.H.cpu().clone(), eng.g.cpu().clone(), eng.cost.cpu().clone())
     a = out["unfused"]
+    for i in (1, 2, 3, 4):                            # the two W reductions of the emission path differ by summation order only
+        assert ((out["emit"][i] - out["emit_a1a2"][i]).double().norm() / out["emit_a1a2"][i].double().norm()).item() <= 1e-5
     for mode, tol_vs, tol in (("stats", 1e-5, 1e-4), ("emit", 1.2e-2, 2e-2)):
         b = out[mode]
         assert ((a[0][:, :, :513] - b[0][:, :, :513]).abs() / a[0][:, :, :513]).max().item() <= tol_vs, mode

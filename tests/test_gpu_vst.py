@@ -62,8 +62,10 @@ def test_pack_unpack_round_trip_and_bounds(N, R):
     assert torch.equal(out2[:N, :, :513], out[:N, :1, :513].expand(-1, R, -1))
 
 
-@pytest.mark.parametrize("N,K,R,split", [(37, 10, 30, None), (185, 10, 10, None), (300, 7, 30, None), (130, 10, 10, [1, 100, 29])])
-def test_m_step_on_emission_matches_oracle_given_its_inputs(N, K, R, split):
+@pytest.mark.parametrize("wpart", [False, True])
+@pytest.mark.parametrize("N,K,R,split", [(37, 10, 30, None), (185, 10, 10, None), (300, 7, 30, None), (130, 10, 10, [1, 100, 29]),
+                                         (400, 10, 10, [3, 120, 5, 1, 128, 143])])
+def test_m_step_on_emission_matches_oracle_given_its_inputs(N, K, R, split, wpart):
     """dvae_vst_frame_stats + dvae_nmf_mstep_vst against the oracle's M-step on the variances the emission actually holds."""
     F, ld = 513, 520
     w = _weights()
@@ -106,8 +108,18 @@ def test_m_step_on_emission_matches_oracle_given_its_inputs(N, K, R, split):
     cost = torch.zeros(B, dtype=torch.float64, device=DEV)
     st = torch.zeros(1, dtype=torch.int32, device=DEV)
     ws = torch.empty(int(_lib.load().dvae_nmf_workspace_floats(B, K, ld, batch.max_frames)), device=DEV)
+    wp = utt_seg = None
+    if wpart:                                    # the W sums reduced per (tile, utterance) segment inside the statistics pass
+        seg_start, tile_seg, utt_seg, S = batch.segments()
+        assert S >= B and int(utt_seg[-1]) == S
+        wp = torch.full((int(_lib.load().dvae_vst_w_partial_floats(S, K, ld)) + 64,), float("nan"), device=DEV)
+        _lib.call("dvae_vst_w_partials", w.dec.ref, _p(img), 16, 0, _p(vst), _p(idx), R, _p(Pd), _p(Vbd), _p(gd), _p(Hd), K, N, ld,
+                  _p(seg_start), _p(tile_seg), _p(wp), _stream())
+        body = wp[:-64].view(S, K, 2, ld)
+        assert bool(torch.isnan(wp[-64:]).all()) and bool(torch.isnan(body[..., F:]).all()), "partials written outside [S][K][2][0..F)"
+        assert bool(torch.isfinite(body[..., :F]).all())
     _lib.call("dvae_nmf_mstep_vst", w.dec.ref, _p(img), 16, 0, _p(Pd), _p(vst), _p(idx), R, _p(Wd), _p(Hd), _p(gd), _p(Vbd), _p(cost),
-              _p(batch.fr_off), B, N, K, ld, batch.max_frames, _p(ws), _p(fstat), _p(st), _stream())
+              _p(batch.fr_off), B, N, K, ld, batch.max_frames, _p(ws), None if wpart else _p(fstat), _p(wp), _p(utt_seg), _p(st), _stream())
     assert int(st.item()) == 0
     off = batch.fr_off_host
     for u in range(B):

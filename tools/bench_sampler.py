@@ -113,7 +113,8 @@ eng.timing = False
 eng.sample_posterior(keep, burn, None, emit=True)
 eng.R = eng.vst_R = keep
 out["frame_stats"] = timed(lambda: tc.vst_frame_stats(eng, keep))
-eng.wstat = tc.vst_frame_stats(eng, keep)
+out["w_partials"] = timed(lambda: tc.vst_w_partials(eng, keep))
+eng.wstat, eng.wpart = None, tc.vst_w_partials(eng, keep)
 eng.timing = True
 eng._events = []
 timed(lambda: eng.m_step(0))
