@@ -1,8 +1,8 @@
 // Second-generation tcgen05 Metropolis-Hastings sampler (the default "tc" sampler).
 //
-// Same math, operand images and TMEM plan as mh_tc.cu (see the notes there); what changes is the schedule inside
-// the CTA, driven by the first ncu capture of mh_tc.cu (early round 1; not kept in profiles/): v1 ran at 0.7 IPC per SM because every phase was
-// serialised behind CTA barriers with only two warps per scheduler and a long single-warp "owner" phase.
+// Operand images and the layer plan are described in tc_decode.cu / DESIGN.md section 4; this file is the schedule inside the
+// CTA, driven by ncu captures: the first sampler of round 1 ran at 0.7 IPC per SM because every phase was serialised behind
+// CTA barriers with only two warps per scheduler and a long single-warp "owner" phase.
 //
 // A second capture (an intermediate 16-warp build) showed 38 % of all stalls on local-memory traffic: with 223 KB of shared
 // memory carved out the L1 is tiny, so every spilled register or dynamically indexed array costs an L2 round trip.

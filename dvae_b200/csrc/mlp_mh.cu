@@ -4,7 +4,7 @@
 // packages/models/mcem.py:207-277 (+ the M2 / M2v2 / M2v3 copies at 372-448, 544-620, 716-792).
 //
 // This is the CUDA-core reference mode of the product: every contraction is an FP32 FFMA chain, so the log
-// acceptance ratio agrees with the CPU reference to FP32 rounding.  The tensor-core sampler (mh_tc.cu) is checked
+// acceptance ratio agrees with the CPU reference to FP32 rounding.  The tensor-core sampler (mh_tc2.cu) is checked
 // against this one.  Restructuring w.r.t. the reference (exact in real arithmetic):
 //   * the chain carries l(z) = sum_f [log Vx + P/Vx]; it only changes on accept, so the post-accept decoder
 //     re-evaluation of mcem.py:268 disappears and a = l(z) - l(z') + .5 sum(z^2 - z'^2);

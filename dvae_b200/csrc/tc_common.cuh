@@ -396,7 +396,7 @@ __device__ __forceinline__ void hidden_epilogue_rows_bf(uint32_t tmem, unsigned 
 
 // Preload of a layer's bias into the thread's own 64 accumulator columns (lanes 32q.., columns 64h..): the following
 // GEMM accumulates onto it, so the epilogue has no bias loads / adds (they cost the layer-2 epilogue of the sampler 0.5 k of
-// its 1.7 k cycles: tools/tc_phase_clocks.py).  bias64: 64 floats in shared memory, 16-byte aligned.  Asynchronous: the caller
+// its 1.7 k cycles, measured with per-phase clock stamps in round 1).  bias64: 64 floats in shared memory, 16-byte aligned.  Asynchronous: the caller
 // runs tmem_wait_st() (and the tcgen05 fence) before handing the columns over.
 __device__ __forceinline__ void tmem_preload_bias64(uint32_t taddr, const float* bias64) {
     const uint32_t bias_s = smem_u32(bias64);
