@@ -64,7 +64,9 @@ PROTOTYPES = {
     "dvae_tc_image_bytes": (C.c_int64, [C.POINTER(DvaeMlp), C.c_int, C.c_int]),
     "dvae_tc_pack_decoder": (C.c_int, [C.POINTER(DvaeMlp), C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_tc_packed_pv_bytes": (C.c_int64, [C.c_int64]),
-    "dvae_tc_pack_pv": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "dvae_tc_row_scale": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, C.c_int64, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "dvae_tc_pack_pv": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr,
+                                  c_ptr]),
     "dvae_vad_workspace_bytes": (C.c_int64, [C.c_int64]),
     "dvae_vad_labels": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_float, c_ptr, c_ptr,
                                   c_ptr]),
@@ -80,7 +82,7 @@ PROTOTYPES = {
     "dvae_decode_tc": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, C.c_int64, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int, c_ptr, C.c_int,
                                  c_ptr, c_ptr]),
     "dvae_vst_bytes": (C.c_int64, [C.c_int64, C.c_int]),
-    "dvae_mh_chain_tc2": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64,
+    "dvae_mh_chain_tc2": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64,
                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(DvaeRng), c_ptr, c_ptr, c_ptr, c_ptr,
                                     C.c_int, c_ptr, c_ptr]),
     "dvae_vst_frame_stats": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,

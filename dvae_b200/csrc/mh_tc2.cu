@@ -43,6 +43,7 @@ struct Mh2Params {
     const float* ybias;           // per-frame layer-1 bias [frames][128] or null (label inputs folded into a bias, see dvae_b200.h)
     const uint4* PVpk;            // [tile][quad][128] {P0P1, P2P3, V0V1, V2V3} in BF16
     const float* g;
+    const float* kscale;          // [frames] per-frame quad scale (power of two) the stream was packed with, or null: 2^15
     float* Z;
     float* Zs;
     const float* eps;             // injected draws [n_iter][rows][L] standard normals, or null: Philox inside the kernel
@@ -67,8 +68,9 @@ struct Mh2Params {
 // 16 bins of the log-likelihood (loglik16_pv of tc_common.cuh) that also hands back 2^v of the 16 bins as eight "VsT words"
 // (common.cuh: bin 2j as bf16 in the low half, the whole word nearest to bin 2j+1): the emission of the kept samples' variances.
 template <int POLY>
-__device__ __forceinline__ void loglik16_pv_emit(const float* v, const uint4* pv, float g_row, float& acc, float& accl, uint32_t* out) {
-    const f32x2 g2 = pk2(g_row, g_row), g2k = pk2(g_row * kPairScale, g_row * kPairScale);
+__device__ __forceinline__ void loglik16_pv_emit(const float* v, const uint4* pv, float g_row, float k_row, float& acc, float& accl,
+                                                 uint32_t* out) {
+    const f32x2 g2 = pk2(g_row, g_row), g2k = pk2(g_row * k_row, g_row * k_row);
 #pragma unroll
     for (int qd = 0; qd < 4; ++qd) {
         const uint4 w = pv[qd];
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
         const bool valid = row_g < p.rows;
         const int64_t fr = valid ? row_g / p.C : 0;
         const float g_row = valid ? p.g[fr] : 1.f;
+        const float k_row = (valid && p.kscale) ? __ldg(p.kscale + fr) : kDefaultQuadScale;      // the frame's quad scale (pack_pv used the same)
         const uint4* PVt = p.PVpk + (tile * NQ) * TM + row;
         const float* ybias_row = p.ybias ? p.ybias + fr * HID : nullptr;
         // this thread's 32 bytes of bin group 0 in slot 0 of the tile's emission
@@ -366,11 +369,11 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
     do {                                                                                      \
         if constexpr (EMIT) {                                                                 \
             uint32_t o[8];                                                                    \
-            loglik16_pv_emit<POLY>(V, PV, g_row, acc, accl, o);                               \
+            loglik16_pv_emit<POLY>(V, PV, g_row, k_row, acc, accl, o);                               \
             uint4* dst = vs_dst + (MH2_BIN(t) >> 4) * (TM * 2);                               \
             st_cell(dst, o, pol_first);                                                       \
         } else {                                                                              \
-            loglik16_pv<POLY>(V, PV, g_row, acc, accl);                                       \
+            loglik16_pv<POLY>(V, PV, g_row, k_row, acc, accl);                                       \
         }                                                                                     \
     } while (0)
             // The 17 sub-chunks are spelled out through a compile-time index (a `#pragma unroll` loop over this body was left
@@ -429,7 +432,7 @@ __global__ void __launch_bounds__(MH2_THREADS, 1) mh2_kernel(Mh2Params p) {
 #undef MH2_COL
 #undef MH2_CH
             tc_fence_before();
-            const float part = fmaf(kLn2, accl, acc * kQuadScale);
+            const float part = fmaf(kLn2, accl, acc * k_row);
             red2[h * TM + row] = make_float2(part, prior_h);
             __syncthreads();                                                    // S4: both halves of l(z') and of the prior term
             {
@@ -489,7 +492,7 @@ extern "C" int64_t dvae_vst_bytes(int64_t chains, int n_keep) {
     return ((chains + TM - 1) / TM) * (int64_t)(n_keep + 1) * (NPAD / 16) * TM * 32;
 }
 
-extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g,
+extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* kscale, const float* g,
                                  const float* y, int y_dim, const float* ybias, const int32_t* frame_utt, const int32_t* frame_idx,
                                  float* Z, float* Zs,
                                  int64_t NT, int L, int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng,
@@ -513,7 +516,7 @@ extern "C" int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const vo
     if (NT == 0) return 0;
     p.image = (const unsigned char*)image;
     p.rows = NT * n_chains; p.C = n_chains; p.y = y; p.ybias = ybias;
-    p.PVpk = (const uint4*)PVpk; p.g = g; p.Z = Z; p.Zs = Zs;
+    p.PVpk = (const uint4*)PVpk; p.kscale = kscale; p.g = g; p.Z = Z; p.Zs = Zs;
     p.eps = rng->eps; p.u = rng->u;
     p.frame_gid = frame_utt; p.frame_idx = frame_idx;
     p.keys = philox_keys((uint32_t)(rng->seed & 0xffffffffu), (uint32_t)(rng->seed >> 32)); p.iter0 = rng->iter0;

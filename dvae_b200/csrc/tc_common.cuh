@@ -309,8 +309,10 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 // Vx in [1e-10, 1e7] (the observation is |STFT|^2 of audio in [-1, 1]: at most 2.6e5); the scale leaves `acc` short
 // of a factor 2^15 (applied once per row by the caller: kQuadScale) and adds a constant to `accl` that cancels in
 // l(z) - l(z').  -> 1.5 MUFU operations per bin instead of 2.
-constexpr float kPairScale = 32768.0f;
-constexpr float kQuadScale = 32768.0f;
+// The scale is a power of two chosen PER FRAME by row_scale_kernel (k^2 X^4 ~ 1 for the frame's typical X = Vx 2^-b): with the
+// fixed 2^15 of round 1 a decoder whose output bias is very small in some bins (2^-b ~ 1e10, e.g. a prior without energy above
+// 3 kHz) overflowed the four-fold product, l(z') became Inf and those chains never moved.
+constexpr float kDefaultQuadScale = 32768.0f;
 // 2^x for a packed pair on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f through the 1.5 * 2^23 magic
 // add, degree-3 minimax polynomial for 2^f on [-1/2, 1/2] (max relative error 7.5e-5, far inside the BF16 noise of the
 // layer-3 pre-activation), exponent patched with an integer add.  Valid for |x| < 125: callers must know the range
@@ -334,14 +336,14 @@ __device__ __forceinline__ f32x2 ex2_poly2(f32x2 x) {
 // third of its transcendental work to the idle FMA pipe shortens the layer-3 epilogue.
 // POLY = 2 (DVAE_TC_POLY_EX2_ALL): all four bins of a quad from the polynomial -> 0.5 MUFU operations per bin (rcp, lg2 only).
 template <int POLY>
-__device__ __forceinline__ void loglik16_pv(const float* v, const uint4* pv, float g_row, float& acc, float& accl) {
+__device__ __forceinline__ void loglik16_pv(const float* v, const uint4* pv, float g_row, float k_row, float& acc, float& accl) {
     // Stream format: see pack_pv_kernel (bias folded in, word j = P'_j with bf16(Vb'_j) in its low half, quad scale k
     // pre-applied to Vb' of bins 0,1 and 1/k to P' of bins 2,3).  Packed FP32 pairs:
     //   A = k (X0, X1),  B = (X2, X3),  X_j = g 2^v_j + Vb'_j
     //   M = A * B = (k X0 X2, k X1 X3)
     //   N = P_A * B + (P_B / k) * A = (P0 X2 + P2 X0, P1 X3 + P3 X1)
     // so that  sum_j P'_j / X_j = (N.lo M.hi + N.hi M.lo) / (M.lo M.hi) / k  and  sum_j log2 X_j = log2(M.lo M.hi) - 30.
-    const f32x2 g2 = pk2(g_row, g_row), g2k = pk2(g_row * kPairScale, g_row * kPairScale);
+    const f32x2 g2 = pk2(g_row, g_row), g2k = pk2(g_row * k_row, g_row * k_row);
 #pragma unroll
     for (int qd = 0; qd < 4; ++qd) {
         const uint4 w = pv[qd];

@@ -81,16 +81,16 @@ __device__ __forceinline__ uint32_t word_with_low_half(float p, uint32_t low16) 
     if ((w & 0x7f800000u) == 0x7f800000u) w -= 0x10000u;                               // never Inf / NaN
     return w;
 }
-__device__ __forceinline__ uint32_t pv_word(float p, float vb, float bias_log2, int j) {
+__device__ __forceinline__ uint32_t pv_word(float p, float vb, float bias_log2, int j, float k) {
     const float sc = exp2f(-bias_log2);
-    const float pj = p * sc * (j < 2 ? 1.0f : 1.0f / kPairScale);
-    const float vj = vb * sc * (j < 2 ? kPairScale : 1.0f);
+    const float pj = p * sc * (j < 2 ? 1.0f : 1.0f / k);
+    const float vj = vb * sc * (j < 2 ? k : 1.0f);
     return word_with_low_half(pj, bf16_bits_rn(vj));
 }
 
 // generic version: one thread per (tile, quad, row), rows fastest (coalesced stores, strided loads)
 __global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restrict__ Vb, const float* __restrict__ bias_log2,
-                               int64_t chains, int C, int F, int ld, uint4* __restrict__ dst) {
+                               const float* __restrict__ kscale, int64_t chains, int C, int F, int ld, uint4* __restrict__ dst) {
     const int64_t n_tiles = (chains + TM - 1) / TM;
     const int64_t total = n_tiles * NQ * TM;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -102,9 +102,10 @@ __global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restr
         if (m < chains) {
             const int64_t fr = m / C;
             const int f = 4 * q;
+            const float k = kscale ? kscale[fr] : kDefaultQuadScale;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (f + j < F) w[j] = pv_word(P[fr * ld + f + j], Vb[fr * ld + f + j], bias_log2[f + j], j);
+                if (f + j < F) w[j] = pv_word(P[fr * ld + f + j], Vb[fr * ld + f + j], bias_log2[f + j], j, k);
         }
         dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -115,8 +116,8 @@ __global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restr
 // (2 KB contiguous).  The padded row stride (129) keeps both shared-memory passes conflict-free.
 constexpr int PPV_Q = 8;
 __global__ void __launch_bounds__(256) pack_pv_tiled_kernel(const float* __restrict__ P, const float* __restrict__ Vb,
-                                                            const float* __restrict__ bias_log2, int64_t chains, int C, int F,
-                                                            int ld, uint4* __restrict__ dst) {
+                                                            const float* __restrict__ bias_log2, const float* __restrict__ kscale,
+                                                            int64_t chains, int C, int F, int ld, uint4* __restrict__ dst) {
     __shared__ uint4 sm[PPV_Q * (TM + 1)];
     const int64_t tile = blockIdx.y;
     const int q0 = blockIdx.x * PPV_Q;
@@ -129,14 +130,15 @@ __global__ void __launch_bounds__(256) pack_pv_tiled_kernel(const float* __restr
         if (m < chains && q < NQ) {
             const int64_t fr = m / C;
             const int f = 4 * q;
+            const float k = kscale ? __ldg(kscale + fr) : kDefaultQuadScale;
             if (f < F) {
                 const float4 p4 = __ldg(reinterpret_cast<const float4*>(P + fr * ld + f));
                 const float4 v4 = __ldg(reinterpret_cast<const float4*>(Vb + fr * ld + f));
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_log2 + f);
-                w[0] = pv_word(p4.x, v4.x, b4.x, 0);
-                if (f + 1 < F) w[1] = pv_word(p4.y, v4.y, b4.y, 1);
-                if (f + 2 < F) w[2] = pv_word(p4.z, v4.z, b4.z, 2);
-                if (f + 3 < F) w[3] = pv_word(p4.w, v4.w, b4.w, 3);
+                w[0] = pv_word(p4.x, v4.x, b4.x, 0, k);
+                if (f + 1 < F) w[1] = pv_word(p4.y, v4.y, b4.y, 1, k);
+                if (f + 2 < F) w[2] = pv_word(p4.z, v4.z, b4.z, 2, k);
+                if (f + 3 < F) w[3] = pv_word(p4.w, v4.w, b4.w, 3, k);
             }
         }
         sm[ql * (TM + 1) + row] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -147,6 +149,32 @@ __global__ void __launch_bounds__(256) pack_pv_tiled_kernel(const float* __restr
         const int e = threadIdx.x + 256 * k;
         const int ql = e / TM, row = e % TM, q = q0 + ql;
         if (q < NQ) dst[(tile * NQ + q) * TM + row] = sm[ql * (TM + 1) + row];
+    }
+}
+
+// Per-frame quad scale of the sampler's likelihood (loglik16_pv): k = 2^(-2 c) with c = mean over the frame's bins of
+// log2(P 2^-b), so that k^2 X^4 ~ 1 for a typical X = Vx 2^-b of the frame (the model fits the observation: Vx ~ P).  P does not
+// change during a run, so this runs once per batch.  One warp per frame, fixed summation order: deterministic and independent
+// of the batch a frame sits in.  Frames without energy keep the default 2^15.
+__global__ void row_scale_kernel(const float* __restrict__ P, const float* __restrict__ bias_log2, int64_t NT, int F, int ld,
+                                 float* __restrict__ kscale) {
+    const int64_t n = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= NT) return;
+    float sum = 0.f, cnt = 0.f;
+    for (int f = lane; f < F; f += 32) {
+        const float p = P[n * ld + f];
+        if (p > 0.f) { sum += log2f(p) - bias_log2[f]; cnt += 1.f; }
+    }
+    sum = warp_sum(sum);
+    cnt = warp_sum(cnt);
+    if (lane == 0) {
+        float k = kDefaultQuadScale;
+        if (cnt > 0.f) {
+            const float e = fminf(fmaxf(rintf(-2.0f * sum / cnt), -60.f), 60.f);
+            k = exp2f(e);
+        }
+        kscale[n] = k;
     }
 }
 
@@ -406,8 +434,20 @@ extern "C" int64_t dvae_tc_packed_pv_bytes(int64_t chains) {
     return ((chains + TM - 1) / TM) * (int64_t)NQ * TM * 16;
 }
 
+extern "C" int dvae_tc_row_scale(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, int64_t NT, int F, int ld,
+                                 float* kscale, void* stream) {
+    Dims d;
+    int rc = check_dims(dec, L, y_dim, "dvae_tc_row_scale", &d);
+    if (rc) return rc;
+    DVAE_REQUIRE(image && P && kscale && NT >= 0 && F == d.F && ld >= F, "dvae_tc_row_scale: bad arguments");
+    if (NT == 0) return 0;
+    const float* bias_log2 = reinterpret_cast<const float*>((const unsigned char*)image + d.off_bias) + (d.n_hidden == 2 ? HID : 0);
+    row_scale_kernel<<<(unsigned)((NT + 7) / 8), 256, 0, (cudaStream_t)stream>>>(P, bias_log2, NT, F, ld, kscale);
+    return check_launch("row_scale_kernel");
+}
+
 extern "C" int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const float* Vb,
-                               int64_t NT, int n_chains, int F, int ld, void* dst, void* stream) {
+                               const float* kscale, int64_t NT, int n_chains, int F, int ld, void* dst, void* stream) {
     Dims d;
     int rc = check_dims(dec, L, y_dim, "dvae_tc_pack_pv", &d);
     if (rc) return rc;
@@ -418,11 +458,11 @@ extern "C" int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int
     const float* bias_log2 = reinterpret_cast<const float*>((const unsigned char*)image + d.off_bias) + (d.n_hidden == 2 ? HID : 0);
     const int64_t chains = NT * n_chains, n_tiles = (chains + TM - 1) / TM;
     if ((ld & 3) == 0 && ld >= ((F + 3) & ~3) && ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(Vb)) & 15) == 0 && n_tiles < 65536) {
-        pack_pv_tiled_kernel<<<dim3((NQ + PPV_Q - 1) / PPV_Q, (unsigned)n_tiles), 256, 0, (cudaStream_t)stream>>>(P, Vb, bias_log2, chains,
+        pack_pv_tiled_kernel<<<dim3((NQ + PPV_Q - 1) / PPV_Q, (unsigned)n_tiles), 256, 0, (cudaStream_t)stream>>>(P, Vb, bias_log2, kscale, chains,
                                                                                                                 n_chains, F, ld, (uint4*)dst);
         return check_launch("pack_pv_tiled_kernel");
     }
-    pack_pv_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(P, Vb, bias_log2, chains, n_chains, F, ld, (uint4*)dst);
+    pack_pv_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(P, Vb, bias_log2, kscale, chains, n_chains, F, ld, (uint4*)dst);
     return check_launch("pack_pv_kernel");
 }
 

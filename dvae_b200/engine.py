@@ -398,7 +398,10 @@ class McemEngine:
             raise ValueError("y must be [NT][y_dim=%d]" % w.y_dim)
         self.batch, self.X, self.P, self.y = batch, X, P, (None if y is None else y.contiguous().float())
         # what the tensor-core kernels see of the labels: the labels themselves (<= 3) or a per-frame layer-1 bias
-        self.tc_y, self.ybias = self.y, None
+        self.tc_y, self.ybias, self.kscale = self.y, None, None
+        if cfg.sampler == "tc":
+            from . import tc
+            self.kscale = tc.row_scale(self)
         if cfg.sampler == "tc" and w.tc_label_bias:
             self.tc_y = None
             self.ybias = mlp_forward(w.ybias_mlp, self.y, _lib.ACT_NONE, out=self._get("ybias", (batch.NT, 128)))

@@ -74,6 +74,15 @@ def check_status(eng):
     raise _lib.DvaeError("device status %d (%s): results are invalid" % (v, "; ".join(what) or "unknown"))
 
 
+def row_scale(eng):
+    """Per-frame quad scale of the sampler's likelihood arithmetic (dvae_tc_row_scale), once per batch: ``[NT]`` float32."""
+    w, b = eng.w, eng.batch
+    k = eng._get("kscale", (max(b.NT, 1),))
+    _lib.call("dvae_tc_row_scale", w.dec_tc.ref, _p(decoder_image(w)), w.z_dim, w.tc_y_dim, _p(eng.P), b.NT, eng.F, eng.ld, _p(k), _stream())
+    eng.kernel_launches += 1
+    return k
+
+
 def vst_supported(eng, keep):
     """The sampler's own emission of the kept samples' variances serves one chain per frame, up to 31 kept samples, and
     (for the fused M-step kernel) R in {10, 30}, K <= 10, F = 513."""
@@ -89,15 +98,15 @@ def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace, emit=False):
     chains = b.NT * cfg.n_chains
     lib = _lib.load()
     pv = eng._get("PVpk", (max(int(lib.dvae_tc_packed_pv_bytes(chains)), 16),), torch.uint8)
-    _lib.call("dvae_tc_pack_pv", w.dec_tc.ref, _p(img), w.z_dim, w.tc_y_dim, _p(eng.P), _p(eng.Vb), b.NT, cfg.n_chains, eng.F, eng.ld,
-              _p(pv), _stream())
+    _lib.call("dvae_tc_pack_pv", w.dec_tc.ref, _p(img), w.z_dim, w.tc_y_dim, _p(eng.P), _p(eng.Vb), _p(eng.kscale), b.NT, cfg.n_chains,
+              eng.F, eng.ld, _p(pv), _stream())
     eng.kernel_launches += 1
     vst = idx = None
     if emit:
         vst = eng._get("VsT", (max(int(lib.dvae_vst_bytes(chains, keep)), 16),), torch.uint8)
         idx = eng._get("vs_idx", (max(chains, 1) * VST_IDX_PITCH,), torch.uint8)
     with eng.stage("mh_kernel"):
-        _lib.call("dvae_mh_chain_tc2", w.dec_tc.ref, _p(img), _p(pv), _p(eng.g), _p(eng.tc_y), w.tc_y_dim, _p(eng.ybias), _p(b.frame_gid), _p(b.frame_idx),
+        _lib.call("dvae_mh_chain_tc2", w.dec_tc.ref, _p(img), _p(pv), _p(eng.kscale), _p(eng.g), _p(eng.tc_y), w.tc_y_dim, _p(eng.ybias), _p(b.frame_gid), _p(b.frame_idx),
                   _p(eng.Z), _p(Zs), b.NT, w.z_dim, cfg.n_chains, burn, keep, float(cfg.var_rw), C.byref(rng), _p(eng.n_accept),
                   _p(a_trace), _p(vst), _p(idx), int(w._tc_flags), _p(_status(eng)), _stream())
     eng.kernel_launches += 1

@@ -187,11 +187,16 @@ int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64
 #define DVAE_TC_POLY_EX2_ALL 2      /* all layer-3 exponentials from the polynomial (same validity condition) */
 #define DVAE_TC_POLY_EX2_LIMIT 120.0f
 int64_t dvae_tc_packed_pv_bytes(int64_t chains);
-int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const float* Vb, int64_t NT,
-                    int n_chains, int F, int ld, void* dst, void* stream);
+/* kscale[NT] (nullable everywhere: 2^15): a power of two per frame that centres the sampler's four-fold variance products in
+ * the FP32 range for THIS frame's spectrum and THIS decoder's output bias; dvae_tc_row_scale derives it once per batch from
+ * P (k = 2^-2c, c = mean_f log2(P 2^-b)); the stream must be packed and sampled with the same array. */
+int dvae_tc_row_scale(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, int64_t NT, int F, int ld,
+                      float* kscale, void* stream);
+int dvae_tc_pack_pv(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const float* Vb,
+                    const float* kscale, int64_t NT, int n_chains, int F, int ld, void* dst, void* stream);
 int dvae_tc_decoder_exponent_bound(const DvaeMlp* dec, int L, int y_dim, float* bound_host, void* stream);
 int64_t dvae_vst_bytes(int64_t chains, int n_keep);
-int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* g, const float* y, int y_dim,
+int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, const float* kscale, const float* g, const float* y, int y_dim,
                       const float* ybias /* nullable: [NT][128] */, const int32_t* frame_utt, const int32_t* frame_idx, float* Z,
                       float* Zs, int64_t NT, int L,
                       int n_chains, int n_burn, int n_keep, float var_rw, const DvaeRng* rng, uint32_t* n_accept,

@@ -282,3 +282,33 @@ def test_fused_wiener_a1_matches_materialised_samples(R_total, chunk):
     assert float((WFn[:, :513] - ref_n).abs().max()) < 2e-4 * R_total
     assert float((WFs[:, :513] - ref_s).abs().max()) < 2e-4 * R_total
     assert float((WFs[:, :513] + WFn[:, :513] - R_total).abs().max()) < 1e-4 * R_total
+
+
+def test_sampler_handles_decoder_biases_spanning_many_decades():
+    """A decoder whose output bias is tiny in part of the spectrum (a prior without energy above 3 kHz: exp(b3) ~ 1e-10 there)
+    makes the sampler's bias-free variances X = Vx exp(-b3) huge in those bins.  With a fixed quad scale the four-fold products
+    of the likelihood overflowed, l(z') became Inf and the affected chains never moved; the per-frame scale of
+    dvae_tc_row_scale keeps them finite: no status bit, and the chains accept as often as the exact FP32 sampler's."""
+    x, s, _ = synth.synth_utterance(5, 1.0)
+    bias = synth.speech_prior_bias(s)
+    assert bias.min() < -20.0 and bias.max() > -8.0                      # > 5 decades between bins
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128], 0, seed=3, out_bias=bias)
+    X = stft_np.stft(x, **KW)
+    N = X.shape[1]
+    P = torch.zeros((N, 520), device=DEV)
+    P[:, :513] = torch.from_numpy(np.ascontiguousarray((np.abs(X) ** 2).T)).to(DEV)
+    rate = {}
+    for sampler in ("fp32", "tc"):
+        w = VaeWeights(sd, "M1", torch.device(DEV))
+        eng = McemEngine(w, McemConfig(niter=2, keep_E=10, burn_E=20, sampler=sampler, seed=4), DEV)
+        eng.init_parameters(torch.zeros((N, 520), dtype=torch.complex64, device=DEV), P, RaggedBatch([N], DEV, utt_ids=[9]))
+        for it in range(2):
+            eng.e_step()
+            eng.m_step(it)
+        if sampler == "tc":
+            tc.check_status(eng)                                         # neither a timeout nor a non-finite likelihood
+            k = eng.kscale.cpu().numpy()
+            assert np.all(k > 0) and np.all(np.log2(k) == np.rint(np.log2(k))) and k.min() < 1.0     # powers of two, far from 2^15
+        rate[sampler] = float(eng.n_accept.sum().item()) / (N * 60)
+        assert bool(torch.isfinite(eng.cost).all())
+    assert rate["fp32"] > 0.3 and abs(rate["tc"] - rate["fp32"]) <= 0.03, rate

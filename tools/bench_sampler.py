@@ -98,17 +98,18 @@ for tag in "BCDEFG":
     pv = eng._get("PVpk", (max(int(lib.dvae_tc_packed_pv_bytes(NT)), 16),), torch.uint8)
     Zs = eng._get("Zs%d" % keep, (NT, keep, L))
     st = tc._status(eng)
-    for mode in ("philox",):
+    for mode in ("philox", "philox+emit"):
         rng = _lib.DvaeRng()
         rng.seed, rng.iter0 = 1, 0
         if mode == "injected":
             rng.eps, rng.u = inj.eps.data_ptr(), inj.u.data_ptr()
 
         def var():
-            rc = fv(w.dec.ref, _p(img), _p(pv), _p(eng.g), _p(eng.y), w.y_dim, None, _p(batch.frame_gid), _p(batch.frame_idx), _p(eng.Z), _p(Zs), NT, L,
-                    1, burn, keep, 0.01, C.byref(rng), _p(eng.n_accept), None, _p(eng.VsT), _p(eng.vs_idx), int(w._tc_flags), _p(st), _stream())
+            rc = fv(w.dec.ref, _p(img), _p(pv), _p(eng.kscale), _p(eng.g), _p(eng.y), w.y_dim, None, _p(batch.frame_gid), _p(batch.frame_idx), _p(eng.Z), _p(Zs), NT, L,
+                    1, burn, keep, 0.01, C.byref(rng), _p(eng.n_accept), None, _p(eng.VsT) if "emit" in mode else None,
+                    _p(eng.vs_idx) if "emit" in mode else None, int(w._tc_flags), _p(st), _stream())
             assert rc == 0
-        out["v%s %s+emit" % (tag, mode)] = timed(var)
+        out["v%s %s" % (tag, mode)] = timed(var)
 eng.timing = False
 eng.sample_posterior(keep, burn, None, emit=True)
 eng.R = eng.vst_R = keep
