@@ -88,11 +88,11 @@ PROTOTYPES = {
     "dvae_vst_frame_stats": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, C.c_int64,
                                        C.c_int, c_ptr, c_ptr, c_ptr]),
     "dvae_nmf_mstep_vst": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr,
-                                     c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
-                                     c_ptr]),
+                                     c_ptr, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int,
+                                     c_ptr, c_ptr]),
     "dvae_vst_w_partial_floats": (C.c_int64, [C.c_int64, C.c_int, C.c_int]),
     "dvae_vst_w_partials": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int,
-                                      C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
+                                      C.c_int64, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "dvae_nmf_w_from_partials": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "dvae_vst_unpack": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, c_ptr, C.c_int, C.c_int64, C.c_int, c_ptr, c_ptr]),
     "dvae_vst_pack": (C.c_int, [C.POINTER(DvaeMlp), c_ptr, C.c_int, C.c_int, c_ptr, C.c_int, C.c_int64, C.c_int, c_ptr, c_ptr, c_ptr]),

@@ -1084,6 +1084,330 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
     }
 }
 
+// ----------------------------------------------------------------------------- H, g, cost on the emission, many samples per frame
+// hg7 for frames that hold C chains x KEEP kept samples (multi-chain runs, BASELINE configs[3]: 16 x 10 = 160 samples, 169 KB
+// per frame): the frame's samples form one flat list (sample j = chain j / KEEP, kept index j % KEEP; the chains of a frame are
+// adjacent rows of one emission tile) that is walked in windows of up to 30 samples, once per pass - three reads of the frame, the
+// first from HBM, the others from L2.  Same thread layout, packed-lane math and double-buffered cp.async staging as hg7; the
+// per-bin partial sums of a pass live in registers across its windows.
+template <int KEEP>
+__global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7w_kernel(const float* __restrict__ P, const uint4* __restrict__ VsT,
+                                                                  const uint8_t* __restrict__ vs_idx, const float* __restrict__ bias_log2,
+                                                                  const float* __restrict__ Wtmp, const float* __restrict__ norm,
+                                                                  float* __restrict__ H, float* __restrict__ g,
+                                                                  float* __restrict__ Vb, double* __restrict__ cost_part,
+                                                                  const int64_t* __restrict__ fr_off, int K, int C) {
+    constexpr int KT = HG2_KT;
+    constexpr int ld = HG5_LD;
+    constexpr int NBG = 33, TMR = 128, RWMAX = 30;
+    static_assert(KEEP % 2 == 0 && KEEP <= 30, "hg7w: an even number of kept samples per chain");
+    extern __shared__ __align__(16) uint32_t smw[];
+    uint32_t* S0 = smw;                              // [2][RWMAX][HG7_ROWW] the current window and the next one being staged
+    float* red = reinterpret_cast<float*>(smw + 2 * RWMAX * HG7_ROWW);  // [8][HG3_NV] per-warp partials of the H sums
+    __shared__ float2 red2[8];
+    __shared__ double redd[8];
+    __shared__ float hs[KT];
+    __shared__ float hs_old[KT];
+    const int u = blockIdx.y;
+    const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
+    const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
+    if (nb >= n1) {
+        if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
+        return;
+    }
+    const int64_t ne = (nb + HG3_FPB < n1) ? nb + HG3_FPB : n1;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int f2 = 2 * t;
+    const int Rtot = C * KEEP, NW = (Rtot + RWMAX - 1) / RWMAX;
+    f32x2 w2[KT];
+    float wX[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+        const float* wk = Wtmp + ((int64_t)u * K + k) * ld;
+        w2[k] = (k < K) ? *reinterpret_cast<const f32x2*>(wk + f2) : 0ull;
+        wX[k] = (k < K) ? wk[512] : 0.f;
+    }
+    const float E0 = exp2f(__ldg(bias_log2 + f2)), E1 = exp2f(__ldg(bias_log2 + f2 + 1)), EX = exp2f(__ldg(bias_log2 + 512));
+    double cost_d = 0.0;
+
+    const unsigned s_base = (unsigned)__cvta_generic_to_shared(S0);
+    const unsigned po0 = (unsigned)((lane >> 1) * (TMR * 32) + 16 * (lane & 1));
+    auto rows_of = [&](int w) { const int left = Rtot - RWMAX * w; return left < RWMAX ? left : RWMAX; };
+    auto stage = [&](int64_t n, int w, int b) {       // window w of frame n -> buffer b; a warp copies the rows wid, wid + 8, ...
+        const int nr = rows_of(w);
+#pragma unroll
+        for (int k = 0; k < (RWMAX + 7) / 8; ++k) {
+            const int rl = wid + 8 * k;
+            if (rl < nr) {
+                const int j = RWMAX * w + rl, chain = j / KEEP, r = j - chain * KEEP;
+                const int64_t m = n * C + chain;
+                const int64_t tile = m / TMR;
+                const int row = (int)(m - tile * TMR);
+                const unsigned slot = __ldg(vs_idx + m * 32 + r);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(VsT) +
+                                           (((size_t)tile * (KEEP + 1) + slot) * NBG * TMR + row) * 32 + po0;
+                const unsigned dst = s_base + (unsigned)((b * RWMAX + rl) * HG7_ROWW * 4 + 16 * lane);
+                hg7_cp16(dst, src);
+                hg7_cp16(dst + 512, src + 16 * (TMR * 32));
+                if (lane < 2) hg7_cp16(dst + 1024, src + 32 * (TMR * 32));
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(nb, 0, 0);
+    if (t >= K && t < KT) { hs_old[t] = 0.f; hs[t] = 0.f; }
+    int buf = 0;
+
+    // one pass over the frame's windows: body(S = this thread's word of row 0, SX = word of bin 512 of row 0, rows)
+    auto walk = [&](int64_t n, bool last_pass, auto&& body) {
+        for (int w = 0; w < NW; ++w) {
+            int64_t nn = n;
+            int nw = w + 1;
+            if (nw == NW) { nw = 0; if (last_pass) nn = n + 1; }
+            if (nn < ne) {
+                stage(nn, nw, buf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();                                            // the window is staged for every thread
+            body(S0 + buf * RWMAX * HG7_ROWW + t, S0 + buf * RWMAX * HG7_ROWW + 256, rows_of(w));
+            __syncthreads();                                            // the window is consumed: its buffer may be refilled
+            buf ^= 1;
+        }
+    };
+
+    for (int64_t n = nb; n < ne; ++n) {
+        const float gg = g[n];
+        const f32x2 p2 = *reinterpret_cast<const f32x2*>(P + n * ld + f2);
+        const float pX = P[n * ld + 512];
+        if (t < K) hs_old[t] = H[n * K + t];
+        __syncthreads();
+        float h[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = hs_old[k];
+        float p_lo, p_hi;
+        upk2(p2, p_lo, p_hi);
+        const f32x2 ga = pk2(gg * E0, gg * E0), gb = pk2(gg * E1, gg * E1);
+        const float ggX = gg * EX;
+#define HG7W_VA(r) pk2(vst_lo(S[(r) * HG7_ROWW]), vst_lo(S[((r) + 1) * HG7_ROWW]))
+#define HG7W_VB(r) pk2(vst_hi(S[(r) * HG7_ROWW]), vst_hi(S[((r) + 1) * HG7_ROWW]))
+        // ---- H update (Vb1 = W_new H_old)
+        f32x2 vb2 = 0ull;
+        float vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        float vb_lo, vb_hi;
+        upk2(vb2, vb_lo, vb_hi);
+        f32x2 va2 = pk2(vb_lo, vb_lo), vbb2 = pk2(vb_hi, vb_hi);
+        f32x2 a1a = 0ull, a2a = 0ull, a1b = 0ull, a2b = 0ull;
+        float a1X = 0.f, a2X = 0.f;
+        walk(n, false, [&](const uint32_t* S, const uint32_t* SX, int nr) {
+            int r = 0;
+            for (; r + 4 <= nr; r += 4) {
+                {
+                    const f32x2 x0 = fma2(ga, HG7W_VA(r), va2), x1 = fma2(ga, HG7W_VA(r + 2), va2);
+                    const f32x2 rr = rcp2(mul2(x0, x1));
+                    const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                    a1a = add2(a1a, add2(i0, i1));
+                    a2a = fma2(i0, i0, fma2(i1, i1, a2a));
+                }
+                {
+                    const f32x2 x0 = fma2(gb, HG7W_VB(r), vbb2), x1 = fma2(gb, HG7W_VB(r + 2), vbb2);
+                    const f32x2 rr = rcp2(mul2(x0, x1));
+                    const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                    a1b = add2(a1b, add2(i0, i1));
+                    a2b = fma2(i0, i0, fma2(i1, i1, a2b));
+                }
+            }
+            if (r < nr) {
+                const f32x2 ia = rcp2(fma2(ga, HG7W_VA(r), va2)), ibb = rcp2(fma2(gb, HG7W_VB(r), vbb2));
+                a1a = add2(a1a, ia); a2a = fma2(ia, ia, a2a);
+                a1b = add2(a1b, ibb); a2b = fma2(ibb, ibb, a2b);
+            }
+            if (t < nr) { const float ix = rcp_fast(fmaf(ggX, vst_lo(SX[t * HG7_ROWW]), vbX)); a1X += ix; a2X = fmaf(ix, ix, a2X); }
+        });
+        f32x2 a1, a2;
+        {
+            float l0, l1, m0, m1;
+            upk2(a1a, l0, l1); upk2(a1b, m0, m1);
+            a1 = pk2(l0 + l1, m0 + m1);
+            upk2(a2a, l0, l1); upk2(a2b, m0, m1);
+            a2 = pk2(l0 + l1, m0 + m1);
+        }
+        {
+            const f32x2 q2 = mul2(p2, a2);
+            const float qX = pX * a2X;
+            const bool b4 = lane & 16, b3 = lane & 8;
+            float a[10];
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float v[10];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const int k = 5 * hf + j;
+                    float nlo, nhi, dlo, dhi;
+                    upk2(mul2(w2[k], q2), nlo, nhi);
+                    upk2(mul2(w2[k], a1), dlo, dhi);
+                    v[2 * j] = fmaf(wX[k], qX, nlo + nhi);
+                    v[2 * j + 1] = fmaf(wX[k], a1X, dlo + dhi);
+                }
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float send = b4 ? v[j] : v[5 + j], keep = b4 ? v[5 + j] : v[j];
+                    a[5 * hf + j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+            }
+            float o5[5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float send = b3 ? a[j] : a[5 + j], keep = b3 ? a[5 + j] : a[j];
+                o5[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) o5[j] += __shfl_xor_sync(0xffffffffu, o5[j], o);
+            if ((lane & 7) == 0) {
+                float* dst = red + wid * HG3_NV + 10 * ((lane >> 3) & 1) + 5 * (lane >> 4);
+#pragma unroll
+                for (int j = 0; j < 5; ++j) dst[j] = o5[j];
+            }
+        }
+        __syncthreads();
+        if (t < K) {
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) { num += red[w * HG3_NV + 2 * t]; den += red[w * HG3_NV + 2 * t + 1]; }
+            hs[t] = hs_old[t] * sqrtf(num / den);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < KT; ++k) h[k] = hs[k];
+
+        // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
+        vb2 = 0ull; vbX = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        *reinterpret_cast<f32x2*>(Vb + n * ld + f2) = vb2;
+        if (t == 0) Vb[n * ld + 512] = vbX;
+        upk2(vb2, vb_lo, vb_hi);
+        va2 = pk2(vb_lo, vb_lo); vbb2 = pk2(vb_hi, vb_hi);
+        f32x2 s1a = 0ull, s2a = 0ull, s1b = 0ull, s2b = 0ull;
+        float s1X = 0.f, s2X = 0.f;
+        walk(n, false, [&](const uint32_t* S, const uint32_t* SX, int nr) {
+            int r = 0;
+            for (; r + 4 <= nr; r += 4) {
+                {
+                    const f32x2 v0 = HG7W_VA(r), v1 = HG7W_VA(r + 2);
+                    const f32x2 x0 = fma2(ga, v0, va2), x1 = fma2(ga, v1, va2);
+                    const f32x2 rr = rcp2(mul2(x0, x1));
+                    const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                    const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
+                    s1a = add2(s1a, add2(t0, t1));
+                    s2a = fma2(t0, i0, fma2(t1, i1, s2a));
+                }
+                {
+                    const f32x2 v0 = HG7W_VB(r), v1 = HG7W_VB(r + 2);
+                    const f32x2 x0 = fma2(gb, v0, vbb2), x1 = fma2(gb, v1, vbb2);
+                    const f32x2 rr = rcp2(mul2(x0, x1));
+                    const f32x2 i0 = mul2(x1, rr), i1 = mul2(x0, rr);
+                    const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
+                    s1b = add2(s1b, add2(t0, t1));
+                    s2b = fma2(t0, i0, fma2(t1, i1, s2b));
+                }
+            }
+            if (r < nr) {
+                const f32x2 v0 = HG7W_VA(r), v1 = HG7W_VB(r);
+                const f32x2 i0 = rcp2(fma2(ga, v0, va2)), i1 = rcp2(fma2(gb, v1, vbb2));
+                const f32x2 t0 = mul2(v0, i0), t1 = mul2(v1, i1);
+                s1a = add2(s1a, t0); s2a = fma2(t0, i0, s2a);
+                s1b = add2(s1b, t1); s2b = fma2(t1, i1, s2b);
+            }
+            if (t < nr) {
+                const float sx = vst_lo(SX[t * HG7_ROWW]);
+                const float ix = rcp_fast(fmaf(ggX, sx, vbX)), tt = EX * sx * ix;
+                s1X += tt;
+                s2X = fmaf(tt, ix, s2X);
+            }
+        });
+        {
+            float l0, l1, m0, m1;
+            upk2(s1a, l0, l1); upk2(s1b, m0, m1);
+            const float s1lo = E0 * (l0 + l1), s1hi = E1 * (m0 + m1);
+            upk2(s2a, l0, l1); upk2(s2b, m0, m1);
+            const float s2lo = E0 * (l0 + l1), s2hi = E1 * (m0 + m1);
+            const float v2 = warp_sum(fmaf(pX, s2X, fmaf(p_lo, s2lo, p_hi * s2hi))), v1 = warp_sum(s1lo + s1hi + s1X);
+            if (lane == 0) red2[wid] = make_float2(v2, v1);
+        }
+        __syncthreads();
+        float t2 = 0.f, t1s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { const float2 rr = red2[w]; t2 += rr.x; t1s += rr.y; }
+        const float gnew = gg * sqrtf(t2 / t1s);
+
+        // ---- cost with Vx = g_new Vs + Vb2 (four samples of a bin share one reciprocal and one log2, c = 2^8: see hg5)
+        constexpr float kC = 256.0f;
+        const f32x2 gca = pk2(gnew * kC * E0, gnew * kC * E0), gcb = pk2(gnew * kC * E1, gnew * kC * E1);
+        const f32x2 vca = pk2(vb_lo * kC, vb_lo * kC), vcb = pk2(vb_hi * kC, vb_hi * kC);
+        float cla = 0.f, cpa = 0.f, clb = 0.f, cpb = 0.f, cX = 0.f;
+        walk(n, true, [&](const uint32_t* S, const uint32_t* SX, int nr) {
+            int r = 0;
+            for (; r + 4 <= nr; r += 4) {
+                {
+                    const f32x2 y01 = fma2(gca, HG7W_VA(r), vca), y23 = fma2(gca, HG7W_VA(r + 2), vca);
+                    float s_lo, s_hi, q_lo, q_hi;
+                    upk2(add2(y01, y23), s_lo, s_hi);
+                    upk2(mul2(y01, y23), q_lo, q_hi);
+                    const float m = q_lo * q_hi;
+                    cla += lg2_fast(m);
+                    cpa = fmaf(fmaf(s_lo, q_hi, s_hi * q_lo), rcp_fast(m), cpa);
+                }
+                {
+                    const f32x2 y01 = fma2(gcb, HG7W_VB(r), vcb), y23 = fma2(gcb, HG7W_VB(r + 2), vcb);
+                    float s_lo, s_hi, q_lo, q_hi;
+                    upk2(add2(y01, y23), s_lo, s_hi);
+                    upk2(mul2(y01, y23), q_lo, q_hi);
+                    const float m = q_lo * q_hi;
+                    clb += lg2_fast(m);
+                    cpb = fmaf(fmaf(s_lo, q_hi, s_hi * q_lo), rcp_fast(m), cpb);
+                }
+            }
+            if (r < nr) {
+                float y0, y1;
+                upk2(fma2(gca, HG7W_VA(r), vca), y0, y1);
+                float m = y0 * y1;
+                cla += lg2_fast(m);
+                cpa = fmaf(y0 + y1, rcp_fast(m), cpa);
+                upk2(fma2(gcb, HG7W_VB(r), vcb), y0, y1);
+                m = y0 * y1;
+                clb += lg2_fast(m);
+                cpb = fmaf(y0 + y1, rcp_fast(m), cpb);
+            }
+            if (t < nr) {
+                const float x0 = fmaf(gnew * EX, vst_lo(SX[t * HG7_ROWW]), vbX);
+                cX += fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0));
+            }
+        });
+#undef HG7W_VA
+#undef HG7W_VB
+        const float fix = -8.0f * (float)Rtot;          // log2 c per sample, both bins of the thread
+        cost_d += (double)(fmaf(0.6931471805599453f, (cla + fix) + (clb + fix), kC * fmaf(p_lo, cpa, p_hi * cpb)) + cX);
+
+        if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
+        if (t == 0) g[n] = gnew;
+    }
+    cost_d = warp_sum_d(cost_d);
+    if (lane == 0) redd[wid] = cost_d;
+    __syncthreads();
+    if (t == 0) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += redd[w];
+        cost_part[(int64_t)u * gridDim.x + blockIdx.x] = sum / ((double)Rtot * 513.0 * (double)(n1 - n0));
+    }
+}
+
 // cost[u] = sum of the per-CTA partials in block order (deterministic, unlike an atomic accumulation)
 __global__ void cost_reduce_kernel(const double* __restrict__ cost_part, int nblk, double* __restrict__ cost, int* __restrict__ status) {
     const int u = blockIdx.x;
@@ -1250,7 +1574,8 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
 extern "C" int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const void* VsT,
                                   const uint8_t* vs_idx, int R, float* W, float* H, float* g, float* Vb, double* cost,
                                   const int64_t* fr_off, int B, int64_t NT, int K, int ld, int max_frames, float* ws,
-                                  const float* fstat, const float* wpart, const int32_t* utt_seg, int* status, void* stream) {
+                                  const float* fstat, const float* wpart, const int32_t* utt_seg, int n_chains, int* status,
+                                  void* stream) {
     tc::Dims d;
     int rc = tc::check_dims(dec, L, y_dim, "dvae_nmf_mstep_vst", &d);
     if (rc) return rc;
@@ -1260,6 +1585,9 @@ extern "C" int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, 
     DVAE_REQUIRE(B >= 1 && NT >= 0 && max_frames >= 0, "dvae_nmf_mstep_vst: bad sizes");
     DVAE_REQUIRE(d.F == 513 && ld == HG5_LD && K >= 1 && K <= HG2_KT && (R == 10 || R == 30),
                  "dvae_nmf_mstep_vst: needs F = 513, ld = %d, K <= %d, R in {10, 30}", HG5_LD, HG2_KT);
+    DVAE_REQUIRE(n_chains >= 1 && n_chains <= 128 && (n_chains & (n_chains - 1)) == 0,
+                 "dvae_nmf_mstep_vst: the chains of a frame must share an emission tile (n_chains a power of two <= 128)");
+    DVAE_REQUIRE(n_chains == 1 || wpart, "dvae_nmf_mstep_vst: several chains per frame need the segment partial sums (wpart)");
     const float* bias_log2 = reinterpret_cast<const float*>((const unsigned char*)image + d.off_bias) + (d.n_hidden == 2 ? tc::HID : 0);
     cudaStream_t st = (cudaStream_t)stream;
     float* Wtmp = ws;
@@ -1282,7 +1610,16 @@ extern "C" int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, 
     }
     const int nblk = (max_frames + HG3_FPB - 1) / HG3_FPB;
     const size_t smem7 = 4 * ((size_t)2 * R * HG7_ROWW + (size_t)HG3_NV * 8);
-    if (R == 10) {
+    if (n_chains > 1) {                            // R kept samples per chain, n_chains x R per frame: windowed kernel
+        const size_t smem7w = 4 * ((size_t)2 * 30 * HG7_ROWW + (size_t)HG3_NV * 8);
+        if (R == 10) {
+            cudaFuncSetAttribute(nmf_hg7w_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7w);
+            nmf_hg7w_kernel<10><<<dim3(nblk, B), HG3_THREADS, smem7w, st>>>(P, (const uint4*)VsT, vs_idx, bias_log2, Wtmp, norm, H, g, Vb, cost_part, fr_off, K, n_chains);
+        } else {
+            cudaFuncSetAttribute(nmf_hg7w_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7w);
+            nmf_hg7w_kernel<30><<<dim3(nblk, B), HG3_THREADS, smem7w, st>>>(P, (const uint4*)VsT, vs_idx, bias_log2, Wtmp, norm, H, g, Vb, cost_part, fr_off, K, n_chains);
+        }
+    } else if (R == 10) {
         cudaFuncSetAttribute(nmf_hg7_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem7);
         nmf_hg7_kernel<10><<<dim3(nblk, B), HG3_THREADS, smem7, st>>>(P, (const uint4*)VsT, vs_idx, bias_log2, Wtmp, norm, H, g, Vb, cost_part, fr_off, K);
     } else {

@@ -38,6 +38,8 @@ __device__ __forceinline__ f32x2 vst_rcp2(f32x2 a) { float lo, hi; upk2(a, lo, h
 // the W update, mcem.py:108-110).  A segment is a maximal run of frames that lies in one tile AND one utterance (host table);
 // every (segment, bin) has exactly one writer and the final sum over an utterance's <= 3-4 segments runs in a fixed order, so
 // the result is deterministic.  Saves the A1 / A2 round trip (2 x 4 x ld x NT bytes out, 3 x in) and the separate W kernel.
+// With 2^cshift chains per frame (rows = chains, frame = row >> cshift) the same sums run over the chain rows: the frame's
+// quantities are looked up per row and the segment table is cut on the row axis.
 struct WPartArgs {
     const float* P;            // [NT][ld]
     const float* H;            // [NT][K]
@@ -50,7 +52,7 @@ struct WPartArgs {
 template <int RT, bool WPART>
 __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __restrict__ VsT, const uint8_t* __restrict__ idx, int r_rt,
                                                                  const float* __restrict__ bias_log2, const float* __restrict__ Vb,
-                                                                 const float* __restrict__ g, int64_t rows, int F, int ld,
+                                                                 const float* __restrict__ g, int64_t rows, int cshift, int F, int ld,
                                                                  float* __restrict__ A1, float* __restrict__ A2, WPartArgs wp) {
     __shared__ float sA1[WPART ? TM : 1][17], sPA2[WPART ? TM : 1][17], sH[WPART ? TM : 1][12];
     const int R = RT > 0 ? RT : r_rt;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
         for (int i = threadIdx.x; i < TM * 12; i += 256) {
             const int r = i / 12, k = i - 12 * r;
             const int64_t n = tile * TM + r;
-            sH[r][k] = (n < rows && k < wp.K) ? __ldg(wp.H + n * wp.K + k) : 0.f;
+            sH[r][k] = (n < rows && k < wp.K) ? __ldg(wp.H + (n >> cshift) * wp.K + k) : 0.f;
         }
     }
     if (m >= rows) {
@@ -72,19 +74,20 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
     const bool rowlive = m < rows;
     const int64_t mm = rowlive ? m : 0;
     const int f0 = 16 * bg + 8 * half;
-    const float gg = __ldg(g + mm);
     f32x2 ge2[4], vb2[4], a1[4], a2[4];
     {
+        const int64_t fr = mm >> cshift;                   // the row's frame: 2^cshift chains per frame (WPART only), else row = frame
+        const float gg = __ldg(g + fr);
         float vb[8];
         if (f0 + 8 <= ld) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(Vb + mm * ld + f0) + j);
+                const float4 t = __ldg(reinterpret_cast<const float4*>(Vb + fr * ld + f0) + j);
                 vb[4 * j] = t.x; vb[4 * j + 1] = t.y; vb[4 * j + 2] = t.z; vb[4 * j + 3] = t.w;
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) vb[j] = (f0 + j < F) ? __ldg(Vb + mm * ld + f0 + j) : 1.f;
+            for (int j = 0; j < 8; ++j) vb[j] = (f0 + j < F) ? __ldg(Vb + fr * ld + f0 + j) : 1.f;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -151,16 +154,17 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
     for (int j = 0; j < 4; ++j) { upk2(a1[j], o1[2 * j], o1[2 * j + 1]); upk2(a2[j], o2[2 * j], o2[2 * j + 1]); }
     if (WPART) {
         if (rowlive) {
+            const int64_t fr = m >> cshift;
             float pp[8];
             if (f0 + 8 <= ld) {
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(wp.P + m * ld + f0) + j);
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(wp.P + fr * ld + f0) + j);
                     pp[4 * j] = t.x; pp[4 * j + 1] = t.y; pp[4 * j + 2] = t.z; pp[4 * j + 3] = t.w;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) pp[j] = (f0 + j < F) ? __ldg(wp.P + m * ld + f0 + j) : 0.f;
+                for (int j = 0; j < 8; ++j) pp[j] = (f0 + j < F) ? __ldg(wp.P + fr * ld + f0 + j) : 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -308,9 +312,9 @@ extern "C" int dvae_vst_frame_stats(const DvaeMlp* dec, const void* image, int L
     const dim3 grid((unsigned)n_tiles, NBG);
     cudaStream_t st = (cudaStream_t)stream;
     const WPartArgs none{};
-    if (R == 30) vst_frame_stats_kernel<30, false><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2, none);
-    else if (R == 10) vst_frame_stats_kernel<10, false><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2, none);
-    else vst_frame_stats_kernel<0, false><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, A1, A2, none);
+    if (R == 30) vst_frame_stats_kernel<30, false><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, 0, d.F, ld, A1, A2, none);
+    else if (R == 10) vst_frame_stats_kernel<10, false><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, 0, d.F, ld, A1, A2, none);
+    else vst_frame_stats_kernel<0, false><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, 0, d.F, ld, A1, A2, none);
     return check_launch("vst_frame_stats_kernel");
 }
 
@@ -320,8 +324,8 @@ extern "C" int64_t dvae_vst_w_partial_floats(int64_t n_segments, int K, int ld) 
 }
 
 extern "C" int dvae_vst_w_partials(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx,
-                                   int R, const float* P, const float* Vb, const float* g, const float* H, int K, int64_t NT, int ld,
-                                   const int64_t* seg_start, const int32_t* tile_seg, float* Wpart, void* stream) {
+                                   int R, const float* P, const float* Vb, const float* g, const float* H, int K, int64_t NT, int n_chains,
+                                   int ld, const int64_t* seg_start, const int32_t* tile_seg, float* Wpart, void* stream) {
     Dims d;
     int rc;
     DVAE_REQUIRE(image != nullptr, "dvae_vst_w_partials: null pointer");
@@ -332,15 +336,20 @@ extern "C" int dvae_vst_w_partials(const DvaeMlp* dec, const void* image, int L,
                  "dvae_vst_w_partials: bad sizes (1 <= R <= 31, K <= 12, ld %% 4 == 0)");
     DVAE_REQUIRE(((reinterpret_cast<uintptr_t>(VsT) | reinterpret_cast<uintptr_t>(vs_idx) | reinterpret_cast<uintptr_t>(Vb) |
                    reinterpret_cast<uintptr_t>(P)) & 15) == 0, "dvae_vst_w_partials: 16-byte alignment required");
+    DVAE_REQUIRE(n_chains >= 1 && n_chains <= TM && (n_chains & (n_chains - 1)) == 0,
+                 "dvae_vst_w_partials: n_chains must be a power of two <= 128 (the chains of a frame share an emission tile)");
     if (NT == 0) return 0;
-    const int64_t n_tiles = (NT + TM - 1) / TM;
+    int cshift = 0;
+    while ((1 << cshift) < n_chains) ++cshift;
+    const int64_t rows = NT * n_chains;
+    const int64_t n_tiles = (rows + TM - 1) / TM;
     DVAE_REQUIRE(n_tiles < (1ll << 31), "dvae_vst_w_partials: too many frames");
     const dim3 grid((unsigned)n_tiles, NBG);
     cudaStream_t st = (cudaStream_t)stream;
     const WPartArgs wp{P, H, K, seg_start, tile_seg, Wpart};
-    if (R == 30) vst_frame_stats_kernel<30, true><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, nullptr, nullptr, wp);
-    else if (R == 10) vst_frame_stats_kernel<10, true><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, nullptr, nullptr, wp);
-    else vst_frame_stats_kernel<0, true><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, NT, d.F, ld, nullptr, nullptr, wp);
+    if (R == 30) vst_frame_stats_kernel<30, true><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, rows, cshift, d.F, ld, nullptr, nullptr, wp);
+    else if (R == 10) vst_frame_stats_kernel<10, true><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, rows, cshift, d.F, ld, nullptr, nullptr, wp);
+    else vst_frame_stats_kernel<0, true><<<grid, 2 * TM, 0, st>>>((const uint4*)VsT, vs_idx, R, bias_log2, Vb, g, rows, cshift, d.F, ld, nullptr, nullptr, wp);
     return check_launch("vst_frame_stats_kernel<wpart>");
 }
 

@@ -183,23 +183,26 @@ class RaggedBatch:
         self._segments = None
         self._device = device
 
-    def segments(self, tile: int = 128):
+    def segments(self, tile: int = 128, n_chains: int = 1):
         """Segment tables of the fused W-update reduction (dvae_vst_w_partials): a segment is a maximal run of frames inside
         one ``tile``-frame tile AND one utterance.  Returns device tensors ``(seg_start [S+1] int64, tile_seg [n_tiles+1]
-        int32, utt_seg [B+1] int32)`` and ``S``; utterance ``u`` owns the segments ``utt_seg[u] .. utt_seg[u+1]``."""
-        if self._segments is None:
-            n_tiles = (self.NT + tile - 1) // tile
-            cuts = np.unique(np.concatenate([np.arange(0, n_tiles + 1, dtype=np.int64) * tile, self.fr_off_host]))
-            cuts = cuts[cuts <= self.NT]
-            if len(cuts) == 0 or cuts[-1] != self.NT:
-                cuts = np.append(cuts, self.NT)
+        int32, utt_seg [B+1] int32)`` and ``S``; utterance ``u`` owns the segments ``utt_seg[u] .. utt_seg[u+1]``.  With
+        ``n_chains`` chains per frame the axis is the chain row ``frame * n_chains + chain`` (``tile`` rows per tile)."""
+        key = (tile, n_chains)
+        if self._segments is None or self._segments[0] != key:
+            rows, off = self.NT * n_chains, self.fr_off_host * n_chains
+            n_tiles = (rows + tile - 1) // tile
+            cuts = np.unique(np.concatenate([np.arange(0, n_tiles + 1, dtype=np.int64) * tile, off]))
+            cuts = cuts[cuts <= rows]
+            if len(cuts) == 0 or cuts[-1] != rows:
+                cuts = np.append(cuts, rows)
             S = len(cuts) - 1
             tile_seg = np.searchsorted(cuts[:-1], np.arange(0, n_tiles + 1, dtype=np.int64) * tile, side="left").astype(np.int32)
-            utt_seg = np.searchsorted(cuts[:-1], self.fr_off_host, side="left").astype(np.int32)
+            utt_seg = np.searchsorted(cuts[:-1], off, side="left").astype(np.int32)
             dev = self._device
-            self._segments = (torch.from_numpy(cuts.astype(np.int64)).to(dev), torch.from_numpy(tile_seg).to(dev),
-                              torch.from_numpy(utt_seg).to(dev), S)
-        return self._segments
+            self._segments = (key, (torch.from_numpy(cuts.astype(np.int64)).to(dev), torch.from_numpy(tile_seg).to(dev),
+                                    torch.from_numpy(utt_seg).to(dev), S))
+        return self._segments[1]
 
 
 # --------------------------------------------------------------------------------------------- STFT / ISTFT
@@ -509,21 +512,21 @@ class McemEngine:
 
     @_on_device
     def e_step(self, draws=None):
-        """E-step (mcem.py:292-308): sample, keep the last state, decode the kept samples.  On the tensor-core path with one
-        chain per frame the sampler emits the variances itself (BF16) and only the per-frame statistics of the W update are
-        computed here; otherwise the kept samples are decoded into FP32 ``Vs``."""
+        """E-step (mcem.py:292-308): sample, keep the last state, decode the kept samples.  On the tensor-core path (one chain
+        per frame, or a power-of-two number of them) the sampler emits the variances itself (BF16) and only the statistics
+        of the W update are computed here; otherwise the kept samples are decoded into FP32 ``Vs``."""
         cfg = self.cfg
         self.wstat, self.wpart, self._Vs, self.vst_R = None, None, None, 0
         if cfg.sampler == "tc":
             from . import tc
             if tc.vst_supported(self, cfg.keep_E):
                 self.sample_posterior(cfg.keep_E, cfg.burn_E, draws, emit=True)
-                self.R = self.vst_R = cfg.keep_E
+                self.vst_R, self.R = cfg.keep_E, cfg.n_chains * cfg.keep_E      # kept per chain, samples per frame
                 with self.stage("decode"):
                     if cfg.w_partials:
-                        self.wpart = tc.vst_w_partials(self, self.R)
+                        self.wpart = tc.vst_w_partials(self, self.vst_R)
                     else:
-                        self.wstat = tc.vst_frame_stats(self, self.R)
+                        self.wstat = tc.vst_frame_stats(self, self.vst_R)
                 return
         Zs = self.sample_posterior(cfg.keep_E, cfg.burn_E, draws)
         self.R = Zs.shape[1]
@@ -546,10 +549,10 @@ class McemEngine:
                 from . import tc
                 w = self.w
                 _lib.call("dvae_nmf_mstep_vst", w.dec_tc.ref, _p(tc.decoder_image(w)), w.z_dim, w.tc_y_dim, _p(self.P), _p(self.VsT),
-                          _p(self.vs_idx), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
+                          _p(self.vs_idx), self.vst_R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
                           C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), b.B, b.NT, cfg.nmf_rank, self.ld, b.max_frames,
-                          _p(ws), _p(self.wstat), _p(self.wpart), _p(b.segments()[2]) if self.wpart is not None else None, _p(st),
-                          _stream())
+                          _p(ws), _p(self.wstat), _p(self.wpart),
+                          _p(b.segments(n_chains=cfg.n_chains)[2]) if self.wpart is not None else None, cfg.n_chains, _p(st), _stream())
             else:
                 _lib.call("dvae_nmf_mstep", _p(self.P), _p(self._Vs), self.R, _p(self.W), _p(self.H), _p(self.g), _p(self.Vb),
                           C.c_void_p(self.cost[it].data_ptr()), _p(b.fr_off), _p(b.frame_utt), b.B, b.NT, self.F, cfg.nmf_rank,

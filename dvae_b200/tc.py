@@ -84,10 +84,12 @@ def row_scale(eng):
 
 
 def vst_supported(eng, keep):
-    """The sampler's own emission of the kept samples' variances serves one chain per frame, up to 31 kept samples, and
-    (for the fused M-step kernel) R in {10, 30}, K <= 10, F = 513."""
-    return (eng.cfg.n_chains == 1 and keep in (10, 30) and eng.cfg.nmf_rank <= 10 and eng.F == 513 and eng.ld == 520
-            and eng.cfg.fuse_wstat and eng.cfg.emit_vs)
+    """The sampler's own emission of the kept samples' variances serves up to 31 kept samples per chain and (for the fused
+    M-step kernels) keep in {10, 30}, K <= 10, F = 513; several chains per frame need a power-of-two count (the chains of a
+    frame share a 128-row tile) and the segment partial sums."""
+    c = eng.cfg.n_chains
+    return ((c == 1 or (c <= 128 and c & (c - 1) == 0 and eng.cfg.w_partials)) and keep in (10, 30) and eng.cfg.nmf_rank <= 10
+            and eng.F == 513 and eng.ld == 520 and eng.cfg.fuse_wstat and eng.cfg.emit_vs)
 
 
 def mh_chain_tc(eng, Zs, keep, burn, rng, a_trace, emit=False):
@@ -127,20 +129,21 @@ def vst_frame_stats(eng, R):
 def vst_w_partials(eng, R):
     """Per-segment partial sums of the W update, reduced inside the statistics pass (dvae_vst_w_partials); ``[S][K][2][ld]``."""
     w, b, K = eng.w, eng.batch, eng.cfg.nmf_rank
-    seg_start, tile_seg, _, S = b.segments()
+    seg_start, tile_seg, _, S = b.segments(n_chains=eng.cfg.n_chains)
     wp = eng._get("wpart", (max(int(_lib.load().dvae_vst_w_partial_floats(S, K, eng.ld)), 1),))
     _lib.call("dvae_vst_w_partials", w.dec_tc.ref, _p(decoder_image(w)), w.z_dim, w.tc_y_dim, _p(eng.VsT), _p(eng.vs_idx), R, _p(eng.P),
-              _p(eng.Vb), _p(eng.g), _p(eng.H), K, b.NT, eng.ld, _p(seg_start), _p(tile_seg), _p(wp), _stream())
+              _p(eng.Vb), _p(eng.g), _p(eng.H), K, b.NT, eng.cfg.n_chains, eng.ld, _p(seg_start), _p(tile_seg), _p(wp), _stream())
     eng.kernel_launches += 1
     return wp
 
 
 def vst_unpack(eng, R, out=None):
-    """Dense FP32 ``Vs [NT][R][ld]`` of the emitted samples (dvae_vst_unpack): the reference's ``self.Vs`` up to layout."""
-    w, b = eng.w, eng.batch
+    """Dense FP32 ``Vs [NT][n_chains * R][ld]`` of the emitted samples (dvae_vst_unpack, ``R`` kept samples per chain): the
+    reference's ``self.Vs`` up to layout."""
+    w, b, c = eng.w, eng.batch, eng.cfg.n_chains
     if out is None:
-        out = torch.zeros((b.NT, R, eng.ld), dtype=torch.float32, device=eng.dev)
-    _lib.call("dvae_vst_unpack", w.dec_tc.ref, _p(decoder_image(w)), w.z_dim, w.tc_y_dim, _p(eng.VsT), _p(eng.vs_idx), R, b.NT, eng.ld,
+        out = torch.zeros((b.NT, c * R, eng.ld), dtype=torch.float32, device=eng.dev)
+    _lib.call("dvae_vst_unpack", w.dec_tc.ref, _p(decoder_image(w)), w.z_dim, w.tc_y_dim, _p(eng.VsT), _p(eng.vs_idx), R, b.NT * c, eng.ld,
               _p(out), _stream())
     return out
 

@@ -203,7 +203,10 @@ int dvae_mh_chain_tc2(const DvaeMlp* dec, const void* image, const void* PVpk, c
                       float* a_trace, void* VsT /* nullable */, uint8_t* vs_idx /* nullable */, int flags, int* status,
                       void* stream);
 
-/* Consumers of the emission (one chain per frame: chain = frame).
+/* Consumers of the emission.  n_chains = 1: chain = frame.  n_chains = 2^c <= 128 (dvae_vst_w_partials, dvae_nmf_mstep_vst,
+ * R = kept samples PER CHAIN): chain row m belongs to frame m / n_chains, the frame's n_chains x R samples enter every sum, the
+ * segment tables are cut on the chain-row axis (tile boundaries and n_chains x the utterances' frame offsets) and the M-step
+ * needs wpart; dvae_vst_unpack with NT = the number of chain rows gives Vs[NT][n_chains * R][ld].
  * dvae_vst_frame_stats: A1[n][f] = sum_r 1/Vx, A2[n][f] = sum_r 1/Vx^2 with Vx = g[n] Vs[n][r][f] + Vb[n][f]: the inner
  *   sums of the W update (mcem.py:108-110); R <= 31.
  * dvae_vst_w_partials: the same pass, but instead of writing A1 / A2 it multiplies them with the activations H and reduces over
@@ -219,11 +222,11 @@ int dvae_vst_frame_stats(const DvaeMlp* dec, const void* image, int L, int y_dim
 int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, int y_dim, const float* P, const void* VsT,
                        const uint8_t* vs_idx, int R, float* W, float* H, float* g, float* Vb, double* cost,
                        const int64_t* fr_off, int B, int64_t NT, int K, int ld, int max_frames, float* ws,
-                       const float* fstat /* nullable */, const float* wpart /* nullable */, const int32_t* utt_seg, int* status,
-                       void* stream);
+                       const float* fstat /* nullable */, const float* wpart /* nullable */, const int32_t* utt_seg, int n_chains,
+                       int* status, void* stream);
 int64_t dvae_vst_w_partial_floats(int64_t n_segments, int K, int ld);
 int dvae_vst_w_partials(const DvaeMlp* dec, const void* image, int L, int y_dim, const void* VsT, const uint8_t* vs_idx, int R,
-                        const float* P, const float* Vb, const float* g, const float* H, int K, int64_t NT, int ld,
+                        const float* P, const float* Vb, const float* g, const float* H, int K, int64_t NT, int n_chains, int ld,
                         const int64_t* seg_start, const int32_t* tile_seg, float* Wpart, void* stream);
 int dvae_nmf_w_from_partials(const float* Wpart, const int32_t* utt_seg, const float* W, int B, int F, int K, int ld, float* Wtmp,
                              void* stream);

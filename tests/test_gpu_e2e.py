@@ -215,7 +215,8 @@ def test_full_size_properties_configs1():
 
 def test_multi_chain_windowed_path_matches_generic_path():
     """4 chains x 10 kept samples = 40 samples per frame: the windowed fused decode + windowed M-step kernel against the
-    generic kernels (materialised decode, generic NMF passes) on the same draws."""
+    generic kernels (materialised decode, generic NMF passes) on the same draws, and the sampler's own emission with the
+    windowed emission M-step kernel (BF16 variances: looser tolerance)."""
     from dvae_b200.engine import Enhancer, McemConfig
     x = synth.synth_utterance(41, 1.2)[0]
     s_clean = synth.synth_utterance(41, 1.2)[1]
@@ -223,13 +224,16 @@ def test_multi_chain_windowed_path_matches_generic_path():
     sd = synth.xavier_state_dict("M2v3", 513, 16, [128, 128], 1, seed=6, out_bias=float(np.log(P0.mean())))
     y = synth.energy_vad(s_clean)
     out = {}
-    for fuse in (True, False):
-        cfg = McemConfig(niter=3, keep_E=10, burn_E=5, keep_WF=25, burn_WF=5, seed=1, n_chains=4, fuse_wstat=fuse)
+    for mode, fuse, emit in (("win", True, False), ("generic", False, False), ("emit", True, True)):
+        cfg = McemConfig(niter=3, keep_E=10, burn_E=5, keep_WF=25, burn_WF=5, seed=1, n_chains=4, fuse_wstat=fuse, emit_vs=emit)
         enh = Enhancer(sd, "M2v3", cfg, device=0)
         s, n, c = enh.enhance([x], y_list=[y], utt_ids=[3])
         assert enh.engine.R == 40 and enh.engine.R_wf == 100
-        out[fuse] = (s[0].copy(), c.copy())
+        out[mode] = (s[0].copy(), c.copy())
     # same draws, same decoder arithmetic up to rounding: the trajectories agree closely (no accept decision is near-tied here)
-    assert np.allclose(out[True][1], out[False][1], rtol=2e-4), (out[True][1], out[False][1])
-    err = np.linalg.norm(out[True][0] - out[False][0]) / np.linalg.norm(out[False][0])
+    assert np.allclose(out["win"][1], out["generic"][1], rtol=2e-4), (out["win"][1], out["generic"][1])
+    err = np.linalg.norm(out["win"][0] - out["generic"][0]) / np.linalg.norm(out["generic"][0])
     assert err < 5e-3, err
+    assert np.allclose(out["emit"][1], out["generic"][1], rtol=5e-3), (out["emit"][1], out["generic"][1])
+    err = np.linalg.norm(out["emit"][0] - out["generic"][0]) / np.linalg.norm(out["generic"][0])
+    assert err < 5e-2, err

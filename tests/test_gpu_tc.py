@@ -253,6 +253,45 @@ def test_fused_decode_stats_and_emission_match_unfused(variant, keep):
             assert err <= tol, "%s: %s differs by %g" % (mode, name, err)
 
 
+@pytest.mark.parametrize("variant,keep,chains", [("M2v3", 10, 16), ("M2", 10, 2), ("M1", 30, 4)])
+def test_multi_chain_emission_matches_decoded_samples(variant, keep, chains):
+    """Several chains per frame: the sampler's emission + dvae_vst_w_partials + the windowed emission M-step kernel against the
+    windowed FP32 decode (dvae_decode_stats_win_tc) + its M-step kernel on the same Philox draws.  The first E-step holds the
+    same samples on both paths (BF16 storage: 1.2 % per variance); M-step outputs after it within 0.5 % relative L2, after a
+    second iteration (accept decisions may differ here and there) within 2 %."""
+    y_dim = 0 if variant == "M1" else 1
+    lens = [70, 37, 1, 20]
+    NT = sum(lens)
+    rng = np.random.default_rng(12)
+    P = torch.tensor(rng.gamma(1.0, 0.05, size=(NT, 520)).astype(np.float32)).to(DEV)
+    X = torch.zeros((NT, 520), dtype=torch.complex64, device=DEV)
+    y = (torch.rand((NT, 1), device=DEV, generator=torch.Generator(device=DEV).manual_seed(4)) > 0.5).float() if y_dim else None
+    sd = synth.xavier_state_dict(variant, 513, 16, [128, 128], y_dim, seed=9, out_bias=float(np.log(0.05)))
+    w = VaeWeights(sd, variant, torch.device(DEV))
+    out = {}
+    for mode, emit in (("decode", False), ("emit", True)):
+        cfg = McemConfig(niter=2, keep_E=keep, burn_E=5, keep_WF=3, burn_WF=3, sampler="tc", seed=3, n_chains=chains, emit_vs=emit)
+        eng = McemEngine(w, cfg, DEV)
+        eng.init_parameters(X, P, RaggedBatch(lens, DEV), y)
+        snap = []
+        for it in range(2):
+            eng.e_step()
+            assert (eng.vst_R == keep) == emit and (eng.wpart is not None) == emit and eng.R == chains * keep
+            if it == 0:
+                vs = eng.Vs.clone()
+                assert tuple(vs.shape) == (NT, chains * keep, 520)
+            eng.m_step(it)
+            snap.append([t.cpu().clone() for t in (eng.W[..., :513], eng.H, eng.g, eng.Vb[:, :513], eng.cost[it])])
+        tc.check_status(eng)
+        out[mode] = (vs.cpu(), snap)
+    a, b = out["decode"], out["emit"]
+    assert ((a[0][:, :, :513] - b[0][:, :, :513]).abs() / a[0][:, :, :513]).max().item() <= 1.2e-2
+    for it, tol in ((0, 5e-3), (1, 2e-2)):
+        for name, ref, got in zip(("W", "H", "g", "Vb", "cost"), a[1][it], b[1][it]):
+            err = ((got - ref).double().norm() / ref.double().norm()).item()
+            assert err <= tol, "iteration %d: %s differs by %g" % (it, name, err)
+
+
 @pytest.mark.parametrize("R_total,chunk", [(75, 25), (30, 30), (25, 25), (20, 10)])
 def test_fused_wiener_a1_matches_materialised_samples(R_total, chunk):
     """dvae_decode_a1_tc + dvae_wiener_from_a1 against the decode that writes Vs followed by dvae_wiener_accum."""

@@ -62,29 +62,37 @@ def test_pack_unpack_round_trip_and_bounds(N, R):
     assert torch.equal(out2[:N, :, :513], out[:N, :1, :513].expand(-1, R, -1))
 
 
-@pytest.mark.parametrize("wpart", [False, True])
-@pytest.mark.parametrize("N,K,R,split", [(37, 10, 30, None), (185, 10, 10, None), (300, 7, 30, None), (130, 10, 10, [1, 100, 29]),
-                                         (400, 10, 10, [3, 120, 5, 1, 128, 143])])
-def test_m_step_on_emission_matches_oracle_given_its_inputs(N, K, R, split, wpart):
-    """dvae_vst_frame_stats + dvae_nmf_mstep_vst against the oracle's M-step on the variances the emission actually holds."""
+@pytest.mark.parametrize("N,K,R,split,C,wpart",
+                         [(n, k, r, sp, 1, wp) for wp in (False, True) for n, k, r, sp in
+                          [(37, 10, 30, None), (185, 10, 10, None), (300, 7, 30, None), (130, 10, 10, [1, 100, 29]),
+                           (400, 10, 10, [3, 120, 5, 1, 128, 143])]] +
+                         # several chains per frame (R kept samples per chain): the windowed M-step kernel; 4 x 10 = 40 samples = one
+                         # full window + 10, 16 x 10 = 160 = five windows + 10 (BASELINE configs[3]), 2 x 30 = two full windows
+                         [(37, 10, 10, None, 4, True), (130, 10, 10, [1, 100, 29], 16, True), (70, 7, 30, [33, 37], 2, True),
+                          (9, 10, 10, [4, 5], 128, True)])
+def test_m_step_on_emission_matches_oracle_given_its_inputs(N, K, R, split, C, wpart):
+    """dvae_vst_frame_stats / dvae_vst_w_partials + dvae_nmf_mstep_vst against the oracle's M-step on the variances the emission
+    actually holds; with C chains per frame the frame's C x R samples are the oracle's sample axis."""
     F, ld = 513, 520
     w = _weights()
-    rng = np.random.default_rng(F + N + R)
+    rng = np.random.default_rng(F + N + R + C)
     P = rng.gamma(1.0, 1.0, size=(F, N)).astype(np.float32) * 0.1
+    Rc, NC = R, N * C                                                            # kept per chain, chain rows
+    R = C * Rc                                                                   # samples per frame
     Vs0 = rng.gamma(2.0, 0.05, size=(R, F, N)).astype(np.float32)
     W = np.maximum(rng.uniform(size=(F, K)), 1e-8).astype(np.float32)
     H = np.maximum(rng.uniform(size=(K, N)), 1e-8).astype(np.float32)
     g = rng.uniform(0.5, 1.5, size=N).astype(np.float32)
     Vsd = torch.zeros((N, R, ld), device=DEV)
     Vsd[:, :, :F] = torch.from_numpy(np.ascontiguousarray(Vs0.transpose(2, 0, 1))).to(DEV)
-    vst, idx, _ = _pack(w, Vsd, R, N)
+    vst, idx, _ = _pack(w, Vsd.view(NC, Rc, ld), Rc, NC)                          # chain row m = frame * C + chain
     # make the index table non-trivial: some samples repeat their predecessor's slot (a rejected proposal)
     it = idx.view(-1, 32)
-    rep = torch.tensor(rng.uniform(size=(N, R)) < 0.2).to(DEV)
+    rep = torch.tensor(rng.uniform(size=(NC, Rc)) < 0.2).to(DEV)
     rep[:, 0] = False
-    for r in range(1, R):
-        it[:N, r] = torch.where(rep[:, r], it[:N, r - 1], it[:N, r])
-    Vq = _unpack(w, vst, idx, R, N)[:N, :, :F]                                    # what the kernels will see
+    for r in range(1, Rc):
+        it[:NC, r] = torch.where(rep[:, r], it[:NC, r - 1], it[:NC, r])
+    Vq = _unpack(w, vst, idx, Rc, NC)[:NC, :, :F].reshape(N, R, F)                # what the kernels will see
     Vs = np.ascontiguousarray(Vq.permute(1, 2, 0).cpu().numpy())
     lens = split or [N]
     batch = RaggedBatch(lens, DEV)
@@ -98,28 +106,30 @@ def test_m_step_on_emission_matches_oracle_given_its_inputs(N, K, R, split, wpar
     _lib.call("dvae_nmf_vb", _p(Wd), _p(Hd), _p(batch.frame_utt), N, F, K, ld, _p(Vbd), _stream())
     fstat = torch.zeros(2 * N * ld, device=DEV)
     img = tc.decoder_image(w)
-    _lib.call("dvae_vst_frame_stats", w.dec.ref, _p(img), 16, 0, _p(vst), _p(idx), R, _p(Vbd), _p(gd), N, ld, _p(fstat),
-              _p(fstat[N * ld:]), _stream())
-    Vx = torch.tensor(g)[None, None, :] * torch.tensor(Vs) + torch.tensor(W @ H)[None]
-    a1 = (1.0 / Vx.double()).sum(0).numpy()
-    a2 = (1.0 / Vx.double() ** 2).sum(0).numpy()
-    assert relerr(unfm(fstat[: N * ld].view(N, ld), F), a1) <= 2e-5
-    assert relerr(unfm(fstat[N * ld:].view(N, ld), F), a2) <= 2e-5
+    if C == 1:
+        _lib.call("dvae_vst_frame_stats", w.dec.ref, _p(img), 16, 0, _p(vst), _p(idx), R, _p(Vbd), _p(gd), N, ld, _p(fstat),
+                  _p(fstat[N * ld:]), _stream())
+        Vx = torch.tensor(g)[None, None, :] * torch.tensor(Vs) + torch.tensor(W @ H)[None]
+        a1 = (1.0 / Vx.double()).sum(0).numpy()
+        a2 = (1.0 / Vx.double() ** 2).sum(0).numpy()
+        assert relerr(unfm(fstat[: N * ld].view(N, ld), F), a1) <= 2e-5
+        assert relerr(unfm(fstat[N * ld:].view(N, ld), F), a2) <= 2e-5
     cost = torch.zeros(B, dtype=torch.float64, device=DEV)
     st = torch.zeros(1, dtype=torch.int32, device=DEV)
     ws = torch.empty(int(_lib.load().dvae_nmf_workspace_floats(B, K, ld, batch.max_frames)), device=DEV)
     wp = utt_seg = None
     if wpart:                                    # the W sums reduced per (tile, utterance) segment inside the statistics pass
-        seg_start, tile_seg, utt_seg, S = batch.segments()
+        seg_start, tile_seg, utt_seg, S = batch.segments(n_chains=C)
         assert S >= B and int(utt_seg[-1]) == S
         wp = torch.full((int(_lib.load().dvae_vst_w_partial_floats(S, K, ld)) + 64,), float("nan"), device=DEV)
-        _lib.call("dvae_vst_w_partials", w.dec.ref, _p(img), 16, 0, _p(vst), _p(idx), R, _p(Pd), _p(Vbd), _p(gd), _p(Hd), K, N, ld,
+        _lib.call("dvae_vst_w_partials", w.dec.ref, _p(img), 16, 0, _p(vst), _p(idx), Rc, _p(Pd), _p(Vbd), _p(gd), _p(Hd), K, N, C, ld,
                   _p(seg_start), _p(tile_seg), _p(wp), _stream())
         body = wp[:-64].view(S, K, 2, ld)
         assert bool(torch.isnan(wp[-64:]).all()) and bool(torch.isnan(body[..., F:]).all()), "partials written outside [S][K][2][0..F)"
         assert bool(torch.isfinite(body[..., :F]).all())
-    _lib.call("dvae_nmf_mstep_vst", w.dec.ref, _p(img), 16, 0, _p(Pd), _p(vst), _p(idx), R, _p(Wd), _p(Hd), _p(gd), _p(Vbd), _p(cost),
-              _p(batch.fr_off), B, N, K, ld, batch.max_frames, _p(ws), None if wpart else _p(fstat), _p(wp), _p(utt_seg), _p(st), _stream())
+    _lib.call("dvae_nmf_mstep_vst", w.dec.ref, _p(img), 16, 0, _p(Pd), _p(vst), _p(idx), Rc, _p(Wd), _p(Hd), _p(gd), _p(Vbd), _p(cost),
+              _p(batch.fr_off), B, N, K, ld, batch.max_frames, _p(ws), None if wpart else _p(fstat), _p(wp), _p(utt_seg), C, _p(st),
+              _stream())
     assert int(st.item()) == 0
     off = batch.fr_off_host
     for u in range(B):

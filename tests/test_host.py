@@ -183,20 +183,24 @@ def test_compute_stats_prints_the_reference_tables():
 
 
 def test_segment_tables_refine_tiles_and_utterances():
-    """RaggedBatch.segments(): every segment lies in one 128-frame tile and one utterance, the segments tile the frame axis, and
-    an utterance's segments are consecutive (the fused W-update reduction relies on all three)."""
+    """RaggedBatch.segments(): every segment lies in one 128-row tile and one utterance, the segments tile the row axis (frames, or
+    frame x chain rows with several chains per frame), and an utterance's segments are consecutive (the fused W-update
+    reduction relies on all three)."""
     from dvae_b200.engine import RaggedBatch
     for lens in ([3, 120, 5, 1, 128, 143], [185] * 7, [1], [0, 5, 0, 300, 0], [128, 128]):
-        b = RaggedBatch(lens, "cpu")
-        seg, tile_seg, utt_seg, S = b.segments()
-        seg, tile_seg, utt_seg = seg.numpy(), tile_seg.numpy(), utt_seg.numpy()
-        assert seg[0] == 0 and seg[-1] == b.NT and np.all(np.diff(seg) > 0) and len(seg) == S + 1
-        off = b.fr_off_host
-        for s in range(S):
-            lo, hi = seg[s], seg[s + 1]
-            assert lo // 128 == (hi - 1) // 128
-            u = np.searchsorted(off, lo, side="right") - 1
-            assert off[u] <= lo and hi <= off[u + 1] and utt_seg[u] <= s < utt_seg[u + 1]
-            t = lo // 128
-            assert tile_seg[t] <= s < tile_seg[t + 1]
-        assert utt_seg[0] == 0 and utt_seg[-1] == S and tile_seg[-1] == S
+        for c in (1, 4, 16, 128):
+            b = RaggedBatch(lens, "cpu")
+            seg, tile_seg, utt_seg, S = b.segments(n_chains=c)
+            assert b.segments(n_chains=c)[0] is seg                      # cached per chain count
+            seg, tile_seg, utt_seg = seg.numpy(), tile_seg.numpy(), utt_seg.numpy()
+            rows = b.NT * c
+            assert seg[0] == 0 and seg[-1] == rows and np.all(np.diff(seg) > 0) and len(seg) == S + 1
+            off = b.fr_off_host * c
+            for s in range(S):
+                lo, hi = seg[s], seg[s + 1]
+                assert lo // 128 == (hi - 1) // 128
+                u = np.searchsorted(off, lo, side="right") - 1
+                assert off[u] <= lo and hi <= off[u + 1] and utt_seg[u] <= s < utt_seg[u + 1]
+                t = lo // 128
+                assert tile_seg[t] <= s < tile_seg[t + 1]
+            assert utt_seg[0] == 0 and utt_seg[-1] == S and tile_seg[-1] == S
