@@ -4,8 +4,8 @@
 //
 // One 1024-point real FFT is computed as a 512-point complex FFT of the even/odd-packed frame followed by the
 // standard split post-processing.  The 512-point FFT is three radix-8 passes (512 = 8*8*8) executed by 64 threads
-// that hold 8 points each in registers; the two digit exchanges go through shared memory (row stride 65 float2 so
-// the strided re-reads are conflict-free), twiddles come from a 1024-entry table built once per device in double.
+// that hold 8 points each in registers; the two digit exchanges go through shared memory (two conflict-free layouts with
+// constant per-access offsets, see kXRow), twiddles come from a 1024-entry table built once per device in double.
 // A CTA of 256 threads works on four frames at a time.
 //
 // HBM traffic per utterance (T samples, N frames, F = 513): STFT reads 4T (frame overlap is served by L1/L2),
@@ -20,13 +20,19 @@ namespace dvae {
 
 constexpr int kNfft = 1024;
 constexpr int kHalf = 512;
-constexpr int kRow = 64;                       // row stride (float2) of the 8 x 64 exchange buffer
-constexpr int kBuf = 8 * kRow;                 // float2 per frame group
-// Exchange-buffer slot of element (row k1, column c): the column is XOR-swizzled with k1 + 8 (k1 & 1).  With 16 float2
-// banks this makes all three access patterns of the FFT conflict-free per half-warp: stage-1 stores (row fixed, 16
-// consecutive columns), stage-2 loads / stores (rows 2a, 2a+1 x columns 8 m1 + 0..7: the rows differ in bank bit 3)
-// and stage-3 loads (rows 0..7 x columns 8 j1 + m2, j1 in {2b, 2b+1}: bank = (8 j1 + m2) ^ (k1 + 8 (k1 & 1)), distinct).
-__device__ __forceinline__ int xslot(int k1, int c) { return k1 * kRow + (c ^ (k1 | ((k1 & 1) << 3))); }
+constexpr int kRow = 64;                       // natural-order row stride (the STFT's post-processing view of the buffer)
+// The two digit exchanges of the 512-point FFT use two different layouts of the same buffer, both chosen so that EVERY access
+// of a thread is "thread-constant base + compile-time offset" (one instruction) and conflict-free per half-warp of 8-byte
+// accesses (16 banks of float2):
+//   exchange 1, element (k1, c = t):            slot = 72 k1 + c
+//       stage-1 stores: k1 fixed, 16 consecutive c;  stage-2 loads: rows k1 in {2a, 2a+1} (72 = 8 mod 16 banks apart) x c = 8 m1 + 0..7
+//   exchange 2, element (j1, k1, m2):           slot = 72 j1 + k1 + 16 (k1 >> 1) + 2 m2
+//       stage-2 stores: j1 fixed, (k1 & 1, m2) -> banks k1 + 2 m2 + const, all distinct;  stage-3 loads: m2 fixed, k1 = 0..7 and
+//       j1 in {2b, 2b+1} -> banks k1 + 8 j1 + const, all distinct.  (k1 + 16 (k1 >> 1) + 2 m2 is injective, <= 69 < 72.)
+// The first versions used one XOR-swizzled layout for both exchanges: conflict-free too, but every access cost a LOP3 and an
+// address add on top of the load / store (3.6 instructions per access, ncu) - a tenth of the kernels' instructions.
+constexpr int kXRow = 72;
+constexpr int kBuf = 8 * kXRow;                // float2 per frame group
 
 __device__ float2 g_tw[kNfft];                 // exp(-2*pi*i*k/1024)
 __device__ float g_win[kNfft];                 // periodic Hann
@@ -121,11 +127,8 @@ __device__ __forceinline__ void fft8(float2* a) {
 // 512-point forward complex FFT by the 64 threads (two warps) of frame group `grp`.
 // in : a[n1] = z[t + 64*n1]            (t = thread in group)
 // out: a[j2] = Z[t + 64*j2]
-// `buf` is the group's kBuf-float2 exchange buffer, `tw` the shared twiddle table.  The groups of a CTA are independent:
-// they synchronise on their own named barrier (id 1 + grp, 64 threads), not on the CTA barrier.  The inter-stage
-// twiddles w^k (k = 1..7) are powers of ONE table entry formed in registers: the first version fetched all of them from
-// the table, and those strided shared-memory reads (up to 8-way bank conflicts) kept the shared-memory pipe 73 % busy
-// (ncu, round 1) - the actual bound of the kernel.
+// `buf` is the group's kBuf-float2 exchange buffer.  The groups of a CTA are independent: they synchronise on their own named
+// barrier (id 1 + grp, 64 threads), not on the CTA barrier.
 __device__ __forceinline__ void group_bar(int grp) {                        // immediate ids: a register id makes ptxas reserve all 16 barriers
     switch (grp) {
         case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
@@ -135,6 +138,12 @@ __device__ __forceinline__ void group_bar(int grp) {                        // i
     }
 }
 
+// Inter-stage twiddles w^k (k = 1..7) are powers of ONE thread-constant value per exchange, formed in registers (4 multiply-adds
+// each).  History: the first version fetched all of them from the 1024-entry table with strides of up to 14 entries (8-way bank
+// conflicts, shared-memory pipe 73 % busy); conflict-free per-thread tables (14 loads per frame and thread) were faster than
+// that, but once the exchanges themselves were down to one instruction per access the bound of both kernels was the
+// shared-memory / L1 data pipe itself (l1tex__data_pipe_lsu_wavefronts 87 % of peak, one 128-byte wavefront per clock and SM,
+// profiles/r02_ncu_stft.txt): a 64-bit load costs that pipe as much time as eight instructions cost the four schedulers.
 __device__ __forceinline__ void twiddle_powers(float2 w, float2* wp) {     // wp[k] = w^k, k = 1..7 (wp[0] unused)
     wp[1] = w;
     wp[2] = cmul(w, w);
@@ -145,33 +154,44 @@ __device__ __forceinline__ void twiddle_powers(float2 w, float2* wp) {     // wp
     wp[7] = cmul(wp[4], wp[3]);
 }
 
-__device__ __forceinline__ void fft512(float2* a, float2* buf, const float2* tw, int t, int grp) {
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `after_stage1()` runs right after the first group barrier, i.e. once every thread of the group has consumed its input
+// registers' sources (the ISTFT issues the next pass's asynchronous row copies there).
+// w1 = exp(-2 pi i t / 512), w2 = exp(-2 pi i (t & 7) / 64): the thread's twiddle bases (g_tw[2 t], g_tw[16 (t & 7)])
+template <class Hook = NoHook>
+__device__ __forceinline__ void fft512(float2* a, float2* buf, float2 w1, float2 w2, int t, int grp, Hook after_stage1 = Hook()) {
     fft8(a);
     {
         float2 wp[8];
-        twiddle_powers(tw[2 * t], wp);             // exp(-2 pi i t k1 / 512)
-        buf[xslot(0, t)] = a[0];
+        twiddle_powers(w1, wp);
+        float2* st = buf + t;
+        st[0] = a[0];
 #pragma unroll
-        for (int k1 = 1; k1 < 8; ++k1) buf[xslot(k1, t)] = cmul(a[k1], wp[k1]);
+        for (int k1 = 1; k1 < 8; ++k1) st[kXRow * k1] = cmul(a[k1], wp[k1]);      // exp(-2 pi i t k1 / 512)
     }
     group_bar(grp);
+    after_stage1();
     {
         const int k1 = t >> 3, m2 = t & 7;
+        const float2* ld = buf + kXRow * k1 + m2;
 #pragma unroll
-        for (int m1 = 0; m1 < 8; ++m1) a[m1] = buf[xslot(k1, 8 * m1 + m2)];
+        for (int m1 = 0; m1 < 8; ++m1) a[m1] = ld[8 * m1];
+        group_bar(grp);                            // exchange 1 is consumed: the buffer may be rewritten in the second layout
         fft8(a);
         float2 wp[8];
-        twiddle_powers(tw[16 * m2], wp);           // exp(-2 pi i m2 j1 / 64)
-        // in place: this thread rewrites exactly the eight slots it has just read
-        buf[xslot(k1, m2)] = a[0];
+        twiddle_powers(w2, wp);
+        float2* st = buf + k1 + 16 * (k1 >> 1) + 2 * m2;
+        st[0] = a[0];
 #pragma unroll
-        for (int j1 = 1; j1 < 8; ++j1) buf[xslot(k1, 8 * j1 + m2)] = cmul(a[j1], wp[j1]);
+        for (int j1 = 1; j1 < 8; ++j1) st[kXRow * j1] = cmul(a[j1], wp[j1]);      // exp(-2 pi i m2 j1 / 64)
     }
     group_bar(grp);
     {
         const int k1 = t & 7, j1 = t >> 3;
+        const float2* ld = buf + kXRow * j1 + k1 + 16 * (k1 >> 1);
 #pragma unroll
-        for (int m2 = 0; m2 < 8; ++m2) a[m2] = buf[xslot(k1, 8 * j1 + m2)];
+        for (int m2 = 0; m2 < 8; ++m2) a[m2] = ld[2 * m2];
         fft8(a);                                   // a[j2] = Z[k1 + 8*j1 + 64*j2] = Z[t + 64*j2]
     }
     group_bar(grp);                                // buf may be reused by the caller
@@ -197,29 +217,52 @@ __device__ __forceinline__ int find_utt(const int64_t* __restrict__ fr_off, int 
 }
 
 // ----------------------------------------------------------------------------- STFT
-__global__ void __launch_bounds__(256, 4) stft_kernel(const float* __restrict__ x, const int64_t* __restrict__ x_off,
+// 80 registers (three resident CTAs per SM): with 64 the two look-ahead stages spill, and the spill-free variants without them are
+// slower (A/B at B = 4 096: 64 registers with spills 1.30 ms, without the utterance look-ahead 1.35, this one 1.20).
+__global__ void __launch_bounds__(256, 3) stft_kernel(const float* __restrict__ x, const int64_t* __restrict__ x_off,
                                                    const int32_t* __restrict__ x_len, int B, float2* __restrict__ X,
                                                    float* __restrict__ P, const int64_t* __restrict__ fr_off,
                                                    int64_t NT, int hop, int ld) {
-    __shared__ float2 tw[kNfft];
+    __shared__ float2 tw[kHalf / 2 + 1];                                      // W^k for k <= 256 (the split step pairs k with 512 - k)
     __shared__ __align__(8) float win[kNfft];
     __shared__ float2 bufs[4][kBuf];
-    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) { tw[i] = g_tw[i]; win[i] = g_win[i]; }
+    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) {
+        win[i] = g_win[i];
+        if (i <= kHalf / 2) tw[i] = g_tw[i];
+    }
     __syncthreads();
 
     const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
     float2* buf = bufs[grp];
+    const float2 w1 = g_tw[2 * t], w2 = g_tw[16 * (t & 7)];
     const int64_t n_pass = (NT + 3) / 4;
     // raw samples of frame n (zeros beyond the signal): 8 even / odd pairs per thread.  The frame of the NEXT pass is
     // requested before the current one is transformed, so its DRAM latency (half of all stall samples in the first
-    // version, profiles/r01_stft_microbench.json) hides behind the FFT.
-    auto fetch = [&](int64_t n, float2* v) {
+    // version, profiles/r01_stft_microbench.json) hides behind the FFT; the utterance of the frame AFTER that is looked up
+    // speculatively at the same time (proportional guess g, then fr_off[g], fr_off[g+1], x_off[g], x_len[g] in one round of
+    // independent loads that nobody waits for until the next pass), which takes the chain of dependent loads
+    // frame -> utterance -> signal pointer -> samples out of the loop's critical path.
+    struct Look { int len; int64_t lo, hi, xo; };
+    auto look = [&](int64_t n) {
+        Look L;
+        L.len = 0; L.lo = 1; L.hi = 0; L.xo = 0;
         if (n < NT) {
-            const int u = find_utt(fr_off, B, n);
-            const int64_t j = n - fr_off[u];
-            const float* xu = x + x_off[u];
-            const int64_t len = x_len[u];
-            const int64_t s0 = j * (int64_t)hop;
+            // single-precision quotient: no 64-bit division; a wrong guess falls back to the search in fetch()
+            int g = (int)((float)n * (float)B / (float)NT);
+            g = min(max(g, 0), B - 1);
+            L.lo = __ldg(fr_off + g); L.hi = __ldg(fr_off + g + 1); L.xo = __ldg(x_off + g); L.len = __ldg(x_len + g);
+        }
+        return L;
+    };
+    auto fetch = [&](int64_t n, const Look& L, float2* v) {
+        if (n < NT) {
+            int64_t lo = L.lo, xo = L.xo, len = L.len;
+            if (!(L.lo <= n && n < L.hi)) {
+                const int u = find_utt(fr_off, B, n);
+                lo = fr_off[u]; xo = x_off[u]; len = x_len[u];
+            }
+            const float* xu = x + xo;
+            const int64_t s0 = (n - lo) * (int64_t)hop;
             // one 8-byte load per pair when the frame start is 8-byte aligned and the whole frame lies inside the signal
             const bool fast = ((reinterpret_cast<uintptr_t>(xu + s0) & 7) == 0) && (s0 + kNfft <= len);
 #pragma unroll
@@ -238,7 +281,8 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const float* __restrict__ 
         }
     };
     float2 nxt[8];
-    fetch((int64_t)blockIdx.x * 4 + grp, nxt);
+    fetch((int64_t)blockIdx.x * 4 + grp, look((int64_t)blockIdx.x * 4 + grp), nxt);
+    Look ahead = look(((int64_t)blockIdx.x + gridDim.x) * 4 + grp);
     for (int64_t pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
         const int64_t n = pass * 4 + grp;
         const bool live = n < NT;
@@ -246,31 +290,39 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const float* __restrict__ 
 #pragma unroll
         for (int n1 = 0; n1 < 8; ++n1) {
             const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * (t + 64 * n1));
-            a[n1] = make_float2(nxt[n1].x * w2.x, nxt[n1].y * w2.y);
+            upk2(mul2(pk2(nxt[n1].x, nxt[n1].y), pk2(w2.x, w2.y)), a[n1].x, a[n1].y);       // one packed multiply per sample pair
         }
-        fetch((pass + gridDim.x) * 4 + grp, nxt);
-        fft512(a, buf, tw, t, grp);
+        fetch((pass + gridDim.x) * 4 + grp, ahead, nxt);
+        ahead = look((pass + 2 * (int64_t)gridDim.x) * 4 + grp);
+        fft512(a, buf, w1, w2, t, grp);
+        // Split step.  X[k] = (s - i W^k d) / 2 with s = Z[k] + conj Z[512-k], d = Z[k] - conj Z[512-k]; the mirrored bin uses the
+        // same two values: X[512-k] = conj(s + i W^k d) / 2 (W^(512-k) = -conj W^k), so a thread produces the pairs (k, 512 - k) of
+        // its own k = t + 64 j, j < 4 (registers a[0..3]) and only needs Z[512 - k] = a[7 - j] of thread 64 - t: the upper halves
+        // a[4..7] go through the buffer (natural order: Z[k] at slot k - 256), nothing else does.
 #pragma unroll
-        for (int j2 = 0; j2 < 8; ++j2) buf[j2 * kRow + t] = a[j2];          // natural order: Z[k] at slot k
+        for (int j2 = 4; j2 < 8; ++j2) buf[(j2 - 4) * kRow + t] = a[j2];
         group_bar(grp);
         if (live) {
             float2* Xn = X + n * (int64_t)ld;
             float* Pn = P ? P + n * (int64_t)ld : nullptr;
-#pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                const int k = t + 64 * j;
-                if (k > kHalf) break;
-                const int km = (kHalf - k) & (kHalf - 1);
-                const float2 zk = buf[k & (kHalf - 1)];
-                float2 zm = buf[km];
+            auto bins = [&](int k, float2 zk, float2 zm, bool both) {
                 zm.y = -zm.y;                                               // conj(Z[512-k])
                 const float2 s = cadd(zk, zm), d = csub(zk, zm);
                 const float2 wd = cmul(tw[k], d);                           // W^k (Zk - conj Zm)
-                // X[k] = 0.5*s - 0.5*i*wd
                 const float2 r = make_float2(0.5f * (s.x + wd.y), 0.5f * (s.y - wd.x));
                 Xn[k] = r;
                 if (Pn) Pn[k] = r.x * r.x + r.y * r.y;
-            }
+                if (both) {
+                    const float2 q = make_float2(0.5f * (s.x - wd.y), -0.5f * (s.y + wd.x));
+                    Xn[kHalf - k] = q;
+                    if (Pn) Pn[kHalf - k] = q.x * q.x + q.y * q.y;
+                }
+            };
+            // Z[512 - k] sits at slot 256 - k; k = 0 pairs with Z[512] = Z[0], the thread's own a[0]
+            bins(t, a[0], t == 0 ? a[0] : buf[kHalf / 2 - t], true);
+#pragma unroll
+            for (int j = 1; j < 4; ++j) bins(t + 64 * j, a[j], buf[kHalf / 2 - t - 64 * j], true);   // k = 64 .. 255 and 448 .. 257
+            if (t == 0) bins(kHalf / 2, a[4], a[4], false);                 // k = 256, its own mirror
         }
         group_bar(grp);
     }
@@ -291,7 +343,7 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
                                                        float* __restrict__ y, const int64_t* __restrict__ y_off,
                                                        const int32_t* __restrict__ y_len, int /*hop: 256*/, int ld, int seg_hops) {
     constexpr int hop = 256;                                                  // = CTA size (checked by the host wrapper): index math in shifts
-    __shared__ float2 tw[kNfft];
+    __shared__ float2 tw[kHalf];                                              // W^k, k < 512
     __shared__ __align__(8) float win[kNfft];
     __shared__ __align__(16) float2 bufs[4 * kBuf];                           // FFT exchange buffers; then the windowed frames
     float* fbuf = reinterpret_cast<float*>(bufs);
@@ -307,15 +359,34 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
     const int jend = min(N - 1, h1 - 1);                                      // last frame that reaches the segment; may be < jstart
     const int sig_len = (N > 0) ? kNfft + hop * (N - 1) : 0;
 
-    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) { tw[i] = g_tw[i]; win[i] = g_win[i]; }
+    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) {
+        // synthesis window with the transform's 1 / 1024 (a power of two: the products are the same numbers) and the sign of the
+        // conjugation that turns the forward FFT into the inverse one folded in: sample pair m = (Re a * win[2m], -Im a * win[2m+1])
+        win[i] = g_win[i] * ((i & 1) ? -1.0f / 1024.0f : 1.0f / 1024.0f);
+        if (i < kHalf) tw[i] = g_tw[i];
+    }
     __syncthreads();
 
     const int grp = threadIdx.x >> 6, t = threadIdx.x & 63, i = threadIdx.x;
+    const float2 w1 = g_tw[2 * t], w2 = g_tw[16 * (t & 7)];
     float2* buf = bufs + grp * kBuf;
     float* yu = y + y_off[u];
+    const float inv_interior = __ldg(g_wss_inv + (9 << 8) + i);                // four frames cover the sample: q = 3, cnt = 4
     float v[7];
 #pragma unroll
     for (int m = 0; m < 7; ++m) v[m] = 0.f;
+    // The group's spectrum of the NEXT pass is requested with prefetch instructions (one 128-byte line per thread, 33 lines per
+    // row) while the current one is transformed: a quarter of all stall samples of the first version waited for these rows at the
+    // top of the pass (profiles/r02_ncu_istft.txt).  Staging the rows in shared memory with 8-byte cp.async one pass ahead was
+    // slower than the plain loads it replaced (1.36 against 1.27 ms at B = 4 096: more work for the load / store pipe);
+    // prefetching into L1 instead of L2 makes no difference.
+    auto prefetch_row = [&](int jq) {
+        const int j = jq + grp;
+        if (jq < h1 && j <= jend && t < 33) {
+            const float2* Xn = X + (f0 + j) * (int64_t)ld + 16 * t;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Xn));
+        }
+    };
     for (int jp = jstart; jp < h1; jp += 4) {
         if (jp <= jend) {                                                     // CTA-uniform: at least one frame of this pass exists
             const int j = jp + grp;
@@ -346,15 +417,16 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
 #pragma unroll
                 for (int n1 = 0; n1 < 8; ++n1) a[n1] = make_float2(0.f, 0.f);
             }
-            fft512(a, buf, tw, t, grp);
+            fft512(a, buf, w1, w2, t, grp, [&] { prefetch_row(jp + 4); });
             {
-                float2* fb = reinterpret_cast<float2*>(fbuf + grp * kNfft);
+                float2* fb = buf;                                             // the group's own exchange buffer (1 024 of its 1 152 floats)
 #pragma unroll
                 for (int j2 = 0; j2 < 8; ++j2) {
                     const int m = t + 64 * j2;
                     const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * m);
-                    const float xe = a[j2].x * (1.0f / 1024.0f), xo = -a[j2].y * (1.0f / 1024.0f);
-                    fb[m] = live ? make_float2(xe * w2.x, xo * w2.y) : make_float2(0.f, 0.f);
+                    float2 o;                                                 // a group without a frame transformed zeros: stores +-0
+                    upk2(mul2(pk2(a[j2].x, a[j2].y), pk2(w2.x, w2.y)), o.x, o.y);
+                    fb[m] = o;
                 }
             }
             __syncthreads();
@@ -362,7 +434,7 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
             for (int g = 0; g < 4; ++g) {                                     // ascending frame order, like the reference's loop
                 if (jp + g <= jend) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) v[g + c] += fbuf[g * kNfft + 256 * c + i];
+                    for (int c = 0; c < 4; ++c) v[g + c] += fbuf[g * (2 * kBuf) + 256 * c + i];
                 }
             }
             __syncthreads();                                                  // fbuf is the next pass's exchange buffer
@@ -374,7 +446,9 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
             const int s = hh * hop + i;
             if (hh >= h0 && hh < h1 && s < len) {
                 float r = 0.f;
-                if (s < sig_len) {
+                if (hh >= 3 && hh < N) {                                      // frames hh-3 .. hh all exist (the bulk of an utterance)
+                    r = v[m] * inv_interior;
+                } else if (s < sig_len) {
                     r = v[m];
                     const int jlo = max(0, (s - kNfft + hop) / hop), jhi = min(N - 1, s / hop);
                     const int o = s - jlo * hop, q = o >> 8, cnt = jhi - jlo + 1;
@@ -404,7 +478,7 @@ extern "C" int dvae_stft_f32(const float* x, const int64_t* x_off, const int32_t
     int rc = ensure_tables(st);
     if (rc) return rc;
     const int64_t n_pass = (NT + 3) / 4;
-    const int grid = (int)(n_pass < 148 * 4 ? n_pass : 148 * 4);          // four resident CTAs per SM (64 registers, 28 KB)
+    const int grid = (int)(n_pass < 148 * 6 ? n_pass : 148 * 6);          // three resident CTAs per SM (80 registers, 24 KB), two rounds
     stft_kernel<<<grid, 256, 0, st>>>(x, x_off, x_len, B, (float2*)X, P, fr_off, NT, hop, ld);
     return check_launch("stft_kernel");
 }
