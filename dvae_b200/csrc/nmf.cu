@@ -854,13 +854,9 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
         const f32x2 p2 = *reinterpret_cast<const f32x2*>(P + n * ld + f2);
         const float pX = P[n * ld + 512];
         if (t < K) hs_old[t] = H[n * K + t];                            // the frame's activations reach every thread through shared memory
-        if (n + 1 < ne) {
-            stage(n + 1, buf ^ 1);                                      // the other buffer was released by the barrier that ended frame n - 1
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();                                                // frame n is staged for every thread
+        asm volatile("cp.async.wait_group 0;" ::: "memory");            // this thread's pieces of frame n (requested one frame earlier)
+        __syncthreads();                                                // frame n is staged for every thread, and every thread is done with frame n - 1:
+        if (n + 1 < ne) stage(n + 1, buf ^ 1);                          // only now may its buffer be refilled (the cost pass reads it to the end)
         float h[KT];
 #pragma unroll
         for (int k = 0; k < KT; ++k) h[k] = hs_old[k];
