@@ -263,6 +263,16 @@ constexpr int HG5_LD = 520;                     // row pitch the engine uses for
 __device__ __forceinline__ f32x2 rcp2(f32x2 a) { float lo, hi; upk2(a, lo, hi); return pk2(rcp_fast(lo), rcp_fast(hi)); }
 __device__ __forceinline__ f32x2 lg22(f32x2 a) { float lo, hi; upk2(a, lo, hi); return pk2(lg2_fast(lo), lg2_fast(hi)); }
 __device__ __forceinline__ f32x2 lds2(const float* p) { return *reinterpret_cast<const f32x2*>(p); }
+// Power of two c with c * y in [1, 2) (y > 0), and log2 c.  The cost passes multiply FOUR samples of one bin before taking one
+// reciprocal and one logarithm; scaled by the c of the bin's first sample the product stays inside FP32 as long as the samples of
+// a bin lie within 2^+-31 of each other, whatever the absolute level of the variances (a fixed scale of 2^8 covered variances
+// from 1e-10 to 1e7 only, and the NMF part of Vx does fall below that in spectral nulls).
+__device__ __forceinline__ float bin_scale(float y, float& log2c) {
+    int e = (int)((__float_as_uint(y) >> 23) & 255u);
+    e = e > 253 ? 253 : e;
+    log2c = (float)(127 - e);
+    return __uint_as_float((uint32_t)(254 - e) << 23);
+}
 
 template <int R, int ld>
 __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __restrict__ P, const float* __restrict__ Vs,
@@ -458,8 +468,15 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
         // ---- cost with Vx = g_new Vs + Vb2: FOUR samples share one reciprocal and one log2.  With y_i = c Vx_i (c = 2^8 keeps
         //      the four-fold products inside FP32 for variances from 1e-10 to 1e7; it rides on g_new and Vb2 for free):
         //      sum_i log2 Vx_i = log2(y0 y1 y2 y3) - 32,  sum_i 1 / Vx_i = c ((y0 + y1) y2 y3 + (y2 + y3) y0 y1) / (y0 y1 y2 y3)
-        constexpr float kC = 256.0f;
-        const f32x2 gc2 = pk2(gnew * kC, gnew * kC), vc2 = mul2(vb2, pk2(kC, kC));
+        float c_lo, c_hi, lc_lo, lc_hi;                 // per-bin scale (bin_scale) from the bin's first sample
+        {
+            float y_lo, y_hi;
+            upk2(fma2(gn2, lds2(S + f2), vb2), y_lo, y_hi);
+            c_lo = bin_scale(y_lo, lc_lo);
+            c_hi = bin_scale(y_hi, lc_hi);
+        }
+        const f32x2 c2 = pk2(c_lo, c_hi);
+        const f32x2 gc2 = mul2(gn2, c2), vc2 = mul2(vb2, c2);
         f32x2 cl = 0ull, cp = 0ull;
         constexpr int R4 = R & ~3;
         constexpr int RA4 = (RA < R) ? RA : 0;          // rows [0, RA4) are released to the next frame's copy half-way
@@ -489,22 +506,20 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
             cl = add2(cl, lg22(m));
             cp = fma2(fma2(add2(y0, y1), p23, mul2(add2(y2, y3), p01)), rcp2(m), cp);
         }
-        float fix = -8.0f * (float)R4;                 // log2 c per sample
 #pragma unroll
         for (int r = R4; r < R; r += 2) {              // R is even: one pair left when R % 4 == 2
             const f32x2 y0 = fma2(gc2, lds2(S + r * ld + f2), vc2), y1 = fma2(gc2, lds2(S + (r + 1) * ld + f2), vc2);
             const f32x2 pr = mul2(y0, y1);
             cl = add2(cl, lg22(pr));
             cp = fma2(add2(y0, y1), rcp2(pr), cp);
-            fix -= 16.0f;
         }
         if (xl && t >= RA4) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
         {
             float cl_lo, cl_hi, pc_lo, pc_hi;
             upk2(cl, cl_lo, cl_hi);
-            upk2(mul2(p2, cp), pc_lo, pc_hi);
-            // both bins of the thread carry the same log2 c offset; the reciprocal sums carry a factor 1 / c
-            cost_d += (double)(fmaf(0.6931471805599453f, (cl_lo + fix) + (cl_hi + fix), kC * (pc_lo + pc_hi)) + cX);
+            upk2(mul2(mul2(p2, c2), cp), pc_lo, pc_hi);
+            // every sample of a bin carries the bin's log2 c; the reciprocal sums carry a factor 1 / c
+            cost_d += (double)(fmaf(0.6931471805599453f, fmaf(-(float)R, lc_lo, cl_lo) + fmaf(-(float)R, lc_hi, cl_hi), pc_lo + pc_hi) + cX);
         }
 
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
@@ -575,7 +590,6 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
     double cost_d = 0.0;
     unsigned phase = 0;
     constexpr unsigned row_bytes = (unsigned)ld * 4u;
-    constexpr float kC = 256.0f;                    // see the cost pass of hg5
 
     // stage window w of frame n (RW bulk row copies) and wait for it; contains the barrier that frees the buffer
     auto stage = [&](int64_t n, int w) {
@@ -713,12 +727,20 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
         const float gnew = gg * sqrtf(t2 / t1s);
 
         // ---- cost with Vx = g_new Vs + Vb2 (scaled by c = 2^8: four samples share one reciprocal and one log2)
-        const f32x2 gn2c = pk2(gnew * kC, gnew * kC), vc2 = mul2(vb2, pk2(kC, kC));
+        f32x2 c2 = 0ull, gn2c = 0ull, vc2 = 0ull;
+        float lc_lo = 0.f, lc_hi = 0.f;
         f32x2 cl = 0ull, cp = 0ull;
         float cX = 0.f;
         constexpr int RW4 = RW & ~3;
         for (int w = 0; w < NW; ++w) {
             stage(n, w);
+            if (w == 0) {                            // per-bin scale from the bin's first sample (bin_scale, see hg5)
+                float y_lo, y_hi;
+                upk2(fma2(pk2(gnew, gnew), lds2(S + f2), vb2), y_lo, y_hi);
+                c2 = pk2(bin_scale(y_lo, lc_lo), bin_scale(y_hi, lc_hi));
+                gn2c = mul2(pk2(gnew, gnew), c2);
+                vc2 = mul2(vb2, c2);
+            }
 #pragma unroll
             for (int r = 0; r < RW4; r += 4) {
                 const f32x2 y0 = fma2(gn2c, lds2(S + r * ld + f2), vc2), y1 = fma2(gn2c, lds2(S + (r + 1) * ld + f2), vc2);
@@ -738,11 +760,10 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
             if (xl) { const float x0 = fmaf(gnew, S[t * ld + 512], vbX); cX += fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
         }
         {
-            const float fix = -8.0f * (float)R;     // log2 c per sample and bin
             float cl_lo, cl_hi, pc_lo, pc_hi;
             upk2(cl, cl_lo, cl_hi);
-            upk2(mul2(p2, cp), pc_lo, pc_hi);
-            cost_d += (double)(fmaf(0.6931471805599453f, (cl_lo + fix) + (cl_hi + fix), kC * (pc_lo + pc_hi)) + cX);
+            upk2(mul2(mul2(p2, c2), cp), pc_lo, pc_hi);
+            cost_d += (double)(fmaf(0.6931471805599453f, fmaf(-(float)R, lc_lo, cl_lo) + fmaf(-(float)R, lc_hi, cl_hi), pc_lo + pc_hi) + cX);
         }
         __syncthreads();                            // hs and the reduction buffers are free for the next frame
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
@@ -1021,9 +1042,16 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
         // ---- cost with Vx = g_new Vs + Vb2: FOUR samples of a bin share one reciprocal and one log2.  With y_i = c Vx_i
         //      (c = 2^8 keeps the four-fold products inside FP32 for variances from 1e-10 to 1e7; it rides on g_new and Vb2):
         //      sum_i log2 Vx_i = log2(y0 y1 y2 y3) - 32,  sum_i 1 / Vx_i = c ((y0 + y2) y1 y3 + (y1 + y3) y0 y2) / (y0 y1 y2 y3)
-        constexpr float kC = 256.0f;
-        const f32x2 gca = pk2(gnew * kC * E0, gnew * kC * E0), gcb = pk2(gnew * kC * E1, gnew * kC * E1);
-        const f32x2 vca = pk2(vb_lo * kC, vb_lo * kC), vcb = pk2(vb_hi * kC, vb_hi * kC);
+        f32x2 gca, gcb, vca, vcb;
+        float fix, pca, pcb;                           // -R (log2 c_a + log2 c_b);  c_a P_a,  c_b P_b
+        {                                              // per-bin scale (bin_scale) from the bin's first sample
+            float lca, lcb;
+            const float ca = bin_scale(fmaf(gnew * E0, vst_lo(S[0]), vb_lo), lca), cb = bin_scale(fmaf(gnew * E1, vst_hi(S[0]), vb_hi), lcb);
+            gca = pk2(gnew * ca * E0, gnew * ca * E0); gcb = pk2(gnew * cb * E1, gnew * cb * E1);
+            vca = pk2(vb_lo * ca, vb_lo * ca); vcb = pk2(vb_hi * cb, vb_hi * cb);
+            fix = -(float)R * (lca + lcb);
+            pca = p_lo * ca; pcb = p_hi * cb;
+        }
         float cla = 0.f, cpa = 0.f, clb = 0.f, cpb = 0.f;
 #pragma unroll
         for (int r = 0; r < R4; r += 4) {
@@ -1046,7 +1074,6 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
                 cpb = fmaf(fmaf(s_lo, q_hi, s_hi * q_lo), rcp_fast(m), cpb);
             }
         }
-        float fix = -8.0f * (float)R4;                 // log2 c per sample
         if (R4 < R) {                                  // one sample pair left: sum 1 / y = (y0 + y1) / (y0 y1)
             float y0, y1;
             upk2(fma2(gca, HG7_VA(R4), vca), y0, y1);
@@ -1057,14 +1084,13 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
             m = y0 * y1;
             clb += lg2_fast(m);
             cpb = fmaf(y0 + y1, rcp_fast(m), cpb);
-            fix -= 16.0f;
         }
 #undef HG7_VA
 #undef HG7_VB
         float cX = 0.f;
         if (xl) { const float x0 = fmaf(gnew * EX, sX, vbX); cX = fmaf(0.6931471805599453f, lg2_fast(x0), pX * rcp_fast(x0)); }
-        // both bins of the thread carry the same log2 c offset; the reciprocal sums carry a factor 1 / c
-        cost_d += (double)(fmaf(0.6931471805599453f, (cla + fix) + (clb + fix), kC * fmaf(p_lo, cpa, p_hi * cpb)) + cX);
+        // every sample of a bin carries the bin's log2 c; the reciprocal sums carry a factor 1 / c
+        cost_d += (double)(fmaf(0.6931471805599453f, (cla + clb) + fix, fmaf(pca, cpa, pcb * cpb)) + cX);
 
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
         if (t == 0) g[n] = gnew;
@@ -1343,11 +1369,18 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7w_kernel(const float* _
         const float gnew = gg * sqrtf(t2 / t1s);
 
         // ---- cost with Vx = g_new Vs + Vb2 (four samples of a bin share one reciprocal and one log2, c = 2^8: see hg5)
-        constexpr float kC = 256.0f;
-        const f32x2 gca = pk2(gnew * kC * E0, gnew * kC * E0), gcb = pk2(gnew * kC * E1, gnew * kC * E1);
-        const f32x2 vca = pk2(vb_lo * kC, vb_lo * kC), vcb = pk2(vb_hi * kC, vb_hi * kC);
+        float lca = 0.f, lcb = 0.f, ca = 0.f, cb = 0.f;       // per-bin scale (bin_scale) from the bin's first sample
+        f32x2 gca = 0ull, gcb = 0ull, vca = 0ull, vcb = 0ull;
+        bool scaled = false;
         float cla = 0.f, cpa = 0.f, clb = 0.f, cpb = 0.f, cX = 0.f;
         walk(n, true, [&](const uint32_t* S, const uint32_t* SX, int nr) {
+            if (!scaled) {                              // first window
+                ca = bin_scale(fmaf(gnew * E0, vst_lo(S[0]), vb_lo), lca);
+                cb = bin_scale(fmaf(gnew * E1, vst_hi(S[0]), vb_hi), lcb);
+                gca = pk2(gnew * ca * E0, gnew * ca * E0); gcb = pk2(gnew * cb * E1, gnew * cb * E1);
+                vca = pk2(vb_lo * ca, vb_lo * ca); vcb = pk2(vb_hi * cb, vb_hi * cb);
+                scaled = true;
+            }
             int r = 0;
             for (; r + 4 <= nr; r += 4) {
                 {
@@ -1387,8 +1420,8 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7w_kernel(const float* _
         });
 #undef HG7W_VA
 #undef HG7W_VB
-        const float fix = -8.0f * (float)Rtot;          // log2 c per sample, both bins of the thread
-        cost_d += (double)(fmaf(0.6931471805599453f, (cla + fix) + (clb + fix), kC * fmaf(p_lo, cpa, p_hi * cpb)) + cX);
+        cost_d += (double)(fmaf(0.6931471805599453f, fmaf(-(float)Rtot, lca, cla) + fmaf(-(float)Rtot, lcb, clb),
+                                fmaf(p_lo * ca, cpa, p_hi * cb * cpb)) + cX);
 
         if (t < K) H[n * K + t] = hs[t] * norm[u * K + t];
         if (t == 0) g[n] = gnew;

@@ -309,6 +309,8 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 // Vx in [1e-10, 1e7] (the observation is |STFT|^2 of audio in [-1, 1]: at most 2.6e5); the scale leaves `acc` short
 // of a factor 2^15 (applied once per row by the caller: kQuadScale) and adds a constant to `accl` that cancels in
 // l(z) - l(z').  -> 1.5 MUFU operations per bin instead of 2.
+// Range: the stream keeps every factor within +-30 octaves of the frame's level (pack_pv floors Vb' 90 dB below it and gives the
+// observation-free padding bins the constant 1 in the quad's scale), so the product cannot underflow and this loop carries no check.
 // The scale is a power of two chosen PER FRAME by row_scale_kernel (k^2 X^4 ~ 1 for the frame's typical X = Vx 2^-b): with the
 // fixed 2^15 of round 1 a decoder whose output bias is very small in some bins (2^-b ~ 1e10, e.g. a prior without energy above
 // 3 kHz) overflowed the four-fold product, l(z') became Inf and those chains never moved.

@@ -81,11 +81,28 @@ __device__ __forceinline__ uint32_t word_with_low_half(float p, uint32_t low16) 
     if ((w & 0x7f800000u) == 0x7f800000u) w -= 0x10000u;                               // never Inf / NaN
     return w;
 }
+// Range of the quad trick (loglik16_pv): the product k^2 X0 X1 X2 X3 of a quad must stay inside FP32.  k = 2^(-2c) centres it on
+// the frame's level 2^c, which leaves +-31 octaves per factor.  Two things would still leave that range and are handled HERE, in
+// the stream, so that the sampler's inner loop carries no check:
+//  * a bin whose noise variance the NMF has driven far below the frame's level while the speech term g 2^v is tiny as well
+//    (spectral nulls; noise-only frames where the gain g collapses): Vb' is floored 30 octaves (90 dB) below the frame's level.
+//    Both l(z) and l(z') see the same floor, the bin carries no energy, the accept decision is unaffected;
+//  * the padding bins 513 .. 543 (no observation, P' = 0): X would be g alone, and g^3 or g^4 underflows once the gain of a frame
+//    has collapsed (the first version did exactly that after ~100 EM iterations on noise-only frames: l(z') = NaN).  They carry
+//    Vb' = 1 in the quad's own scale (pv_pad_word), i.e. the constant factor 1 + g 2^0.
 __device__ __forceinline__ uint32_t pv_word(float p, float vb, float bias_log2, int j, float k) {
     const float sc = exp2f(-bias_log2);
+    const float level = rsqrtf(k);                                   // 2^c
     const float pj = p * sc * (j < 2 ? 1.0f : 1.0f / k);
-    const float vj = vb * sc * (j < 2 ? k : 1.0f);
+    const float vf = fmaxf(vb * sc, level * 9.313225746e-10f);       // 2^-30 below the frame's level
+    const float vj = vf * (j < 2 ? k : 1.0f);
     return word_with_low_half(pj, bf16_bits_rn(vj));
+}
+// a padding bin of quad position j: k Vb' = level^-1 (j < 2) or Vb' = level (j >= 2), so that the quad's product sees a factor
+// of the same size as its real bins; P' = 0
+__device__ __forceinline__ uint32_t pv_pad_word(int j, float k) {
+    const float level = rsqrtf(k);
+    return word_with_low_half(0.f, bf16_bits_rn(j < 2 ? k * level : level));
 }
 
 // generic version: one thread per (tile, quad, row), rows fastest (coalesced stores, strided loads)
@@ -105,7 +122,7 @@ __global__ void pack_pv_kernel(const float* __restrict__ P, const float* __restr
             const float k = kscale ? kscale[fr] : kDefaultQuadScale;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (f + j < F) w[j] = pv_word(P[fr * ld + f + j], Vb[fr * ld + f + j], bias_log2[f + j], j, k);
+                w[j] = (f + j < F) ? pv_word(P[fr * ld + f + j], Vb[fr * ld + f + j], bias_log2[f + j], j, k) : pv_pad_word(j, k);
         }
         dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -136,9 +153,12 @@ __global__ void __launch_bounds__(256) pack_pv_tiled_kernel(const float* __restr
                 const float4 v4 = __ldg(reinterpret_cast<const float4*>(Vb + fr * ld + f));
                 const float4 b4 = *reinterpret_cast<const float4*>(bias_log2 + f);
                 w[0] = pv_word(p4.x, v4.x, b4.x, 0, k);
-                if (f + 1 < F) w[1] = pv_word(p4.y, v4.y, b4.y, 1, k);
-                if (f + 2 < F) w[2] = pv_word(p4.z, v4.z, b4.z, 2, k);
-                if (f + 3 < F) w[3] = pv_word(p4.w, v4.w, b4.w, 3, k);
+                w[1] = (f + 1 < F) ? pv_word(p4.y, v4.y, b4.y, 1, k) : pv_pad_word(1, k);
+                w[2] = (f + 2 < F) ? pv_word(p4.z, v4.z, b4.z, 2, k) : pv_pad_word(2, k);
+                w[3] = (f + 3 < F) ? pv_word(p4.w, v4.w, b4.w, 3, k) : pv_pad_word(3, k);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w[j] = pv_pad_word(j, k);
             }
         }
         sm[ql * (TM + 1) + row] = make_uint4(w[0], w[1], w[2], w[3]);

@@ -351,3 +351,40 @@ def test_sampler_handles_decoder_biases_spanning_many_decades():
         rate[sampler] = float(eng.n_accept.sum().item()) / (N * 60)
         assert bool(torch.isfinite(eng.cost).all())
     assert rate["fp32"] > 0.3 and abs(rate["tc"] - rate["fp32"]) <= 0.03, rate
+
+
+def test_sampler_and_cost_survive_collapsed_gains_and_spectral_nulls():
+    """Late in a run the NMF explains noise-only frames alone: the gain g of such a frame collapses by many decades, and in
+    spectral nulls both the observation and Vb lie far below the frame's level.  The sampler's quad products (four bins, including
+    the observation-free padding bins whose variance is g alone) and the cost pass's products of four samples must stay finite:
+    no status bit, finite cost, and the chains of those frames accept like the exact FP32 sampler's (their likelihood hardly
+    depends on z: almost every proposal is accepted).  The first version of the quad trick produced NaN here (bench run, after
+    ~100 EM iterations)."""
+    x, s, _ = synth.synth_utterance(5, 1.0)
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128], 0, seed=3, out_bias=float(np.log(0.05)))
+    X = stft_np.stft(x, **KW)
+    N = X.shape[1]
+    P = torch.zeros((N, 520), device=DEV)
+    P[:, :513] = torch.from_numpy(np.ascontiguousarray((np.abs(X) ** 2).T)).to(DEV)
+    P[:, 100:140] *= 1e-12                                               # a spectral null, 120 dB deep
+    P[:, :513].clamp_(min=1e-30)
+    rate = {}
+    for sampler in ("fp32", "tc"):
+        w = VaeWeights(sd, "M1", torch.device(DEV))
+        eng = McemEngine(w, McemConfig(niter=2, keep_E=10, burn_E=20, sampler=sampler, seed=4), DEV)
+        eng.init_parameters(torch.zeros((N, 520), dtype=torch.complex64, device=DEV), P, RaggedBatch([N], DEV, utt_ids=[9]))
+        for it in range(2):
+            eng.Vb.copy_(P)                                              # the noise model explains the observation alone ...
+            eng.g[::3] = 1e-22                                           # ... and the gain of every third frame has collapsed
+            eng.g[1::6] = 1e-30
+            eng.e_step()
+            if sampler == "tc":
+                tc.check_status(eng)                                     # neither a timeout nor a non-finite likelihood
+            eng.m_step(it)
+        if sampler == "tc":
+            tc.check_status(eng)
+        assert bool(torch.isfinite(eng.cost).all()), eng.cost
+        acc = eng.n_accept.view(-1).float()
+        rate[sampler] = (float(acc[::3].sum().item()) / (len(acc[::3]) * 60), float(acc.sum().item()) / (N * 60))
+    assert rate["fp32"][0] > 0.5 and abs(rate["tc"][0] - rate["fp32"][0]) <= 0.05, rate
+    assert abs(rate["tc"][1] - rate["fp32"][1]) <= 0.05, rate
