@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Status probe: the bench workload (M1, 512 utterances, 100 EM iterations) stage by stage, reporting the first place where the
+device status word (DVAE_STATUS_*) is set or a tensor stops being finite; then six full runs.  python tools/dbg_nan.py [B]"""
 import sys, numpy as np, torch
 sys.path.insert(0, ".")
 import bench
