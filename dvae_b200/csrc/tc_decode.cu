@@ -172,27 +172,30 @@ __global__ void __launch_bounds__(256) pack_pv_tiled_kernel(const float* __restr
     }
 }
 
-// Per-frame quad scale of the sampler's likelihood (loglik16_pv): k = 2^(-2 c) with c = mean over the frame's bins of
-// log2(P 2^-b), so that k^2 X^4 ~ 1 for a typical X = Vx 2^-b of the frame (the model fits the observation: Vx ~ P).  P does not
-// change during a run, so this runs once per batch.  One warp per frame, fixed summation order: deterministic and independent
-// of the batch a frame sits in.  Frames without energy keep the default 2^15.
+// Per-frame quad scale of the sampler's likelihood (loglik16_pv): k = 2^(-2 c) with the frame's level 2^c = 2^-16 x the loudest
+// bin of the frame's bias-free spectrum P 2^-b.  The quad product k^2 X0 X1 X2 X3 of X = Vx 2^-b then has 2^15.75 of headroom per
+// factor above the loudest observation (a model that overshoots it by more than 55 000 x is rejected as Inf) and, with the Vb'
+// floor of pack_pv 30 octaves below the level, 138 dB of range below it.  (The first version centred on the MEAN of log2 P: a
+// frame with one loud partial over a quiet floor - geometric mean near the floor - overflowed.)  P does not change during a run,
+// so this runs once per batch.  One warp per frame: deterministic and independent of the batch a frame sits in.  Frames without
+// energy keep the default 2^15; c is clamped to +-30 so that P' / k stays a normal number.
 __global__ void row_scale_kernel(const float* __restrict__ P, const float* __restrict__ bias_log2, int64_t NT, int F, int ld,
                                  float* __restrict__ kscale) {
     const int64_t n = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (n >= NT) return;
-    float sum = 0.f, cnt = 0.f;
+    float top = -1e30f;
     for (int f = lane; f < F; f += 32) {
         const float p = P[n * ld + f];
-        if (p > 0.f) { sum += log2f(p) - bias_log2[f]; cnt += 1.f; }
+        if (p > 0.f) top = fmaxf(top, log2f(p) - bias_log2[f]);
     }
-    sum = warp_sum(sum);
-    cnt = warp_sum(cnt);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) top = fmaxf(top, __shfl_xor_sync(0xffffffffu, top, o));
     if (lane == 0) {
         float k = kDefaultQuadScale;
-        if (cnt > 0.f) {
-            const float e = fminf(fmaxf(rintf(-2.0f * sum / cnt), -60.f), 60.f);
-            k = exp2f(e);
+        if (top > -1e29f) {
+            const float c = fminf(fmaxf(rintf(top) - 16.0f, -30.f), 30.f);
+            k = exp2f(-2.0f * c);
         }
         kscale[n] = k;
     }

@@ -189,7 +189,7 @@ int dvae_decode_tc(const DvaeMlp* dec, const void* image, const float* Zs, int64
 int64_t dvae_tc_packed_pv_bytes(int64_t chains);
 /* kscale[NT] (nullable everywhere: 2^15): a power of two per frame that centres the sampler's four-fold variance products in
  * the FP32 range for THIS frame's spectrum and THIS decoder's output bias; dvae_tc_row_scale derives it once per batch from
- * P (k = 2^-2c, c = mean_f log2(P 2^-b)); the stream must be packed and sampled with the same array.  dvae_tc_pack_pv keeps
+ * P (k = 2^-2c, 2^c = 2^-16 x the frame's loudest bin of P 2^-b); the stream must be packed and sampled with the same array.  dvae_tc_pack_pv keeps
  * every factor of those products within 30 octaves of the frame's level 2^c: it floors Vb' at 2^(c-30) (90 dB below the frame,
  * identical under l(z) and l(z'), in bins that carry no energy) and packs the observation-free padding bins 513..543 as the
  * constant 1 in the quad's scale, so that a collapsed gain g or a spectral null cannot underflow the product. */

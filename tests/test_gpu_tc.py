@@ -388,3 +388,32 @@ def test_sampler_and_cost_survive_collapsed_gains_and_spectral_nulls():
         rate[sampler] = (float(acc[::3].sum().item()) / (len(acc[::3]) * 60), float(acc.sum().item()) / (N * 60))
     assert rate["fp32"][0] > 0.5 and abs(rate["tc"][0] - rate["fp32"][0]) <= 0.05, rate
     assert abs(rate["tc"][1] - rate["fp32"][1]) <= 0.05, rate
+
+
+def test_sampler_handles_140_db_of_dynamic_range_inside_a_frame():
+    """Frames with a few loud partials over a floor 140 dB below them (a quiet room with a tonal source; 16-bit material reaches
+    96 dB).  The geometric mean of such a frame sits near the floor, so a scale centred on it overflowed the four-fold product at
+    the partials; centred 16 octaves below the loudest bin, with the Vb' floor underneath, everything stays finite and the chains
+    accept like the exact FP32 sampler's."""
+    rng = np.random.default_rng(3)
+    N = 96
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128], 0, seed=3, out_bias=float(np.log(0.05)))
+    Pn = rng.gamma(1.0, 1e-12, size=(N, 513)).astype(np.float32)
+    Pn[:, 40::64] = rng.gamma(2.0, 50.0, size=Pn[:, 40::64].shape).astype(np.float32)       # eight partials per frame
+    P = torch.zeros((N, 520), device=DEV)
+    P[:, :513] = torch.from_numpy(Pn).to(DEV)
+    rate = {}
+    for sampler in ("fp32", "tc"):
+        w = VaeWeights(sd, "M1", torch.device(DEV))
+        eng = McemEngine(w, McemConfig(niter=3, keep_E=10, burn_E=20, sampler=sampler, seed=4), DEV)
+        eng.init_parameters(torch.zeros((N, 520), dtype=torch.complex64, device=DEV), P, RaggedBatch([N], DEV, utt_ids=[9]))
+        for it in range(3):
+            eng.e_step()
+            if sampler == "tc":
+                tc.check_status(eng)
+            eng.m_step(it)
+        if sampler == "tc":
+            tc.check_status(eng)
+        assert bool(torch.isfinite(eng.cost).all()), eng.cost
+        rate[sampler] = float(eng.n_accept.sum().item()) / (N * 90)
+    assert abs(rate["tc"] - rate["fp32"]) <= 0.05, rate
