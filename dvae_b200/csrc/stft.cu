@@ -343,7 +343,6 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
                                                        float* __restrict__ y, const int64_t* __restrict__ y_off,
                                                        const int32_t* __restrict__ y_len, int /*hop: 256*/, int ld, int seg_hops) {
     constexpr int hop = 256;                                                  // = CTA size (checked by the host wrapper): index math in shifts
-    __shared__ float2 tw[kHalf];                                              // W^k, k < 512
     __shared__ __align__(8) float win[kNfft];
     __shared__ __align__(16) float2 bufs[4 * kBuf];                           // FFT exchange buffers; then the windowed frames
     float* fbuf = reinterpret_cast<float*>(bufs);
@@ -363,12 +362,11 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
         // synthesis window with the transform's 1 / 1024 (a power of two: the products are the same numbers) and the sign of the
         // conjugation that turns the forward FFT into the inverse one folded in: sample pair m = (Re a * win[2m], -Im a * win[2m+1])
         win[i] = g_win[i] * ((i & 1) ? -1.0f / 1024.0f : 1.0f / 1024.0f);
-        if (i < kHalf) tw[i] = g_tw[i];
     }
     __syncthreads();
 
     const int grp = threadIdx.x >> 6, t = threadIdx.x & 63, i = threadIdx.x;
-    const float2 w1 = g_tw[2 * t], w2 = g_tw[16 * (t & 7)];
+    const float2 w1 = g_tw[2 * t], w2 = g_tw[16 * (t & 7)], wt = g_tw[t];
     float2* buf = bufs + grp * kBuf;
     float* yu = y + y_off[u];
     const float inv_interior = __ldg(g_wss_inv + (9 << 8) + i);                // four frames cover the sample: q = 3, cnt = 4
@@ -407,7 +405,13 @@ __global__ void __launch_bounds__(256, 4) istft_kernel(const float2* __restrict_
                     if (k == 0) { xk.y = 0.f; xm.y = 0.f; }                   // irfft ignores Im of DC and Nyquist
                     xm.y = -xm.y;                                             // conj(X[512-k])
                     const float2 s = cadd(xk, xm), d = csub(xk, xm);
-                    float2 w = tw[k];
+                    // W^k = W^t W^(64 n1): the second factor is a compile-time constant, the first sits in two registers - no
+                    // table load (the shared-memory / L1 data pipe is the tighter bound here, see twiddle_powers)
+                    const float cr[8] = {1.f, 0.92387953251128675613f, 0.70710678118654752440f, 0.38268343236508977173f, 0.f,
+                                         -0.38268343236508977173f, -0.70710678118654752440f, -0.92387953251128675613f};
+                    const float ci[8] = {0.f, -0.38268343236508977173f, -0.70710678118654752440f, -0.92387953251128675613f, -1.f,
+                                         -0.92387953251128675613f, -0.70710678118654752440f, -0.38268343236508977173f};
+                    float2 w = (n1 == 0) ? wt : cmul(wt, make_float2(cr[n1], ci[n1]));
                     w.y = -w.y;                                               // conj(W^k)
                     const float2 wd = cmul(w, d);
                     const float2 zb = make_float2(s.x - wd.y, s.y + wd.x);    // s + i*wd
