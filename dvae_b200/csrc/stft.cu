@@ -223,18 +223,14 @@ __global__ void __launch_bounds__(256, 3) stft_kernel(const float* __restrict__ 
                                                    const int32_t* __restrict__ x_len, int B, float2* __restrict__ X,
                                                    float* __restrict__ P, const int64_t* __restrict__ fr_off,
                                                    int64_t NT, int hop, int ld) {
-    __shared__ float2 tw[kHalf / 2 + 1];                                      // W^k for k <= 256 (the split step pairs k with 512 - k)
     __shared__ __align__(8) float win[kNfft];
     __shared__ float2 bufs[4][kBuf];
-    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) {
-        win[i] = g_win[i];
-        if (i <= kHalf / 2) tw[i] = g_tw[i];
-    }
+    for (int i = threadIdx.x; i < kNfft; i += blockDim.x) win[i] = g_win[i];
     __syncthreads();
 
     const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
     float2* buf = bufs[grp];
-    const float2 w1 = g_tw[2 * t], w2 = g_tw[16 * (t & 7)];
+    const float2 w1 = g_tw[2 * t], w2 = g_tw[16 * (t & 7)], wt = g_tw[t];
     const int64_t n_pass = (NT + 3) / 4;
     // raw samples of frame n (zeros beyond the signal): 8 even / odd pairs per thread.  The frame of the NEXT pass is
     // requested before the current one is transformed, so its DRAM latency (half of all stall samples in the first
@@ -305,10 +301,10 @@ __global__ void __launch_bounds__(256, 3) stft_kernel(const float* __restrict__ 
         if (live) {
             float2* Xn = X + n * (int64_t)ld;
             float* Pn = P ? P + n * (int64_t)ld : nullptr;
-            auto bins = [&](int k, float2 zk, float2 zm, bool both) {
+            auto bins = [&](int k, float2 wk, float2 zk, float2 zm, bool both) {
                 zm.y = -zm.y;                                               // conj(Z[512-k])
                 const float2 s = cadd(zk, zm), d = csub(zk, zm);
-                const float2 wd = cmul(tw[k], d);                           // W^k (Zk - conj Zm)
+                const float2 wd = cmul(wk, d);                              // W^k (Zk - conj Zm)
                 const float2 r = make_float2(0.5f * (s.x + wd.y), 0.5f * (s.y - wd.x));
                 Xn[k] = r;
                 if (Pn) Pn[k] = r.x * r.x + r.y * r.y;
@@ -319,10 +315,14 @@ __global__ void __launch_bounds__(256, 3) stft_kernel(const float* __restrict__ 
                 }
             };
             // Z[512 - k] sits at slot 256 - k; k = 0 pairs with Z[512] = Z[0], the thread's own a[0]
-            bins(t, a[0], t == 0 ? a[0] : buf[kHalf / 2 - t], true);
+            // W^k = W^t W^(64 j): a register pair times a compile-time constant (no table load, see twiddle_powers)
+            const float cr[4] = {1.f, 0.92387953251128675613f, 0.70710678118654752440f, 0.38268343236508977173f};
+            const float ci[4] = {0.f, -0.38268343236508977173f, -0.70710678118654752440f, -0.92387953251128675613f};
+            bins(t, wt, a[0], t == 0 ? a[0] : buf[kHalf / 2 - t], true);
 #pragma unroll
-            for (int j = 1; j < 4; ++j) bins(t + 64 * j, a[j], buf[kHalf / 2 - t - 64 * j], true);   // k = 64 .. 255 and 448 .. 257
-            if (t == 0) bins(kHalf / 2, a[4], a[4], false);                 // k = 256, its own mirror
+            for (int j = 1; j < 4; ++j)                                     // k = 64 .. 255 and 448 .. 257
+                bins(t + 64 * j, cmul(wt, make_float2(cr[j], ci[j])), a[j], buf[kHalf / 2 - t - 64 * j], true);
+            if (t == 0) bins(kHalf / 2, make_float2(0.f, -1.f), a[4], a[4], false);      // k = 256, its own mirror (W^256 = -i)
         }
         group_bar(grp);
     }
