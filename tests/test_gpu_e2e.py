@@ -187,7 +187,8 @@ def test_full_size_properties_configs1():
     * the two Wiener masks sum to one, so s_hat + n_hat reproduces the mixture (away from the first hop, where the
       reference's ISTFT divides by a vanishing window sum);
     * the run is bit-reproducible, and a shard of the batch (rank 1 of 2) gives bit-identical results for its utterances:
-      the Philox counters are keyed by global utterance id, not by position in the batch;
+      the Philox counters are keyed by global utterance id, not by position in the batch (the shard starts on a 128-frame tile
+      boundary here, 256 x 185 = 370 x 128; for other offsets see the summation-order test below);
     * the cost of every utterance is finite and does not increase from the first to the second EM iteration.
     """
     from dvae_b200.engine import Enhancer, McemConfig
@@ -237,3 +238,31 @@ def test_multi_chain_windowed_path_matches_generic_path():
     assert np.allclose(out["emit"][1], out["generic"][1], rtol=5e-3), (out["emit"][1], out["generic"][1])
     err = np.linalg.norm(out["emit"][0] - out["generic"][0]) / np.linalg.norm(out["generic"][0])
     assert err < 5e-2, err
+
+
+def test_results_of_an_utterance_do_not_depend_on_its_batch_beyond_summation_order():
+    """The random draws of an utterance are keyed by its global id, so the same utterance enhanced inside different batches sees
+    the same numbers.  What may differ is floating-point association: the fused W-update reduction (McemConfig.w_partials) sums
+    an utterance's frames in runs cut at 128-frame tile boundaries, which fall elsewhere when the utterance sits at another offset
+    of the batch.  * with w_partials=False (per-frame statistics, summed per utterance in frame order) a sub-batch is bit-identical
+    whatever its offset;  * with the default, a tile-aligned sub-batch is bit-identical and a misaligned one agrees to rounding
+    (no accept decision flips in this short run)."""
+    from dvae_b200.engine import Enhancer, McemConfig
+    B = 24
+    xs = [np.asarray(x, np.float32) for x in synth.synth_batch(40, B, seconds=2.0)[0]]       # 123 frames each
+    P0 = np.abs(stft_np.stft(xs[0], **KW)) ** 2
+    sd = synth.xavier_state_dict("M1", 513, 16, [128, 128], 0, seed=1234, out_bias=float(np.log(P0.mean())))
+    ids = list(range(500, 500 + B))
+    for wp in (False, True):
+        cfg = McemConfig(niter=3, keep_E=30, burn_E=10, keep_WF=25, burn_WF=10, seed=7, w_partials=wp)
+        enh = Enhancer(sd, "M1", cfg, device=0)
+        s1, n1, c1 = enh.enhance(xs, utt_ids=ids)
+        s1 = [a.copy() for a in s1]
+        lo, hi = 5, 17                                                   # 5 x 123 frames: not a multiple of 128
+        s2, _, c2 = enh.enhance(xs[lo:hi], utt_ids=ids[lo:hi])
+        if not wp:
+            assert all(np.array_equal(a, b) for a, b in zip(s1[lo:hi], s2)) and np.array_equal(c1[lo:hi], c2)
+        else:
+            err = max(float(np.linalg.norm(a - b) / np.linalg.norm(a)) for a, b in zip(s1[lo:hi], s2))
+            assert err <= 1e-3, err
+            np.testing.assert_allclose(c2, c1[lo:hi], rtol=1e-4)
