@@ -121,7 +121,7 @@ def _cpu_worker(variant, niter, u, barrier, queue):
     torch.set_num_threads(1)
     torch.manual_seed(u)
     cpu_reference_run(variant, max(1, niter // 20), u)                      # warm-up (imports, caches)
-    barrier.wait()
+    barrier.wait(timeout=600)
     t0 = time.time()
     cpu_reference_run(variant, niter, u)
     queue.put((t0, time.time()))
@@ -135,8 +135,17 @@ def cpu_process_per_core(variant, niter, n_proc, u0=200):
     procs = [ctx.Process(target=_cpu_worker, args=(variant, niter, u0 + i, barrier, queue)) for i in range(n_proc)]
     for pr in procs:
         pr.start()
+    import queue as _queue
+    spans, deadline = [], time.time() + 900
     try:
-        spans = [queue.get(timeout=900) for _ in procs]
+        while len(spans) < n_proc:
+            try:
+                spans.append(queue.get(timeout=2))
+            except _queue.Empty:
+                if any(pr.exitcode not in (None, 0) for pr in procs):
+                    raise RuntimeError("a CPU worker exited with an error")
+                if time.time() > deadline:
+                    raise RuntimeError("CPU workers did not finish within 900 s")
     finally:
         for pr in procs:
             pr.join(timeout=5)
