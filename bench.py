@@ -155,6 +155,17 @@ def cpu_process_per_core(variant, niter, n_proc, u0=200):
     return n_proc * SECONDS / wall, wall
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline_block(variant, niter, t_all_threads, cores, what):
     """The CPU side of the comparison in both layouts the host offers: one utterance on all threads (``t_all_threads`` seconds,
     measured by the caller) and one single-threaded process per core; ``value`` is the better of the two."""
@@ -164,12 +175,12 @@ def cpu_baseline_block(variant, niter, t_all_threads, cores, what):
         v_par, wall = cpu_process_per_core(variant, niter, cores)
     except Exception as e:                                              # a host that cannot spawn workers still gets a bench line
         sample = "%s; the process-per-core layout could not be measured here (%s: %s)" % (what, type(e).__name__, e)
-        return dict(value=v_seq, unit=UNIT, cores=cores, kind="port", sample=sample, layouts=layouts)
+        return dict(value=v_seq, unit=UNIT, cores=cores, kind="port", sample=sample, layouts=layouts, cpu_model=cpu_model())
     layouts["process_per_core"] = dict(value=v_par, processes=cores, threads_each=1, wall_seconds=wall)
     best = "process_per_core" if v_par >= v_seq else "one_utterance_all_threads"
     sample = ("%s; process-per-core layout (the reference's own, evaluate_ntcd_M1.py:249-259): %d utterances at once, one "
               "single-threaded process each, %.1f s; value = the better layout (%s)" % (what, cores, wall, best))
-    return dict(value=max(v_seq, v_par), unit=UNIT, cores=cores, kind="port", sample=sample, layouts=layouts)
+    return dict(value=max(v_seq, v_par), unit=UNIT, cores=cores, kind="port", sample=sample, layouts=layouts, cpu_model=cpu_model())
 
 
 def run_reference(args):
