@@ -358,7 +358,11 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
         f32x2 vb2 = 0ull;
         float vbX = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        for (int k = 0; k < KT; ++k) vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2);
+        if (wid == 0) {                             // bin 512 lives on threads of warp 0 only (warp-uniform branch)
+#pragma unroll
+            for (int k = 0; k < KT; ++k) vbX = fmaf(wX[k], h[k], vbX);
+        }
         f32x2 a1 = 0ull, a2 = 0ull;
         wait_rows(bar_a, phase_a);
 #pragma unroll 4
@@ -396,8 +400,15 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
                     float nlo, nhi, dlo, dhi;
                     upk2(mul2(w2[k], q2), nlo, nhi);
                     upk2(mul2(w2[k], a1), dlo, dhi);
-                    v[2 * j] = fmaf(wX[k], qX, nlo + nhi);
-                    v[2 * j + 1] = fmaf(wX[k], a1X, dlo + dhi);
+                    v[2 * j] = nlo + nhi;
+                    v[2 * j + 1] = dlo + dhi;
+                }
+                if (wid == 0) {                     // the other warps hold no sample of bin 512 (qX = a1X = 0 there)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        v[2 * j] = fmaf(wX[5 * hf + j], qX, v[2 * j]);
+                        v[2 * j + 1] = fmaf(wX[5 * hf + j], a1X, v[2 * j + 1]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
@@ -435,7 +446,11 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg5_kernel(const float* __
         // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
         vb2 = 0ull; vbX = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        for (int k = 0; k < KT; ++k) vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2);
+        if (wid == 0) {                             // bin 512 lives on threads of warp 0 only (warp-uniform branch)
+#pragma unroll
+            for (int k = 0; k < KT; ++k) vbX = fmaf(wX[k], h[k], vbX);
+        }
         *reinterpret_cast<f32x2*>(Vb + n * ld + f2) = vb2;
         if (t == 0) Vb[n * ld + 512] = vbX;
         f32x2 s1 = 0ull, s2 = 0ull;
@@ -626,7 +641,11 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
         f32x2 vb2 = 0ull;
         float vbX = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        for (int k = 0; k < KT; ++k) vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2);
+        if (wid == 0) {                             // bin 512 lives on threads of warp 0 only (warp-uniform branch)
+#pragma unroll
+            for (int k = 0; k < KT; ++k) vbX = fmaf(wX[k], h[k], vbX);
+        }
         f32x2 a1 = 0ull, a2 = 0ull;
         float a1X = 0.f, a2X = 0.f;
         for (int w = 0; w < NW; ++w) {
@@ -655,8 +674,15 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
                     float nlo, nhi, dlo, dhi;
                     upk2(mul2(w2[k], q2), nlo, nhi);
                     upk2(mul2(w2[k], a1), dlo, dhi);
-                    v[2 * j] = fmaf(wX[k], qX, nlo + nhi);
-                    v[2 * j + 1] = fmaf(wX[k], a1X, dlo + dhi);
+                    v[2 * j] = nlo + nhi;
+                    v[2 * j + 1] = dlo + dhi;
+                }
+                if (wid == 0) {                     // the other warps hold no sample of bin 512 (qX = a1X = 0 there)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        v[2 * j] = fmaf(wX[5 * hf + j], qX, v[2 * j]);
+                        v[2 * j + 1] = fmaf(wX[5 * hf + j], a1X, v[2 * j + 1]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
@@ -694,7 +720,11 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg6_kernel(const float* __
         // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
         vb2 = 0ull; vbX = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        for (int k = 0; k < KT; ++k) vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2);
+        if (wid == 0) {                             // bin 512 lives on threads of warp 0 only (warp-uniform branch)
+#pragma unroll
+            for (int k = 0; k < KT; ++k) vbX = fmaf(wX[k], h[k], vbX);
+        }
         *reinterpret_cast<f32x2*>(Vb + n * ld + f2) = vb2;
         if (t == 0) Vb[n * ld + 512] = vbX;
         f32x2 s1 = 0ull, s2 = 0ull;
@@ -1150,8 +1180,9 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7w_kernel(const float* _
     float* red = reinterpret_cast<float*>(smw + 2 * RWMAX * HG7_ROWW);  // [8][HG3_NV] per-warp partials of the H sums
     __shared__ float2 red2[8];
     __shared__ double redd[8];
-    __shared__ float hs[KT];
-    __shared__ float hs_old[KT];
+    __shared__ __align__(16) float hs[12];          // KT = 10 activations, read back as two 16-byte and one 8-byte load
+    __shared__ __align__(16) float hs_old[12];
+    static_assert(KT == 10, "hg7w reads its ten activations as float4 + float4 + float2");
     const int u = blockIdx.y;
     const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
     const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
@@ -1228,8 +1259,11 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7w_kernel(const float* _
         if (t < K) hs_old[t] = H[n * K + t];
         __syncthreads();
         float h[KT];
-#pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = hs_old[k];
+        {
+            const float4 h0 = *reinterpret_cast<const float4*>(hs_old), h1 = *reinterpret_cast<const float4*>(hs_old + 4);
+            const float2 h2 = *reinterpret_cast<const float2*>(hs_old + 8);
+            h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w; h[8] = h2.x; h[9] = h2.y;
+        }
         float p_lo, p_hi;
         upk2(p2, p_lo, p_hi);
         const f32x2 ga = pk2(gg * E0, gg * E0), gb = pk2(gg * E1, gg * E1);
@@ -1240,7 +1274,11 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7w_kernel(const float* _
         f32x2 vb2 = 0ull;
         float vbX = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        for (int k = 0; k < KT; ++k) vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2);
+        if (wid == 0) {                             // bin 512 lives on the threads t < 30 of warp 0 only (warp-uniform branch)
+#pragma unroll
+            for (int k = 0; k < KT; ++k) vbX = fmaf(wX[k], h[k], vbX);
+        }
         float vb_lo, vb_hi;
         upk2(vb2, vb_lo, vb_hi);
         f32x2 va2 = pk2(vb_lo, vb_lo), vbb2 = pk2(vb_hi, vb_hi);
@@ -1293,8 +1331,15 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7w_kernel(const float* _
                     float nlo, nhi, dlo, dhi;
                     upk2(mul2(w2[k], q2), nlo, nhi);
                     upk2(mul2(w2[k], a1), dlo, dhi);
-                    v[2 * j] = fmaf(wX[k], qX, nlo + nhi);
-                    v[2 * j + 1] = fmaf(wX[k], a1X, dlo + dhi);
+                    v[2 * j] = nlo + nhi;
+                    v[2 * j + 1] = dlo + dhi;
+                }
+                if (wid == 0) {                     // the other warps hold no sample of bin 512 (qX = a1X = 0 there)
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        v[2 * j] = fmaf(wX[5 * hf + j], qX, v[2 * j]);
+                        v[2 * j + 1] = fmaf(wX[5 * hf + j], a1X, v[2 * j + 1]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 5; ++j) {
@@ -1326,13 +1371,20 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7w_kernel(const float* _
             hs[t] = hs_old[t] * sqrtf(num / den);
         }
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < KT; ++k) h[k] = hs[k];
+        {
+            const float4 h0 = *reinterpret_cast<const float4*>(hs), h1 = *reinterpret_cast<const float4*>(hs + 4);
+            const float2 h2 = *reinterpret_cast<const float2*>(hs + 8);
+            h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w; h[8] = h2.x; h[9] = h2.y;
+        }
 
         // ---- g update (Vb2 = W_new H_new, kept as the model's Vb)
         vb2 = 0ull; vbX = 0.f;
 #pragma unroll
-        for (int k = 0; k < KT; ++k) { vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2); vbX = fmaf(wX[k], h[k], vbX); }
+        for (int k = 0; k < KT; ++k) vb2 = fma2(w2[k], pk2(h[k], h[k]), vb2);
+        if (wid == 0) {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) vbX = fmaf(wX[k], h[k], vbX);
+        }
         *reinterpret_cast<f32x2*>(Vb + n * ld + f2) = vb2;
         if (t == 0) Vb[n * ld + 512] = vbX;
         upk2(vb2, vb_lo, vb_hi);
