@@ -59,12 +59,22 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
     const int64_t tile = blockIdx.x;
     const int bg = blockIdx.y, row = threadIdx.x >> 1, half = threadIdx.x & 1;
     const int64_t m = tile * TM + row;
+    // Order of the requests matters more than anything else here: a CTA lives for a few microseconds, and the first version
+    // waited for three or four DRAM round trips one after the other (H -> shared memory, then g / Vb / bias, then the slot
+    // indices, then the cells, then P).  Now: the activations go to shared memory asynchronously (cp.async, nobody waits before
+    // the tail), the slot indices are requested first, the first cells right behind them, and only then the frame's scalars.
     if (WPART) {
         for (int i = threadIdx.x; i < TM * 12; i += 256) {
             const int r = i / 12, k = i - 12 * r;
             const int64_t n = tile * TM + r;
-            sH[r][k] = (n < rows && k < wp.K) ? __ldg(wp.H + (n >> cshift) * wp.K + k) : 0.f;
+            if (n < rows && k < wp.K) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&sH[r][k]);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(wp.H + (n >> cshift) * wp.K + k) : "memory");
+            } else {
+                sH[r][k] = 0.f;
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     if (m >= rows) {
         if (!WPART) return;
@@ -74,6 +84,25 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
     const bool rowlive = m < rows;
     const int64_t mm = rowlive ? m : 0;
     const int f0 = 16 * bg + 8 * half;
+    const size_t slot_stride = (size_t)NBG * TM * 2;
+    const uint4* cell = VsT + ((size_t)tile * (R + 1) * NBG + bg) * (TM * 2) + row * 2 + half;
+    const uint8_t* ib = idx + mm * VST_IDX_PITCH;
+    uint32_t iw[8];
+    if (RT > 0) {
+        const uint4 i0 = __ldg(reinterpret_cast<const uint4*>(ib)), i1 = __ldg(reinterpret_cast<const uint4*>(ib) + 1);
+        iw[0] = i0.x; iw[1] = i0.y; iw[2] = i0.z; iw[3] = i0.w; iw[4] = i1.x; iw[5] = i1.y; iw[6] = i1.z; iw[7] = i1.w;
+    }
+    auto slot_of = [&](int r) -> uint32_t {
+        if (RT > 0) return (iw[r >> 2] >> (8 * (r & 3))) & 255u;
+        return (uint32_t)__ldg(ib + r);
+    };
+    // software pipeline over sample pairs (RT > 0): pairs k+1 and k+2 are in flight while pair k is reduced
+    constexpr int NP = RT / 2;
+    uint4 c[2], n1[2], n2[2];
+    if (RT > 0) {
+        c[0] = __ldcs(cell + slot_of(0) * slot_stride); c[1] = __ldcs(cell + slot_of(1) * slot_stride);
+        if (NP > 1) { n1[0] = __ldcs(cell + slot_of(2) * slot_stride); n1[1] = __ldcs(cell + slot_of(3) * slot_stride); }
+    }
     f32x2 ge2[4], vb2[4], a1[4], a2[4];
     {
         const int64_t fr = mm >> cshift;                   // the row's frame: 2^cshift chains per frame (WPART only), else row = frame
@@ -99,18 +128,6 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
             a2[j] = 0ull;
         }
     }
-    const size_t slot_stride = (size_t)NBG * TM * 2;
-    const uint4* cell = VsT + ((size_t)tile * (R + 1) * NBG + bg) * (TM * 2) + row * 2 + half;
-    const uint8_t* ib = idx + mm * VST_IDX_PITCH;
-    uint32_t iw[8];
-    if (RT > 0) {
-        const uint4 i0 = __ldg(reinterpret_cast<const uint4*>(ib)), i1 = __ldg(reinterpret_cast<const uint4*>(ib) + 1);
-        iw[0] = i0.x; iw[1] = i0.y; iw[2] = i0.z; iw[3] = i0.w; iw[4] = i1.x; iw[5] = i1.y; iw[6] = i1.z; iw[7] = i1.w;
-    }
-    auto slot_of = [&](int r) -> uint32_t {
-        if (RT > 0) return (iw[r >> 2] >> (8 * (r & 3))) & 255u;
-        return (uint32_t)__ldg(ib + r);
-    };
     auto word_pair = [&](uint32_t w0, uint32_t w1, int j) {
         // two samples share one reciprocal: 1 / X0 = X1 / (X0 X1)
         const f32x2 x0 = fma2(ge2[j], pk2(vst_lo(w0), vst_hi(w0)), vb2[j]), x1 = fma2(ge2[j], pk2(vst_lo(w1), vst_hi(w1)), vb2[j]);
@@ -122,20 +139,33 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
     auto pair = [&](const uint4& p, const uint4& q) {
         word_pair(p.x, q.x, 0); word_pair(p.y, q.y, 1); word_pair(p.z, q.z, 2); word_pair(p.w, q.w, 3);
     };
+    float pp[8];                                           // WPART: the frame's observation for the tail, requested before the last pairs are reduced
+    auto load_p = [&]() {
+        if (WPART && rowlive) {
+            const int64_t fr = m >> cshift;
+            if (f0 + 8 <= ld) {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(wp.P + fr * ld + f0) + j);
+                    pp[4 * j] = t.x; pp[4 * j + 1] = t.y; pp[4 * j + 2] = t.z; pp[4 * j + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pp[j] = (f0 + j < F) ? __ldg(wp.P + fr * ld + f0 + j) : 0.f;
+            }
+        }
+    };
     if (RT > 0) {
-        // software pipeline over sample pairs: pairs k+1 and k+2 are in flight while pair k is reduced
-        constexpr int NP = RT / 2;
-        uint4 c[2], n1[2], n2[2];
-        c[0] = __ldcs(cell + slot_of(0) * slot_stride); c[1] = __ldcs(cell + slot_of(1) * slot_stride);
-        if (NP > 1) { n1[0] = __ldcs(cell + slot_of(2) * slot_stride); n1[1] = __ldcs(cell + slot_of(3) * slot_stride); }
 #pragma unroll
         for (int k = 0; k < NP; ++k) {
             if (k + 2 < NP) { n2[0] = __ldcs(cell + slot_of(2 * k + 4) * slot_stride); n2[1] = __ldcs(cell + slot_of(2 * k + 5) * slot_stride); }
+            if (k == (NP > 2 ? NP - 2 : 0)) load_p();      // the last cells are on their way: n2's registers are free from here on
             pair(c[0], c[1]);
             c[0] = n1[0]; c[1] = n1[1];
             n1[0] = n2[0]; n1[1] = n2[1];
         }
     } else {
+        load_p();
         const int R2 = R & ~1;
         for (int r = 0; r < R2; r += 2) pair(__ldcs(cell + slot_of(r) * slot_stride), __ldcs(cell + slot_of(r + 1) * slot_stride));
         if (R & 1) {
@@ -154,18 +184,6 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
     for (int j = 0; j < 4; ++j) { upk2(a1[j], o1[2 * j], o1[2 * j + 1]); upk2(a2[j], o2[2 * j], o2[2 * j + 1]); }
     if (WPART) {
         if (rowlive) {
-            const int64_t fr = m >> cshift;
-            float pp[8];
-            if (f0 + 8 <= ld) {
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(wp.P + fr * ld + f0) + j);
-                    pp[4 * j] = t.x; pp[4 * j + 1] = t.y; pp[4 * j + 2] = t.z; pp[4 * j + 3] = t.w;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) pp[j] = (f0 + j < F) ? __ldg(wp.P + fr * ld + f0 + j) : 0.f;
-            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const bool ok = f0 + j < F;
@@ -173,6 +191,7 @@ __global__ void __launch_bounds__(256, 4) vst_frame_stats_kernel(const uint4* __
                 sPA2[row][8 * half + j] = ok ? pp[j] * o2[j] : 0.f;
             }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const int j = threadIdx.x & 15, k = threadIdx.x >> 4;               // threads 0 .. 16 K - 1: (bin of the group, rank)
         const int f = 16 * bg + j;
