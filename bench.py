@@ -474,7 +474,7 @@ def run_b200(args):
     extra = []
     if headline and not args.no_extra:
         # configs[2]: M2, 4 096 utterances sharded over the ranks (strong scaling, scripts/evaluate_ntcd_M2.py:298-327)
-        blk = measure("M2", 4096, 1, min(args.steps, 2), 1, not args.no_e2e, "strong", args.niter, args.sampler, rank, world, dev,
+        blk = measure("M2", 4096, 1, min(args.steps, 3), 1, not args.no_e2e, "strong", args.niter, args.sampler, rank, world, dev,
                       "BASELINE.json configs[2]: M2 speech-activity-conditioned VAE, 4 096 synthetic 3 s utterances in total, sharded over "
                       "%d GPU(s) with shard_range" % world)
         if blk:
