@@ -204,3 +204,40 @@ def test_segment_tables_refine_tiles_and_utterances():
                 t = lo // 128
                 assert tile_seg[t] <= s < tile_seg[t + 1]
             assert utt_seg[0] == 0 and utt_seg[-1] == S and tile_seg[-1] == S
+
+
+def test_emission_consumers_validate_their_arguments_before_any_launch():
+    """dvae_vst_w_partials / dvae_nmf_mstep_vst: chain counts that are not a power of two <= 128, several chains without the
+    segment partial sums, both or neither of fstat / wpart, a wrong sample count - all refused with a negative status and a
+    message before anything touches the device (runs without a GPU)."""
+    lib = _lib.load()
+    dec = _lib.DvaeMlp()
+    dec.n_layers = 3
+    for i, d in enumerate((16, 128, 128, 513)):
+        dec.dims[i] = d
+    buf = (ctypes.c_float * 64)()
+    off = (ctypes.c_int64 * 2)(0, 1)
+    seg = (ctypes.c_int32 * 2)(0, 1)
+    p = lambda a: ctypes.cast(a, ctypes.c_void_p)
+    D = ctypes.byref(dec)
+
+    def w_partials(n_chains, R=10):
+        return lib.dvae_vst_w_partials(D, p(buf), 16, 0, p(buf), ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint8)), R, p(buf), p(buf), p(buf),
+                                       p(buf), 10, 1, n_chains, 520, p(off), p(seg), p(buf), None)
+
+    for bad in (0, 3, 12, 256):
+        assert w_partials(bad) < 0 and b"power of two" in lib.dvae_last_error(), bad
+    assert w_partials(1, R=40) < 0 and b"bad sizes" in lib.dvae_last_error()
+
+    def mstep(n_chains, fstat, wpart, R=10, K=10):
+        return lib.dvae_nmf_mstep_vst(D, p(buf), 16, 0, p(buf), p(buf), ctypes.cast(buf, ctypes.POINTER(ctypes.c_uint8)), R, p(buf), p(buf), p(buf),
+                                      p(buf), p(buf), p(off), 1, 1, K, 520, 1, p(buf), fstat, wpart, p(seg), n_chains, None, None)
+
+    assert mstep(1, None, None) < 0 and b"exactly one" in lib.dvae_last_error()
+    assert mstep(1, p(buf), p(buf)) < 0 and b"exactly one" in lib.dvae_last_error()
+    assert mstep(6, None, p(buf)) < 0 and b"power of two" in lib.dvae_last_error()
+    assert mstep(4, p(buf), None) < 0 and b"segment partial sums" in lib.dvae_last_error()
+    assert mstep(1, p(buf), None, R=20) < 0 and b"R in" in lib.dvae_last_error()
+    assert mstep(1, p(buf), None, K=11) < 0 and b"K <=" in lib.dvae_last_error()
+    dec.dims[3] = 257                                                   # not the 513-bin decoder the tensor-core path is built for
+    assert mstep(1, p(buf), None) < 0 and b"F=513" in lib.dvae_last_error()
