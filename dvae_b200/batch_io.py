@@ -93,16 +93,20 @@ def process_sublist(sublist, enhancer, processed_wav_dir, output_data_dir, batch
     video-length frame cap the reference reads from HDF5; ``labels(noisy_path, clean_path) -> (y_dim, N) array`` supplies the
     labels of the M2 models.  ``utt_ids(noisy_path) -> int`` names the utterances for the random number generator
     (default: ``utterance_id``, a hash of the path), so every utterance gets its own draws whatever ``batch_size`` and
-    sharding are - the reference draws fresh numbers per utterance too.  Returns the list of written stems.
+    sharding are - the reference draws fresh numbers per utterance too.  File I/O overlaps the GPU work: the next batch is read and
+    the previous one written by ``io_threads`` workers while the current one is enhanced.  Returns the list of written stems.
     """
     utt_ids = utt_ids or utterance_id
     todo = [(a, b) for a, b in sublist if not os.path.exists(output_stem(output_data_dir, a) + "_s_est.wav")]
     written = []
     with ThreadPoolExecutor(max(1, io_threads)) as pool:
         pending = None                                               # futures of the previous batch's wav writes
+        submit_reads = lambda part: [pool.submit(read_wav, processed_wav_dir + ab[0]) for ab in part]
+        reads = submit_reads(todo[:batch_size])
         for lo in range(0, len(todo), batch_size):
             part = todo[lo:lo + batch_size]
-            sigs = list(pool.map(lambda ab: read_wav(processed_wav_dir + ab[0]), part))
+            sigs = [f.result() for f in reads]
+            reads = submit_reads(todo[lo + batch_size:lo + 2 * batch_size])      # read ahead: the next batch loads while this one runs
             for (x, f), ab in zip(sigs, part):
                 if f != fs:
                     raise ValueError("%s: sampling rate %d, expected %d" % (ab[0], f, fs))

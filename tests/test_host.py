@@ -241,3 +241,40 @@ def test_emission_consumers_validate_their_arguments_before_any_launch():
     assert mstep(1, p(buf), None, K=11) < 0 and b"K <=" in lib.dvae_last_error()
     dec.dims[3] = 257                                                   # not the 513-bin decoder the tensor-core path is built for
     assert mstep(1, p(buf), None) < 0 and b"F=513" in lib.dvae_last_error()
+
+
+def test_process_sublist_batches_reads_and_writes_with_a_stub_enhancer(tmp_path):
+    """File plumbing of batch_io.process_sublist without a GPU: every input is read exactly once and in order (the next batch is
+    read ahead while the current one runs), both estimates are written per utterance, ids come from the paths, finished
+    utterances are skipped on a second run."""
+    from dvae_b200 import batch_io
+    wav_dir, out_dir = str(tmp_path / "in"), str(tmp_path / "out")
+    rng = np.random.default_rng(0)
+    sub, sigs = [], {}
+    for i in range(7):
+        rel = "/spk%d/utt%d.wav" % (i % 2, i)
+        x = (0.1 * rng.standard_normal(4000 + 100 * i)).astype(np.float32)
+        batch_io.write_wav(wav_dir + rel, x, 16000)
+        sigs[rel] = batch_io.read_wav(wav_dir + rel)[0]
+        sub.append((rel, "/clean" + rel))
+
+    class Stub:
+        def __init__(self):
+            self.calls = []
+
+        def enhance(self, xs, y_list=None, max_frames_list=None, utt_ids=None):
+            self.calls.append((len(xs), list(utt_ids)))
+            return [0.5 * x for x in xs], [0.25 * x for x in xs], None
+
+    for bs in (3, 7, 100):
+        stub = Stub()
+        out = out_dir + str(bs)
+        done = batch_io.process_sublist(sub, stub, wav_dir, out, batch_size=bs)
+        assert done == [batch_io.output_stem(out, rel) for rel, _ in sub]
+        assert [n for n, _ in stub.calls] == [min(bs, 7 - lo) for lo in range(0, 7, bs)]
+        assert [i for _, ids in stub.calls for i in ids] == [batch_io.utterance_id(rel) for rel, _ in sub]
+        for rel, _ in sub:
+            s, fs = batch_io.read_wav(batch_io.output_stem(out, rel) + "_s_est.wav")
+            n, _ = batch_io.read_wav(batch_io.output_stem(out, rel) + "_n_est.wav")
+            assert fs == 16000 and np.allclose(s, 0.5 * sigs[rel], atol=1e-4) and np.allclose(n, 0.25 * sigs[rel], atol=1e-4)
+        assert batch_io.process_sublist(sub, stub, wav_dir, out, batch_size=bs) == []
