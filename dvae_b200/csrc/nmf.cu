@@ -854,12 +854,17 @@ __global__ void __launch_bounds__(HG3_THREADS, 3) nmf_hg7_kernel(const float* __
     static_assert(KT == 10, "hg7 reads its ten activations as float4 + float4 + float2");
     const int u = blockIdx.y;
     const int64_t n0 = fr_off[u], n1 = fr_off[u + 1];
-    const int64_t nb = n0 + (int64_t)blockIdx.x * HG3_FPB;
-    if (nb >= n1) {
+    // blocks of HG3_FPB = 8 frames aligned in the GLOBAL frame index (the first and last block of an utterance may be shorter): a
+    // block's rows then fill whole 64-byte pairs of sectors of every (slot, bin group) of the emission - with blocks counted from
+    // the utterance's first frame (185 frames per utterance: odd offsets) a block straddled five pairs instead of four
+    static_assert(HG3_FPB == 8, "aligned blocks of eight frames");
+    const int64_t nb0 = ((n0 >> 3) + (int64_t)blockIdx.x) << 3;
+    const int64_t nb = nb0 > n0 ? nb0 : n0;
+    const int64_t ne = (nb0 + HG3_FPB < n1) ? nb0 + HG3_FPB : n1;
+    if (nb >= ne) {
         if (threadIdx.x == 0) cost_part[(int64_t)u * gridDim.x + blockIdx.x] = 0.0;
         return;
     }
-    const int64_t ne = (nb + HG3_FPB < n1) ? nb + HG3_FPB : n1;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     const int f2 = 2 * t;                           // bins 2t, 2t+1; sample t of bin 512 lives on threads t < R
     const bool xl = t < R;
@@ -1592,7 +1597,7 @@ extern "C" int dvae_nmf_vb(const float* W, const float* H, const int32_t* frame_
     return check_launch("nmf_vb_kernel");
 }
 
-static int64_t hg_blocks(int max_frames) { return max_frames > 0 ? (max_frames + FPB - 1) / FPB : 1; }   // generic path: upper bound for both
+static int64_t hg_blocks(int max_frames) { return (max_frames > 0 ? (max_frames + FPB - 1) / FPB : 1) + 1; }   // generic path (+ 1 for hg7's aligned blocks): upper bound for all
 
 extern "C" int64_t dvae_nmf_workspace_floats(int B, int K, int ld, int max_frames) {
     if (B <= 0 || K <= 0 || ld <= 0 || max_frames < 0) return 0;
@@ -1617,7 +1622,7 @@ extern "C" int dvae_nmf_mstep(const float* P, const float* Vs, int R, float* W, 
     off += off & 1;
     double* cost_part = reinterpret_cast<double*>(ws + off);
     DVAE_REQUIRE((reinterpret_cast<uintptr_t>(cost_part) & 7) == 0, "dvae_nmf_mstep: workspace must be 8-byte aligned");
-    const int nblk = (int)hg_blocks(max_frames);
+    const int nblk = (int)hg_blocks(max_frames) - 1;
     int rc;
     if (wstat) {                                   // per-frame reciprocal sums A1 | A2 from dvae_decode_stats_tc
         rc = dvae_nmf_w_from_frame_stats(wstat, wstat + NT * (int64_t)ld, P, H, W, fr_off, B, F, K, ld, Wtmp, stream);
@@ -1711,7 +1716,7 @@ extern "C" int dvae_nmf_mstep_vst(const DvaeMlp* dec, const void* image, int L, 
         cudaMemsetAsync(cost, 0, sizeof(double) * B, st);
         return 0;
     }
-    const int nblk = (max_frames + HG3_FPB - 1) / HG3_FPB;
+    const int nblk = (max_frames + HG3_FPB - 1) / HG3_FPB + 1;          // + 1: hg7's blocks are aligned in the global frame index
     const size_t smem7 = 4 * ((size_t)2 * R * HG7_ROWW + (size_t)HG3_NV * 8);
     if (n_chains > 1) {                            // R kept samples per chain, n_chains x R per frame: windowed kernel
         const size_t smem7w = 4 * ((size_t)2 * 30 * HG7_ROWW + (size_t)HG3_NV * 8);
