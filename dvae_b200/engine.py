@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
-import math
 import os
 from typing import Optional, Sequence
 

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from ... import _lib
-from ...engine import RaggedBatch, _ld_for, _p, _stream, stft_batch
+from ...engine import RaggedBatch, _ld_for, _p, _stream
 from ...synth import num_frames
 
 

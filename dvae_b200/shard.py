@@ -7,7 +7,6 @@ bytes per utterance and a MAX-reduce of the elapsed time.  Works with the ``nccl
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -12,11 +12,10 @@ import json
 import os
 import sys
 
-import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from dvae_b200 import _lib, synth                                                   # noqa: E402
+from dvae_b200 import _lib                                                          # noqa: E402
 from dvae_b200.engine import RaggedBatch, _p, _stream, istft_batch, istft_masked_batch, stft_batch        # noqa: E402
 
 DEV = torch.device("cuda:0")

@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """Diagnostics of the tcgen05 decoder kernels on a GPU box: crafted weights isolate layer 1 / 2 / 3, then random
 weights against the FP32 kernels, then the sampler's log-acceptance values.  Prints error maps per column / row block."""
-import ctypes as C
 import sys
 
 import numpy as np
@@ -9,7 +8,7 @@ import torch
 
 sys.path.insert(0, ".")
 from dvae_b200 import _lib, synth, tc                                    # noqa: E402
-from dvae_b200.engine import (InjectedDraws, McemConfig, McemEngine, RaggedBatch, VaeWeights, _ld_for, _p, _stream,  # noqa: E402
+from dvae_b200.engine import (InjectedDraws, McemConfig, McemEngine, RaggedBatch, VaeWeights, _p, _stream,  # noqa: E402
                               mlp_forward)
 
 DEV = torch.device("cuda:0")
